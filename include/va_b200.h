@@ -1,0 +1,226 @@
+/*
+ * va_b200.h -- C ABI of libva_b200.so: the B200 (sm_100a) filter -> segment path
+ * of david-zwicker/video-analysis.
+ *
+ * The reference is pure Python and has no FFI; each entry point below replaces
+ * the body of one reference `_process_frame` / analysis helper (cited per
+ * function, paths relative to the reference root) for a BATCH of frames.
+ * INTEGRATION.md shows the ctypes stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - every function returns VA_OK (0) or a negative va_status; nothing throws.
+ *    va_last_error(ctx) holds a human readable message for the last failure.
+ *  - all image pointers are DEVICE pointers owned by the caller.  Kernels are
+ *    enqueued on `stream` (a cudaStream_t passed as void*) and never
+ *    synchronise; the call returns as soon as the work is queued.
+ *  - u8 images: `pitch` = bytes between rows, `fstride` = bytes between frames
+ *    of the batch.  Colour frames are interleaved (H, W, 3) as in the reference
+ *    (video/io/backend_ffmpeg.py:318-319).  Nothing needs to be aligned; 16-byte
+ *    aligned pointers / pitches take the vector paths.
+ *  - bit masks: 32-bit words, bit i of word j of a row = pixel x = 32*j + i
+ *    (LSB = lowest x).  `pitch_w` / `fstride_w` are counted in words.  Bits at
+ *    x >= w in the last word of a row are written as 0 and ignored on input.
+ *  - labels: int32, `pitch_e` / `fstride_e` counted in elements.
+ *  - one ctx per GPU per host thread; a ctx owns only scratch memory.
+ */
+#ifndef VA_B200_H
+#define VA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct va_ctx va_ctx;
+typedef void *va_stream; /* cudaStream_t */
+
+typedef enum va_status {
+    VA_OK = 0,
+    VA_ERR_INVALID = -1,     /* bad argument (ValueError on the Python side) */
+    VA_ERR_CUDA = -2,        /* a CUDA runtime call failed */
+    VA_ERR_NOMEM = -3,       /* scratch allocation failed */
+    VA_ERR_CAPACITY = -4,    /* w, h or batch exceed what the ctx was created for */
+    VA_ERR_UNSUPPORTED = -5  /* parameter combination not implemented on the device */
+} va_status;
+
+/* morphology: operations and structuring-element shapes (cv2.MORPH_* order) */
+enum { VA_MORPH_ERODE = 0, VA_MORPH_DILATE = 1, VA_MORPH_OPEN = 2, VA_MORPH_CLOSE = 3 };
+enum { VA_SE_RECT = 0, VA_SE_CROSS = 1, VA_SE_ELLIPSE = 2 };
+/* luma modes: FilterMonochrome(mode=...) video/filters.py:351-368 */
+enum { VA_MONO_MEAN = -1, VA_MONO_CH0 = 0, VA_MONO_CH1 = 1, VA_MONO_CH2 = 2 };
+
+int va_version(void);
+const char *va_status_string(int status);
+
+/* scratch is sized for frames up to max_w x max_h and batches up to max_batch */
+int va_create(va_ctx **out, int device, int max_w, int max_h, int max_batch);
+int va_destroy(va_ctx *ctx);
+const char *va_last_error(const va_ctx *ctx);
+/* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
+long long va_launch_count(const va_ctx *ctx);
+
+/* K1 FilterMonochrome._process_frame, video/filters.py:359-374:
+ *    mode VA_MONO_MEAN: out = (c0 + c1 + c2) / 3  (== np.mean(axis=2).astype(u8), :366)
+ *    mode 0/1/2:        out = in[:, :, mode]      (:368; also FilterCrop's color_channel, :245)
+ * A crop (FilterCrop._process_frame, video/filters.py:238-248) is expressed by
+ * the caller offsetting `in` to the first pixel of the rectangle. */
+int va_luma_u8(va_ctx *ctx, va_stream stream,
+               const uint8_t *in, size_t in_pitch, size_t in_fstride,
+               uint8_t *out, size_t out_pitch, size_t out_fstride,
+               int w, int h, int batch, int mode);
+
+/* strided 2-D copy of `row_bytes` x h x batch (FilterCrop on frames that stay
+ * colour / monochrome, video/filters.py:241) */
+int va_copy2d_u8(va_ctx *ctx, va_stream stream,
+                 const uint8_t *in, size_t in_pitch, size_t in_fstride,
+                 uint8_t *out, size_t out_pitch, size_t out_fstride,
+                 int row_bytes, int h, int batch);
+
+/* K2 FilterBlur._process_frame, video/filters.py:388-392:
+ *    cv2.GaussianBlur(u8, (0, 0), sigma), bit-exact: 8-bit fixed-point kernel,
+ *    out = (sum_ky sum_kx K[ky] K[kx] src + 32768) >> 16, BORDER_REFLECT_101.
+ * channels = 1 or 3 (interleaved, filtered independently). in != out. */
+int va_gauss_u8(va_ctx *ctx, va_stream stream,
+                const uint8_t *in, size_t in_pitch, size_t in_fstride,
+                uint8_t *out, size_t out_pitch, size_t out_fstride,
+                int w, int h, int channels, int batch, double sigma);
+/* the integer taps va_gauss_u8 uses for `sigma` (host side; taps[] needs room
+ * for 6*sigma+3 entries); returns ksize or a negative status */
+int va_gauss_taps(double sigma, int *taps, int capacity);
+
+/* K1+K2 fused: FilterBlur(FilterMonochrome(video)) without materialising the
+ * monochrome frame (same results as va_luma_u8 followed by va_gauss_u8) */
+int va_luma_gauss_u8(va_ctx *ctx, va_stream stream,
+                     const uint8_t *in, size_t in_pitch, size_t in_fstride,
+                     uint8_t *out, size_t out_pitch, size_t out_fstride,
+                     int w, int h, int batch, int mode, double sigma);
+
+/* K2b FilterResize._process_frame, video/filters.py:308-315, for the exact
+ * integer case cv2.resize(INTER_AREA) by 1/2: out = (a + b + c + d + 2) >> 2.
+ * (w, h) is the INPUT size; output is (w/2, h/2); w and h must be even. */
+int va_resize_half_u8(va_ctx *ctx, va_stream stream,
+                      const uint8_t *in, size_t in_pitch, size_t in_fstride,
+                      uint8_t *out, size_t out_pitch, size_t out_fstride,
+                      int w, int h, int channels, int batch);
+
+/* K3 running-average background + |difference| > thr -> packed mask bits.
+ * Not in the reference; fold shape follows
+ * video/analysis/video.py:14-35, signed difference video/filters.py:564-568:
+ *    d = float(x_t) - bg;  mask_t = |d| > thr;  bg = bg + alpha * d   (float32,
+ *    multiply and add rounded separately, frames of the batch in order)
+ * `bg` (float32, pitch_e elements per row) is the state before frame 0 of the
+ * batch and is updated in place.  If first_frame_inits != 0, frame 0 of the
+ * batch initialises bg = float(x_0) and gets an all-zero mask. */
+int va_ema_diff_thresh(va_ctx *ctx, va_stream stream,
+                       const uint8_t *in, size_t in_pitch, size_t in_fstride,
+                       float *bg, size_t bg_pitch_e,
+                       uint32_t *mask, size_t mask_pitch_w, size_t mask_fstride_w,
+                       int w, int h, int batch,
+                       float alpha, float thr, int first_frame_inits);
+
+/* mask = in > thr (strict, == cv2.threshold(..., THRESH_BINARY)) -> packed bits */
+int va_threshold_bits(va_ctx *ctx, va_stream stream,
+                      const uint8_t *in, size_t in_pitch, size_t in_fstride,
+                      uint32_t *mask, size_t mask_pitch_w, size_t mask_fstride_w,
+                      int w, int h, int batch, int thr);
+
+/* packed bits <-> u8 masks ({0,255} out; nonzero in) */
+int va_unpack_bits_u8(va_ctx *ctx, va_stream stream,
+                      const uint32_t *mask, size_t mask_pitch_w, size_t mask_fstride_w,
+                      uint8_t *out, size_t out_pitch, size_t out_fstride,
+                      int w, int h, int batch);
+int va_pack_bits_u8(va_ctx *ctx, va_stream stream,
+                    const uint8_t *in, size_t in_pitch, size_t in_fstride,
+                    uint32_t *mask, size_t mask_pitch_w, size_t mask_fstride_w,
+                    int w, int h, int batch);
+
+/* K4 binary morphology on packed bits; replaces cv2.erode / cv2.dilate
+ * (video/analysis/image.py:248-256) and cv2.morphologyEx(OPEN / CLOSE) with
+ * cv2.getStructuringElement(shape, (kx, ky)) and OpenCV's default border
+ * (pixels outside the image never win the min / max).  in != out. */
+int va_morph_bits(va_ctx *ctx, va_stream stream,
+                  const uint32_t *in, size_t in_pitch_w, size_t in_fstride_w,
+                  uint32_t *out, size_t out_pitch_w, size_t out_fstride_w,
+                  int w, int h, int batch, int op, int shape, int kx, int ky);
+
+/* K5 connected-component labelling; replaces
+ * ndimage.measurements.label(mask) at video/analysis/regions.py:162.
+ * connectivity 4 (scipy default) or 8.  labels: 0 background, 1..n numbered in
+ * raster order of each component's first pixel.  counts[b] = n of frame b. */
+int va_label_bits(va_ctx *ctx, va_stream stream,
+                  const uint32_t *mask, size_t mask_pitch_w, size_t mask_fstride_w,
+                  int32_t *labels, size_t labels_pitch_e, size_t labels_fstride_e,
+                  int32_t *counts, int w, int h, int batch, int connectivity);
+
+/* per-label pixel counts (video/analysis/regions.py:165-166) and the largest
+ * region (regions.py:169): areas[b * max_labels + (l-1)], largest[b] = label */
+int va_region_areas(va_ctx *ctx, va_stream stream,
+                    const int32_t *labels, size_t labels_pitch_e, size_t labels_fstride_e,
+                    int32_t *areas, int max_labels, int32_t *largest,
+                    int w, int h, int batch);
+
+/* K6 apply-mask: out = mask != 0 ? in : 0 (not in the reference; idioms
+ * video/io/composer.py:154,186,208).  mask is u8 (H, W); mask_fstride = 0
+ * broadcasts one static mask over the batch. */
+int va_apply_mask_u8(va_ctx *ctx, va_stream stream,
+                     const uint8_t *in, size_t in_pitch, size_t in_fstride,
+                     const uint8_t *mask, size_t mask_pitch, size_t mask_fstride,
+                     uint8_t *out, size_t out_pitch, size_t out_fstride,
+                     int w, int h, int channels, int batch);
+
+/* frame-sharded EMA.  The recurrence is affine,
+ *    bg_t = a * bg_{t-1} + alpha * x_t,   a = 1 - alpha,
+ * so a rank can fold its frames from a zero state into S and the true state is
+ * recovered from the ranks before it.
+ * va_ema_partial:  S = a^batch * S + sum_i alpha * a^(batch-1-i) * x_i
+ *                  (S is overwritten when accumulate == 0)
+ * va_ema_fold:     carry = scale * carry + S          (element-wise, float32) */
+int va_ema_partial(va_ctx *ctx, va_stream stream,
+                   const uint8_t *in, size_t in_pitch, size_t in_fstride,
+                   float *S, size_t s_pitch_e, int w, int h, int batch,
+                   float alpha, int accumulate);
+int va_ema_fold(va_ctx *ctx, va_stream stream, float *carry, const float *S,
+                size_t pitch_e, int w, int h, float scale);
+
+/* seeded synthetic RGB video generated on the device; replaces
+ * the unseeded VideoGaussianNoise (video/io/computed.py:15-41).  `blobs` is a
+ * HOST array of n_blobs x 5 int32 (x0, y0, vx16, vy16, r). Frames t0..t0+batch-1. */
+int va_synth_rgb(va_ctx *ctx, va_stream stream,
+                 uint8_t *out, size_t out_pitch, size_t out_fstride,
+                 int w, int h, int t0, int batch, uint32_t seed,
+                 const int32_t *blobs, int n_blobs);
+
+/* the whole chain of BASELINE.json configs 1-3 on one device-resident batch:
+ * mono -> blur -> EMA/diff/threshold -> morphology -> label.  Intermediates live
+ * in ctx scratch unless an output pointer is given (NULL = not wanted). */
+typedef struct va_chain_desc {
+    int w, h, batch;
+    int mono_mode;           /* VA_MONO_* */
+    double sigma;            /* <= 0: no blur */
+    float alpha, thr;
+    int first_frame_inits;   /* this batch starts the video */
+    int morph_op;            /* VA_MORPH_* or -1 for none */
+    int morph_shape, morph_kx, morph_ky;
+    int connectivity;        /* 4 or 8; 0 = no labelling */
+    int fuse_luma_blur;      /* 1: use va_luma_gauss_u8 when `mono` is not wanted */
+} va_chain_desc;
+
+typedef struct va_chain_io {
+    const uint8_t *rgb; size_t rgb_pitch, rgb_fstride;         /* in  (H, W, 3) u8 */
+    float *bg; size_t bg_pitch_e;                              /* in/out state */
+    uint8_t *mono; size_t mono_pitch, mono_fstride;            /* out, optional */
+    uint8_t *blur; size_t blur_pitch, blur_fstride;            /* out, optional */
+    uint32_t *mask; size_t mask_pitch_w, mask_fstride_w;       /* out, optional (after threshold) */
+    uint32_t *morph; size_t morph_pitch_w, morph_fstride_w;    /* out, optional (after morphology) */
+    int32_t *labels; size_t labels_pitch_e, labels_fstride_e;  /* out, optional */
+    int32_t *counts;                                           /* out, optional */
+} va_chain_io;
+
+int va_chain_run(va_ctx *ctx, va_stream stream, const va_chain_desc *desc, const va_chain_io *io);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VA_B200_H */

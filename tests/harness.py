@@ -1,0 +1,397 @@
+"""
+Test harness: calls the C ABI of include/va_b200.h on NumPy inputs and returns
+NumPy outputs, on one of two backends
+
+  cuda  csrc/libva_b200.so on cuda:0 (tests marked `gpu`; the parity gate)
+  emu   tests/emu/libva_b200_emu.so, the same kernel sources compiled for the CPU
+        with the thread-emulation shim (development-time logic check only)
+
+Nothing here is product code.
+"""
+
+import ctypes
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from video_analysis_b200 import _lib as valib  # noqa: E402
+
+
+class EmuBackend(object):
+    name = 'emu'
+
+    def __init__(self):
+        from tests.emu import build_emu
+        self.lib = valib.bind(ctypes.CDLL(build_emu.build()))
+        self.stream = None
+
+    def empty(self, shape, dtype, fill=None):
+        a = np.empty(shape, dtype)
+        a[...] = 0xCD if fill is None else fill
+        return a
+
+    def to_dev(self, a):
+        return np.array(a, copy=True, order='C')
+
+    def to_host(self, d):
+        return np.array(d, copy=True)
+
+    def ptr(self, d, offset_bytes=0):
+        return d.ctypes.data + offset_bytes
+
+    def sync(self):
+        pass
+
+
+class CudaBackend(object):
+    name = 'cuda'
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.lib = valib.load()
+        self.dev = torch.device('cuda:0')
+        self.stream = None
+
+    def empty(self, shape, dtype, fill=None):
+        a = np.empty(shape, dtype)
+        a[...] = 0xCD if fill is None else fill
+        return self.to_dev(a)
+
+    def to_dev(self, a):
+        a = np.ascontiguousarray(a)
+        if a.dtype == np.uint32:
+            return self.torch.from_numpy(a.view(np.int32)).to(self.dev)
+        return self.torch.from_numpy(a).to(self.dev)
+
+    def to_host(self, d):
+        self.torch.cuda.synchronize()
+        return d.cpu().numpy()
+
+    def ptr(self, d, offset_bytes=0):
+        return d.data_ptr() + offset_bytes
+
+    def sync(self):
+        self.torch.cuda.synchronize()
+
+
+class Ctx(object):
+    def __init__(self, be, max_w, max_h, max_batch):
+        self.be = be
+        self.lib = be.lib
+        h = ctypes.c_void_p()
+        rc = self.lib.va_create(ctypes.byref(h), 0, max_w, max_h, max_batch)
+        assert rc == 0, rc
+        self.h = h
+
+    def check(self, rc):
+        valib.check(self.lib, self.h, rc)
+
+    def close(self):
+        if self.h:
+            self.lib.va_destroy(self.h)
+            self.h = None
+
+
+def _round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+class Img(object):
+    """ a batch of u8 / u32 / i32 / f32 images on the backend with explicit pitch """
+
+    def __init__(self, be, batch, h, row_elems, dtype, pitch_elems=None, data=None, offset_elems=0, fill=None):
+        self.be = be
+        self.dtype = np.dtype(dtype)
+        self.batch, self.h, self.row = batch, h, row_elems
+        self.pitch = pitch_elems or row_elems
+        self.offset = offset_elems
+        host = np.empty((batch, h, self.pitch), self.dtype)
+        host.view(np.uint8)[...] = 0xCD if fill is None else fill
+        if data is not None:
+            host[:, :, offset_elems:offset_elems + row_elems] = np.asarray(data).reshape(batch, h, row_elems)
+        self.dev = be.to_dev(host)
+
+    @property
+    def ptr(self):
+        return self.be.ptr(self.dev, self.offset * self.dtype.itemsize)
+
+    @property
+    def fstride(self):
+        return self.h * self.pitch
+
+    def get(self):
+        host = self.be.to_host(self.dev)
+        if self.dtype == np.uint32:
+            host = host.view(np.uint32)
+        return host.reshape(self.batch, self.h, self.pitch)[:, :, self.offset:self.offset + self.row].copy()
+
+    def raw(self):
+        host = self.be.to_host(self.dev)
+        if self.dtype == np.uint32:
+            host = host.view(np.uint32)
+        return host.reshape(self.batch, self.h, self.pitch)
+
+
+# ---------------------------------------------------------------------------------------
+# one wrapper per entry point: NumPy in, NumPy out
+# ---------------------------------------------------------------------------------------
+def luma(ctx, frames, mode=-1, in_pad=0, in_off=0, out_pad=0):
+    be = ctx.be
+    B, H, W, _ = frames.shape
+    src = Img(be, B, H, 3 * W, np.uint8, 3 * W + in_pad + in_off, frames.reshape(B, H, 3 * W), in_off)
+    dst = Img(be, B, H, W, np.uint8, W + out_pad)
+    ctx.check(ctx.lib.va_luma_u8(ctx.h, be.stream, src.ptr, src.pitch, src.fstride, dst.ptr, dst.pitch, dst.fstride,
+                                 W, H, B, mode))
+    raw = dst.raw()
+    assert (raw[:, :, W:] == 0xCD).all(), 'luma wrote outside its rows'
+    return dst.get()
+
+
+def crop_luma(ctx, frames, rect, mode=-1):
+    """ crop by pointer offset into a larger frame, then luma """
+    be = ctx.be
+    B, H, W, _ = frames.shape
+    left, top, w, h = rect
+    src = Img(be, B, H, 3 * W, np.uint8, data=frames.reshape(B, H, 3 * W))
+    dst = Img(be, B, h, w, np.uint8)
+    ptr = be.ptr(src.dev, top * 3 * W + 3 * left)
+    ctx.check(ctx.lib.va_luma_u8(ctx.h, be.stream, ptr, 3 * W, H * 3 * W, dst.ptr, dst.pitch, dst.fstride, w, h, B, mode))
+    return dst.get()
+
+
+def copy2d(ctx, frames, rect):
+    be = ctx.be
+    B, H = frames.shape[:2]
+    rowb = int(np.prod(frames.shape[2:]))
+    ch = frames.shape[3] if frames.ndim == 4 else 1
+    left, top, w, h = rect
+    src = Img(be, B, H, rowb, np.uint8, data=frames.reshape(B, H, rowb))
+    dst = Img(be, B, h, w * ch, np.uint8)
+    ptr = be.ptr(src.dev, top * rowb + left * ch)
+    ctx.check(ctx.lib.va_copy2d_u8(ctx.h, be.stream, ptr, rowb, H * rowb, dst.ptr, dst.pitch, dst.fstride, w * ch, h, B))
+    out = dst.get()
+    return out.reshape(B, h, w, ch) if frames.ndim == 4 else out
+
+
+def gauss(ctx, frames, sigma, in_pad=0, out_pad=0):
+    be = ctx.be
+    if frames.ndim == 3:
+        B, H, W = frames.shape
+        ch = 1
+    else:
+        B, H, W, ch = frames.shape
+    src = Img(be, B, H, W * ch, np.uint8, W * ch + in_pad, frames.reshape(B, H, W * ch))
+    dst = Img(be, B, H, W * ch, np.uint8, W * ch + out_pad)
+    ctx.check(ctx.lib.va_gauss_u8(ctx.h, be.stream, src.ptr, src.pitch, src.fstride, dst.ptr, dst.pitch, dst.fstride,
+                                  W, H, ch, B, float(sigma)))
+    raw = dst.raw()
+    assert (raw[:, :, W * ch:] == 0xCD).all(), 'gauss wrote outside its rows'
+    return dst.get().reshape(frames.shape)
+
+
+def luma_gauss(ctx, frames, sigma, mode=-1):
+    be = ctx.be
+    B, H, W, _ = frames.shape
+    src = Img(be, B, H, 3 * W, np.uint8, data=frames.reshape(B, H, 3 * W))
+    dst = Img(be, B, H, W, np.uint8)
+    ctx.check(ctx.lib.va_luma_gauss_u8(ctx.h, be.stream, src.ptr, src.pitch, src.fstride, dst.ptr, dst.pitch,
+                                       dst.fstride, W, H, B, mode, float(sigma)))
+    return dst.get()
+
+
+def gauss_taps(lib, sigma):
+    buf = (ctypes.c_int * 1024)()
+    n = lib.va_gauss_taps(float(sigma), buf, 1024)
+    assert n > 0, n
+    return np.array(buf[:n], dtype=np.int64)
+
+
+def resize_half(ctx, frames, in_pad=0):
+    be = ctx.be
+    if frames.ndim == 3:
+        B, H, W = frames.shape
+        ch = 1
+    else:
+        B, H, W, ch = frames.shape
+    src = Img(be, B, H, W * ch, np.uint8, W * ch + in_pad, frames.reshape(B, H, W * ch))
+    dst = Img(be, B, H // 2, (W // 2) * ch, np.uint8)
+    ctx.check(ctx.lib.va_resize_half_u8(ctx.h, be.stream, src.ptr, src.pitch, src.fstride, dst.ptr, dst.pitch,
+                                        dst.fstride, W, H, ch, B))
+    out = dst.get()
+    return out if frames.ndim == 3 else out.reshape(B, H // 2, W // 2, ch)
+
+
+def mask_words(W):
+    return (W + 31) // 32
+
+
+def ema_diff_thresh(ctx, frames, alpha, thr, bg0=None, pad=0):
+    """ returns (packed masks [B,H,Wp] uint32, bg float32 [H,W]) """
+    be = ctx.be
+    B, H, W = frames.shape
+    src = Img(be, B, H, W, np.uint8, W + pad, frames)
+    first = bg0 is None
+    bg = Img(be, 1, H, W, np.float32, W + (pad // 4) * 4, None if first else np.asarray(bg0, np.float32)[None])
+    Wp = mask_words(W)
+    msk = Img(be, B, H, Wp, np.uint32, Wp + (1 if pad else 0))
+    ctx.check(ctx.lib.va_ema_diff_thresh(ctx.h, be.stream, src.ptr, src.pitch, src.fstride, bg.ptr, bg.pitch,
+                                         msk.ptr, msk.pitch, msk.fstride, W, H, B, float(alpha), float(thr), int(first)))
+    return msk.get(), bg.get()[0]
+
+
+def threshold_bits(ctx, frames, thr, pad=0):
+    be = ctx.be
+    B, H, W = frames.shape
+    src = Img(be, B, H, W, np.uint8, W + pad, frames)
+    Wp = mask_words(W)
+    msk = Img(be, B, H, Wp, np.uint32)
+    ctx.check(ctx.lib.va_threshold_bits(ctx.h, be.stream, src.ptr, src.pitch, src.fstride, msk.ptr, msk.pitch,
+                                        msk.fstride, W, H, B, int(thr)))
+    return msk.get()
+
+
+def pack_bits(ctx, masks, pad=0):
+    be = ctx.be
+    B, H, W = masks.shape
+    src = Img(be, B, H, W, np.uint8, W + pad, masks)
+    Wp = mask_words(W)
+    msk = Img(be, B, H, Wp, np.uint32)
+    ctx.check(ctx.lib.va_pack_bits_u8(ctx.h, be.stream, src.ptr, src.pitch, src.fstride, msk.ptr, msk.pitch,
+                                      msk.fstride, W, H, B))
+    return msk.get()
+
+
+def unpack_bits(ctx, words, W, pad=0):
+    be = ctx.be
+    B, H, Wp = words.shape
+    msk = Img(be, B, H, Wp, np.uint32, data=words)
+    dst = Img(be, B, H, W, np.uint8, W + pad)
+    ctx.check(ctx.lib.va_unpack_bits_u8(ctx.h, be.stream, msk.ptr, msk.pitch, msk.fstride, dst.ptr, dst.pitch,
+                                        dst.fstride, W, H, B))
+    raw = dst.raw()
+    assert (raw[:, :, W:] == 0xCD).all()
+    return dst.get()
+
+
+def morph(ctx, words, W, op, shape='rect', ksize=3):
+    be = ctx.be
+    B, H, Wp = words.shape
+    kx, ky = (ksize, ksize) if np.isscalar(ksize) else ksize
+    src = Img(be, B, H, Wp, np.uint32, data=words)
+    dst = Img(be, B, H, Wp, np.uint32)
+    ctx.check(ctx.lib.va_morph_bits(ctx.h, be.stream, src.ptr, src.pitch, src.fstride, dst.ptr, dst.pitch, dst.fstride,
+                                    W, H, B, valib.MORPH_OPS[op], valib.SE_SHAPES[shape], int(kx), int(ky)))
+    return dst.get()
+
+
+def label(ctx, words, W, connectivity=4, lab_pad=0):
+    """ returns (labels int32 [B,H,W], counts int32 [B]) """
+    be = ctx.be
+    B, H, Wp = words.shape
+    src = Img(be, B, H, Wp, np.uint32, data=words)
+    lab = Img(be, B, H, W, np.int32, W + lab_pad)
+    cnt = Img(be, 1, 1, B, np.int32)
+    ctx.check(ctx.lib.va_label_bits(ctx.h, be.stream, src.ptr, src.pitch, src.fstride, lab.ptr, lab.pitch, lab.fstride,
+                                    cnt.ptr, W, H, B, connectivity))
+    return lab.get(), cnt.get()[0, 0]
+
+
+def region_areas(ctx, labels, max_labels):
+    be = ctx.be
+    B, H, W = labels.shape
+    lab = Img(be, B, H, W, np.int32, data=labels)
+    areas = Img(be, 1, B, max_labels, np.int32)
+    largest = Img(be, 1, 1, B, np.int32)
+    ctx.check(ctx.lib.va_region_areas(ctx.h, be.stream, lab.ptr, lab.pitch, lab.fstride, areas.ptr, max_labels,
+                                      largest.ptr, W, H, B))
+    return areas.get()[0], largest.get()[0, 0]
+
+
+def apply_mask(ctx, frames, mask):
+    be = ctx.be
+    if frames.ndim == 3:
+        B, H, W = frames.shape
+        ch = 1
+    else:
+        B, H, W, ch = frames.shape
+    src = Img(be, B, H, W * ch, np.uint8, data=frames.reshape(B, H, W * ch))
+    dst = Img(be, B, H, W * ch, np.uint8)
+    static = mask.ndim == 2
+    m = Img(be, 1 if static else B, H, W, np.uint8, data=mask[None] if static else mask)
+    ctx.check(ctx.lib.va_apply_mask_u8(ctx.h, be.stream, src.ptr, src.pitch, src.fstride, m.ptr, m.pitch,
+                                       0 if static else m.fstride, dst.ptr, dst.pitch, dst.fstride, W, H, ch, B))
+    return dst.get().reshape(frames.shape)
+
+
+def ema_partial(ctx, frames, alpha, S0=None):
+    be = ctx.be
+    B, H, W = frames.shape
+    src = Img(be, B, H, W, np.uint8, data=frames)
+    S = Img(be, 1, H, W, np.float32, data=None if S0 is None else np.asarray(S0, np.float32)[None])
+    ctx.check(ctx.lib.va_ema_partial(ctx.h, be.stream, src.ptr, src.pitch, src.fstride, S.ptr, S.pitch, W, H, B,
+                                     float(alpha), 0 if S0 is None else 1))
+    return S.get()[0]
+
+
+def ema_fold(ctx, carry, S, scale):
+    be = ctx.be
+    H, W = carry.shape
+    c = Img(be, 1, H, W, np.float32, data=carry[None])
+    s = Img(be, 1, H, W, np.float32, data=S[None])
+    ctx.check(ctx.lib.va_ema_fold(ctx.h, be.stream, c.ptr, s.ptr, c.pitch, W, H, float(scale)))
+    return c.get()[0]
+
+
+def synth(ctx, seed, t0, n, W, H, blobs):
+    be = ctx.be
+    dst = Img(be, n, H, 3 * W, np.uint8)
+    tab = np.ascontiguousarray(blobs, dtype=np.int32)
+    ctx.check(ctx.lib.va_synth_rgb(ctx.h, be.stream, dst.ptr, dst.pitch, dst.fstride, W, H, t0, n, seed,
+                                   tab.ctypes.data, len(tab)))
+    return dst.get().reshape(n, H, W, 3)
+
+
+def chain(ctx, frames, sigma=2.0, alpha=0.05, thr=25.0, morph_op='open', shape='rect', k=3, connectivity=4,
+          bg0=None, fuse=False, want=('mono', 'blur', 'mask', 'morph', 'labels')):
+    be = ctx.be
+    B, H, W, _ = frames.shape
+    Wp = mask_words(W)
+    src = Img(be, B, H, 3 * W, np.uint8, data=frames.reshape(B, H, 3 * W))
+    first = bg0 is None
+    bg = Img(be, 1, H, W, np.float32, data=None if first else np.asarray(bg0, np.float32)[None])
+    bufs = {
+        'mono': Img(be, B, H, W, np.uint8), 'blur': Img(be, B, H, W, np.uint8),
+        'mask': Img(be, B, H, Wp, np.uint32), 'morph': Img(be, B, H, Wp, np.uint32),
+        'labels': Img(be, B, H, W, np.int32),
+    }
+    cnt = Img(be, 1, 1, B, np.int32)
+    d = valib.ChainDesc(w=W, h=H, batch=B, mono_mode=-1, sigma=float(sigma), alpha=alpha, thr=thr,
+                        first_frame_inits=int(first), morph_op=valib.MORPH_OPS[morph_op] if morph_op else -1,
+                        morph_shape=valib.SE_SHAPES[shape], morph_kx=k, morph_ky=k, connectivity=connectivity,
+                        fuse_luma_blur=int(fuse))
+    io = valib.ChainIO()
+    io.rgb, io.rgb_pitch, io.rgb_fstride = src.ptr, src.pitch, src.fstride
+    io.bg, io.bg_pitch_e = bg.ptr, bg.pitch
+    for name in want:
+        b = bufs[name]
+        setattr(io, name, b.ptr)
+        if name in ('mono', 'blur'):
+            setattr(io, name + '_pitch', b.pitch)
+            setattr(io, name + '_fstride', b.fstride)
+        elif name in ('mask', 'morph'):
+            setattr(io, name + '_pitch_w', b.pitch)
+            setattr(io, name + '_fstride_w', b.fstride)
+        else:
+            io.labels_pitch_e, io.labels_fstride_e = b.pitch, b.fstride
+    io.counts = cnt.ptr
+    ctx.check(ctx.lib.va_chain_run(ctx.h, be.stream, ctypes.byref(d), ctypes.byref(io)))
+    out = {name: bufs[name].get() for name in want}
+    out['counts'] = cnt.get()[0, 0]
+    out['bg'] = bg.get()[0]
+    return out

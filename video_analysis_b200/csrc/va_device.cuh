@@ -1,0 +1,81 @@
+// va_device.cuh -- small device helpers shared by the kernels.
+#pragma once
+#include "va_common.cuh"
+
+// 16-byte asynchronous global -> shared copy (LDGSTS); both addresses 16-byte aligned
+__device__ __forceinline__ void va_cp_async16(void *smem_dst, const void *gmem_src) {
+#ifdef VA_EMU
+    std::memcpy(smem_dst, gmem_src, 16);
+#else
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
+#endif
+}
+__device__ __forceinline__ void va_cp_async_wait_all() {
+#ifndef VA_EMU
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+#endif
+}
+
+// streaming loads / stores that do not pollute L1
+__device__ __forceinline__ uint4 va_ld_stream16(const void *p) {
+#ifdef VA_EMU
+    return *reinterpret_cast<const uint4 *>(p);
+#else
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+#endif
+}
+__device__ __forceinline__ void va_st_stream16(void *p, uint4 v) {
+#ifdef VA_EMU
+    *reinterpret_cast<uint4 *>(p) = v;
+#else
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+                 ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+#endif
+}
+// load that bypasses L1 (union-find forest is mutated by other CTAs)
+__device__ __forceinline__ int va_ld_cg(const int *p) {
+#ifdef VA_EMU
+    return __atomic_load_n(p, __ATOMIC_RELAXED);
+#else
+    return __ldcg(p);
+#endif
+}
+
+// BORDER_REFLECT_101 index (... d c b | a b c d | c b a ...), any i
+__device__ __forceinline__ int va_reflect101(int i, int n) {
+    if (n == 1) return 0;
+    int p = 2 * n - 2;
+    i %= p;
+    if (i < 0) i += p;
+    return i < n ? i : p - i;
+}
+
+// (c0 + c1 + c2) / 3 for four interleaved RGB pixels held in three words
+__device__ __forceinline__ unsigned va_mean3_x4(unsigned w0, unsigned w1, unsigned w2) {
+    unsigned s0 = __dp4a(w0, 0x00010101u, 0u);
+    unsigned s1 = __dp4a(w0, 0x01000000u, __dp4a(w1, 0x00000101u, 0u));
+    unsigned s2 = __dp4a(w1, 0x01010000u, __dp4a(w2, 0x00000001u, 0u));
+    unsigned s3 = __dp4a(w2, 0x01010100u, 0u);
+    // floor(s / 3) == umulhi(s, (2^32 + 2) / 3) for s < 2^31
+    unsigned q0 = __umulhi(s0, 0x55555556u), q1 = __umulhi(s1, 0x55555556u);
+    unsigned q2 = __umulhi(s2, 0x55555556u), q3 = __umulhi(s3, 0x55555556u);
+    return q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
+}
+// channel c of four interleaved RGB pixels held in three words
+__device__ __forceinline__ unsigned va_pick3_x4(unsigned w0, unsigned w1, unsigned w2, int c) {
+    if (c == 0) return __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);
+    if (c == 1) return __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);
+    return __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);
+}
+__device__ __forceinline__ unsigned va_luma_x4(unsigned w0, unsigned w1, unsigned w2, int mode) {
+    return mode < 0 ? va_mean3_x4(w0, w1, w2) : va_pick3_x4(w0, w1, w2, mode);
+}
+// scalar version for edges
+__device__ __forceinline__ unsigned va_luma_px(const uint8_t *p, int mode) {
+    if (mode >= 0) return p[mode];
+    return ((unsigned)p[0] + p[1] + p[2]) / 3u;
+}

@@ -1,0 +1,220 @@
+// va_ema.cu -- K3: running-average background + |difference| > thr -> packed bits,
+// and the affine partial / carry folds used when a video is frame-sharded over GPUs.
+//
+// The recurrence is sequential in t, parallel in pixels: a thread owns PX pixels,
+// keeps their float32 background in registers across the whole batch of T frames
+// and streams the T u8 frames through (4 frames of loads in flight per thread).
+// Algorithmic HBM bytes per frame: N (u8 in) + N/8 (bits out) + 8N/T (state in/out).
+//   d = float(x) - bg;  bit = |d| > thr;  bg = bg + alpha * d     (mul and add rounded
+// separately: __fmul_rn / __fadd_rn keep the compiler from contracting to an FMA, so the
+// result is bit-identical to the NumPy float32 oracle).
+#include "va_device.cuh"
+
+#define EMA_THREADS 256
+#define EMA_DEPTH 4
+
+template <int PX> struct EmaVec;
+template <> struct EmaVec<16> { typedef uint4 type; };
+template <> struct EmaVec<4> { typedef unsigned type; };
+
+template <int PX>
+__device__ __forceinline__ void ema_load(const uint8_t *rp, int x, int w, bool vec, unsigned (&v)[PX / 4]) {
+    if (vec && x + PX <= w) {
+        if (PX == 16) {
+            const uint4 q = va_ld_stream16(rp + x);
+            v[0] = q.x; v[PX / 4 > 1 ? 1 : 0] = q.y; v[PX / 4 > 2 ? 2 : 0] = q.z; v[PX / 4 > 3 ? 3 : 0] = q.w;
+        } else {
+            v[0] = __ldg(reinterpret_cast<const unsigned *>(rp + x));
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < PX / 4; k++) v[k] = 0;
+        for (int i = 0; i < PX; i++)
+            if (x + i < w) v[i >> 2] |= (unsigned)rp[x + i] << (8 * (i & 3));
+    }
+}
+
+// byte i of `word` as an exact float: bits 0x4B0000bb = 2^23 + b, minus 2^23
+__device__ __forceinline__ float ema_byte_to_float(unsigned word, int i) {
+    return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540u + i)) - 8388608.0f;
+}
+
+template <int PX>
+__global__ void __launch_bounds__(EMA_THREADS)
+ema_diff_thresh_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstride,
+                       float *__restrict__ bg, size_t bg_pitch_e,
+                       uint32_t *__restrict__ mask, size_t mask_pitch_w, size_t mask_fstride_w,
+                       int w, int h, int batch, float alpha, float thr, int first_init, int vec_in, int vec_bg) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = EMA_THREADS >> 5;
+    const int span = 32 * PX;                         // pixels per warp step
+    const int chunks = (w + span - 1) / span;
+    const long long total = (long long)chunks * h;
+    constexpr int NW = PX / 4;
+
+    for (long long item = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); item < total;
+         item += (long long)gridDim.x * warps_per_block) {
+        const int y = (int)(item / chunks);
+        const int c = (int)(item - (long long)y * chunks);
+        const int x = c * span + lane * PX;
+        const uint8_t *rp = in + (size_t)y * in_pitch;
+        float *bgp = bg + (size_t)y * bg_pitch_e + x;
+        const unsigned valid = x >= w ? 0u : (x + PX <= w ? (PX == 32 ? 0xffffffffu : ((1u << PX) - 1u)) : ((1u << (w - x)) - 1u));
+
+        float s[PX];
+        if (vec_bg && x + PX <= w) {
+#pragma unroll
+            for (int k = 0; k < NW; k++) {
+                const float4 q = *reinterpret_cast<const float4 *>(bgp + 4 * k);
+                s[4 * k] = q.x; s[4 * k + 1] = q.y; s[4 * k + 2] = q.z; s[4 * k + 3] = q.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < PX; i++) s[i] = (x + i < w) ? bgp[i] : 0.0f;
+        }
+
+        for (int t0 = 0; t0 < batch; t0 += EMA_DEPTH) {
+            unsigned v[EMA_DEPTH][NW];
+#pragma unroll
+            for (int u = 0; u < EMA_DEPTH; u++)
+                if (t0 + u < batch) ema_load<PX>(rp + (size_t)(t0 + u) * in_fstride, x, w, vec_in != 0, v[u]);
+#pragma unroll
+            for (int u = 0; u < EMA_DEPTH; u++) {
+                const int t = t0 + u;
+                if (t >= batch) break;
+                unsigned m = 0;
+                if (t == 0 && first_init) {
+#pragma unroll
+                    for (int i = 0; i < PX; i++) s[i] = ema_byte_to_float(v[u][i >> 2], i & 3);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < PX; i++) {
+                        const float xf = ema_byte_to_float(v[u][i >> 2], i & 3);
+                        const float d = __fadd_rn(xf, -s[i]);
+                        if (fabsf(d) > thr) m |= 1u << i;
+                        s[i] = __fadd_rn(s[i], __fmul_rn(alpha, d));
+                    }
+                }
+                m &= valid;
+                // merge the PX-bit pieces of 32 / PX neighbouring lanes into one word
+#pragma unroll
+                for (int sh = PX, d = 1; sh < 32; sh <<= 1, d <<= 1)
+                    m |= __shfl_down_sync(0xffffffffu, m, d) << sh;
+                if ((lane & (32 / PX - 1)) == 0 && x < w)
+                    mask[(size_t)t * mask_fstride_w + (size_t)y * mask_pitch_w + (x >> 5)] = m;
+            }
+        }
+
+        if (vec_bg && x + PX <= w) {
+#pragma unroll
+            for (int k = 0; k < NW; k++)
+                *reinterpret_cast<float4 *>(bgp + 4 * k) = make_float4(s[4 * k], s[4 * k + 1], s[4 * k + 2], s[4 * k + 3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < PX; i++)
+                if (x + i < w) bgp[i] = s[i];
+        }
+    }
+}
+
+extern "C" int va_ema_diff_thresh(va_ctx *ctx, va_stream stream,
+                                  const uint8_t *in, size_t in_pitch, size_t in_fstride,
+                                  float *bg, size_t bg_pitch_e,
+                                  uint32_t *mask, size_t mask_pitch_w, size_t mask_fstride_w,
+                                  int w, int h, int batch, float alpha, float thr, int first_frame_inits) {
+    VA_CHECK_CTX(ctx);
+    VA_REQUIRE(ctx, in && bg && mask, "va_ema_diff_thresh: null pointer");
+    VA_REQUIRE(ctx, w > 0 && h > 0 && batch > 0, "va_ema_diff_thresh: bad size");
+    VA_REQUIRE(ctx, mask_pitch_w >= (size_t)((w + 31) / 32) && bg_pitch_e >= (size_t)w, "va_ema_diff_thresh: pitch smaller than a row");
+    const int vec_bg = va_aligned(bg, 16) && bg_pitch_e % 4 == 0;
+    // 16 pixels per thread when that still fills the machine, else 4
+    const long long threads16 = (long long)((w + 511) / 512) * 32 * h;
+    const bool use16 = threads16 >= (long long)ctx->sm_count * 1024;
+    if (use16) {
+        const int vec_in = va_aligned(in, 16) && in_pitch % 16 == 0 && in_fstride % 16 == 0;
+        const long long warps = (long long)((w + 511) / 512) * h;
+        const int grid = va_grid(ctx, (warps + 7) / 8, 8);
+        auto kfn = ema_diff_thresh_kernel<16>;
+        VA_LAUNCH(ctx, kfn, grid, EMA_THREADS, 0, stream, in, in_pitch, in_fstride, bg, bg_pitch_e, mask, mask_pitch_w,
+                  mask_fstride_w, w, h, batch, alpha, thr, first_frame_inits, vec_in, vec_bg);
+    } else {
+        const int vec_in = va_aligned(in, 4) && in_pitch % 4 == 0 && in_fstride % 4 == 0;
+        const long long warps = (long long)((w + 127) / 128) * h;
+        const int grid = va_grid(ctx, (warps + 7) / 8, 8);
+        auto kfn = ema_diff_thresh_kernel<4>;
+        VA_LAUNCH(ctx, kfn, grid, EMA_THREADS, 0, stream, in, in_pitch, in_fstride, bg, bg_pitch_e, mask, mask_pitch_w,
+                  mask_fstride_w, w, h, batch, alpha, thr, first_frame_inits, vec_in, vec_bg);
+    }
+    return VA_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// frame-sharded EMA: partial fold from a zero state and carry combination
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ema_partial_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstride,
+                   float *__restrict__ S, size_t s_pitch_e, int w, int h, int batch,
+                   float alpha, float a, int accumulate, int vec_in) {
+    const int groups = (w + 3) >> 2;
+    const long long total = (long long)groups * h;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(i / groups);
+        const int x = 4 * (int)(i - (long long)y * groups);
+        const uint8_t *rp = in + (size_t)y * in_pitch;
+        float *sp = S + (size_t)y * s_pitch_e + x;
+        float s[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) s[k] = (accumulate && x + k < w) ? sp[k] : 0.0f;
+        for (int t = 0; t < batch; t++) {
+            unsigned v[1];
+            ema_load<4>(rp + (size_t)t * in_fstride, x, w, vec_in != 0, v);
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                s[k] = __fadd_rn(__fmul_rn(a, s[k]), __fmul_rn(alpha, ema_byte_to_float(v[0], k)));
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (x + k < w) sp[k] = s[k];
+    }
+}
+
+extern "C" int va_ema_partial(va_ctx *ctx, va_stream stream,
+                              const uint8_t *in, size_t in_pitch, size_t in_fstride,
+                              float *S, size_t s_pitch_e, int w, int h, int batch,
+                              float alpha, int accumulate) {
+    VA_CHECK_CTX(ctx);
+    VA_REQUIRE(ctx, in && S, "va_ema_partial: null pointer");
+    VA_REQUIRE(ctx, w > 0 && h > 0 && batch > 0 && s_pitch_e >= (size_t)w, "va_ema_partial: bad size");
+    const int vec_in = va_aligned(in, 4) && in_pitch % 4 == 0 && in_fstride % 4 == 0;
+    const long long items = (long long)((w + 3) / 4) * h;
+    const int grid = va_grid(ctx, (items + 255) / 256, 8);
+    auto kfn = ema_partial_kernel;
+    VA_LAUNCH(ctx, kfn, grid, 256, 0, stream, in, in_pitch, in_fstride, S, s_pitch_e, w, h, batch,
+              alpha, 1.0f - alpha, accumulate, vec_in);
+    return VA_OK;
+}
+
+__global__ void __launch_bounds__(256)
+ema_fold_kernel(float *__restrict__ carry, const float *__restrict__ S, size_t pitch_e, int w, int h, float scale) {
+    const long long total = (long long)w * h;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(i / w);
+        const int x = (int)(i - (long long)y * w);
+        const size_t o = (size_t)y * pitch_e + x;
+        carry[o] = __fadd_rn(__fmul_rn(scale, carry[o]), S[o]);
+    }
+}
+
+extern "C" int va_ema_fold(va_ctx *ctx, va_stream stream, float *carry, const float *S,
+                           size_t pitch_e, int w, int h, float scale) {
+    VA_CHECK_CTX(ctx);
+    VA_REQUIRE(ctx, carry && S, "va_ema_fold: null pointer");
+    VA_REQUIRE(ctx, w > 0 && h > 0 && pitch_e >= (size_t)w, "va_ema_fold: bad size");
+    const long long items = (long long)w * h;
+    const int grid = va_grid(ctx, (items + 255) / 256, 8);
+    auto kfn = ema_fold_kernel;
+    VA_LAUNCH(ctx, kfn, grid, 256, 0, stream, carry, S, pitch_e, w, h, scale);
+    return VA_OK;
+}

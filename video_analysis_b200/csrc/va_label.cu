@@ -1,0 +1,467 @@
+// va_label.cu -- K5: connected-component labelling of packed bit masks, replacing
+// scipy.ndimage.label at video/analysis/regions.py:162 (4-connectivity by default,
+// labels 1..n numbered in raster order of each component's first pixel), plus the
+// per-label areas of regions.py:165-169.
+//
+// Run-based union-find.  The unit of equivalence is a horizontal run of foreground
+// pixels, represented by the pixel index (y * P + x) of its first pixel; the forest
+// `parent` lives in ctx scratch and is only ever touched at run starts, so its HBM
+// traffic scales with the number of runs, not pixels.  Hooking always points the larger
+// index at the smaller one, hence the root of a component is its first pixel in raster
+// order, and ranking the roots in index order IS the canonical numbering.
+//
+// One warp owns one image row (lane = 32-pixel word); run starts that continue across
+// words are resolved with one ballot + one shuffle per 32 words.
+//   A init     parent[s] = s for every run start s
+//   B merge    for every maximal overlap segment between a run in row y and one in row
+//              y-1: union(run start, run start)        (atomicMin hooking)
+//   C flatten  parent[s] = root(s); count roots per row
+//   D scan     exclusive prefix of the per-row root counts (one CTA per frame) -> n
+//   E rank     root s of row y gets label rowoff[y] + (its position among the row's
+//              roots) + 1, stored as parent[s] = -label
+//   F resolve  every other run start copies its root's -label
+//   G write    label image: one coalesced 128-byte store per warp per word; the run start
+//              of each pixel comes from bit scans, its label from one forest lookup
+// Algorithmic HBM bytes per frame: N/8 (mask) + 4N (labels).
+#include "va_device.cuh"
+
+#define LAB_THREADS 256
+#define LAB_WARPS (LAB_THREADS / 32)
+#define FULL 0xffffffffu
+
+// ---- row helpers ---------------------------------------------------------------------
+__device__ __forceinline__ unsigned lab_load_word(const uint32_t *row, int wpw, int j, unsigned lastmask) {
+    if (j >= wpw) return 0u;
+    unsigned v = row[j];
+    if (j == wpw - 1) v &= lastmask;
+    return v;
+}
+
+// For the 32 words of a chunk (lane = word): x position of the start of the run that
+// reaches bit 0 of this word from the left (== 32 * word index when nothing continues),
+// and `top` = start of the run that reaches past bit 31 (== 32 * (word + 1) when none).
+// `carry` is `top` of the word preceding the chunk.
+__device__ __forceinline__ void lab_scan_chunk(unsigned wd, int lane, int base_word, int carry, int &st_in, int &top) {
+    const unsigned nf = __ballot_sync(FULL, wd != FULL);
+    const unsigned below = nf & ((1u << lane) - 1u);
+    const int k = 31 - __clz((int)below);                        // nearest not-all-ones word to the left, -1: none
+    const unsigned wk = __shfl_sync(FULL, wd, k < 0 ? 0 : k);
+    st_in = k < 0 ? carry : 32 * (base_word + k) + (32 - __clz((int)~wk));
+    top = wd != FULL ? 32 * (base_word + lane) + (32 - __clz((int)~wd)) : st_in;
+}
+
+// start (x position) of the run containing bit `bit` of word `wd` (bit must be set)
+__device__ __forceinline__ int lab_run_start(unsigned wd, int bit, int word_index, int st_in) {
+    const unsigned z = ~wd & ((1u << bit) - 1u);
+    return z ? 32 * word_index + (32 - __clz((int)z)) : st_in;
+}
+
+// ---- union-find ------------------------------------------------------------------------
+__device__ __forceinline__ int lab_find(const int *parent, int x) {
+    int p;
+    while ((p = va_ld_cg(parent + x)) != x) x = p;
+    return x;
+}
+__device__ __forceinline__ void lab_union(int *parent, int a, int b) {
+    while (true) {
+        a = lab_find(parent, a);
+        b = lab_find(parent, b);
+        if (a == b) return;
+        if (a < b) { const int t = a; a = b; b = t; }
+        const int old = atomicMin(parent + a, b);
+        if (old == a) return;        // a was a root and now hangs under b
+        a = old;                     // lost a race: keep merging what a pointed to with b
+    }
+}
+
+// ---- A: init -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(LAB_THREADS)
+label_init_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
+                  int *__restrict__ parent, size_t P, size_t pf, int w, int h, int batch) {
+    const int lane = threadIdx.x & 31;
+    const int wpw = (w + 31) >> 5;
+    const unsigned lastmask = (w & 31) ? ((1u << (w & 31)) - 1u) : FULL;
+    const long long rows = (long long)h * batch;
+    for (long long row = (long long)blockIdx.x * LAB_WARPS + (threadIdx.x >> 5); row < rows;
+         row += (long long)gridDim.x * LAB_WARPS) {
+        const int b = (int)(row / h), y = (int)(row - (long long)b * h);
+        const uint32_t *mr = mask + (size_t)b * mfw + (size_t)y * mpw;
+        int *pr = parent + (size_t)b * pf;
+        unsigned prev_top = 0;     // bit 31 of the word before the chunk
+        for (int base = 0; base < wpw; base += 32) {
+            const unsigned wd = lab_load_word(mr, wpw, base + lane, lastmask);
+            unsigned pw = __shfl_up_sync(FULL, wd, 1);
+            const unsigned pbit = lane ? (pw >> 31) : prev_top;
+            unsigned starts = wd & ~((wd << 1) | pbit);
+            while (starts) {
+                const int bit = __ffs((int)starts) - 1;
+                starts &= starts - 1;
+                const int idx = (int)((size_t)y * P) + 32 * (base + lane) + bit;
+                pr[idx] = idx;
+            }
+            prev_top = __shfl_sync(FULL, wd, 31) >> 31;
+        }
+    }
+}
+
+// ---- B: merge with the row above -----------------------------------------------------------
+// one "probe" row: the row above shifted by dx in {-1, 0, +1} (dx != 0 only for 8-connectivity)
+__device__ __forceinline__ void lab_merge_probe(int *pr, unsigned cur, int cur_stin, unsigned pu, int pu_stin,
+                                                unsigned ov_prev_bit, int lane, int base, int rowc, int rowu,
+                                                int dx, bool up_bit0) {
+    const unsigned ov = cur & pu;
+    unsigned ss = ov & ~((ov << 1) | ov_prev_bit);     // first pixel of every overlap segment
+    while (ss) {
+        const int bit = __ffs((int)ss) - 1;
+        ss &= ss - 1;
+        const int a = lab_run_start(cur, bit, base + lane, cur_stin);
+        int bq = lab_run_start(pu, bit, base + lane, pu_stin);      // in the shifted row
+        // undo the shift: probe(x) = up(x - dx)
+        if (dx == 1) bq -= 1;
+        else if (dx == -1) bq += (bq == 0 && up_bit0) ? 0 : 1;
+        lab_union(pr, rowc + a, rowu + bq);
+    }
+}
+
+__global__ void __launch_bounds__(LAB_THREADS)
+label_merge_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
+                   int *__restrict__ parent, size_t P, size_t pf, int w, int h, int batch, int conn8) {
+    const int lane = threadIdx.x & 31;
+    const int wpw = (w + 31) >> 5;
+    const unsigned lastmask = (w & 31) ? ((1u << (w & 31)) - 1u) : FULL;
+    const long long rows = (long long)h * batch;
+    for (long long row = (long long)blockIdx.x * LAB_WARPS + (threadIdx.x >> 5); row < rows;
+         row += (long long)gridDim.x * LAB_WARPS) {
+        const int b = (int)(row / h), y = (int)(row - (long long)b * h);
+        if (y == 0) continue;
+        const uint32_t *mc = mask + (size_t)b * mfw + (size_t)y * mpw;
+        const uint32_t *mu = mc - mpw;
+        int *pr = parent + (size_t)b * pf;
+        const int rowc = (int)((size_t)y * P), rowu = (int)((size_t)(y - 1) * P);
+        const bool up_bit0 = (lab_load_word(mu, wpw, 0, lastmask) & 1u) != 0;
+        int carry_c = 0, carry_u = 0, carry_l = 0, carry_r = 0;
+        unsigned ovp0 = 0, ovpl = 0, ovpr = 0;          // bit 31 of the overlap word before the chunk
+        unsigned up_prev_top = 0;                        // bit 31 of the up word before the chunk
+        for (int base = 0; base < wpw; base += 32) {
+            const unsigned cur = lab_load_word(mc, wpw, base + lane, lastmask);
+            const unsigned up = lab_load_word(mu, wpw, base + lane, lastmask);
+            int cs, ct, us, ut;
+            lab_scan_chunk(cur, lane, base, carry_c, cs, ct);
+            lab_scan_chunk(up, lane, base, carry_u, us, ut);
+            {
+                const unsigned ov = cur & up;
+                const unsigned pv = __shfl_up_sync(FULL, ov, 1);
+                lab_merge_probe(pr, cur, cs, up, us, lane ? (pv >> 31) : ovp0, lane, base, rowc, rowu, 0, up_bit0);
+                ovp0 = __shfl_sync(FULL, ov, 31) >> 31;
+            }
+            if (conn8) {
+                // upl(x) = up(x - 1)
+                const unsigned upw = __shfl_up_sync(FULL, up, 1);
+                const unsigned upl = (up << 1) | (lane ? (upw >> 31) : up_prev_top);
+                // upr(x) = up(x + 1): needs bit 0 of the next word (next chunk for lane 31)
+                const unsigned upn = __shfl_down_sync(FULL, up, 1);
+                const unsigned nxt = lab_load_word(mu, wpw, base + 32, lastmask);
+                const unsigned upr = (up >> 1) | ((lane < 31 ? (upn & 1u) : (nxt & 1u)) << 31);
+                int ls, lt, rs, rt;
+                lab_scan_chunk(upl, lane, base, carry_l, ls, lt);
+                lab_scan_chunk(upr, lane, base, carry_r, rs, rt);
+                {
+                    const unsigned ov = cur & upl;
+                    const unsigned pv = __shfl_up_sync(FULL, ov, 1);
+                    lab_merge_probe(pr, cur, cs, upl, ls, lane ? (pv >> 31) : ovpl, lane, base, rowc, rowu, 1, up_bit0);
+                    ovpl = __shfl_sync(FULL, ov, 31) >> 31;
+                }
+                {
+                    const unsigned ov = cur & upr;
+                    const unsigned pv = __shfl_up_sync(FULL, ov, 1);
+                    lab_merge_probe(pr, cur, cs, upr, rs, lane ? (pv >> 31) : ovpr, lane, base, rowc, rowu, -1, up_bit0);
+                    ovpr = __shfl_sync(FULL, ov, 31) >> 31;
+                }
+                carry_l = __shfl_sync(FULL, lt, 31);
+                carry_r = __shfl_sync(FULL, rt, 31);
+                up_prev_top = __shfl_sync(FULL, up, 31) >> 31;
+            }
+            carry_c = __shfl_sync(FULL, ct, 31);
+            carry_u = __shfl_sync(FULL, ut, 31);
+        }
+    }
+}
+
+// ---- C: flatten + count roots per row ------------------------------------------------------
+__global__ void __launch_bounds__(LAB_THREADS)
+label_flatten_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
+                     int *__restrict__ parent, size_t P, size_t pf, int *__restrict__ rowcnt,
+                     int w, int h, int batch) {
+    const int lane = threadIdx.x & 31;
+    const int wpw = (w + 31) >> 5;
+    const unsigned lastmask = (w & 31) ? ((1u << (w & 31)) - 1u) : FULL;
+    const long long rows = (long long)h * batch;
+    for (long long row = (long long)blockIdx.x * LAB_WARPS + (threadIdx.x >> 5); row < rows;
+         row += (long long)gridDim.x * LAB_WARPS) {
+        const int b = (int)(row / h), y = (int)(row - (long long)b * h);
+        const uint32_t *mr = mask + (size_t)b * mfw + (size_t)y * mpw;
+        int *pr = parent + (size_t)b * pf;
+        unsigned prev_top = 0;
+        int nroots = 0;
+        for (int base = 0; base < wpw; base += 32) {
+            const unsigned wd = lab_load_word(mr, wpw, base + lane, lastmask);
+            const unsigned pw = __shfl_up_sync(FULL, wd, 1);
+            const unsigned pbit = lane ? (pw >> 31) : prev_top;
+            unsigned starts = wd & ~((wd << 1) | pbit);
+            while (starts) {
+                const int bit = __ffs((int)starts) - 1;
+                starts &= starts - 1;
+                const int idx = (int)((size_t)y * P) + 32 * (base + lane) + bit;
+                const int root = lab_find(pr, idx);
+                if (root == idx) nroots++;
+                else pr[idx] = root;
+            }
+            prev_top = __shfl_sync(FULL, wd, 31) >> 31;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) nroots += __shfl_xor_sync(FULL, nroots, d);
+        if (lane == 0) rowcnt[row] = nroots;
+    }
+}
+
+// ---- D: exclusive scan of row counts, one CTA per frame --------------------------------------
+__global__ void __launch_bounds__(LAB_THREADS)
+label_scan_kernel(int *__restrict__ rowcnt, int *__restrict__ counts, int h) {
+    __shared__ int part[LAB_THREADS];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    int *rc = rowcnt + (size_t)b * h;
+    const int per = (h + LAB_THREADS - 1) / LAB_THREADS;
+    const int lo = min(tid * per, h), hi = min(lo + per, h);
+    int sum = 0;
+    for (int i = lo; i < hi; i++) sum += rc[i];
+    part[tid] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int i = 0; i < LAB_THREADS; i++) { const int v = part[i]; part[i] = run; run += v; }
+        if (counts) counts[b] = run;
+    }
+    __syncthreads();
+    int run = part[tid];
+    for (int i = lo; i < hi; i++) { const int v = rc[i]; rc[i] = run; run += v; }
+}
+
+// ---- E: rank the roots ------------------------------------------------------------------------
+__global__ void __launch_bounds__(LAB_THREADS)
+label_rank_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
+                  int *__restrict__ parent, size_t P, size_t pf, const int *__restrict__ rowoff,
+                  int w, int h, int batch) {
+    const int lane = threadIdx.x & 31;
+    const int wpw = (w + 31) >> 5;
+    const unsigned lastmask = (w & 31) ? ((1u << (w & 31)) - 1u) : FULL;
+    const long long rows = (long long)h * batch;
+    for (long long row = (long long)blockIdx.x * LAB_WARPS + (threadIdx.x >> 5); row < rows;
+         row += (long long)gridDim.x * LAB_WARPS) {
+        const int b = (int)(row / h), y = (int)(row - (long long)b * h);
+        const uint32_t *mr = mask + (size_t)b * mfw + (size_t)y * mpw;
+        int *pr = parent + (size_t)b * pf;
+        unsigned prev_top = 0;
+        int next_label = rowoff[row] + 1;
+        for (int base = 0; base < wpw; base += 32) {
+            const unsigned wd = lab_load_word(mr, wpw, base + lane, lastmask);
+            const unsigned pw = __shfl_up_sync(FULL, wd, 1);
+            const unsigned pbit = lane ? (pw >> 31) : prev_top;
+            const unsigned starts = wd & ~((wd << 1) | pbit);
+            // which of my run starts are roots?
+            unsigned rootbits = 0;
+            unsigned s = starts;
+            while (s) {
+                const int bit = __ffs((int)s) - 1;
+                s &= s - 1;
+                const int idx = (int)((size_t)y * P) + 32 * (base + lane) + bit;
+                if (pr[idx] == idx) rootbits |= 1u << bit;
+            }
+            const int mine = __popc(rootbits);
+            int incl = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(FULL, incl, d);
+                if (lane >= d) incl += v;
+            }
+            int lab = next_label + incl - mine;
+            while (rootbits) {
+                const int bit = __ffs((int)rootbits) - 1;
+                rootbits &= rootbits - 1;
+                const int idx = (int)((size_t)y * P) + 32 * (base + lane) + bit;
+                pr[idx] = -lab;
+                lab++;
+            }
+            next_label += __shfl_sync(FULL, incl, 31);
+            prev_top = __shfl_sync(FULL, wd, 31) >> 31;
+        }
+    }
+}
+
+// ---- F: every run start takes its root's label -------------------------------------------------
+__global__ void __launch_bounds__(LAB_THREADS)
+label_resolve_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
+                     int *__restrict__ parent, size_t P, size_t pf, int w, int h, int batch) {
+    const int lane = threadIdx.x & 31;
+    const int wpw = (w + 31) >> 5;
+    const unsigned lastmask = (w & 31) ? ((1u << (w & 31)) - 1u) : FULL;
+    const long long rows = (long long)h * batch;
+    for (long long row = (long long)blockIdx.x * LAB_WARPS + (threadIdx.x >> 5); row < rows;
+         row += (long long)gridDim.x * LAB_WARPS) {
+        const int b = (int)(row / h), y = (int)(row - (long long)b * h);
+        const uint32_t *mr = mask + (size_t)b * mfw + (size_t)y * mpw;
+        int *pr = parent + (size_t)b * pf;
+        unsigned prev_top = 0;
+        for (int base = 0; base < wpw; base += 32) {
+            const unsigned wd = lab_load_word(mr, wpw, base + lane, lastmask);
+            const unsigned pw = __shfl_up_sync(FULL, wd, 1);
+            const unsigned pbit = lane ? (pw >> 31) : prev_top;
+            unsigned starts = wd & ~((wd << 1) | pbit);
+            while (starts) {
+                const int bit = __ffs((int)starts) - 1;
+                starts &= starts - 1;
+                const int idx = (int)((size_t)y * P) + 32 * (base + lane) + bit;
+                const int p = va_ld_cg(pr + idx);
+                if (p >= 0) pr[idx] = va_ld_cg(pr + p);     // roots already hold -label (kernel E)
+            }
+            prev_top = __shfl_sync(FULL, wd, 31) >> 31;
+        }
+    }
+}
+
+// ---- G: write the label image --------------------------------------------------------------------
+__global__ void __launch_bounds__(LAB_THREADS)
+label_write_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
+                   const int *__restrict__ parent, size_t P, size_t pf,
+                   int32_t *__restrict__ labels, size_t lpe, size_t lfe, int w, int h, int batch) {
+    const int lane = threadIdx.x & 31;
+    const int wpw = (w + 31) >> 5;
+    const unsigned lastmask = (w & 31) ? ((1u << (w & 31)) - 1u) : FULL;
+    const long long rows = (long long)h * batch;
+    for (long long row = (long long)blockIdx.x * LAB_WARPS + (threadIdx.x >> 5); row < rows;
+         row += (long long)gridDim.x * LAB_WARPS) {
+        const int b = (int)(row / h), y = (int)(row - (long long)b * h);
+        const uint32_t *mr = mask + (size_t)b * mfw + (size_t)y * mpw;
+        const int *pr = parent + (size_t)b * pf + (size_t)y * P;
+        int32_t *lr = labels + (size_t)b * lfe + (size_t)y * lpe;
+        int carry = 0;
+        for (int base = 0; base < wpw; base += 32) {
+            const unsigned wd = lab_load_word(mr, wpw, base + lane, lastmask);
+            int st_in, top;
+            lab_scan_chunk(wd, lane, base, carry, st_in, top);
+            const int nwords = min(32, wpw - base);
+#pragma unroll 4
+            for (int i = 0; i < nwords; i++) {
+                const unsigned wi = __shfl_sync(FULL, wd, i);
+                const int si = __shfl_sync(FULL, st_in, i);
+                const int x = 32 * (base + i) + lane;
+                int lab = 0;
+                if ((wi >> lane) & 1u) lab = -pr[lab_run_start(wi, lane, base + i, si)];
+                if (x < w) lr[x] = lab;
+            }
+            carry = __shfl_sync(FULL, top, 31);
+        }
+    }
+}
+
+extern "C" int va_label_bits(va_ctx *ctx, va_stream stream,
+                             const uint32_t *mask, size_t mask_pitch_w, size_t mask_fstride_w,
+                             int32_t *labels, size_t labels_pitch_e, size_t labels_fstride_e,
+                             int32_t *counts, int w, int h, int batch, int connectivity) {
+    VA_CHECK_CTX(ctx);
+    VA_REQUIRE(ctx, mask && labels, "va_label_bits: null pointer");
+    VA_REQUIRE(ctx, w > 0 && h > 0 && batch > 0, "va_label_bits: bad size");
+    VA_REQUIRE(ctx, connectivity == 4 || connectivity == 8, "va_label_bits: connectivity must be 4 or 8");
+    VA_REQUIRE(ctx, mask_pitch_w >= (size_t)((w + 31) / 32) && labels_pitch_e >= (size_t)w, "va_label_bits: pitch smaller than a row");
+    if (w > ctx->max_w || h > ctx->max_h || batch > ctx->max_batch)
+        VA_FAIL(ctx, VA_ERR_CAPACITY, "va_label_bits: %dx%dx%d exceeds the ctx capacity %dx%dx%d", w, h, batch,
+                ctx->max_w, ctx->max_h, ctx->max_batch);
+    const size_t P = ctx->lab_pitch;
+    const size_t pf = P * (size_t)ctx->max_h;
+    const long long rows = (long long)h * batch;
+    const int grid = va_grid(ctx, (rows + LAB_WARPS - 1) / LAB_WARPS, 8);
+    int *parent = ctx->lab_parent;
+    int *rowcnt = ctx->lab_rowcnt;
+    { auto k = label_init_kernel;
+      VA_LAUNCH(ctx, k, grid, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, parent, P, pf, w, h, batch); }
+    { auto k = label_merge_kernel;
+      VA_LAUNCH(ctx, k, grid, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, parent, P, pf, w, h, batch,
+                connectivity == 8 ? 1 : 0); }
+    { auto k = label_flatten_kernel;
+      VA_LAUNCH(ctx, k, grid, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, parent, P, pf, rowcnt, w, h, batch); }
+    { auto k = label_scan_kernel;
+      VA_LAUNCH(ctx, k, batch, LAB_THREADS, 0, stream, rowcnt, counts, h); }
+    { auto k = label_rank_kernel;
+      VA_LAUNCH(ctx, k, grid, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, parent, P, pf,
+                (const int *)rowcnt, w, h, batch); }
+    { auto k = label_resolve_kernel;
+      VA_LAUNCH(ctx, k, grid, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, parent, P, pf, w, h, batch); }
+    { auto k = label_write_kernel;
+      VA_LAUNCH(ctx, k, grid, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, (const int *)parent, P, pf,
+                labels, labels_pitch_e, labels_fstride_e, w, h, batch); }
+    return VA_OK;
+}
+
+// =====================================================================================
+// per-label areas + largest region (video/analysis/regions.py:165-169)
+// =====================================================================================
+__global__ void __launch_bounds__(LAB_THREADS)
+region_area_kernel(const int32_t *__restrict__ labels, size_t lpe, size_t lfe,
+                   int *__restrict__ areas, int max_labels, int w, int h, int batch) {
+    const int lane = threadIdx.x & 31;
+    const int chunks = (w + 31) >> 5;
+    const long long total = (long long)chunks * h * batch;
+    for (long long it = (long long)blockIdx.x * LAB_WARPS + (threadIdx.x >> 5); it < total;
+         it += (long long)gridDim.x * LAB_WARPS) {
+        const long long row = it / chunks;
+        const int c = (int)(it - row * chunks);
+        const int b = (int)(row / h), y = (int)(row - (long long)b * h);
+        const int x = 32 * c + lane;
+        const int lab = x < w ? labels[(size_t)b * lfe + (size_t)y * lpe + x] : 0;
+        // heads of runs of equal labels inside the 32-pixel chunk add the run length once
+        const int left = __shfl_up_sync(FULL, lab, 1);
+        const bool head = lane == 0 || left != lab;
+        const unsigned heads = __ballot_sync(FULL, head);
+        if (head && lab > 0 && lab <= max_labels) {
+            const unsigned above = heads & ~((2u << lane) - 1u);       // heads to the right of me
+            const int end = above ? __ffs((int)above) - 1 : 32;
+            atomicAdd(areas + (size_t)b * max_labels + (lab - 1), end - lane);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(LAB_THREADS)
+region_largest_kernel(const int *__restrict__ areas, int max_labels, int *__restrict__ largest) {
+    __shared__ int best_a[LAB_THREADS];
+    __shared__ int best_l[LAB_THREADS];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    int ba = 0, bl = 0;
+    for (int l = tid; l < max_labels; l += LAB_THREADS) {
+        const int a = areas[(size_t)b * max_labels + l];
+        if (a > ba) { ba = a; bl = l + 1; }       // strided ascending: the first maximum wins below
+    }
+    best_a[tid] = ba; best_l[tid] = bl;
+    __syncthreads();
+    if (tid == 0) {
+        for (int i = 1; i < LAB_THREADS; i++)
+            if (best_a[i] > ba || (best_a[i] == ba && best_a[i] > 0 && best_l[i] < bl)) { ba = best_a[i]; bl = best_l[i]; }
+        largest[b] = bl;      // np.argmax(areas) + 1; 0 when the frame has no region
+    }
+}
+
+extern "C" int va_region_areas(va_ctx *ctx, va_stream stream,
+                               const int32_t *labels, size_t labels_pitch_e, size_t labels_fstride_e,
+                               int32_t *areas, int max_labels, int32_t *largest, int w, int h, int batch) {
+    VA_CHECK_CTX(ctx);
+    VA_REQUIRE(ctx, labels && areas, "va_region_areas: null pointer");
+    VA_REQUIRE(ctx, w > 0 && h > 0 && batch > 0 && max_labels > 0, "va_region_areas: bad size");
+    VA_CUDA(ctx, cudaMemsetAsync(areas, 0, (size_t)batch * max_labels * sizeof(int), (cudaStream_t)stream));
+    const long long warps = (long long)((w + 31) / 32) * h * batch;
+    const int grid = va_grid(ctx, (warps + LAB_WARPS - 1) / LAB_WARPS, 8);
+    { auto k = region_area_kernel;
+      VA_LAUNCH(ctx, k, grid, LAB_THREADS, 0, stream, labels, labels_pitch_e, labels_fstride_e, areas, max_labels, w, h, batch); }
+    if (largest) {
+        auto k = region_largest_kernel;
+        VA_LAUNCH(ctx, k, batch, LAB_THREADS, 0, stream, (const int *)areas, max_labels, largest);
+    }
+    return VA_OK;
+}

@@ -1,0 +1,213 @@
+// va_morph.cu -- K4: binary erode / dilate / open / close on packed bit masks.
+//
+// Replaces cv2.erode / cv2.dilate (video/analysis/image.py:248-256) and
+// cv2.morphologyEx(MORPH_OPEN / MORPH_CLOSE) for structuring elements built by
+// cv2.getStructuringElement(RECT | CROSS | ELLIPSE, (kx, ky)), default anchor
+// (kx/2, ky/2) and OpenCV's default morphology border: pixels outside the image
+// never win the min / max.  OpenCV evaluates BOTH erode and dilate as
+//     dst(x, y) = op over {(i, j): se(i, j) != 0} of src(x + i - ax, y + j - ay),
+// so no reflection of the element is applied (matters for even sizes).
+//
+// 32 pixels per word: a horizontal run [a, b] of the element becomes AND / OR of
+// funnel-shifted words, evaluated by doubling in O(log(run length)).  Every row j of
+// the element is one run (true for RECT, CROSS and ELLIPSE), so an op is
+//     out(y) = AND/OR_j  hrun_j( in(y + j - ay) ).
+// OPEN / CLOSE run both passes in one CTA on a band of rows; the intermediate stays
+// in shared memory.  Algorithmic HBM bytes: N/8 in + N/8 out per frame.
+#include <cmath>
+
+#include "va_device.cuh"
+
+#define MORPH_THREADS 256
+#define MORPH_MAX_K 63
+#define MORPH_BAND 32
+
+struct MorphSE {
+    int kx, ky, ax, ay;
+    signed char a[MORPH_MAX_K];   // run of row j: offsets a[j]..b[j] relative to the anchor; a > b: empty row
+    signed char b[MORPH_MAX_K];
+};
+
+// cv::getStructuringElement restated as per-row runs
+static int morph_build_se(int shape, int kx, int ky, MorphSE *se) {
+    if (kx < 1 || ky < 1 || kx > MORPH_MAX_K || ky > MORPH_MAX_K) return VA_ERR_UNSUPPORTED;
+    if (shape != VA_SE_RECT && shape != VA_SE_CROSS && shape != VA_SE_ELLIPSE) return VA_ERR_INVALID;
+    memset(se, 0, sizeof(*se));
+    se->kx = kx; se->ky = ky; se->ax = kx / 2; se->ay = ky / 2;
+    if (kx == 1 && ky == 1) shape = VA_SE_RECT;
+    const int r = ky / 2, c = kx / 2;
+    const double inv_r2 = r ? 1.0 / ((double)r * r) : 0.0;
+    for (int i = 0; i < ky; i++) {
+        int j1 = 0, j2 = 0;
+        if (shape == VA_SE_RECT || (shape == VA_SE_CROSS && i == r)) {
+            j2 = kx;
+        } else if (shape == VA_SE_CROSS) {
+            j1 = c; j2 = c + 1;
+        } else {
+            const int dy = i - r;
+            if (std::abs(dy) <= r) {
+                const int dx = (int)std::lrint(c * std::sqrt((r * r - dy * dy) * inv_r2));   // cvRound
+                j1 = c - dx > 0 ? c - dx : 0;
+                j2 = c + dx + 1 < kx ? c + dx + 1 : kx;
+            }
+        }
+        se->a[i] = (signed char)(j1 - se->ax);
+        se->b[i] = (signed char)(j2 - 1 - se->ax);
+    }
+    return VA_OK;
+}
+
+// AND (ERODE) or OR over src(x + d), d in [a, b], for the 32 pixels of the middle word of
+// the window (prev, cur, next).  |a|, |b| <= 31.
+template <bool ERODE>
+__device__ __forceinline__ unsigned morph_hrun(unsigned prev, unsigned cur, unsigned next, int a, int b) {
+    // acc_L(x) = op_{i<L} src(x + i) by doubling on the 96-bit window, then read at x + a
+    unsigned w0 = prev, w1 = cur, w2 = next;
+    const int L = b - a + 1;
+    int len = 1;
+    while (len < L) {
+        const int s = (2 * len <= L) ? len : L - len;
+        const unsigned n0 = __funnelshift_r(w0, w1, s), n1 = __funnelshift_r(w1, w2, s);
+        const unsigned n2 = ERODE ? ((w2 >> s) | ~(0xffffffffu >> s)) : (w2 >> s);
+        if (ERODE) { w0 &= n0; w1 &= n1; w2 &= n2; } else { w0 |= n0; w1 |= n1; w2 |= n2; }
+        len += s;
+    }
+    // bits [32 + a, 64 + a) of the window
+    if (a == 0) return w1;
+    if (a > 0) return __funnelshift_r(w1, w2, a);
+    return __funnelshift_l(w0, w1, -a);
+}
+
+// one morphological pass over rows held in shared memory.
+//   src rows: index sr = (image row) - src_row0, words [0, wpw); rows / words outside the
+//   staged range are never requested (the caller sizes the halo).
+template <bool ERODE>
+__device__ __forceinline__ unsigned morph_word(const unsigned *src, int src_rows, int wpw, int sr, int j,
+                                               const MorphSE &se) {
+    const unsigned ident = ERODE ? 0xffffffffu : 0u;
+    unsigned acc = ident;
+    for (int i = 0; i < se.ky; i++) {
+        const int a = se.a[i], b = se.b[i];
+        if (a > b) continue;
+        const int rr = sr + i - se.ay;
+        if (rr < 0 || rr >= src_rows) continue;       // outside the staged band == outside the image
+        const unsigned *row = src + (size_t)rr * wpw;
+        const unsigned prev = j > 0 ? row[j - 1] : ident;
+        const unsigned cur = row[j];
+        const unsigned next = j + 1 < wpw ? row[j + 1] : ident;
+        const unsigned v = morph_hrun<ERODE>(prev, cur, next, a, b);
+        if (ERODE) acc &= v; else acc |= v;
+    }
+    return acc;
+}
+
+// first  : 0 erode, 1 dilate;  second: -1 none, 0 erode, 1 dilate
+__global__ void __launch_bounds__(MORPH_THREADS)
+morph_bits_kernel(const uint32_t *__restrict__ in, size_t in_pitch_w, size_t in_fstride_w,
+                  uint32_t *__restrict__ out, size_t out_pitch_w, size_t out_fstride_w,
+                  int w, int h, int bands_per_frame, int n_bands, int first, int second,
+                  const __grid_constant__ MorphSE se) {
+    VA_DYN_SMEM(unsigned, smem);
+    const int tid = threadIdx.x;
+    const int wpw = (w + 31) >> 5;
+    const unsigned lastmask = (w & 31) ? ((1u << (w & 31)) - 1u) : 0xffffffffu;
+    const int up = se.ay, dn = se.ky - 1 - se.ay;          // rows needed above / below per pass
+    const int passes = second >= 0 ? 2 : 1;
+    const int rows_a = MORPH_BAND + passes * (up + dn);    // staged input rows
+    const int rows_b = MORPH_BAND + (up + dn);             // intermediate rows (two-pass only)
+    unsigned *sa = smem;
+    unsigned *sb = smem + (size_t)rows_a * wpw;
+
+    for (int band = blockIdx.x; band < n_bands; band += gridDim.x) {
+        const int b = band / bands_per_frame;
+        const int y0 = (band - b * bands_per_frame) * MORPH_BAND;
+        const int nrows = min(MORPH_BAND, h - y0);
+        const uint32_t *fin = in + (size_t)b * in_fstride_w;
+        uint32_t *fout = out + (size_t)b * out_fstride_w;
+
+        // ---- stage input rows [ya0, ya0 + rows_a); outside the image = identity of the first op
+        const int ya0 = y0 - passes * up;
+        const unsigned id1 = first == 0 ? 0xffffffffu : 0u;
+        for (int it = tid; it < rows_a * wpw; it += MORPH_THREADS) {
+            const int rr = it / wpw, j = it - rr * wpw;
+            const int y = ya0 + rr;
+            unsigned v = id1;
+            if (y >= 0 && y < h) {
+                v = fin[(size_t)y * in_pitch_w + j];
+                if (j == wpw - 1) v = first == 0 ? (v | ~lastmask) : (v & lastmask);
+            }
+            sa[it] = v;
+        }
+        __syncthreads();
+
+        if (passes == 1) {
+            for (int it = tid; it < nrows * wpw; it += MORPH_THREADS) {
+                const int rr = it / wpw, j = it - rr * wpw;
+                unsigned v = first == 0 ? morph_word<true>(sa, rows_a, wpw, rr + up, j, se)
+                                        : morph_word<false>(sa, rows_a, wpw, rr + up, j, se);
+                if (j == wpw - 1) v &= lastmask;
+                fout[(size_t)(y0 + rr) * out_pitch_w + j] = v;
+            }
+        } else {
+            // ---- first pass -> intermediate rows [yb0, yb0 + rows_b); rows outside the image and
+            //      bits beyond w take the identity of the SECOND op
+            const int yb0 = y0 - up;
+            const unsigned id2 = second == 0 ? 0xffffffffu : 0u;
+            for (int it = tid; it < rows_b * wpw; it += MORPH_THREADS) {
+                const int rr = it / wpw, j = it - rr * wpw;
+                const int y = yb0 + rr;
+                unsigned v = id2;
+                if (y >= 0 && y < h) {
+                    v = first == 0 ? morph_word<true>(sa, rows_a, wpw, rr + up, j, se)
+                                   : morph_word<false>(sa, rows_a, wpw, rr + up, j, se);
+                    if (j == wpw - 1) v = second == 0 ? (v | ~lastmask) : (v & lastmask);
+                }
+                sb[it] = v;
+            }
+            __syncthreads();
+            for (int it = tid; it < nrows * wpw; it += MORPH_THREADS) {
+                const int rr = it / wpw, j = it - rr * wpw;
+                unsigned v = second == 0 ? morph_word<true>(sb, rows_b, wpw, rr + up, j, se)
+                                         : morph_word<false>(sb, rows_b, wpw, rr + up, j, se);
+                if (j == wpw - 1) v &= lastmask;
+                fout[(size_t)(y0 + rr) * out_pitch_w + j] = v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+extern "C" int va_morph_bits(va_ctx *ctx, va_stream stream,
+                             const uint32_t *in, size_t in_pitch_w, size_t in_fstride_w,
+                             uint32_t *out, size_t out_pitch_w, size_t out_fstride_w,
+                             int w, int h, int batch, int op, int shape, int kx, int ky) {
+    VA_CHECK_CTX(ctx);
+    VA_REQUIRE(ctx, in && out && in != out, "va_morph_bits: null or aliased pointers");
+    VA_REQUIRE(ctx, w > 0 && h > 0 && batch > 0, "va_morph_bits: bad size");
+    VA_REQUIRE(ctx, op >= VA_MORPH_ERODE && op <= VA_MORPH_CLOSE, "va_morph_bits: unknown morphological operation %d", op);
+    const size_t wpw = (size_t)(w + 31) / 32;
+    VA_REQUIRE(ctx, in_pitch_w >= wpw && out_pitch_w >= wpw, "va_morph_bits: pitch smaller than a row");
+    MorphSE se;
+    const int rc = morph_build_se(shape, kx, ky, &se);
+    if (rc != VA_OK) VA_FAIL(ctx, rc, "va_morph_bits: structuring element shape %d size %dx%d not supported (max %d)", shape, kx, ky, MORPH_MAX_K);
+    int first, second;
+    switch (op) {
+        case VA_MORPH_ERODE: first = 0; second = -1; break;
+        case VA_MORPH_DILATE: first = 1; second = -1; break;
+        case VA_MORPH_OPEN: first = 0; second = 1; break;
+        default: first = 1; second = 0; break;
+    }
+    const int passes = second >= 0 ? 2 : 1;
+    const int halo = ky - 1;
+    const size_t smem = ((size_t)(MORPH_BAND + passes * halo) + (passes == 2 ? (size_t)(MORPH_BAND + halo) : 0)) * wpw * 4;
+    VA_REQUIRE(ctx, smem <= 200 * 1024, "va_morph_bits: %d-pixel rows with a %d-row element do not fit in shared memory", w, ky);
+    const int bands_per_frame = va_div_up(h, MORPH_BAND);
+    const int n_bands = bands_per_frame * batch;
+    auto kfn = morph_bits_kernel;
+    if (smem > 48 * 1024)
+        VA_CUDA(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = va_grid(ctx, n_bands, 8);
+    VA_LAUNCH(ctx, kfn, grid, MORPH_THREADS, smem, stream, in, in_pitch_w, in_fstride_w, out, out_pitch_w, out_fstride_w,
+              w, h, bands_per_frame, n_bands, first, second, se);
+    return VA_OK;
+}
