@@ -1,0 +1,330 @@
+"""
+Parity of every C-ABI entry point against the oracle (bit-exact unless stated).
+
+Each test runs on the `cuda` backend (marked gpu: the parity gate, through
+csrc/libva_b200.so on a B200) and on the `emu` backend (same kernel sources under the CPU
+thread-emulation shim, small sizes only -- a logic check that runs without a GPU).
+"""
+
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ops, synth
+from tests import harness as hz
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'golden.npz'))
+
+
+@pytest.fixture
+def ctx(be):
+    big = be.name == 'cuda'
+    c = hz.Ctx(be, 4096 if big else 1300, 2304 if big else 256, 8)
+    yield c
+    c.close()
+
+
+def rng_frames(seed, shape):
+    return np.random.default_rng(seed).integers(0, 256, shape, dtype=np.uint8)
+
+
+def rmask(seed, shape, p):
+    return ((np.random.default_rng(seed).random(shape) < p) * 255).astype(np.uint8)
+
+
+def sizes(be, small, large):
+    return small + (large if be.name == 'cuda' else [])
+
+
+# ---- K1 -----------------------------------------------------------------------------------------
+def test_luma_mean_and_channels(be, ctx):
+    for (H, W) in sizes(be, [(13, 37), (24, 64), (9, 130)], [(480, 640), (1080, 1920), (271, 1003)]):
+        fr = rng_frames(H * W, (2, H, W, 3))
+        ref = np.stack([ops.mono(f) for f in fr])
+        assert np.array_equal(hz.luma(ctx, fr), ref)
+        assert np.array_equal(hz.luma(ctx, fr, in_pad=5, in_off=3, out_pad=3), ref)
+        for c in (0, 1, 2):
+            assert np.array_equal(hz.luma(ctx, fr, mode=c), fr[..., c])
+
+
+def test_luma_every_sum(be, ctx):
+    s = np.arange(766)
+    fr = np.zeros((1, 1, 768, 3), np.uint8)
+    fr[0, 0, :766, 0] = np.minimum(s, 255)
+    fr[0, 0, :766, 1] = np.clip(s - 255, 0, 255)
+    fr[0, 0, :766, 2] = np.clip(s - 510, 0, 255)
+    assert np.array_equal(hz.luma(ctx, fr)[0, 0, :766], s // 3)
+
+
+def test_crop_by_pointer_offset(be, ctx):
+    for (H, W) in sizes(be, [(20, 50)], [(480, 640)]):
+        fr = rng_frames(7, (2, H, W, 3))
+        for rect in ((3, 2, W - 7, H - 5), (1, 0, 17, 9), (16, 4, 32, 8)):
+            assert np.array_equal(hz.crop_luma(ctx, fr, rect), np.stack([ops.mono(ops.crop(f, rect)) for f in fr]))
+            assert np.array_equal(hz.crop_luma(ctx, fr, rect, mode=2), np.stack([ops.crop(f, rect, 'red') for f in fr]))
+            assert np.array_equal(hz.copy2d(ctx, fr, rect), np.stack([ops.crop(f, rect) for f in fr]))
+        mono = fr[..., 0].copy()
+        assert np.array_equal(hz.copy2d(ctx, mono, (16, 2, 32, 8)), mono[:, 2:10, 16:48])
+
+
+def test_luma_rejects_bad_arguments(be, ctx):
+    fr = rng_frames(1, (1, 4, 8, 3))
+    with pytest.raises(ValueError):
+        hz.luma(ctx, fr, mode=7)
+
+
+# ---- K2 -----------------------------------------------------------------------------------------
+def test_gauss_bit_exact(be, ctx):
+    for (H, W) in sizes(be, [(13, 37), (70, 140)], [(480, 640), (1080, 1920), (333, 1001)]):
+        g = rng_frames(H + W, (2, H, W))
+        for s in sizes(be, [0.3, 1, 2, 3], [0.5, 5]):
+            assert np.array_equal(hz.gauss(ctx, g, s), np.stack([ops.blur(f, s) for f in g])), (H, W, s)
+        assert np.array_equal(hz.gauss(ctx, g, 2, in_pad=3, out_pad=5), np.stack([ops.blur(f, 2) for f in g]))
+
+
+def test_gauss_large_sigma_identity_and_generic_paths(be, ctx):
+    g = rng_frames(3, (1, 50, 70))
+    for s in (0.05, 0.2, 10, 15, 21):          # ksize 1 (copy), tap 256 (generic), wide (TH=96)
+        assert np.array_equal(hz.gauss(ctx, g, s), np.stack([ops.blur(f, s) for f in g])), s
+    c = rng_frames(4, (1, 30, 45, 3))
+    for s in (1, 2, 4):
+        assert np.array_equal(hz.gauss(ctx, c, s), np.stack([ops.blur(f, s) for f in c])), s
+    with pytest.raises(NotImplementedError):
+        hz.gauss(ctx, g, 60)
+
+
+def test_gauss_golden(be, ctx):
+    assert np.array_equal(hz.gauss(ctx, GOLD['s_mono'], 2), GOLD['s_blur'])
+    assert np.array_equal(hz.gauss(ctx, GOLD['r_mono'], 3), GOLD['r_blur'])
+
+
+def test_luma_gauss_fused_equals_two_step(be, ctx):
+    for (H, W) in sizes(be, [(33, 150)], [(1080, 1920), (480, 640)]):
+        fr = rng_frames(5, (2, H, W, 3))
+        for s in (1, 2, 5):
+            assert np.array_equal(hz.luma_gauss(ctx, fr, s), np.stack([ops.blur(ops.mono(f), s) for f in fr]))
+    fr = rng_frames(6, (1, 20, 40, 3))
+    assert np.array_equal(hz.luma_gauss(ctx, fr, 2, mode=1), np.stack([ops.blur(f[..., 1], 2) for f in fr]))
+
+
+# ---- K2b ----------------------------------------------------------------------------------------
+def test_resize_half(be, ctx):
+    for (H, W) in sizes(be, [(12, 40), (20, 64)], [(1080, 1920)]):
+        g = rng_frames(H, (2, H, W))
+        ref = np.stack([ops.resize(f, 0.5) for f in g])
+        assert np.array_equal(hz.resize_half(ctx, g), ref)
+        assert np.array_equal(hz.resize_half(ctx, g, in_pad=3), ref)
+        c = rng_frames(W, (2, H, W, 3))
+        assert np.array_equal(hz.resize_half(ctx, c), np.stack([ops.resize(f, 0.5) for f in c]))
+    with pytest.raises(ValueError):
+        hz.resize_half(ctx, rng_frames(0, (1, 7, 8)))
+
+
+# ---- threshold / pack / unpack / apply-mask ------------------------------------------------------
+def test_threshold_pack_unpack(be, ctx):
+    for (H, W) in sizes(be, [(7, 37), (5, 64), (3, 1100)], [(1080, 1920)]):
+        g = rng_frames(W, (2, H, W))
+        assert np.array_equal(hz.threshold_bits(ctx, g, 100), ops.pack_bits(g > 100))
+        assert np.array_equal(hz.threshold_bits(ctx, g, 100, pad=3), ops.pack_bits(g > 100))
+        m = rmask(H, (2, H, W), 0.4) & g
+        assert np.array_equal(hz.pack_bits(ctx, m), ops.pack_bits(m))
+        p = ops.pack_bits(m)
+        assert np.array_equal(hz.unpack_bits(ctx, p, W), ops.unpack_bits(p, W))
+        assert np.array_equal(hz.unpack_bits(ctx, p, W, pad=5), ops.unpack_bits(p, W))
+
+
+def test_apply_mask(be, ctx):
+    for (H, W) in sizes(be, [(7, 37), (6, 64)], [(720, 1280)]):
+        g, c = rng_frames(1, (2, H, W)), rng_frames(2, (2, H, W, 3))
+        m = rmask(3, (H, W), 0.5) & rng_frames(4, (H, W))
+        assert np.array_equal(hz.apply_mask(ctx, g, m), np.stack([ops.apply_mask(f, m) for f in g]))
+        assert np.array_equal(hz.apply_mask(ctx, c, m), np.stack([ops.apply_mask(f, m) for f in c]))
+
+
+# ---- synthetic source -------------------------------------------------------------------------------
+def test_synth_equals_numpy_generator(be, ctx):
+    for (H, W, nb) in sizes(be, [(20, 37, 3), (32, 64, 8)], [(480, 640, 8)]):
+        tab = synth.blob_table(5, W, H, nb)
+        assert np.array_equal(hz.synth(ctx, 5, 7, 3, W, H, tab), synth.make_frames(5, 7, 3, W, H, nb))
+    assert np.array_equal(hz.synth(ctx, 0, 0, 6, 64, 48, synth.blob_table(0, 64, 48, 4)), GOLD['s_frames'])
+
+
+# ---- K3 -----------------------------------------------------------------------------------------
+def noisy_video(seed, shape):
+    rng = np.random.default_rng(seed)
+    return (rng.integers(0, 256, shape) // 8 + 100 + rng.integers(0, 2, shape) * 60).astype(np.uint8)
+
+
+def test_ema_diff_threshold_bit_exact(be, ctx):
+    for (B, H, W) in sizes(be, [(6, 9, 37), (9, 5, 600), (5, 64, 1100)], [(8, 1080, 1920), (7, 480, 640)]):
+        g = noisy_video(B, (B, H, W))
+        m_ref, bg_ref = ops.background_ema(list(g), 0.05, 25)
+        for pad in (0, 4):
+            m, bg = hz.ema_diff_thresh(ctx, g, 0.05, 25, pad=pad)
+            assert np.array_equal(m, ops.pack_bits(m_ref))
+            assert np.array_equal(bg.view(np.uint32), bg_ref.view(np.uint32))       # float32 state, bit for bit
+        m2_ref, bg2_ref = ops.background_ema(list(g), 0.05, 25, bg0=bg_ref)         # continuation batch
+        m2, bg2 = hz.ema_diff_thresh(ctx, g, 0.05, 25, bg0=bg_ref)
+        assert np.array_equal(m2, ops.pack_bits(m2_ref))
+        assert np.array_equal(bg2.view(np.uint32), bg2_ref.view(np.uint32))
+
+
+def test_ema_golden(be, ctx):
+    m, bg = hz.ema_diff_thresh(ctx, GOLD['s_blur'], 0.05, 25)
+    assert np.array_equal(m, ops.pack_bits(GOLD['s_mask']))
+    assert np.array_equal(bg.view(np.uint32), GOLD['s_bg'].view(np.uint32))
+
+
+def test_ema_partial_and_fold(be, ctx):
+    # frame-sharded recurrence: tolerance 1e-5 relative (re-association), SURVEY.md 8e
+    g = noisy_video(1, (12, 10, 50))
+    alpha = 0.05
+    _, bg_seq = ops.background_ema(list(g), alpha, 25)
+    # rank 0 owns frames 0..6 (true state), rank 1 folds frames 7..11 from a zero state
+    _, bg_r0 = ops.background_ema(list(g[:7]), alpha, 25)
+    S1 = hz.ema_partial(ctx, g[7:], alpha)
+    state = hz.ema_fold(ctx, bg_r0, S1, (1 - alpha) ** 5)
+    assert np.allclose(state, bg_seq, rtol=1e-5, atol=1e-4)
+    # accumulate form: two halves equal one pass
+    Sa = hz.ema_partial(ctx, g[7:9], alpha)
+    Sb = hz.ema_partial(ctx, g[9:], alpha, S0=Sa)
+    assert np.allclose(Sb, S1, rtol=1e-6)
+
+
+# ---- K4 -----------------------------------------------------------------------------------------
+SES = [('rect', 3), ('cross', 3), ('rect', 5), ('ellipse', 5), ('ellipse', 7), ('rect', (2, 2)), ('rect', (4, 3)),
+       ('cross', (5, 7)), ('ellipse', (9, 5)), ('rect', 7)]
+
+
+def test_morphology_bit_exact(be, ctx):
+    for (H, W) in sizes(be, [(9, 37), (40, 64), (70, 100)], [(1080, 1920)]):
+        for p in (0.3, 0.7, 0.95):
+            m = rmask(int(p * 100) + W, (2, H, W), p)
+            packed = ops.pack_bits(m)
+            for op in ('erode', 'dilate', 'open', 'close'):
+                for shape, k in (SES if H < 1000 else SES[:3]):
+                    ref = np.stack([ops.morph(f, op, shape, k) for f in m])
+                    assert np.array_equal(hz.morph(ctx, packed, W, op, shape, k), ops.pack_bits(ref)), (H, W, p, op, shape, k)
+
+
+def test_morphology_large_elements(be, ctx):
+    m = rmask(9, (1, 50, 90), 0.9)
+    for k in (9, 15, 31):
+        for shape in ('ellipse', 'rect', 'cross'):
+            for op in ('erode', 'open', 'close'):
+                ref = np.stack([ops.morph(f, op, shape, k) for f in m])
+                assert np.array_equal(hz.morph(ctx, ops.pack_bits(m), 90, op, shape, k), ops.pack_bits(ref)), (k, shape, op)
+    with pytest.raises(NotImplementedError):
+        hz.morph(ctx, ops.pack_bits(m), 90, 'open', 'rect', 65)
+
+
+def test_morphology_golden_and_edges(be, ctx):
+    assert np.array_equal(hz.morph(ctx, ops.pack_bits(GOLD['s_mask']), 64, 'open', 'rect', 3), ops.pack_bits(GOLD['s_morph']))
+    assert np.array_equal(hz.morph(ctx, ops.pack_bits(GOLD['r_mask']), 53, 'close', 'ellipse', 5), ops.pack_bits(GOLD['r_morph']))
+    for fill in (0, 255):
+        m = np.full((1, 11, 45), fill, np.uint8)
+        for op in ('erode', 'dilate', 'open', 'close'):
+            assert np.array_equal(hz.morph(ctx, ops.pack_bits(m), 45, op), ops.pack_bits(m))
+
+
+# ---- K5 -----------------------------------------------------------------------------------------
+def check_labels(ctx, m, conns=(4, 8)):
+    B, H, W = m.shape
+    for conn in conns:
+        lab, cnt = hz.label(ctx, ops.pack_bits(m), W, conn)
+        refs = [ops.label(f, conn) for f in m]
+        assert np.array_equal(cnt, np.array([r[1] for r in refs], np.int32)), conn
+        assert np.array_equal(lab, np.stack([r[0] for r in refs])), conn
+
+
+def test_label_random_masks(be, ctx):
+    for (H, W) in sizes(be, [(9, 37), (40, 64), (12, 1100)], [(1080, 1920), (2160, 3840)]):
+        for p in (0.1, 0.5, 0.6, 0.9):
+            check_labels(ctx, rmask(int(p * 10) + H, (2 if H < 2000 else 1, H, W), p))
+
+
+def adversarial_masks(H, W):
+    out = {}
+    out['zeros'] = np.zeros((H, W), np.uint8)
+    out['ones'] = np.full((H, W), 255, np.uint8)
+    out['checker'] = ((np.indices((H, W)).sum(0) % 2) * 255).astype(np.uint8)      # N/2 components at 4-conn
+    u = np.zeros((H, W), np.uint8)                                                 # U and n shapes: late merges
+    u[5:H - 8, 10] = u[5:H - 8, 30] = 255
+    u[H - 9, 10:31] = 255
+    u[5:H - 8, 50] = u[5:H - 8, 70] = 255
+    u[5, 50:71] = 255
+    out['u_shapes'] = u
+    s = np.zeros((H, W), np.uint8)                                                 # frame-spanning serpentine
+    for i in range(0, H, 4):
+        s[i, :] = 255
+    for i in range(0, H - 4, 8):
+        s[i:i + 5, W - 1] = 255
+        s[i + 4:min(i + 9, H), 0] = 255
+    out['serpentine'] = s
+    c = np.zeros((H, W), np.uint8)                                                 # comb: long run over many short ones
+    c[1::2, ::2] = 255
+    c[0::4, :] = 255
+    out['comb'] = c
+    d = np.zeros((H, W), np.uint8)                                                 # diagonal: 8-conn only
+    idx = np.arange(min(H, W))
+    d[idx, idx] = 255
+    d[idx, W - 1 - idx] = 255
+    out['diagonals'] = d
+    return out
+
+
+def test_label_adversarial(be, ctx):
+    for (H, W) in sizes(be, [(48, 96), (33, 75)], [(1080, 1920)]):
+        for name, m in adversarial_masks(H, W).items():
+            check_labels(ctx, m[None])
+
+
+def test_label_golden_and_pitch(be, ctx):
+    lab, cnt = hz.label(ctx, ops.pack_bits(GOLD['s_morph']), 64, 4, lab_pad=4)
+    assert np.array_equal(lab, GOLD['s_labels']) and np.array_equal(cnt, GOLD['s_counts'])
+    lab, cnt = hz.label(ctx, ops.pack_bits(GOLD['r_morph']), 53, 8)
+    assert np.array_equal(lab, GOLD['r_labels']) and np.array_equal(cnt, GOLD['r_counts'])
+
+
+def test_label_capacity_error(be, ctx):
+    m = np.zeros((9, 4, 40), np.uint8)
+    with pytest.raises(MemoryError):
+        hz.label(ctx, ops.pack_bits(m), 40)
+
+
+def test_region_areas_and_largest(be, ctx):
+    fr = synth.make_frames(0, 0, 6, 200, 120, 6)
+    r = ops.chain(fr)
+    lab, cnt = hz.label(ctx, ops.pack_bits(r['morph']), 200, 4)
+    areas, largest = hz.region_areas(ctx, lab, 64)
+    for b in range(6):
+        ra = ops.region_areas(lab[b], cnt[b])
+        assert np.array_equal(areas[b, :cnt[b]], ra)
+        assert largest[b] == (np.argmax(ra) + 1 if cnt[b] else 0)
+
+
+# ---- the whole chain ---------------------------------------------------------------------------------
+@pytest.mark.parametrize('fuse', [False, True])
+def test_chain_run_matches_oracle_stagewise_and_end_to_end(be, ctx, fuse):
+    W, H, T = (200, 120, 8) if be.name == 'emu' else (640, 480, 24)
+    fr = synth.make_frames(0, 0, T, W, H, 6)
+    ref = ops.chain(fr)
+    want = ('blur', 'mask', 'morph', 'labels') if fuse else ('mono', 'blur', 'mask', 'morph', 'labels')
+    cut = T // 2 + 1
+    a = hz.chain(ctx, fr[:cut], fuse=fuse, want=want)
+    b = hz.chain(ctx, fr[cut:], fuse=fuse, want=want, bg0=a['bg'])          # second batch continues the model
+    for k in want:
+        got = np.concatenate([a[k], b[k]])
+        exp = ops.pack_bits(ref[k]) if k in ('mask', 'morph') else ref[k]
+        assert np.array_equal(got, exp), k
+    assert np.array_equal(np.concatenate([a['counts'], b['counts']]), ref['counts'])
+    assert np.array_equal(b['bg'].view(np.uint32), ref['bg'].view(np.uint32))
+    assert ref['counts'][1:].min() >= 1
+
+
+def test_chain_golden_ragged(be, ctx):
+    out = hz.chain(ctx, GOLD['r_frames'], sigma=3, alpha=0.1, thr=12, morph_op='close', shape='ellipse', k=5, connectivity=8)
+    assert np.array_equal(out['labels'], GOLD['r_labels'])
+    assert np.array_equal(out['counts'], GOLD['r_counts'])
+    assert np.array_equal(out['blur'], GOLD['r_blur'])

@@ -1,0 +1,185 @@
+"""
+SegmentChain -- the whole filter -> segment chain of BASELINE.json configs 1-3 as one
+batched operator:
+
+    monochrome -> Gaussian blur -> running-average background / |diff| > thr
+               -> binary morphology -> connected-component labels
+
+One `va_chain_run` call per batch enqueues every kernel back to back on one stream, the
+intermediates never leave the GPU.  It is the same arithmetic as stacking the filter
+classes of `video_analysis_b200.filters` (and is tested against them and the oracle); what
+it adds is (a) the fused RGB -> luma -> blur kernel and (b) a three-stream pipeline that
+overlaps the host->device copy of batch k+1, the kernels of batch k and the device->host
+copy of batch k-1 when frames come from / results go to host memory.
+"""
+
+import collections
+
+import numpy as np
+
+from . import _lib
+from .device import DeviceBatch, get_runtime, torch
+from .filters import COLOR_CHANNELS
+
+
+class SegmentChain(object):
+    def __init__(self, size, sigma=2.0, alpha=0.05, threshold=25.0, morph_op='open', morph_shape='rect',
+                 morph_ksize=3, connectivity=4, mono_mode='mean', batch=64, device=None, fuse=True, depth=3):
+        self.w, self.h = int(size[0]), int(size[1])
+        self.sigma, self.alpha, self.threshold = float(sigma), float(alpha), float(threshold)
+        if morph_op is not None and morph_op not in _lib.MORPH_OPS:
+            raise ValueError('unknown morphological operation %r' % (morph_op,))
+        if morph_shape not in _lib.SE_SHAPES:
+            raise ValueError('unknown structuring element shape %r' % (morph_shape,))
+        if connectivity not in (0, 4, 8):
+            raise ValueError('connectivity must be 4 or 8 (0 disables labelling)')
+        mode = COLOR_CHANNELS.get(mono_mode.lower(), mono_mode.lower()) if isinstance(mono_mode, str) else mono_mode
+        if mode != 'mean' and mode not in (0, 1, 2):
+            raise ValueError('Unsupported conversion method to monochrome: %s' % mono_mode)
+        self.mono_mode = _lib.MONO_MEAN if mode == 'mean' else mode
+        self.morph_op, self.morph_shape = morph_op, morph_shape
+        self.kx, self.ky = (morph_ksize, morph_ksize) if np.isscalar(morph_ksize) else morph_ksize
+        self.connectivity = connectivity
+        self.batch, self.fuse, self.depth = int(batch), bool(fuse), int(depth)
+        self.rt = get_runtime(device)
+        self.rt.ensure(self.w, self.h, self.batch)
+        self._bg = self.rt.empty_f32(self.h, self.w)
+        self._started = False
+        self._slots = None
+
+    # ---- state ---------------------------------------------------------------------------------
+    def reset(self):
+        """ forget the background model: the next frame initialises it """
+        self._started = False
+
+    @property
+    def background(self):
+        torch().cuda.synchronize(self.rt.device)
+        return self._bg[:, :self.w].cpu().numpy()
+
+    def set_background(self, bg):
+        """ start from a given model (H, W) float32 -- e.g. the carry of the preceding frame range """
+        t = torch()
+        if isinstance(bg, np.ndarray):
+            bg = t.from_numpy(np.ascontiguousarray(bg, dtype=np.float32))
+        self._bg[:, :self.w].copy_(bg.to(self.rt.device)[:, :self.w])
+        self._started = True
+
+    # ---- one batch, everything on the device ---------------------------------------------------------
+    def run_device(self, rgb, labels=None, counts=None, blur=None, mask=None, morph=None):
+        """ rgb: DeviceBatch (n, h, w, 3).  Enqueues the chain on the current stream and returns
+        (labels DeviceBatch, counts tensor).  Optional DeviceBatches `blur`, `mask`, `morph`
+        receive the intermediates. """
+        rt, t = self.rt, torch()
+        n = rgb.n
+        if (rgb.w, rgb.h, rgb.channels) != (self.w, self.h, 3):
+            raise ValueError('chain built for %dx%d colour frames, got %dx%dx%d' % (self.w, self.h, rgb.w, rgb.h, rgb.channels))
+        if labels is None and self.connectivity:
+            labels = rt.empty_i32(n, self.h, self.w)
+        if counts is None and self.connectivity:
+            counts = t.empty((n,), dtype=t.int32, device=rt.device)
+        d = _lib.ChainDesc(w=self.w, h=self.h, batch=n, mono_mode=self.mono_mode, sigma=self.sigma,
+                           alpha=self.alpha, thr=self.threshold, first_frame_inits=0 if self._started else 1,
+                           morph_op=_lib.MORPH_OPS[self.morph_op] if self.morph_op else -1,
+                           morph_shape=_lib.SE_SHAPES[self.morph_shape], morph_kx=int(self.kx), morph_ky=int(self.ky),
+                           connectivity=self.connectivity, fuse_luma_blur=1 if self.fuse else 0)
+        io = _lib.ChainIO()
+        io.rgb, io.rgb_pitch, io.rgb_fstride = rgb.img()
+        io.bg, io.bg_pitch_e = self._bg.data_ptr(), self._bg.stride(0)
+        if blur is not None:
+            io.blur, io.blur_pitch, io.blur_fstride = blur.img()
+        if mask is not None:
+            io.mask, io.mask_pitch_w, io.mask_fstride_w = mask.img()
+        if morph is not None:
+            io.morph, io.morph_pitch_w, io.morph_fstride_w = morph.img()
+        if labels is not None:
+            io.labels, io.labels_pitch_e, io.labels_fstride_e = labels.img()
+        if counts is not None:
+            io.counts = counts.data_ptr()
+        rt.chain_run(d, io, self.w, self.h, n)
+        self._started = True
+        return labels, counts
+
+    # ---- host frames in, host labels out: pipelined -------------------------------------------------------
+    def _make_slots(self):
+        t, rt = torch(), self.rt
+        slots = []
+        for _ in range(self.depth):
+            s = {
+                'in': t.empty((self.batch, self.h, self.w * 3), dtype=t.uint8, device=rt.device),
+                'labels': rt.empty_i32(self.batch, self.h, self.w),
+                'counts': t.empty((self.batch,), dtype=t.int32, device=rt.device),
+                'ev_in': t.cuda.Event(), 'ev_run': t.cuda.Event(), 'ev_out': t.cuda.Event(),
+            }
+            s['labels_host'] = t.empty(tuple(s['labels'].t.shape), dtype=t.int32, pin_memory=True)
+            s['counts_host'] = t.empty((self.batch,), dtype=t.int32, pin_memory=True)
+            slots.append(s)
+        self._slots = slots
+        self._s_in = t.cuda.Stream(device=rt.device)
+        self._s_run = t.cuda.Stream(device=rt.device)
+        self._s_out = t.cuda.Stream(device=rt.device)
+
+    def process_blocks(self, blocks):
+        """ blocks: iterable of host arrays (m, h, w, 3) uint8 with m <= batch (page-locked memory
+        gives asynchronous copies).  Yields (labels (m, h, w) int32, counts (m,) int32) per block,
+        in order.  The yielded arrays are views of a ring of pinned buffers: they are valid until
+        the next block is requested (copy them if you keep them, as `process` does). """
+        t, rt = torch(), self.rt
+        if self._slots is None:
+            self._make_slots()
+        pending = collections.deque()
+        with t.cuda.device(rt.device):
+            for k, block in enumerate(blocks):
+                block = np.ascontiguousarray(block)
+                m = len(block)
+                if m == 0:
+                    continue
+                if m > self.batch or block.shape[1:] != (self.h, self.w, 3) or block.dtype != np.uint8:
+                    raise ValueError('expected blocks of up to %d uint8 frames of shape (%d, %d, 3)' % (self.batch, self.h, self.w))
+                s = self._slots[k % self.depth]
+                if len(pending) == self.depth:             # the slot is still owned by an unyielded block
+                    yield self._finish(pending.popleft())
+                with t.cuda.stream(self._s_in):
+                    self._s_in.wait_event(s['ev_run'])     # previous kernels that read this input are done
+                    s['in'][:m].copy_(t.from_numpy(block.reshape(m, self.h, self.w * 3)), non_blocking=True)
+                    s['ev_in'].record(self._s_in)
+                with t.cuda.stream(self._s_run):
+                    self._s_run.wait_event(s['ev_in'])
+                    self._s_run.wait_event(s['ev_out'])    # previous download of this slot's labels is done
+                    rgb = DeviceBatch('u8', s['in'][:m], m, self.h, self.w, 3)
+                    lab = DeviceBatch('i32', s['labels'].t[:m], m, self.h, self.w)
+                    self.run_device(rgb, lab, s['counts'][:m])
+                    s['ev_run'].record(self._s_run)
+                with t.cuda.stream(self._s_out):
+                    self._s_out.wait_event(s['ev_run'])
+                    s['labels_host'][:m].copy_(s['labels'].t[:m], non_blocking=True)
+                    s['counts_host'][:m].copy_(s['counts'][:m], non_blocking=True)
+                    s['ev_out'].record(self._s_out)
+                pending.append((s, m))
+            while pending:
+                yield self._finish(pending.popleft())
+
+    def _finish(self, item):
+        s, m = item
+        s['ev_out'].synchronize()
+        return s['labels_host'].numpy()[:m, :, :self.w], s['counts_host'].numpy()[:m]
+
+    def process(self, frames):
+        """ frames: ndarray (n, h, w, 3) uint8 or a video object -> (labels (n, h, w) int32,
+        counts (n,) int32), continuing the background model from earlier calls """
+        if hasattr(frames, 'frame_block'):
+            video = frames
+            n = video.frame_count
+            blocks = (video.frame_block(a, min(a + self.batch, n)) for a in range(0, n, self.batch))
+        else:
+            frames = np.asarray(frames)
+            n = len(frames)
+            blocks = (frames[a:a + self.batch] for a in range(0, n, self.batch))
+        labels = np.empty((n, self.h, self.w), np.int32)
+        counts = np.empty((n,), np.int32)
+        k = 0
+        for lab, cnt in self.process_blocks(blocks):
+            labels[k:k + len(lab)] = lab
+            counts[k:k + len(cnt)] = cnt
+            k += len(lab)
+        return labels[:k], counts[:k]

@@ -1,0 +1,324 @@
+"""
+Device runtime: one `va_ctx` per (process, GPU) plus typed wrappers that enqueue the
+kernels of libva_b200 on torch's current CUDA stream.
+
+PyTorch is used for plumbing only -- device / pinned allocations, streams, events.
+Every pixel is touched by the hand-written kernels behind include/va_b200.h.  There
+is no CPU path: without the built library or without a GPU these calls raise.
+"""
+
+import ctypes
+import threading
+
+import numpy as np
+
+from . import _lib
+
+_torch = None
+
+
+def torch():
+    global _torch
+    if _torch is None:
+        import torch as _t
+        _torch = _t
+    return _torch
+
+
+def _round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+class DeviceBatch(object):
+    """ a batch of images resident on the GPU.
+
+    kind 'u8'  : uint8 tensor (n, h, pitch), pitch >= w * channels bytes
+    kind 'bits': int32 tensor (n, h, pitch) of packed mask words, LSB = lowest x
+    kind 'i32' : int32 tensor (n, h, pitch) label image
+    """
+    __slots__ = ('kind', 't', 'n', 'h', 'w', 'channels', 'extra')
+
+    def __init__(self, kind, t, n, h, w, channels=1, extra=None):
+        self.kind, self.t, self.n, self.h, self.w, self.channels = kind, t, n, h, w, channels
+        self.extra = extra or {}
+
+    @property
+    def pitch(self):
+        return self.t.stride(1)
+
+    @property
+    def fstride(self):
+        return self.t.stride(0)
+
+    @property
+    def ptr(self):
+        return self.t.data_ptr()
+
+    def img(self):
+        """ (pointer, pitch, frame stride) in the units the C ABI expects for this kind """
+        return self.ptr, self.pitch, self.fstride
+
+
+class DeviceRuntime(object):
+    """ owns the va_ctx of one GPU; grows its scratch capacity on demand """
+
+    def __init__(self, device=0):
+        t = torch()
+        if not t.cuda.is_available():
+            raise _lib.VAError('no CUDA device available: video_analysis_b200 has no CPU fallback')
+        self.lib = _lib.load()
+        self.device = t.device('cuda', device if isinstance(device, int) else t.device(device).index or 0)
+        self._h = ctypes.c_void_p()
+        self._cap = (0, 0, 0)
+        self._retired_launches = 0
+
+    # ---- ctx management ------------------------------------------------------------------
+    def ensure(self, w, h, n):
+        cw, ch, cn = self._cap
+        if w <= cw and h <= ch and n <= cn and self._h:
+            return
+        cap = (max(w, cw), max(h, ch), max(n, cn))
+        if self._h:
+            torch().cuda.synchronize(self.device)
+            self._retired_launches += self.lib.va_launch_count(self._h)
+            self.lib.va_destroy(self._h)
+            self._h = ctypes.c_void_p()
+        with torch().cuda.device(self.device):
+            rc = self.lib.va_create(ctypes.byref(self._h), self.device.index, cap[0], cap[1], cap[2])
+        if rc != _lib.VA_OK:
+            self._cap = (0, 0, 0)
+            _lib.check(self.lib, None, rc)
+        self._cap = cap
+
+    @property
+    def launches(self):
+        """ kernels launched through this runtime so far """
+        return self._retired_launches + (self.lib.va_launch_count(self._h) if self._h else 0)
+
+    def close(self):
+        if self._h:
+            torch().cuda.synchronize(self.device)
+            self._retired_launches += self.lib.va_launch_count(self._h)
+            self.lib.va_destroy(self._h)
+            self._h = ctypes.c_void_p()
+            self._cap = (0, 0, 0)
+
+    @property
+    def stream(self):
+        return torch().cuda.current_stream(self.device).cuda_stream
+
+    def _check(self, rc):
+        _lib.check(self.lib, self._h, rc)
+
+    # ---- allocation ------------------------------------------------------------------------
+    def empty_u8(self, n, h, w, channels=1):
+        pitch = _round_up(w * channels, 16)
+        t = torch().empty((n, h, pitch), dtype=torch().uint8, device=self.device)
+        return DeviceBatch('u8', t, n, h, w, channels)
+
+    def empty_bits(self, n, h, w):
+        pitch = _round_up((w + 31) // 32, 4)
+        t = torch().empty((n, h, pitch), dtype=torch().int32, device=self.device)
+        return DeviceBatch('bits', t, n, h, w)
+
+    def empty_i32(self, n, h, w):
+        pitch = _round_up(w, 4)
+        t = torch().empty((n, h, pitch), dtype=torch().int32, device=self.device)
+        return DeviceBatch('i32', t, n, h, w)
+
+    def empty_f32(self, h, w):
+        return torch().empty((h, _round_up(w, 4)), dtype=torch().float32, device=self.device)
+
+    # ---- host <-> device -----------------------------------------------------------------------
+    def upload(self, frames):
+        """ frames: ndarray (n, h, w[, 3]) uint8, C-contiguous -> dense DeviceBatch.
+        Page-locked arrays (VideoMemory.pin(), pinned torch buffers) go by async DMA. """
+        t = torch()
+        frames = np.ascontiguousarray(frames)
+        if frames.dtype != np.uint8:
+            raise ValueError('the device path handles uint8 frames, got %s' % frames.dtype)
+        n, h, w = frames.shape[:3]
+        ch = frames.shape[3] if frames.ndim == 4 else 1
+        host = t.from_numpy(frames.reshape(n, h, w * ch))
+        dev = t.empty((n, h, w * ch), dtype=t.uint8, device=self.device)
+        dev.copy_(host, non_blocking=True)
+        return DeviceBatch('u8', dev, n, h, w, ch, extra={'keepalive': host})
+
+    def download(self, batch):
+        """ DeviceBatch -> pinned host tensor of the same (n, h, pitch) layout (async; the
+        caller synchronises) """
+        t = torch()
+        host = t.empty(tuple(batch.t.shape), dtype=batch.t.dtype, pin_memory=True)
+        host.copy_(batch.t, non_blocking=True)
+        return host
+
+    @staticmethod
+    def host_view(batch, host):
+        """ numpy view (n, h, w[, 3]) of a downloaded batch """
+        a = host.numpy()
+        if batch.kind == 'u8':
+            a = a[:, :, :batch.w * batch.channels]
+            if batch.channels == 3:
+                a = a.reshape(batch.n, batch.h, batch.w, 3) if a.flags['C_CONTIGUOUS'] else \
+                    np.lib.stride_tricks.as_strided(a, (batch.n, batch.h, batch.w, 3),
+                                                    (a.strides[0], a.strides[1], 3, 1))
+            return a
+        if batch.kind == 'i32':
+            return a[:, :, :batch.w]
+        raise ValueError('packed masks are unpacked on the device before download')
+
+    # ---- kernels ------------------------------------------------------------------------------------
+    def luma(self, src, mode=_lib.MONO_MEAN, rect=None):
+        """ K1 (+ crop by pointer offset): (n,h,w,3) -> (n,h',w') """
+        left, top, w, h = rect if rect is not None else (0, 0, src.w, src.h)
+        self.ensure(w, h, src.n)
+        out = self.empty_u8(src.n, h, w)
+        ptr = src.ptr + top * src.pitch + left * 3
+        self._check(self.lib.va_luma_u8(self._h, self.stream, ptr, src.pitch, src.fstride,
+                                        out.ptr, out.pitch, out.fstride, w, h, src.n, mode))
+        return out
+
+    def crop(self, src, rect):
+        left, top, w, h = rect
+        self.ensure(w, h, src.n)
+        out = self.empty_u8(src.n, h, w, src.channels)
+        ptr = src.ptr + top * src.pitch + left * src.channels
+        self._check(self.lib.va_copy2d_u8(self._h, self.stream, ptr, src.pitch, src.fstride,
+                                          out.ptr, out.pitch, out.fstride, w * src.channels, h, src.n))
+        return out
+
+    def gauss(self, src, sigma):
+        self.ensure(src.w, src.h, src.n)
+        out = self.empty_u8(src.n, src.h, src.w, src.channels)
+        self._check(self.lib.va_gauss_u8(self._h, self.stream, src.ptr, src.pitch, src.fstride,
+                                         out.ptr, out.pitch, out.fstride, src.w, src.h, src.channels, src.n,
+                                         float(sigma)))
+        return out
+
+    def luma_gauss(self, src, sigma, mode=_lib.MONO_MEAN):
+        self.ensure(src.w, src.h, src.n)
+        out = self.empty_u8(src.n, src.h, src.w)
+        self._check(self.lib.va_luma_gauss_u8(self._h, self.stream, src.ptr, src.pitch, src.fstride,
+                                              out.ptr, out.pitch, out.fstride, src.w, src.h, src.n, mode,
+                                              float(sigma)))
+        return out
+
+    def resize_half(self, src):
+        self.ensure(src.w, src.h, src.n)
+        out = self.empty_u8(src.n, src.h // 2, src.w // 2, src.channels)
+        self._check(self.lib.va_resize_half_u8(self._h, self.stream, src.ptr, src.pitch, src.fstride,
+                                               out.ptr, out.pitch, out.fstride, src.w, src.h, src.channels, src.n))
+        return out
+
+    def apply_mask(self, src, mask_dev):
+        """ mask_dev: uint8 device tensor (h, w) """
+        self.ensure(src.w, src.h, src.n)
+        out = self.empty_u8(src.n, src.h, src.w, src.channels)
+        self._check(self.lib.va_apply_mask_u8(self._h, self.stream, src.ptr, src.pitch, src.fstride,
+                                              mask_dev.data_ptr(), mask_dev.stride(0), 0,
+                                              out.ptr, out.pitch, out.fstride, src.w, src.h, src.channels, src.n))
+        return out
+
+    def ema_diff_thresh(self, src, bg, alpha, thr, first_frame_inits):
+        self.ensure(src.w, src.h, src.n)
+        out = self.empty_bits(src.n, src.h, src.w)
+        self._check(self.lib.va_ema_diff_thresh(self._h, self.stream, src.ptr, src.pitch, src.fstride,
+                                                bg.data_ptr(), bg.stride(0), out.ptr, out.pitch, out.fstride,
+                                                src.w, src.h, src.n, float(alpha), float(thr),
+                                                1 if first_frame_inits else 0))
+        return out
+
+    def threshold(self, src, thr):
+        self.ensure(src.w, src.h, src.n)
+        out = self.empty_bits(src.n, src.h, src.w)
+        self._check(self.lib.va_threshold_bits(self._h, self.stream, src.ptr, src.pitch, src.fstride,
+                                               out.ptr, out.pitch, out.fstride, src.w, src.h, src.n, int(thr)))
+        return out
+
+    def pack_bits(self, src):
+        self.ensure(src.w, src.h, src.n)
+        out = self.empty_bits(src.n, src.h, src.w)
+        self._check(self.lib.va_pack_bits_u8(self._h, self.stream, src.ptr, src.pitch, src.fstride,
+                                             out.ptr, out.pitch, out.fstride, src.w, src.h, src.n))
+        return out
+
+    def unpack_bits(self, src):
+        self.ensure(src.w, src.h, src.n)
+        out = self.empty_u8(src.n, src.h, src.w)
+        self._check(self.lib.va_unpack_bits_u8(self._h, self.stream, src.ptr, src.pitch, src.fstride,
+                                               out.ptr, out.pitch, out.fstride, src.w, src.h, src.n))
+        return out
+
+    def morph(self, src, op, shape='rect', ksize=3):
+        kx, ky = (ksize, ksize) if np.isscalar(ksize) else ksize
+        try:
+            op_id, shape_id = _lib.MORPH_OPS[op], _lib.SE_SHAPES[shape]
+        except KeyError as e:
+            raise ValueError('unknown morphological operation or shape: %s' % e)
+        self.ensure(src.w, src.h, src.n)
+        out = self.empty_bits(src.n, src.h, src.w)
+        self._check(self.lib.va_morph_bits(self._h, self.stream, src.ptr, src.pitch, src.fstride,
+                                           out.ptr, out.pitch, out.fstride, src.w, src.h, src.n,
+                                           op_id, shape_id, int(kx), int(ky)))
+        return out
+
+    def label(self, src, connectivity=4):
+        """ -> (labels DeviceBatch 'i32', counts int32 device tensor (n,)) """
+        self.ensure(src.w, src.h, src.n)
+        out = self.empty_i32(src.n, src.h, src.w)
+        counts = torch().empty((src.n,), dtype=torch().int32, device=self.device)
+        self._check(self.lib.va_label_bits(self._h, self.stream, src.ptr, src.pitch, src.fstride,
+                                           out.ptr, out.pitch, out.fstride, counts.data_ptr(),
+                                           src.w, src.h, src.n, int(connectivity)))
+        return out, counts
+
+    def region_areas(self, labels, max_labels):
+        t = torch()
+        areas = t.empty((labels.n, max_labels), dtype=t.int32, device=self.device)
+        largest = t.empty((labels.n,), dtype=t.int32, device=self.device)
+        self.ensure(labels.w, labels.h, labels.n)
+        self._check(self.lib.va_region_areas(self._h, self.stream, labels.ptr, labels.pitch, labels.fstride,
+                                             areas.data_ptr(), int(max_labels), largest.data_ptr(),
+                                             labels.w, labels.h, labels.n))
+        return areas, largest
+
+    def ema_partial(self, src, S, alpha, accumulate):
+        self.ensure(src.w, src.h, src.n)
+        self._check(self.lib.va_ema_partial(self._h, self.stream, src.ptr, src.pitch, src.fstride,
+                                            S.data_ptr(), S.stride(0), src.w, src.h, src.n, float(alpha),
+                                            1 if accumulate else 0))
+
+    def ema_fold(self, carry, S, scale, w, h):
+        self.ensure(w, h, 1)
+        self._check(self.lib.va_ema_fold(self._h, self.stream, carry.data_ptr(), S.data_ptr(), carry.stride(0),
+                                         w, h, float(scale)))
+
+    def synth_rgb(self, out, t0, seed, blobs):
+        """ fill DeviceBatch `out` (n,h,w,3) with frames t0.. of the seeded synthetic video """
+        tab = np.ascontiguousarray(blobs, dtype=np.int32).reshape(-1, 5)
+        self.ensure(out.w, out.h, 1)
+        self._check(self.lib.va_synth_rgb(self._h, self.stream, out.ptr, out.pitch, out.fstride, out.w, out.h,
+                                          int(t0), out.n, int(seed) & 0xFFFFFFFF, tab.ctypes.data, len(tab)))
+
+    def chain_run(self, desc, io, w, h, n):
+        self.ensure(w, h, n)
+        self._check(self.lib.va_chain_run(self._h, self.stream, ctypes.byref(desc), ctypes.byref(io)))
+
+
+_runtimes = {}
+_lock = threading.Lock()
+
+
+def get_runtime(device=None):
+    """ the process-wide runtime of `device` (default: torch's current CUDA device) """
+    t = torch()
+    if device is None:
+        if not t.cuda.is_available():
+            raise _lib.VAError('no CUDA device available: video_analysis_b200 has no CPU fallback')
+        device = t.cuda.current_device()
+    idx = device if isinstance(device, int) else (t.device(device).index or 0)
+    with _lock:
+        rt = _runtimes.get(idx)
+        if rt is None:
+            rt = _runtimes[idx] = DeviceRuntime(idx)
+        return rt
