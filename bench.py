@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""
+bench.py -- frames/sec of the full filter + segment chain (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (config.workload): BASELINE.json configs[1] -- 1920x1080 RGB uint8 synthetic video,
+chain mono -> blur sigma=2 -> running background (alpha .05) -> |diff| > 25 -> 3x3 open ->
+label (4-conn).  A step is one batch of `--batch` frames through the whole chain.
+
+  value      device-resident: the synthetic video lives in HBM (generated there by
+             va_synth_rgb), every step reads a different batch of it (working set >> L2)
+  e2e        the same chain through the plug-in API (SegmentChain.process_blocks) with the
+             frames in pinned HOST memory and the int32 labels + counts copied back to host,
+             copies inside the timed region
+  roofline   the kernel with the largest share of the step, timed with CUDA events around
+             its launches on the launch stream in a second, instrumented pass over the same
+             steps; achieved = algorithmic bytes / duration (DESIGN.md states the bytes)
+  cpu_baseline  the oracle (same cv2 / NumPy / SciPy calls as the reference) on this box's
+             host cores, one process, one frame per iteration, on a bounded sample
+
+`--impl reference` times that CPU chain alone, frame-sharded over all host cores.
+N > 1 (torchrun): frames are sharded by contiguous ranges, one process per GPU, the only
+exchange is the background-EMA carry (video_analysis_b200/parallel.py).
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 1920, 1080
+CHAIN = dict(sigma=2.0, alpha=0.05, threshold=25.0, morph_op='open', morph_shape='rect', morph_ksize=3, connectivity=4)
+WORKLOAD = '1920x1080 RGB uint8 synthetic video, mono->blur s=2->EMA bg a=.05->|diff|>25->3x3 open->label(4)'
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        return float(p['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+# ------------------------------------------------------------------------------------------
+# clocks: sample nvidia-smi during the timed region
+# ------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith('active') for r in self.rows)]
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU reference chain (oracle): the only places bench.py touches oracle/
+# ------------------------------------------------------------------------------------------
+def cpu_frames(n_unique):
+    from oracle import synth
+    return synth.make_frames(0, 0, n_unique, W, H, 8)
+
+
+def cpu_chain_run(frames, n_frames, bg=None):
+    """ reference-style loop: one frame per iteration; returns (seconds, bg) """
+    from oracle import ops
+    alpha32, thr32 = np.float32(CHAIN['alpha']), np.float32(CHAIN['threshold'])
+    t0 = time.perf_counter()
+    for i in range(n_frames):
+        f = frames[i % len(frames)]
+        b = ops.blur(ops.mono(f), CHAIN['sigma'])
+        x = b.astype(np.float32)
+        if bg is None:
+            bg = x.copy()
+            mask = np.zeros(b.shape, np.uint8)
+        else:
+            d = x - bg
+            mask = np.where(np.abs(d) > thr32, 255, 0).astype(np.uint8)
+            bg = bg + alpha32 * d
+        mo = ops.morph(mask, CHAIN['morph_op'], CHAIN['morph_shape'], CHAIN['morph_ksize'])
+        ops.label(mo, CHAIN['connectivity'])
+    return time.perf_counter() - t0, bg
+
+
+def cpu_baseline_single(budget_s=12.0):
+    import cv2
+    frames = cpu_frames(8)
+    dt, bg = cpu_chain_run(frames, 8)                 # warm-up + rate estimate
+    n = int(max(16, min(400, budget_s / (dt / 8))))
+    dt, _ = cpu_chain_run(frames, n, bg)
+    return {'value': round(n / dt, 2), 'unit': 'frames/s', 'cores': int(cv2.getNumThreads()), 'kind': 'port',
+            'sample': '%d frames 1080p (8 unique synthetic frames cycled), one process, one frame per iteration, '
+                      'cv2 threads=%d' % (n, cv2.getNumThreads())}
+
+
+_W = {}
+
+
+def _worker_init():
+    import cv2
+    cv2.setNumThreads(1)
+    _W['frames'] = cpu_frames(4)
+    _W['bg'] = None
+
+
+def _worker_step(n):
+    dt, _W['bg'] = cpu_chain_run(_W['frames'], n, _W['bg'])
+    return dt
+
+
+def reference_arm(args):
+    """ the reference's CPU chain on all host cores: frames sharded over processes """
+    import multiprocessing as mp
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    procs = max(1, min(os.cpu_count() or 1, 64))
+    per = 4                                           # frames per process per step
+    ctx = mp.get_context('fork')
+    with ctx.Pool(procs, initializer=_worker_init) as pool:
+        for _ in range(max(args.warmup, 1)):
+            pool.map(_worker_step, [per] * procs)
+        steps = min(args.steps, 20)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            pool.map(_worker_step, [per] * procs)
+        dt = time.perf_counter() - t0
+    fps = steps * procs * per / dt
+    line = {
+        'impl': 'reference', 'metric': 'frames/sec full filter+segment chain', 'value': round(fps, 2), 'unit': 'frames/s',
+        'n_gpus': args.gpus, 'steps': steps, 'warmup': max(args.warmup, 1), 'ms_per_step': round(dt / steps * 1e3, 3),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'frames_per_step': procs * per},
+        'cpu_baseline': {'value': round(fps, 2), 'unit': 'frames/s', 'cores': procs, 'kind': 'port',
+                         'sample': '%d steps x %d processes x %d frames 1080p, frame-sharded, cv2 threads=1 per process, '
+                                   'oracle restatement of the reference calls (reference is Python 2, not importable)'
+                                   % (steps, procs, per)},
+        'e2e': {'value': round(fps, 2), 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from video_analysis_b200 import synth
+    from video_analysis_b200.chain import SegmentChain
+    from video_analysis_b200.device import DeviceBatch, get_runtime
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    rt = get_runtime(local)
+    B, K, Wm = args.batch, args.steps, args.warmup
+    N = W * H
+    hbm_peak, peak_src = peaks()
+
+    # ---- the synthetic video of this rank, resident in HBM ------------------------------------
+    n_frames = min(args.frames, (K + Wm) * B)
+    n_frames = max(B, n_frames // B * B)
+    free, _ = torch.cuda.mem_get_info()
+    while n_frames * N * 3 > free * 0.45 and n_frames > 2 * B:
+        n_frames = n_frames // 2 // B * B
+    t0_rank = rank * args.frames                       # rank r owns frames [r*T, (r+1)*T) of the global video
+    video = torch.empty((n_frames, H, W * 3), dtype=torch.uint8, device=rt.device)
+    for a in range(0, n_frames, B):
+        synth.generate(rt, 0, t0_rank + a, B, W, H, out=video[a:a + B])
+    torch.cuda.synchronize()
+
+    def batch_of(step):
+        a = (step * B) % n_frames
+        return DeviceBatch('u8', video[a:a + B], B, H, W, 3)
+
+    chain = SegmentChain((W, H), batch=B, fuse=not args.no_fuse, **CHAIN)
+    labels = [rt.empty_i32(B, H, W) for _ in range(2)]
+    counts = torch.empty((B,), dtype=torch.int32, device=rt.device)
+
+    if world > 1:
+        from video_analysis_b200.parallel import ShardedSegmentChain
+        sharded = ShardedSegmentChain(chain)
+
+    def run_steps(first, n):
+        if world > 1:
+            sharded.run_device_range([batch_of(first + i) for i in range(n)], labels, counts)
+        else:
+            for i in range(n):
+                chain.run_device(batch_of(first + i), labels[i & 1], counts)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-resident ------------------------------------------------------------------
+    run_steps(0, Wm)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = rt.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    run_steps(Wm, K)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = rt.launches - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        tmax = torch.tensor([ms], device=rt.device)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    fps = world * K * B / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel: instrumented pass, events around each launch group ------
+    roof = None
+    if rank == 0:
+        roof = instrumented_pass(rt, chain, batch_of, labels, counts, Wm, K, B, N, hbm_peak, peak_src, args)
+
+    # ---- e2e: host frames -> labels on host ---------------------------------------------------------
+    ring = max(2, min(4, n_frames // B))
+    host = torch.empty((ring * B, H, W, 3), dtype=torch.uint8, pin_memory=True)
+    host.view(ring * B, H, W * 3).copy_(video[:ring * B])
+    torch.cuda.synchronize()
+    host_np = host.numpy()
+    e2e_chain = SegmentChain((W, H), batch=B, fuse=not args.no_fuse, **CHAIN)
+    Ke = max(3, min(K, args.e2e_steps))
+
+    def blocks(n):
+        for i in range(n):
+            a = (i % ring) * B
+            yield host_np[a:a + B]
+
+    sink = 0
+    for lab, cnt in e2e_chain.process_blocks(blocks(max(3, min(Wm, 5)))):
+        sink += int(cnt[0])
+    barrier()
+    t0 = time.perf_counter()
+    for lab, cnt in e2e_chain.process_blocks(blocks(Ke)):
+        sink += int(cnt[-1]) + int(lab[0, H // 2, W // 2])       # touch the results on the host
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tmax = torch.tensor([e2e_s], device=rt.device)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        e2e_s = float(tmax.item())
+    e2e_fps = world * Ke * B / e2e_s
+
+    if rank == 0:
+        line = {
+            'metric': 'frames/sec full filter+segment chain', 'value': round(fps, 1), 'unit': 'frames/s',
+            'n_gpus': world, 'steps': K, 'warmup': Wm, 'ms_per_step': round(ms / K, 4),
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'frames_per_step': B, 'resident_frames_per_gpu': n_frames,
+                       'parallelism': 'frame-range shards x%d, EMA carry via NCCL all-gather' % world if world > 1 else 'single GPU',
+                       'l2': 'every step reads a different %d MB batch of the resident video (>> 126 MB L2)' % (B * N * 3 >> 20),
+                       'fused_luma_blur': not args.no_fuse},
+            'clocks': clocks,
+            'e2e': {'value': round(e2e_fps, 1), 'unit': 'frames/s', 'h2d_bytes_per_step': B * N * 3,
+                    'd2h_bytes_per_step': B * N * 4 + B * 4, 'steps': Ke,
+                    'api': 'SegmentChain.process_blocks (pinned host frames in, int32 labels + counts out)'},
+            'gpu_launches': int(launches),
+            'roofline': roof,
+        }
+        if world == 1 and not args.no_cpu:
+            line['cpu_baseline'] = cpu_baseline_single()
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def instrumented_pass(rt, chain, batch_of, labels, counts, Wm, K, B, N, hbm_peak, peak_src, args):
+    """ same steps, one C-ABI call per kernel with CUDA events in between """
+    import torch
+    from video_analysis_b200 import _lib
+    fuse = not args.no_fuse
+    blur, mono = rt.empty_u8(B, H, W), rt.empty_u8(B, H, W)
+    mask, morph = rt.empty_bits(B, H, W), rt.empty_bits(B, H, W)
+    bg = rt.empty_f32(H, W)
+    lib, h = rt.lib, rt._h
+    stages = (['luma_gauss'] if fuse else ['luma', 'gauss']) + ['ema_diff_thresh', 'morph_open', 'label']
+    alg_bytes = {'luma_gauss': 4 * N, 'luma': 4 * N, 'gauss': 2 * N, 'ema_diff_thresh': N + N / 8 + 8 * N / B,
+                 'morph_open': N / 4, 'label': N / 8 + 4 * N}
+    tot = {s: 0.0 for s in stages}
+    n_timed = 0
+    for step in range(Wm + K):
+        rgb = batch_of(step)
+        lab = labels[step & 1]
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(stages) + 1)]
+        evs[0].record()
+        i = 1
+        if fuse:
+            rt._check(lib.va_luma_gauss_u8(h, rt.stream, *rgb.img(), *blur.img(), W, H, B, -1, CHAIN['sigma'])); evs[i].record(); i += 1
+        else:
+            rt._check(lib.va_luma_u8(h, rt.stream, *rgb.img(), *mono.img(), W, H, B, -1)); evs[i].record(); i += 1
+            rt._check(lib.va_gauss_u8(h, rt.stream, *mono.img(), *blur.img(), W, H, 1, B, CHAIN['sigma'])); evs[i].record(); i += 1
+        rt._check(lib.va_ema_diff_thresh(h, rt.stream, *blur.img(), bg.data_ptr(), bg.stride(0), *mask.img(), W, H, B,
+                                         CHAIN['alpha'], CHAIN['threshold'], 1 if step == 0 else 0)); evs[i].record(); i += 1
+        rt._check(lib.va_morph_bits(h, rt.stream, *mask.img(), *morph.img(), W, H, B, _lib.MORPH_OPS['open'],
+                                    _lib.SE_SHAPES['rect'], 3, 3)); evs[i].record(); i += 1
+        rt._check(lib.va_label_bits(h, rt.stream, *morph.img(), *lab.img(), counts.data_ptr(), W, H, B, 4)); evs[i].record()
+        torch.cuda.synchronize()
+        if step >= Wm:
+            n_timed += 1
+            for j, s in enumerate(stages):
+                tot[s] += evs[j].elapsed_time(evs[j + 1])
+    avg = {s: tot[s] / n_timed for s in stages}
+    step_ms = sum(avg.values())
+    dom = max(avg, key=avg.get)
+    achieved = alg_bytes[dom] * B / (avg[dom] * 1e-3) / 1e9
+    per_kernel = {s: {'ms': round(avg[s], 4), 'share': round(avg[s] / step_ms, 3),
+                      'alg_GBps': round(alg_bytes[s] * B / (avg[s] * 1e-3) / 1e9, 1),
+                      'frac': round(alg_bytes[s] * B / (avg[s] * 1e-3) / 1e9 / hbm_peak, 3)} for s in stages}
+    return {'bound': 'hbm', 'kernel': dom, 'achieved': round(achieved, 1), 'peak': hbm_peak, 'unit': 'GB/s',
+            'frac': round(achieved / hbm_peak, 3), 'traffic': None, 'peak_source': peak_src,
+            'launch_ms': round(avg[dom], 4), 'alg_bytes_per_launch': int(alg_bytes[dom] * B),
+            'per_kernel': per_kernel}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200')
+    ap.add_argument('--batch', type=int, default=64)
+    ap.add_argument('--frames', type=int, default=10000, help='frames of the synthetic video per GPU')
+    ap.add_argument('--e2e-steps', type=int, default=30)
+    ap.add_argument('--no-fuse', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == 'reference':
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == '__main__':
+    main()

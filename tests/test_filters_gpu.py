@@ -1,0 +1,200 @@
+"""
+The reference-facing plug-in API on a real GPU: filter classes, SegmentChain and the
+analysis helpers, compared with the oracle on the same seeded frames (bit-exact).
+"""
+
+import numpy as np
+import pytest
+
+from oracle import ops, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def frames():
+    return synth.make_frames(0, 0, 40, 320, 240, 6)
+
+
+@pytest.fixture(scope='module')
+def ref(frames):
+    return ops.chain(frames)
+
+
+def mods():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from video_analysis_b200 import filters
+    from video_analysis_b200.io.memory import VideoMemory
+    return filters, VideoMemory
+
+
+def test_filter_chain_iteration_matches_reference_chain(frames, ref):
+    F, VideoMemory = mods()
+    v = VideoMemory(frames, copy_data=False)
+    mono = F.FilterMonochrome(v, batch=16)
+    assert np.array_equal(np.stack(list(mono)), ref['mono'])
+    blur = F.FilterBlur(F.FilterMonochrome(v, batch=16), sigma=2)          # fused luma+blur path
+    assert np.array_equal(np.stack(list(blur)), ref['blur'])
+    mask = F.FilterBackgroundMask(F.FilterBlur(F.FilterMonochrome(v, batch=7), 2), 0.05, 25)
+    assert np.array_equal(np.stack(list(mask)), ref['mask'])
+    assert np.array_equal(mask.background.view(np.uint32), ref['bg'].view(np.uint32))
+    assert np.array_equal(np.stack(list(mask)), ref['mask'])              # rewinding restarts the model
+    full = F.FilterLabel(F.FilterMorphology(
+        F.FilterBackgroundMask(F.FilterBlur(F.FilterMonochrome(v, batch=16), 2)), 'open', 'rect', 3))
+    labels = np.stack(list(full))
+    assert labels.dtype == np.int32 and np.array_equal(labels, ref['labels'])
+    assert full.num_features == list(ref['counts'])
+    assert full.get_frame_pos() == 40
+
+
+def test_listeners_fire_per_frame_source_first_and_blur_stays_silent(frames, ref):
+    F, VideoMemory = mods()
+    v = VideoMemory(frames[:10], copy_data=False)
+    log = []
+    mono = F.FilterMonochrome(v, batch=4)
+    mono.register_listener(lambda f: log.append(('mono', f.copy())))
+    blur = F.FilterBlur(mono, 2)
+    blur.register_listener(lambda f: log.append(('blur', None)))           # must never fire (filters.py:388-392)
+    thr = F.FilterThreshold(blur, 100)
+    thr.register_listener(lambda f: log.append(('thr', f.copy())))
+    out = list(thr)
+    assert [k for k, _ in log] == ['mono', 'thr'] * 10
+    assert all(np.array_equal(log[2 * i][1], ref['mono'][i]) for i in range(10))
+    assert all(np.array_equal(out[i], np.where(ref['blur'][i] > 100, 255, 0)) for i in range(10))
+
+
+def test_crop_resize_applymask_and_random_access(frames):
+    F, VideoMemory = mods()
+    v = VideoMemory(frames[:9], copy_data=False)
+    rect = (33, 10, 160, 120)
+    crop = F.FilterCrop(v, rect, batch=4)
+    assert np.array_equal(np.stack(list(crop)), np.stack([ops.crop(f, rect) for f in frames[:9]]))
+    cm = F.FilterMonochrome(F.FilterCrop(v, rect, batch=4))
+    exp = np.stack([ops.mono(ops.crop(f, rect)) for f in frames[:9]])
+    assert np.array_equal(np.stack(list(cm)), exp)
+    assert np.array_equal(cm.get_frame(5), exp[5]) and np.array_equal(cm[-1], exp[8])
+    red = F.FilterCrop(v, rect, color_channel='red', batch=4)
+    assert np.array_equal(np.stack(list(red)), np.stack([ops.crop(f, rect, 'red') for f in frames[:9]]))
+    half = F.FilterResize(cm, 0.5)
+    assert np.array_equal(np.stack(list(half)), np.stack([ops.resize(f, 0.5) for f in exp]))
+    with pytest.raises(NotImplementedError):
+        next(iter(F.FilterResize(cm, 0.3)))
+    m = np.zeros((120, 160), bool)
+    m[20:90, 30:140] = True
+    masked = F.FilterApplyMask(cm, m)
+    assert np.array_equal(np.stack(list(masked)), np.stack([ops.apply_mask(f, m) for f in exp]))
+    colour_blur = F.FilterBlur(crop, 1.5)
+    assert np.array_equal(np.stack(list(colour_blur)), np.stack([ops.blur(ops.crop(f, rect), 1.5) for f in frames[:9]]))
+    sl = F.FilterMonochrome(v[2:7], batch=3)                               # VideoSlice as the root
+    assert np.array_equal(np.stack(list(sl)), np.stack([ops.mono(f) for f in frames[2:7]]))
+
+
+def test_copy_and_iter_batches(frames, ref):
+    F, VideoMemory = mods()
+    v = VideoMemory(frames, copy_data=False)
+    blur = F.FilterBlur(F.FilterMonochrome(v, batch=16), 2)
+    c = blur.copy()
+    assert isinstance(c, VideoMemory) and np.array_equal(c.data, ref['blur'])
+    blocks = list(blur.iter_batches())
+    assert [len(b) for b in blocks] == [16, 16, 8] and np.array_equal(np.concatenate(blocks), ref['blur'])
+
+
+def test_function_filter_breaks_the_device_chain(frames):
+    F, VideoMemory = mods()
+    v = VideoMemory(frames[:6], copy_data=False)
+    chain = F.FilterBlur(F.FilterFunction(F.FilterMonochrome(v, batch=4), lambda f: 255 - f), 1)
+    assert np.array_equal(np.stack(list(chain)), np.stack([ops.blur(255 - ops.mono(f), 1) for f in frames[:6]]))
+
+
+def test_segment_chain_host_pipeline(frames, ref):
+    mods()
+    from video_analysis_b200.chain import SegmentChain
+    for fuse in (True, False):
+        ch = SegmentChain((320, 240), sigma=2, alpha=0.05, threshold=25, morph_op='open', morph_ksize=3,
+                          batch=8, fuse=fuse)
+        labels, counts = ch.process(frames)
+        assert np.array_equal(labels, ref['labels']) and np.array_equal(counts, ref['counts'])
+        assert np.array_equal(ch.background.view(np.uint32), ref['bg'].view(np.uint32))
+        # continuing in two calls == one call
+        ch.reset()
+        l1, c1 = ch.process(frames[:13])
+        l2, c2 = ch.process(frames[13:])
+        assert np.array_equal(np.concatenate([l1, l2]), ref['labels'])
+
+
+def test_config5_like_chain(frames):
+    """ stencil-heavy variant: sigma 5, 7x7 close then labelling with 8-connectivity """
+    mods()
+    from video_analysis_b200.chain import SegmentChain
+    r = ops.chain(frames[:12], sigma=5, alpha=0.1, thr=15, morph_op='close', morph_shape='ellipse', morph_ksize=7, connectivity=8)
+    ch = SegmentChain((320, 240), sigma=5, alpha=0.1, threshold=15, morph_op='close', morph_shape='ellipse',
+                      morph_ksize=7, connectivity=8, batch=5)
+    labels, counts = ch.process(frames[:12])
+    assert np.array_equal(labels, r['labels']) and np.array_equal(counts, r['counts'])
+
+
+def test_analysis_helpers(frames, ref):
+    mods()
+    from video_analysis_b200.analysis import image, regions
+    m = ref['morph'][20]
+    lab, n = regions.label(m)
+    assert n == ref['counts'][20] and np.array_equal(lab, ref['labels'][20])
+    lab8, n8 = regions.label(ref['mask'][20] > 0, connectivity=8)
+    r8 = ops.label(ref['mask'][20], 8)
+    assert n8 == r8[1] and np.array_equal(lab8, r8[0])
+    big, area = regions.get_largest_region(m, ret_area=True)
+    rbig, rarea = ops.get_largest_region(m, ret_area=True)
+    assert area == rarea and np.array_equal(big, rbig)
+    with pytest.raises(ValueError):
+        regions.get_largest_region(np.zeros((20, 30), np.uint8))
+    assert np.array_equal(image.opening(ref['mask'][20]), ops.morph(ref['mask'][20], 'open'))
+    assert np.array_equal(image.erode(ref['mask'][20]), ops.morph(ref['mask'][20], 'erode', 'cross', 3))
+    assert np.array_equal(image.closing(ref['mask'][20], 'ellipse', 5), ops.morph(ref['mask'][20], 'close', 'ellipse', 5))
+
+
+def test_synthetic_video_source():
+    mods()
+    from video_analysis_b200.synth import VideoSynthetic
+    v = VideoSynthetic((160, 120), 20, seed=3, n_blobs=5)
+    exp = synth.make_frames(3, 0, 20, 160, 120, 5)
+    assert np.array_equal(v.get_frame(7), exp[7]) and np.array_equal(v[-1], exp[19])
+    assert np.array_equal(np.stack(list(v[4:9])), exp[4:9])
+
+
+def test_full_size_properties_1080p():
+    """ config-2 size: properties that need no CPU oracle at full size """
+    mods()
+    import torch
+    from video_analysis_b200 import synth as dsynth
+    from video_analysis_b200.chain import SegmentChain
+    from video_analysis_b200.device import get_runtime
+    rt = get_runtime(0)
+    W, H, B = 1920, 1080, 16
+    rgb = dsynth.generate(rt, 0, 0, B, W, H)
+    ch = SegmentChain((W, H), batch=B)
+    mask, morph, blur = rt.empty_bits(B, H, W), rt.empty_bits(B, H, W), rt.empty_u8(B, H, W)
+    labels, counts = ch.run_device(rgb, blur=blur, mask=mask, morph=morph)
+    # fused and unfused paths agree
+    ch2 = SegmentChain((W, H), batch=B, fuse=False)
+    labels2, counts2 = ch2.run_device(rgb)
+    assert torch.equal(labels.t, labels2.t) and torch.equal(counts, counts2)
+    lab = labels.t[:, :, :W]
+    fg = rt.unpack_bits(morph).t[:, :, :W] > 0
+    assert torch.equal(lab > 0, fg)                                        # labels cover exactly the mask
+    assert torch.equal(lab.reshape(B, -1).max(1).values.int(), counts)     # labels are 1..n
+    # opening is anti-extensive and idempotent
+    m_u8, o_u8 = rt.unpack_bits(mask).t, rt.unpack_bits(morph).t
+    assert bool((o_u8 <= m_u8).all())
+    assert torch.equal(rt.morph(morph, 'open').t, morph.t)
+    # raster-order numbering: first occurrences of 1..n are increasing (frame 5)
+    flat = lab[5].reshape(-1)
+    n = int(counts[5])
+    first = torch.stack([(flat == k).nonzero()[0, 0] for k in range(1, n + 1)]) if n else torch.zeros(0)
+    assert n > 0 and bool((first[1:] > first[:-1]).all())
+    # one frame of the full-size batch against the oracle
+    f5 = rgb.t[5].cpu().numpy().reshape(H, W, 3)
+    assert np.array_equal(blur.t[5, :, :W].cpu().numpy(), ops.blur(ops.mono(f5), 2))
+    rl, rn = ops.label(o_u8[5, :, :W].cpu().numpy())
+    assert rn == n and np.array_equal(lab[5].cpu().numpy(), rl)

@@ -20,7 +20,7 @@ GOLD = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'golden.npz'))
 @pytest.fixture
 def ctx(be):
     big = be.name == 'cuda'
-    c = hz.Ctx(be, 4096 if big else 1300, 2304 if big else 256, 8)
+    c = hz.Ctx(be, 4096 if big else 1300, 2304 if big else 256, 16 if big else 8)
     yield c
     c.close()
 
@@ -307,7 +307,7 @@ def test_region_areas_and_largest(be, ctx):
 # ---- the whole chain ---------------------------------------------------------------------------------
 @pytest.mark.parametrize('fuse', [False, True])
 def test_chain_run_matches_oracle_stagewise_and_end_to_end(be, ctx, fuse):
-    W, H, T = (200, 120, 8) if be.name == 'emu' else (640, 480, 24)
+    W, H, T = (200, 120, 8) if be.name == "emu" else (640, 480, 24)
     fr = synth.make_frames(0, 0, T, W, H, 6)
     ref = ops.chain(fr)
     want = ('blur', 'mask', 'morph', 'labels') if fuse else ('mono', 'blur', 'mask', 'morph', 'labels')

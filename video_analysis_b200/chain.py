@@ -100,6 +100,38 @@ class SegmentChain(object):
         self._started = True
         return labels, counts
 
+    # ---- the two halves, used when the background state arrives between them (parallel.py) ------
+    def blur_device(self, rgb, out=None):
+        """ monochrome + blur of a device batch -> DeviceBatch 'u8' """
+        rt = self.rt
+        if out is None:
+            out = rt.empty_u8(rgb.n, self.h, self.w)
+        rt.ensure(self.w, self.h, rgb.n)
+        if self.fuse and self.sigma >= 0.5 and 6 * self.sigma + 1 <= 127:
+            rt._check(rt.lib.va_luma_gauss_u8(rt._h, rt.stream, *rgb.img(), *out.img(), self.w, self.h, rgb.n,
+                                              self.mono_mode, self.sigma))
+        else:
+            mono = rt.luma(rgb, self.mono_mode)
+            rt._check(rt.lib.va_gauss_u8(rt._h, rt.stream, *mono.img(), *out.img(), self.w, self.h, 1, rgb.n, self.sigma))
+        return out
+
+    def segment_device(self, blur, labels=None, counts=None):
+        """ background / threshold / morphology / labelling of an already blurred batch """
+        rt, t = self.rt, torch()
+        mask = rt.ema_diff_thresh(blur, self._bg, self.alpha, self.threshold, not self._started)
+        self._started = True
+        if self.morph_op:
+            mask = rt.morph(mask, self.morph_op, self.morph_shape, (self.kx, self.ky))
+        if not self.connectivity:
+            return mask, None
+        if labels is None:
+            labels = rt.empty_i32(blur.n, self.h, self.w)
+        if counts is None:
+            counts = t.empty((blur.n,), dtype=t.int32, device=rt.device)
+        rt._check(rt.lib.va_label_bits(rt._h, rt.stream, *mask.img(), *labels.img(), counts.data_ptr(),
+                                       self.w, self.h, blur.n, self.connectivity))
+        return labels, counts
+
     # ---- host frames in, host labels out: pipelined -------------------------------------------------------
     def _make_slots(self):
         t, rt = torch(), self.rt

@@ -1,0 +1,133 @@
+"""
+Frame-range sharding over the GPUs of one box.
+
+Frames are independent except for the running-average background, an affine recurrence
+
+    bg_t = a * bg_{t-1} + alpha * x_t,      a = 1 - alpha.
+
+Rank r owns the contiguous frames [r*T/R, (r+1)*T/R) (the `VideoSlice` partition of the
+reference, video/io/base.py:392-474).  Pass 1: every rank blurs its frames and folds them
+from a ZERO state into S_r (rank 0 from its first frame, as the sequential model does).
+One `all_gather` of S_r (one float32 frame per rank) over NCCL / NVLink is the only data
+that crosses GPUs; rank r then combines
+
+    carry_r = sum_{j<r} a^(n_{j+1} + ... + n_{r-1}) * S_j
+
+locally (at most R-1 AXPYs, va_ema_fold) and pass 2 runs the ordinary K3/K4/K5 kernels from
+that state.  Rank 0 is bit-identical to the single-GPU run; later ranks differ by the
+re-association of the recurrence (<= 1e-5 relative on the background), which
+decays as a^k into their chunk.
+
+Terms older than `tail` frames are below float32 resolution (a^tail < 2^-30) and are not
+folded: S_r only reads the last `tail` blurred frames of a shard.
+"""
+
+import math
+
+
+def shard_range(total, rank, world):
+    """ frames [a, b) of rank `rank` """
+    return rank * total // world, (rank + 1) * total // world
+
+
+def ema_tail(alpha, bits=30):
+    """ number of trailing frames whose weight a^k is still above 2^-bits """
+    if not 0 < alpha < 1:
+        return 1
+    return int(math.ceil(-bits * math.log(2.0) / math.log(1.0 - alpha)))
+
+
+def exchange_carry(S_local, n_local, alpha, fold, group=None):
+    """ all-gather the per-rank partial states and fold the ones of the ranks before us.
+
+    S_local : torch tensor (H, pitch) float32 -- this rank's partial (rank 0: its true state)
+    n_local : number of frames this rank owns
+    fold    : callable(carry, S, scale) doing carry = scale * carry + S in place
+    returns the background state before this rank's first frame, or None on rank 0 """
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    gathered = [torch.empty_like(S_local) for _ in range(world)]
+    dist.all_gather(gathered, S_local.contiguous(), group=group)
+    n_t = torch.tensor([n_local], dtype=torch.int64, device=S_local.device)
+    counts = [torch.empty_like(n_t) for _ in range(world)]
+    dist.all_gather(counts, n_t, group=group)
+    counts = [int(c.item()) for c in counts]
+    if rank == 0:
+        return None
+    a = 1.0 - alpha
+    carry = gathered[0].clone()
+    for j in range(1, rank):
+        fold(carry, gathered[j], a ** counts[j])
+    return carry
+
+
+class ShardedSegmentChain(object):
+    """ runs a SegmentChain over this rank's frame range of a video sharded over the
+    ranks of a torch.distributed group (NCCL) """
+
+    def __init__(self, chain, group=None, tail=None):
+        self.chain = chain
+        self.group = group
+        self.tail = tail if tail is not None else ema_tail(chain.alpha)
+        self._blurs = []
+        self._S = None
+        self._scratch_mask = None
+
+    def _partial_state(self, blurs):
+        """ S of this rank from its blurred batches (device) """
+        import torch.distributed as dist
+        ch, rt = self.chain, self.chain.rt
+        if self._S is None:
+            self._S = rt.empty_f32(ch.h, ch.w)
+            self._S.zero_()
+        n = sum(b.n for b in blurs)
+        rank = dist.get_rank(self.group)
+        # only the last `tail` frames matter
+        skip = max(0, n - self.tail)
+        first = True
+        seen = 0
+        for b in blurs:
+            lo = max(0, skip - seen)
+            seen += b.n
+            if lo >= b.n:
+                continue
+            part = b if lo == 0 else _slice_batch(b, lo, b.n)
+            if first and rank == 0 and skip == 0:
+                # the sequential model starts from its first frame: S = float(x_0)
+                if self._scratch_mask is None:
+                    self._scratch_mask = rt.empty_bits(1, ch.h, ch.w)
+                rt.ema_diff_thresh(_slice_batch(part, 0, 1), self._S, ch.alpha, ch.threshold, True)
+                if part.n > 1:
+                    rt.ema_partial(_slice_batch(part, 1, part.n), self._S, ch.alpha, True)
+            else:
+                rt.ema_partial(part, self._S, ch.alpha, not first)
+            first = False
+        return self._S, n
+
+    def run_device_range(self, rgb_batches, labels_ring, counts):
+        """ rgb_batches: this rank's frames as a list of DeviceBatch (n, h, w, 3), in order.
+        labels_ring: list of label DeviceBatches reused round-robin; counts: int32 tensor. """
+        ch, rt = self.chain, self.chain.rt
+        # pass 1: blur (kept for pass 2) + partial state
+        while len(self._blurs) < len(rgb_batches):
+            self._blurs.append(rt.empty_u8(ch.batch, ch.h, ch.w))
+        blurs = []
+        for i, rgb in enumerate(rgb_batches):
+            out = self._blurs[i] if rgb.n == ch.batch else _slice_batch(self._blurs[i], 0, rgb.n)
+            blurs.append(ch.blur_device(rgb, out))
+        S, n = self._partial_state(blurs)
+        carry = exchange_carry(S, n, ch.alpha, lambda c, s, sc: rt.ema_fold(c, s, sc, ch.w, ch.h), self.group)
+        # pass 2: background / threshold / morphology / labels from the exact incoming state
+        if carry is None:
+            ch.reset()
+        else:
+            ch.set_background(carry)
+        for i, blur in enumerate(blurs):
+            ch.segment_device(blur, labels_ring[i % len(labels_ring)], counts)
+
+
+def _slice_batch(b, lo, hi):
+    from .device import DeviceBatch
+    return DeviceBatch(b.kind, b.t[lo:hi], hi - lo, b.h, b.w, b.channels)
