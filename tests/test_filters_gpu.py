@@ -87,7 +87,8 @@ def test_crop_resize_applymask_and_random_access(frames):
     assert np.array_equal(np.stack(list(masked)), np.stack([ops.apply_mask(f, m) for f in exp]))
     colour_blur = F.FilterBlur(crop, 1.5)
     assert np.array_equal(np.stack(list(colour_blur)), np.stack([ops.blur(ops.crop(f, rect), 1.5) for f in frames[:9]]))
-    sl = F.FilterMonochrome(v[2:7], batch=3)                               # VideoSlice as the root
+    from video_analysis_b200.io.base import VideoSlice
+    sl = F.FilterMonochrome(VideoSlice(v, 2, 7), batch=3)                  # VideoSlice as the root
     assert np.array_equal(np.stack(list(sl)), np.stack([ops.mono(f) for f in frames[2:7]]))
 
 

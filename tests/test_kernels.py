@@ -288,7 +288,7 @@ def test_label_golden_and_pitch(be, ctx):
 
 
 def test_label_capacity_error(be, ctx):
-    m = np.zeros((9, 4, 40), np.uint8)
+    m = np.zeros((17, 4, 40), np.uint8)
     with pytest.raises(MemoryError):
         hz.label(ctx, ops.pack_bits(m), 40)
 

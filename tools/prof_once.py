@@ -1,0 +1,34 @@
+"""
+Launches every kernel of the chain exactly once (after a warm-up of 23 launches) so that
+`ncu -s 23 -c 12` captures one profile per kernel:
+  luma, gauss, luma_gauss, ema_diff_thresh, morph, label x7 (init merge flatten scan rank resolve write)
+"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from video_analysis_b200 import synth  # noqa: E402
+from video_analysis_b200.chain import SegmentChain  # noqa: E402
+from video_analysis_b200.device import get_runtime  # noqa: E402
+
+W, H, B = 1920, 1080, int(os.environ.get('PROF_BATCH', '32'))
+rt = get_runtime(0)
+rt.ensure(W, H, B)
+rgbs = [synth.generate(rt, 0, i * B, B, W, H) for i in range(2)]          # 2 launches
+for fuse in (True, False):                                                  # 10 + 11 launches
+    ch = SegmentChain((W, H), batch=B, fuse=fuse)
+    ch.run_device(rgbs[0])
+torch.cuda.synchronize()
+# ---- profiled region: 12 launches
+mono = rt.luma(rgbs[1])
+blur = rt.gauss(mono, 2.0)
+blur2 = rt.luma_gauss(rgbs[1], 2.0)
+bg = rt.empty_f32(H, W)
+bg.copy_(ch._bg)
+mask = rt.ema_diff_thresh(blur, bg, 0.05, 25.0, False)
+mo = rt.morph(mask, 'open', 'rect', 3)
+lab, cnt = rt.label(mo, 4)
+torch.cuda.synchronize()
+print('ok', cnt[:4].tolist(), rt.launches)

@@ -13,10 +13,6 @@
 #define EMA_THREADS 256
 #define EMA_DEPTH 4
 
-template <int PX> struct EmaVec;
-template <> struct EmaVec<16> { typedef uint4 type; };
-template <> struct EmaVec<4> { typedef unsigned type; };
-
 template <int PX>
 __device__ __forceinline__ void ema_load(const uint8_t *rp, int x, int w, bool vec, unsigned (&v)[PX / 4]) {
     if (vec && x + PX <= w) {
@@ -37,6 +33,20 @@ __device__ __forceinline__ void ema_load(const uint8_t *rp, int x, int w, bool v
 // byte i of `word` as an exact float: bits 0x4B0000bb = 2^23 + b, minus 2^23
 __device__ __forceinline__ float ema_byte_to_float(unsigned word, int i) {
     return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540u + i)) - 8388608.0f;
+}
+
+// one frame for the PX pixels of a thread: returns the PX mask bits, updates the state
+template <int PX>
+__device__ __forceinline__ unsigned ema_step(const unsigned (&v)[PX / 4], float (&s)[PX], float alpha, float thr) {
+    unsigned m = 0;
+#pragma unroll
+    for (int i = 0; i < PX; i++) {
+        const float xf = ema_byte_to_float(v[i >> 2], i & 3);
+        const float d = __fadd_rn(xf, -s[i]);
+        if (fabsf(d) > thr) m |= 1u << i;
+        s[i] = __fadd_rn(s[i], __fmul_rn(alpha, d));
+    }
+    return m;
 }
 
 template <int PX>
@@ -73,36 +83,37 @@ ema_diff_thresh_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t i
             for (int i = 0; i < PX; i++) s[i] = (x + i < w) ? bgp[i] : 0.0f;
         }
 
-        for (int t0 = 0; t0 < batch; t0 += EMA_DEPTH) {
+        uint32_t *mrow = mask + (size_t)y * mask_pitch_w + (x >> 5);
+        const bool writer = (lane & (32 / PX - 1)) == 0 && x < w;
+        int t = 0;
+        if (first_init) {            // frame 0 initialises the model and gets an empty mask
+            unsigned v0[NW];
+            ema_load<PX>(rp, x, w, vec_in != 0, v0);
+#pragma unroll
+            for (int i = 0; i < PX; i++) s[i] = ema_byte_to_float(v0[i >> 2], i & 3);
+            if (writer) mrow[0] = 0u;
+            t = 1;
+        }
+        // EMA_DEPTH frames of loads in flight, then their arithmetic
+        for (; t + EMA_DEPTH <= batch; t += EMA_DEPTH) {
             unsigned v[EMA_DEPTH][NW];
 #pragma unroll
-            for (int u = 0; u < EMA_DEPTH; u++)
-                if (t0 + u < batch) ema_load<PX>(rp + (size_t)(t0 + u) * in_fstride, x, w, vec_in != 0, v[u]);
+            for (int u = 0; u < EMA_DEPTH; u++) ema_load<PX>(rp + (size_t)(t + u) * in_fstride, x, w, vec_in != 0, v[u]);
 #pragma unroll
             for (int u = 0; u < EMA_DEPTH; u++) {
-                const int t = t0 + u;
-                if (t >= batch) break;
-                unsigned m = 0;
-                if (t == 0 && first_init) {
+                unsigned m = ema_step<PX>(v[u], s, alpha, thr) & valid;
 #pragma unroll
-                    for (int i = 0; i < PX; i++) s[i] = ema_byte_to_float(v[u][i >> 2], i & 3);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < PX; i++) {
-                        const float xf = ema_byte_to_float(v[u][i >> 2], i & 3);
-                        const float d = __fadd_rn(xf, -s[i]);
-                        if (fabsf(d) > thr) m |= 1u << i;
-                        s[i] = __fadd_rn(s[i], __fmul_rn(alpha, d));
-                    }
-                }
-                m &= valid;
-                // merge the PX-bit pieces of 32 / PX neighbouring lanes into one word
-#pragma unroll
-                for (int sh = PX, d = 1; sh < 32; sh <<= 1, d <<= 1)
-                    m |= __shfl_down_sync(0xffffffffu, m, d) << sh;
-                if ((lane & (32 / PX - 1)) == 0 && x < w)
-                    mask[(size_t)t * mask_fstride_w + (size_t)y * mask_pitch_w + (x >> 5)] = m;
+                for (int sh = PX, d = 1; sh < 32; sh <<= 1, d <<= 1) m |= __shfl_down_sync(0xffffffffu, m, d) << sh;
+                if (writer) mrow[(size_t)(t + u) * mask_fstride_w] = m;
             }
+        }
+        for (; t < batch; t++) {
+            unsigned v[NW];
+            ema_load<PX>(rp + (size_t)t * in_fstride, x, w, vec_in != 0, v);
+            unsigned m = ema_step<PX>(v, s, alpha, thr) & valid;
+#pragma unroll
+            for (int sh = PX, d = 1; sh < 32; sh <<= 1, d <<= 1) m |= __shfl_down_sync(0xffffffffu, m, d) << sh;
+            if (writer) mrow[(size_t)t * mask_fstride_w] = m;
         }
 
         if (vec_bg && x + PX <= w) {
@@ -129,7 +140,7 @@ extern "C" int va_ema_diff_thresh(va_ctx *ctx, va_stream stream,
     const int vec_bg = va_aligned(bg, 16) && bg_pitch_e % 4 == 0;
     // 16 pixels per thread when that still fills the machine, else 4
     const long long threads16 = (long long)((w + 511) / 512) * 32 * h;
-    const bool use16 = threads16 >= (long long)ctx->sm_count * 1024;
+    const bool use16 = threads16 >= (long long)ctx->sm_count * 512;
     if (use16) {
         const int vec_in = va_aligned(in, 16) && in_pitch % 16 == 0 && in_fstride % 16 == 0;
         const long long warps = (long long)((w + 511) / 512) * h;

@@ -16,6 +16,7 @@
 // Generic path (3 interleaved channels, tap 256, radius <= 127): same structure with
 // scalar multiply-adds.
 #include <cmath>
+#include <cstdlib>
 
 #include "va_device.cuh"
 
@@ -75,108 +76,134 @@ struct GaussGeneric {
 };
 
 // ---------------------------------------------------------------------------------
-// fast kernel
+// fast kernel.  RT > 0: radius known at compile time (tap loops fully unrolled, taps read
+// straight from the constant bank, index divisions by constants); RT == 0: any radius.
+// Work split: lane = 4-pixel column group (32 groups = 128 pixels), warp = row (pair).
 // ---------------------------------------------------------------------------------
-template <bool FUSE_LUMA>
+__device__ __forceinline__ int gauss_reflect_fast(int i, int n) {
+    if ((unsigned)i >= (unsigned)n) {
+        i = i < 0 ? -i : 2 * n - 2 - i;
+        if ((unsigned)i >= (unsigned)n) i = va_reflect101(i, n);
+    }
+    return i;
+}
+
+template <int RT, bool FUSE_LUMA>
 __global__ void __launch_bounds__(GAUSS_THREADS)
 gauss_fast_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstride,
                   uint8_t *__restrict__ out, size_t out_pitch, size_t out_fstride,
                   int w, int h, int mode, int TH, int tiles_x, int tiles_y, int n_tiles,
                   int vec_in, const __grid_constant__ GaussFast g) {
     VA_DYN_SMEM(uint8_t, smem);
-    const int tid = threadIdx.x;
-    const int r = g.r;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r = RT ? RT : g.r;
     const int R16 = (r + 15) & ~15;
-    const int SW = GAUSS_TW + 2 * R16 + 16;        // staged bytes per row
-    const int R = TH + 2 * r;                      // staged rows (even)
+    const int SW = GAUSS_TW + 2 * R16 + 16;                 // staged bytes per row
+    const int O = (4 - (r & 3)) & 3;
+    const int NW = (O + 2 * r + 4 + 3) >> 2;                // staged words feeding one 4-pixel group
+    const int NP = r + 1;                                   // row pairs feeding one output row pair
+    const int WOFS = (R16 >> 2) - ((r + 3) >> 2);           // first staged word needed by group 0
+    const int NWORDS = (32 + NW) & ~1;                      // staged words needed per row (even)
+    const int R = TH + 2 * r;                               // staged rows (even)
     uint8_t *s8 = smem;
     unsigned *hp = reinterpret_cast<unsigned *>(smem + (size_t)R * SW);   // [R/2][TW] u16 pairs
     const bool out_words = (((uintptr_t)out | out_pitch | out_fstride) & 3) == 0;
+    const int tiles_per_frame = tiles_x * tiles_y;
 
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int b = tile / (tiles_x * tiles_y);
-        const int rem = tile - b * tiles_x * tiles_y;
+        const int b = tile / tiles_per_frame;
+        const int rem = tile - b * tiles_per_frame;
         const int tyi = rem / tiles_x;
         const int tx0 = (rem - tyi * tiles_x) * GAUSS_TW;
         const int ty0 = tyi * TH;
         const uint8_t *fin = in + (size_t)b * in_fstride;
 
-        // ---- stage the tile (+ halo)
+        // ---- stage the tile (+ halo): only the staged words the row pass will read
         if (!FUSE_LUMA) {
-            const int chunks = SW >> 4;
-            for (int it = tid; it < R * chunks; it += GAUSS_THREADS) {
-                const int tr = it / chunks, c = it - tr * chunks;
-                const int gy = va_reflect101(ty0 + tr - r, h);
+            const int c0 = WOFS >> 2;                              // first / last+1 16-byte chunk
+            const int c1 = (WOFS + NWORDS + 3) >> 2;
+            const int NCH = c1 - c0;
+            for (int it = tid; it < R * NCH; it += GAUSS_THREADS) {
+                const int tr = it / NCH, c = c0 + (it - tr * NCH);
+                const int gy = gauss_reflect_fast(ty0 + tr - r, h);
                 const uint8_t *rp = fin + (size_t)gy * in_pitch;
                 const int gx0 = tx0 - R16 + 16 * c;
-                uint8_t *d = s8 + (size_t)tr * SW + 16 * c;
+                uint8_t *d = s8 + tr * SW + 16 * c;
                 if (vec_in && gx0 >= 0 && gx0 + 16 <= w) {
                     va_cp_async16(d, rp + gx0);
                 } else {
                     unsigned v[4] = {0, 0, 0, 0};
+#pragma unroll
                     for (int i = 0; i < 16; i++)
-                        v[i >> 2] |= (unsigned)rp[va_reflect101(gx0 + i, w)] << (8 * (i & 3));
+                        v[i >> 2] |= (unsigned)rp[gauss_reflect_fast(gx0 + i, w)] << (8 * (i & 3));
                     *reinterpret_cast<uint4 *>(d) = make_uint4(v[0], v[1], v[2], v[3]);
                 }
             }
             va_cp_async_wait_all();
         } else {
-            const int groups = SW >> 2;
-            for (int it = tid; it < R * groups; it += GAUSS_THREADS) {
-                const int tr = it / groups, u = it - tr * groups;
-                const int gy = va_reflect101(ty0 + tr - r, h);
+            // 8 pixels (24 bytes of RGB) per item -> two staged words
+            const int NG = NWORDS >> 1;
+            for (int it = tid; it < R * NG; it += GAUSS_THREADS) {
+                const int tr = it / NG, u = WOFS + 2 * (it - tr * NG);
+                const int gy = gauss_reflect_fast(ty0 + tr - r, h);
                 const uint8_t *rp = fin + (size_t)gy * in_pitch;
                 const int gx0 = tx0 - R16 + 4 * u;
-                unsigned res;
-                if (vec_in && gx0 >= 0 && gx0 + 4 <= w) {
-                    const unsigned *p = reinterpret_cast<const unsigned *>(rp + 3 * (size_t)gx0);
-                    res = va_luma_x4(__ldg(p), __ldg(p + 1), __ldg(p + 2), mode);
+                unsigned lo, hi;
+                if (vec_in && gx0 >= 0 && gx0 + 8 <= w && ((gx0 & 7) == 0)) {
+                    const uint2 *p = reinterpret_cast<const uint2 *>(rp + 3 * (size_t)gx0);
+                    const uint2 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2);
+                    lo = va_luma_x4(q0.x, q0.y, q1.x, mode);
+                    hi = va_luma_x4(q1.y, q2.x, q2.y, mode);
                 } else {
-                    res = 0;
-                    for (int i = 0; i < 4; i++)
-                        res |= va_luma_px(rp + 3 * (size_t)va_reflect101(gx0 + i, w), mode) << (8 * i);
-                }
-                *reinterpret_cast<unsigned *>(s8 + (size_t)tr * SW + 4 * u) = res;
-            }
-        }
-        __syncthreads();
-
-        // ---- row pass: item = (row pair q, 4-pixel group gx)
-        {
-            const int groups = GAUSS_TW >> 2;
-            const int wofs = (R16 >> 2) - ((r + 3) >> 2);     // first staged word of group 0
-            for (int it = tid; it < (R >> 1) * groups; it += GAUSS_THREADS) {
-                const int q = it / groups, gx = it - q * groups;
-                const unsigned *r0 = reinterpret_cast<const unsigned *>(s8 + (size_t)(2 * q) * SW) + wofs + gx;
-                const unsigned *r1 = reinterpret_cast<const unsigned *>(s8 + (size_t)(2 * q + 1) * SW) + wofs + gx;
-                unsigned a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0};
-                for (int j = 0; j < g.nw; j++) {
-                    const unsigned x0 = r0[j], x1 = r1[j];
+                    lo = hi = 0;
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
-                        const unsigned c = g.cw[i][j];
-                        a0[i] = __dp4a(x0, c, a0[i]);
-                        a1[i] = __dp4a(x1, c, a1[i]);
+                        lo |= va_luma_px(rp + 3 * (size_t)gauss_reflect_fast(gx0 + i, w), mode) << (8 * i);
+                        hi |= va_luma_px(rp + 3 * (size_t)gauss_reflect_fast(gx0 + 4 + i, w), mode) << (8 * i);
                     }
                 }
-                *reinterpret_cast<uint4 *>(hp + (size_t)q * GAUSS_TW + 4 * gx) =
-                    make_uint4(a0[0] | (a1[0] << 16), a0[1] | (a1[1] << 16), a0[2] | (a1[2] << 16), a0[3] | (a1[3] << 16));
+                *reinterpret_cast<uint2 *>(s8 + tr * SW + 4 * u) = make_uint2(lo, hi);
             }
         }
         __syncthreads();
 
-        // ---- column pass: item = (output row pair yp, 4-column group gx)
+        // ---- row pass: warp = row pair q, lane = 4-pixel group
+        for (int q = warp; q < (R >> 1); q += GAUSS_THREADS / 32) {
+            const unsigned *r0 = reinterpret_cast<const unsigned *>(s8 + (2 * q) * SW) + WOFS + lane;
+            const unsigned *r1 = reinterpret_cast<const unsigned *>(s8 + (2 * q + 1) * SW) + WOFS + lane;
+            unsigned a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int j = 0; j < NW; j++) {
+                const unsigned x0 = r0[j], x1 = r1[j];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const unsigned c = g.cw[i][j];
+                    a0[i] = __dp4a(x0, c, a0[i]);
+                    a1[i] = __dp4a(x1, c, a1[i]);
+                }
+            }
+            *reinterpret_cast<uint4 *>(hp + q * GAUSS_TW + 4 * lane) =
+                make_uint4(__byte_perm(a0[0], a1[0], 0x5410), __byte_perm(a0[1], a1[1], 0x5410),
+                           __byte_perm(a0[2], a1[2], 0x5410), __byte_perm(a0[3], a1[3], 0x5410));
+        }
+        __syncthreads();
+
+        // ---- column pass: warp = output row pair yp, lane = 4-column group
         {
-            const int groups = GAUSS_TW >> 2;
-            for (int it = tid; it < (TH >> 1) * groups; it += GAUSS_THREADS) {
-                const int yp = it / groups, gx = it - yp * groups;
-                const int x = tx0 + 4 * gx;
+            const int x = tx0 + 4 * lane;
+            uint8_t *obase = out + (size_t)b * out_fstride + x;
+            for (int yp = warp; yp < (TH >> 1); yp += GAUSS_THREADS / 32) {
                 const int y = ty0 + 2 * yp;
                 if (x >= w || y >= h) continue;
-                unsigned acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
-                const uint4 *col = reinterpret_cast<const uint4 *>(hp + (size_t)yp * GAUSS_TW + 4 * gx);
-                for (int j = 0; j < g.np; j++) {
-                    const uint4 v = col[(size_t)j * (GAUSS_TW >> 2)];
+                unsigned acc[2][4];
+#pragma unroll
+                for (int i = 0; i < 2; i++)
+#pragma unroll
+                    for (int k = 0; k < 4; k++) acc[i][k] = 32768u;
+                const uint4 *col = reinterpret_cast<const uint4 *>(hp + yp * GAUSS_TW + 4 * lane);
+#pragma unroll
+                for (int j = 0; j < NP; j++) {
+                    const uint4 v = col[j * (GAUSS_TW >> 2)];
                     const unsigned c0 = g.cp[0][j], c1 = g.cp[1][j];
                     acc[0][0] = __dp2a_lo(v.x, c0, acc[0][0]); acc[1][0] = __dp2a_lo(v.x, c1, acc[1][0]);
                     acc[0][1] = __dp2a_lo(v.y, c0, acc[0][1]); acc[1][1] = __dp2a_lo(v.y, c1, acc[1][1]);
@@ -186,9 +213,10 @@ gauss_fast_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fst
 #pragma unroll
                 for (int i = 0; i < 2; i++) {
                     if (y + i >= h) break;
-                    const unsigned res = ((acc[i][0] + 32768u) >> 16) | (((acc[i][1] + 32768u) >> 16) << 8) |
-                                         (((acc[i][2] + 32768u) >> 16) << 16) | (((acc[i][3] + 32768u) >> 16) << 24);
-                    uint8_t *op = out + (size_t)b * out_fstride + (size_t)(y + i) * out_pitch + x;
+                    // byte 2 of every accumulator (sum + 32768 < 2^24) is the rounded result
+                    const unsigned res = __byte_perm(__byte_perm(acc[i][0], acc[i][1], 0x0062),
+                                                     __byte_perm(acc[i][2], acc[i][3], 0x0062), 0x5410);
+                    uint8_t *op = obase + (size_t)(y + i) * out_pitch;
                     if (out_words && x + 4 <= w) {
                         *reinterpret_cast<unsigned *>(op) = res;
                     } else {
@@ -302,31 +330,51 @@ static int gauss_launch(va_ctx *ctx, va_stream stream, const char *name, bool fu
                 if (k1 >= 0 && k1 < ksize) wd |= (unsigned)taps[k1] << 8;
                 g.cp[i][j] = wd;
             }
-        const int TH = r <= 16 ? 64 : 96;
+        // tile height: minimise staged rows + idle warp rounds + rows wasted below the image
         const int R16 = (r + 15) & ~15;
         const int SW = GAUSS_TW + 2 * R16 + 16;
+        int TH = 0;
+        {
+            const char *env = getenv("VA_GAUSS_TH");
+            const int forced = env ? atoi(env) : 0;
+            double best = 1e30;
+            for (int th = 32; th <= 192; th += 8) {
+                const int R = th + 2 * r;
+                const size_t sm = (size_t)R * SW + (size_t)(R / 2) * GAUSS_TW * 4;
+                if (sm > (r <= 16 ? 74 : 112) * 1024) break;
+                const int ty = va_div_up(h, th);
+                const double cost = ty * (1.3 * R + 8.0 * ((R / 2 + 7) / 8) * 1.0 + 10.0 * ((th / 2 + 7) / 8));
+                if (cost < best) { best = cost; TH = th; }
+            }
+            if (forced >= 8 && forced % 2 == 0) TH = forced;
+            if (TH == 0) TH = 32;
+        }
         const int R = TH + 2 * r;
         const size_t smem = (size_t)R * SW + (size_t)(R / 2) * GAUSS_TW * 4;
+        VA_REQUIRE(ctx, smem <= 220 * 1024, "%s: tile does not fit in shared memory", name);
         const int tiles_x = va_div_up(w, GAUSS_TW), tiles_y = va_div_up(h, TH);
         const int n_tiles = tiles_x * tiles_y * batch;
-        const int ctas = smem <= 36 * 1024 ? 6 : (smem <= 56 * 1024 ? 4 : (smem <= 110 * 1024 ? 2 : 1));
+        int ctas = (int)((220 * 1024) / (smem + 1024));
+        if (ctas > 6) ctas = 6;
+        if (ctas < 1) ctas = 1;
         const int grid = va_grid(ctx, n_tiles, ctas);
-        int vec_in;
-        if (fuse) {
-            vec_in = va_aligned(in, 4) && in_pitch % 4 == 0 && in_fstride % 4 == 0;
-            auto kfn = gauss_fast_kernel<true>;
-            if (smem > 48 * 1024)
-                VA_CUDA(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            VA_LAUNCH(ctx, kfn, grid, GAUSS_THREADS, smem, stream, in, in_pitch, in_fstride, out, out_pitch, out_fstride,
-                      w, h, mode, TH, tiles_x, tiles_y, n_tiles, vec_in, g);
-        } else {
-            vec_in = va_aligned(in, 16) && in_pitch % 16 == 0 && in_fstride % 16 == 0;
-            auto kfn = gauss_fast_kernel<false>;
-            if (smem > 48 * 1024)
-                VA_CUDA(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            VA_LAUNCH(ctx, kfn, grid, GAUSS_THREADS, smem, stream, in, in_pitch, in_fstride, out, out_pitch, out_fstride,
-                      w, h, mode, TH, tiles_x, tiles_y, n_tiles, vec_in, g);
+        const int vec_in = fuse ? (va_aligned(in, 8) && in_pitch % 8 == 0 && in_fstride % 8 == 0)
+                                : (va_aligned(in, 16) && in_pitch % 16 == 0 && in_fstride % 16 == 0);
+#define GAUSS_GO(RT, FUSE)                                                                                       \
+        do {                                                                                                     \
+            auto kfn = gauss_fast_kernel<RT, FUSE>;                                                              \
+            if (smem > 48 * 1024)                                                                                \
+                VA_CUDA(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            VA_LAUNCH(ctx, kfn, grid, GAUSS_THREADS, smem, stream, in, in_pitch, in_fstride, out, out_pitch,     \
+                      out_fstride, w, h, mode, TH, tiles_x, tiles_y, n_tiles, vec_in, g);                        \
+        } while (0)
+#define GAUSS_CASE(RT) case RT: if (fuse) GAUSS_GO(RT, true); else GAUSS_GO(RT, false); break;
+        switch (r) {
+            GAUSS_CASE(3) GAUSS_CASE(4) GAUSS_CASE(5) GAUSS_CASE(6) GAUSS_CASE(8) GAUSS_CASE(9) GAUSS_CASE(12) GAUSS_CASE(15)
+            default: if (fuse) GAUSS_GO(0, true); else GAUSS_GO(0, false); break;
         }
+#undef GAUSS_CASE
+#undef GAUSS_GO
         return VA_OK;
     }
 

@@ -329,11 +329,20 @@ label_resolve_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
 }
 
 // ---- G: write the label image --------------------------------------------------------------------
+// Two steps per 1024-pixel chunk of a row, both inside one warp (no block barrier):
+//   fill   lane = word: for each run of the word fetch its label once (one forest lookup per
+//          run) and write it to the run's pixels in a per-warp shared-memory slab
+//   store  lane = 4 consecutive pixels: background pixels become 0, foreground pixels read
+//          the slab; one 16-byte store per lane, 512 contiguous bytes per warp instruction
+// The slab index is skewed by one word per 32 pixels so that both steps are conflict-free.
+#define LAB_SKEW(p) ((p) + ((p) >> 5))
 __global__ void __launch_bounds__(LAB_THREADS)
 label_write_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
                    const int *__restrict__ parent, size_t P, size_t pf,
-                   int32_t *__restrict__ labels, size_t lpe, size_t lfe, int w, int h, int batch) {
+                   int32_t *__restrict__ labels, size_t lpe, size_t lfe, int w, int h, int batch, int vec_out) {
+    __shared__ int slab_all[LAB_WARPS][1024 + 32];
     const int lane = threadIdx.x & 31;
+    int *slab = slab_all[threadIdx.x >> 5];
     const int wpw = (w + 31) >> 5;
     const unsigned lastmask = (w & 31) ? ((1u << (w & 31)) - 1u) : FULL;
     const long long rows = (long long)h * batch;
@@ -348,16 +357,43 @@ label_write_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
             const unsigned wd = lab_load_word(mr, wpw, base + lane, lastmask);
             int st_in, top;
             lab_scan_chunk(wd, lane, base, carry, st_in, top);
-            const int nwords = min(32, wpw - base);
-#pragma unroll 4
-            for (int i = 0; i < nwords; i++) {
-                const unsigned wi = __shfl_sync(FULL, wd, i);
-                const int si = __shfl_sync(FULL, st_in, i);
-                const int x = 32 * (base + i) + lane;
-                int lab = 0;
-                if ((wi >> lane) & 1u) lab = -pr[lab_run_start(wi, lane, base + i, si)];
-                if (x < w) lr[x] = lab;
+            // ---- fill: one lookup per run
+            unsigned rem = wd;
+            while (rem) {
+                const int bit = __ffs((int)rem) - 1;
+                const unsigned t = ~(wd >> bit);
+                const int ones = t ? __ffs((int)t) - 1 : 32;
+                const int start_x = bit == 0 ? st_in : 32 * (base + lane) + bit;
+                const int lab = -pr[start_x];
+                const int p0 = 32 * lane + bit;
+                for (int k = 0; k < ones; k++) slab[LAB_SKEW(p0 + k)] = lab;
+                rem &= ~((ones >= 32 ? FULL : ((1u << ones) - 1u)) << bit);
             }
+            __syncwarp();
+            // ---- store: 128 pixels per step
+            const int nwords = min(32, wpw - base);
+            for (int it = 0; 4 * it < nwords; it++) {
+                const unsigned wi = __shfl_sync(FULL, wd, 4 * it + (lane >> 3));
+                const unsigned nib = (wi >> (4 * (lane & 7))) & 0xFu;
+                const int px = 128 * it + 4 * lane;
+                const int x = 32 * base + px;
+                int4 v = make_int4(0, 0, 0, 0);
+                if (nib) {
+                    if (nib & 1u) v.x = slab[LAB_SKEW(px)];
+                    if (nib & 2u) v.y = slab[LAB_SKEW(px + 1)];
+                    if (nib & 4u) v.z = slab[LAB_SKEW(px + 2)];
+                    if (nib & 8u) v.w = slab[LAB_SKEW(px + 3)];
+                }
+                if (vec_out && x + 4 <= w) {
+                    *reinterpret_cast<int4 *>(lr + x) = v;
+                } else {
+                    if (x < w) lr[x] = v.x;
+                    if (x + 1 < w) lr[x + 1] = v.y;
+                    if (x + 2 < w) lr[x + 2] = v.z;
+                    if (x + 3 < w) lr[x + 3] = v.w;
+                }
+            }
+            __syncwarp();
             carry = __shfl_sync(FULL, top, 31);
         }
     }
@@ -396,8 +432,9 @@ extern "C" int va_label_bits(va_ctx *ctx, va_stream stream,
     { auto k = label_resolve_kernel;
       VA_LAUNCH(ctx, k, grid, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, parent, P, pf, w, h, batch); }
     { auto k = label_write_kernel;
+      const int vec_out = va_aligned(labels, 16) && labels_pitch_e % 4 == 0 && labels_fstride_e % 4 == 0;
       VA_LAUNCH(ctx, k, grid, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, (const int *)parent, P, pf,
-                labels, labels_pitch_e, labels_fstride_e, w, h, batch); }
+                labels, labels_pitch_e, labels_fstride_e, w, h, batch, vec_out); }
     return VA_OK;
 }
 

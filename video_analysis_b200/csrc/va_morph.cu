@@ -78,37 +78,59 @@ __device__ __forceinline__ unsigned morph_hrun(unsigned prev, unsigned cur, unsi
     return __funnelshift_l(w0, w1, -a);
 }
 
-// one morphological pass over rows held in shared memory.
-//   src rows: index sr = (image row) - src_row0, words [0, wpw); rows / words outside the
-//   staged range are never requested (the caller sizes the halo).
-template <bool ERODE>
+// one output word of a morphological pass over rows held in shared memory.
+//   src rows: index sr = (image row) - (first staged row), words [0, wpw); rows outside the
+//   staged band are outside the image (the caller sizes the halo) and never win.
+// RECT: every row of the element has the same run, so the ky rows are combined first
+// (3 words each) and the horizontal run is evaluated once.
+template <bool ERODE, bool RECT>
 __device__ __forceinline__ unsigned morph_word(const unsigned *src, int src_rows, int wpw, int sr, int j,
                                                const MorphSE &se) {
     const unsigned ident = ERODE ? 0xffffffffu : 0u;
+    const bool has_p = j > 0, has_n = j + 1 < wpw;
+    if (RECT) {
+        unsigned p = ident, c = ident, n = ident;
+        int r0 = sr - se.ay, r1 = r0 + se.ky;
+        r0 = r0 < 0 ? 0 : r0;
+        r1 = r1 > src_rows ? src_rows : r1;
+        const unsigned *row = src + r0 * wpw + j;
+        for (int rr = r0; rr < r1; rr++, row += wpw) {
+            const unsigned vp = has_p ? row[-1] : ident, vc = row[0], vn = has_n ? row[1] : ident;
+            if (ERODE) { p &= vp; c &= vc; n &= vn; } else { p |= vp; c |= vc; n |= vn; }
+        }
+        return morph_hrun<ERODE>(p, c, n, se.a[0], se.b[0]);
+    }
     unsigned acc = ident;
     for (int i = 0; i < se.ky; i++) {
         const int a = se.a[i], b = se.b[i];
         if (a > b) continue;
         const int rr = sr + i - se.ay;
-        if (rr < 0 || rr >= src_rows) continue;       // outside the staged band == outside the image
-        const unsigned *row = src + (size_t)rr * wpw;
-        const unsigned prev = j > 0 ? row[j - 1] : ident;
-        const unsigned cur = row[j];
-        const unsigned next = j + 1 < wpw ? row[j + 1] : ident;
-        const unsigned v = morph_hrun<ERODE>(prev, cur, next, a, b);
+        if (rr < 0 || rr >= src_rows) continue;
+        const unsigned *row = src + rr * wpw + j;
+        const unsigned v = morph_hrun<ERODE>(has_p ? row[-1] : ident, row[0], has_n ? row[1] : ident, a, b);
         if (ERODE) acc &= v; else acc |= v;
     }
     return acc;
 }
 
+template <bool RECT>
+__device__ __forceinline__ unsigned morph_word_op(int erode, const unsigned *src, int src_rows, int wpw, int sr, int j,
+                                                  const MorphSE &se) {
+    return erode ? morph_word<true, RECT>(src, src_rows, wpw, sr, j, se)
+                 : morph_word<false, RECT>(src, src_rows, wpw, sr, j, se);
+}
+
 // first  : 0 erode, 1 dilate;  second: -1 none, 0 erode, 1 dilate
+// work split: warp = row of the band, lane = word of the row
+template <bool RECT>
 __global__ void __launch_bounds__(MORPH_THREADS)
 morph_bits_kernel(const uint32_t *__restrict__ in, size_t in_pitch_w, size_t in_fstride_w,
                   uint32_t *__restrict__ out, size_t out_pitch_w, size_t out_fstride_w,
                   int w, int h, int bands_per_frame, int n_bands, int first, int second,
                   const __grid_constant__ MorphSE se) {
     VA_DYN_SMEM(unsigned, smem);
-    const int tid = threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int NWARP = MORPH_THREADS / 32;
     const int wpw = (w + 31) >> 5;
     const unsigned lastmask = (w & 31) ? ((1u << (w & 31)) - 1u) : 0xffffffffu;
     const int up = se.ay, dn = se.ky - 1 - se.ay;          // rows needed above / below per pass
@@ -116,7 +138,9 @@ morph_bits_kernel(const uint32_t *__restrict__ in, size_t in_pitch_w, size_t in_
     const int rows_a = MORPH_BAND + passes * (up + dn);    // staged input rows
     const int rows_b = MORPH_BAND + (up + dn);             // intermediate rows (two-pass only)
     unsigned *sa = smem;
-    unsigned *sb = smem + (size_t)rows_a * wpw;
+    unsigned *sb = smem + rows_a * wpw;
+    const unsigned id1 = first == 0 ? 0xffffffffu : 0u;
+    const unsigned id2 = second == 0 ? 0xffffffffu : 0u;
 
     for (int band = blockIdx.x; band < n_bands; band += gridDim.x) {
         const int b = band / bands_per_frame;
@@ -127,50 +151,54 @@ morph_bits_kernel(const uint32_t *__restrict__ in, size_t in_pitch_w, size_t in_
 
         // ---- stage input rows [ya0, ya0 + rows_a); outside the image = identity of the first op
         const int ya0 = y0 - passes * up;
-        const unsigned id1 = first == 0 ? 0xffffffffu : 0u;
-        for (int it = tid; it < rows_a * wpw; it += MORPH_THREADS) {
-            const int rr = it / wpw, j = it - rr * wpw;
+        for (int rr = warp; rr < rows_a; rr += NWARP) {
             const int y = ya0 + rr;
-            unsigned v = id1;
-            if (y >= 0 && y < h) {
-                v = fin[(size_t)y * in_pitch_w + j];
-                if (j == wpw - 1) v = first == 0 ? (v | ~lastmask) : (v & lastmask);
+            const bool inside = y >= 0 && y < h;
+            const uint32_t *grow = fin + (size_t)(inside ? y : 0) * in_pitch_w;
+            for (int j = lane; j < wpw; j += 32) {
+                unsigned v = id1;
+                if (inside) {
+                    v = grow[j];
+                    if (j == wpw - 1) v = first == 0 ? (v | ~lastmask) : (v & lastmask);
+                }
+                sa[rr * wpw + j] = v;
             }
-            sa[it] = v;
         }
         __syncthreads();
 
         if (passes == 1) {
-            for (int it = tid; it < nrows * wpw; it += MORPH_THREADS) {
-                const int rr = it / wpw, j = it - rr * wpw;
-                unsigned v = first == 0 ? morph_word<true>(sa, rows_a, wpw, rr + up, j, se)
-                                        : morph_word<false>(sa, rows_a, wpw, rr + up, j, se);
-                if (j == wpw - 1) v &= lastmask;
-                fout[(size_t)(y0 + rr) * out_pitch_w + j] = v;
+            for (int rr = warp; rr < nrows; rr += NWARP) {
+                uint32_t *orow = fout + (size_t)(y0 + rr) * out_pitch_w;
+                for (int j = lane; j < wpw; j += 32) {
+                    unsigned v = morph_word_op<RECT>(first == 0, sa, rows_a, wpw, rr + up, j, se);
+                    if (j == wpw - 1) v &= lastmask;
+                    orow[j] = v;
+                }
             }
         } else {
             // ---- first pass -> intermediate rows [yb0, yb0 + rows_b); rows outside the image and
             //      bits beyond w take the identity of the SECOND op
             const int yb0 = y0 - up;
-            const unsigned id2 = second == 0 ? 0xffffffffu : 0u;
-            for (int it = tid; it < rows_b * wpw; it += MORPH_THREADS) {
-                const int rr = it / wpw, j = it - rr * wpw;
+            for (int rr = warp; rr < rows_b; rr += NWARP) {
                 const int y = yb0 + rr;
-                unsigned v = id2;
-                if (y >= 0 && y < h) {
-                    v = first == 0 ? morph_word<true>(sa, rows_a, wpw, rr + up, j, se)
-                                   : morph_word<false>(sa, rows_a, wpw, rr + up, j, se);
-                    if (j == wpw - 1) v = second == 0 ? (v | ~lastmask) : (v & lastmask);
+                const bool inside = y >= 0 && y < h;
+                for (int j = lane; j < wpw; j += 32) {
+                    unsigned v = id2;
+                    if (inside) {
+                        v = morph_word_op<RECT>(first == 0, sa, rows_a, wpw, rr + up, j, se);
+                        if (j == wpw - 1) v = second == 0 ? (v | ~lastmask) : (v & lastmask);
+                    }
+                    sb[rr * wpw + j] = v;
                 }
-                sb[it] = v;
             }
             __syncthreads();
-            for (int it = tid; it < nrows * wpw; it += MORPH_THREADS) {
-                const int rr = it / wpw, j = it - rr * wpw;
-                unsigned v = second == 0 ? morph_word<true>(sb, rows_b, wpw, rr + up, j, se)
-                                         : morph_word<false>(sb, rows_b, wpw, rr + up, j, se);
-                if (j == wpw - 1) v &= lastmask;
-                fout[(size_t)(y0 + rr) * out_pitch_w + j] = v;
+            for (int rr = warp; rr < nrows; rr += NWARP) {
+                uint32_t *orow = fout + (size_t)(y0 + rr) * out_pitch_w;
+                for (int j = lane; j < wpw; j += 32) {
+                    unsigned v = morph_word_op<RECT>(second == 0, sb, rows_b, wpw, rr + up, j, se);
+                    if (j == wpw - 1) v &= lastmask;
+                    orow[j] = v;
+                }
             }
         }
         __syncthreads();
@@ -203,11 +231,21 @@ extern "C" int va_morph_bits(va_ctx *ctx, va_stream stream,
     VA_REQUIRE(ctx, smem <= 200 * 1024, "va_morph_bits: %d-pixel rows with a %d-row element do not fit in shared memory", w, ky);
     const int bands_per_frame = va_div_up(h, MORPH_BAND);
     const int n_bands = bands_per_frame * batch;
-    auto kfn = morph_bits_kernel;
-    if (smem > 48 * 1024)
-        VA_CUDA(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bool rect = true;
+    for (int i = 1; i < ky; i++) rect = rect && se.a[i] == se.a[0] && se.b[i] == se.b[0];
     const int grid = va_grid(ctx, n_bands, 8);
-    VA_LAUNCH(ctx, kfn, grid, MORPH_THREADS, smem, stream, in, in_pitch_w, in_fstride_w, out, out_pitch_w, out_fstride_w,
-              w, h, bands_per_frame, n_bands, first, second, se);
+    if (rect) {
+        auto kfn = morph_bits_kernel<true>;
+        if (smem > 48 * 1024)
+            VA_CUDA(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VA_LAUNCH(ctx, kfn, grid, MORPH_THREADS, smem, stream, in, in_pitch_w, in_fstride_w, out, out_pitch_w, out_fstride_w,
+                  w, h, bands_per_frame, n_bands, first, second, se);
+    } else {
+        auto kfn = morph_bits_kernel<false>;
+        if (smem > 48 * 1024)
+            VA_CUDA(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VA_LAUNCH(ctx, kfn, grid, MORPH_THREADS, smem, stream, in, in_pitch_w, in_fstride_w, out, out_pitch_w, out_fstride_w,
+                  w, h, bands_per_frame, n_bands, first, second, se);
+    }
     return VA_OK;
 }
