@@ -50,7 +50,7 @@ __device__ __forceinline__ unsigned ema_step(const unsigned (&v)[PX / 4], float 
 }
 
 template <int PX>
-__global__ void __launch_bounds__(EMA_THREADS)
+__global__ void __launch_bounds__(EMA_THREADS, PX == 16 ? 4 : 5)
 ema_diff_thresh_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstride,
                        float *__restrict__ bg, size_t bg_pitch_e,
                        uint32_t *__restrict__ mask, size_t mask_pitch_w, size_t mask_fstride_w,
@@ -61,6 +61,7 @@ ema_diff_thresh_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t i
     const int chunks = (w + span - 1) / span;
     const long long total = (long long)chunks * h;
     constexpr int NW = PX / 4;
+    constexpr int DEPTH = PX == 16 ? 3 : 4;           // frames of loads in flight per thread
 
     for (long long item = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); item < total;
          item += (long long)gridDim.x * warps_per_block) {
@@ -94,13 +95,13 @@ ema_diff_thresh_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t i
             if (writer) mrow[0] = 0u;
             t = 1;
         }
-        // EMA_DEPTH frames of loads in flight, then their arithmetic
-        for (; t + EMA_DEPTH <= batch; t += EMA_DEPTH) {
-            unsigned v[EMA_DEPTH][NW];
+        // DEPTH frames of loads in flight, then their arithmetic
+        for (; t + DEPTH <= batch; t += DEPTH) {
+            unsigned v[DEPTH][NW];
 #pragma unroll
-            for (int u = 0; u < EMA_DEPTH; u++) ema_load<PX>(rp + (size_t)(t + u) * in_fstride, x, w, vec_in != 0, v[u]);
+            for (int u = 0; u < DEPTH; u++) ema_load<PX>(rp + (size_t)(t + u) * in_fstride, x, w, vec_in != 0, v[u]);
 #pragma unroll
-            for (int u = 0; u < EMA_DEPTH; u++) {
+            for (int u = 0; u < DEPTH; u++) {
                 unsigned m = ema_step<PX>(v[u], s, alpha, thr) & valid;
 #pragma unroll
                 for (int sh = PX, d = 1; sh < 32; sh <<= 1, d <<= 1) m |= __shfl_down_sync(0xffffffffu, m, d) << sh;

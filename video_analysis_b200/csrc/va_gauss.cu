@@ -103,7 +103,7 @@ gauss_fast_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fst
     const int NW = (O + 2 * r + 4 + 3) >> 2;                // staged words feeding one 4-pixel group
     const int NP = r + 1;                                   // row pairs feeding one output row pair
     const int WOFS = (R16 >> 2) - ((r + 3) >> 2);           // first staged word needed by group 0
-    const int NWORDS = (32 + NW) & ~1;                      // staged words needed per row (even)
+    const int NWORDS = 32 + NW;                             // staged words the row pass reads per row
     const int R = TH + 2 * r;                               // staged rows (even)
     uint8_t *s8 = smem;
     unsigned *hp = reinterpret_cast<unsigned *>(smem + (size_t)R * SW);   // [R/2][TW] u16 pairs
@@ -141,10 +141,11 @@ gauss_fast_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fst
             }
             va_cp_async_wait_all();
         } else {
-            // 8 pixels (24 bytes of RGB) per item -> two staged words
-            const int NG = NWORDS >> 1;
+            // 8 pixels (24 bytes of RGB) per item -> two staged words, starting at an even word
+            const int U0 = WOFS & ~1;
+            const int NG = (WOFS - U0 + 32 + NW + 1) >> 1;
             for (int it = tid; it < R * NG; it += GAUSS_THREADS) {
-                const int tr = it / NG, u = WOFS + 2 * (it - tr * NG);
+                const int tr = it / NG, u = U0 + 2 * (it - tr * NG);
                 const int gy = gauss_reflect_fast(ty0 + tr - r, h);
                 const uint8_t *rp = fin + (size_t)gy * in_pitch;
                 const int gx0 = tx0 - R16 + 4 * u;
