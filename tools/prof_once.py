@@ -1,7 +1,7 @@
 """
-Launches every kernel of the chain exactly once (after a warm-up of 23 launches) so that
-`ncu -s 23 -c 12` captures one profile per kernel:
-  luma, gauss, luma_gauss, ema_diff_thresh, morph, label x7 (init merge flatten scan rank resolve write)
+Launches every kernel of the chain exactly once (after a warm-up of 19 launches) so that
+`ncu -s 19 -c 10` captures one profile per kernel:
+  luma, gauss, luma_gauss, ema_diff_thresh, morph, label x5 (init merge flatten scan write)
 """
 import os
 import sys
@@ -17,11 +17,11 @@ W, H, B = 1920, 1080, int(os.environ.get('PROF_BATCH', '32'))
 rt = get_runtime(0)
 rt.ensure(W, H, B)
 rgbs = [synth.generate(rt, 0, i * B, B, W, H) for i in range(2)]          # 2 launches
-for fuse in (True, False):                                                  # 10 + 11 launches
+for fuse in (True, False):                                                  # 8 + 9 launches
     ch = SegmentChain((W, H), batch=B, fuse=fuse)
     ch.run_device(rgbs[0])
 torch.cuda.synchronize()
-# ---- profiled region: 12 launches
+# ---- profiled region: 10 launches
 mono = rt.luma(rgbs[1])
 blur = rt.gauss(mono, 2.0)
 blur2 = rt.luma_gauss(rgbs[1], 2.0)

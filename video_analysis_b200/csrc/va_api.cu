@@ -35,7 +35,8 @@ extern "C" int va_create(va_ctx **out, int device, int max_w, int max_h, int max
         return VA_ERR_CUDA;
     }
     ctx->sm_count = sms;
-    ctx->lab_pitch = ((size_t)max_w + 31) / 32 * 32;
+    ctx->lab_pitch = 32;                       // power of two: forest index = (y << log2 pitch) + x
+    while (ctx->lab_pitch < (size_t)max_w) ctx->lab_pitch <<= 1;
     if (ctx->lab_pitch * (size_t)max_h >= ((size_t)1 << 31)) { free(ctx); return VA_ERR_CAPACITY; }
     const size_t n_parent = ctx->lab_pitch * (size_t)max_h * (size_t)max_batch;
     if (cudaMalloc((void **)&ctx->lab_parent, n_parent * sizeof(int32_t)) != cudaSuccess ||

@@ -11,6 +11,26 @@ __device__ __forceinline__ void va_cp_async16(void *smem_dst, const void *gmem_s
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
 #endif
 }
+// 4-byte variant, explicit group commit and wait-for-all-but-N
+__device__ __forceinline__ void va_cp_async4(void *smem_dst, const void *gmem_src) {
+#ifdef VA_EMU
+    std::memcpy(smem_dst, gmem_src, 4);
+#else
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem_src) : "memory");
+#endif
+}
+__device__ __forceinline__ void va_cp_async_commit() {
+#ifndef VA_EMU
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+#endif
+}
+template <int N>
+__device__ __forceinline__ void va_cp_async_wait_group() {
+#ifndef VA_EMU
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+#endif
+}
 __device__ __forceinline__ void va_cp_async_wait_all() {
 #ifndef VA_EMU
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");

@@ -49,19 +49,41 @@ __device__ __forceinline__ unsigned ema_step(const unsigned (&v)[PX / 4], float 
     return m;
 }
 
+// Frames are streamed through a per-thread ring in shared memory filled by cp.async: RING
+// frames of loads are in flight per thread at no register cost, and nobody waits on a block
+// barrier because a thread only ever reads the slots it filled itself.
+#define EMA_RING 8
+
+template <int PX>
+__device__ __forceinline__ void ema_issue(unsigned *slot, const uint8_t *rp, int x, int w, bool fast) {
+    if (fast) {
+        if (PX == 16) va_cp_async16(slot, rp + x);
+        else va_cp_async4(slot, rp + x);
+    } else {
+        unsigned v[PX / 4];
+        ema_load<PX>(rp, x, w, false, v);
+#pragma unroll
+        for (int k = 0; k < PX / 4; k++) slot[k] = v[k];
+    }
+    va_cp_async_commit();
+}
+
 template <int PX>
 __global__ void __launch_bounds__(EMA_THREADS, PX == 16 ? 4 : 5)
 ema_diff_thresh_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstride,
                        float *__restrict__ bg, size_t bg_pitch_e,
                        uint32_t *__restrict__ mask, size_t mask_pitch_w, size_t mask_fstride_w,
                        int w, int h, int batch, float alpha, float thr, int first_init, int vec_in, int vec_bg) {
+    constexpr int NW = PX / 4;
+    __shared__ uint4 ring_raw[EMA_RING * EMA_THREADS * NW / 4];      // uint4: 16-byte aligned slots
+    unsigned(*ring)[EMA_THREADS * NW] = reinterpret_cast<unsigned(*)[EMA_THREADS * NW]>(ring_raw);
     const int lane = threadIdx.x & 31;
     const int warps_per_block = EMA_THREADS >> 5;
     const int span = 32 * PX;                         // pixels per warp step
     const int chunks = (w + span - 1) / span;
     const long long total = (long long)chunks * h;
-    constexpr int NW = PX / 4;
-    constexpr int DEPTH = PX == 16 ? 3 : 4;           // frames of loads in flight per thread
+    unsigned *myslot = &ring[0][threadIdx.x * NW];
+    constexpr int SLOT_STRIDE = EMA_THREADS * NW;
 
     for (long long item = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); item < total;
          item += (long long)gridDim.x * warps_per_block) {
@@ -70,7 +92,15 @@ ema_diff_thresh_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t i
         const int x = c * span + lane * PX;
         const uint8_t *rp = in + (size_t)y * in_pitch;
         float *bgp = bg + (size_t)y * bg_pitch_e + x;
-        const unsigned valid = x >= w ? 0u : (x + PX <= w ? (PX == 32 ? 0xffffffffu : ((1u << PX) - 1u)) : ((1u << (w - x)) - 1u));
+        const unsigned valid = x >= w ? 0u : (x + PX <= w ? ((1u << PX) - 1u) : ((1u << (w - x)) - 1u));
+        const bool fast = vec_in && x + PX <= w;
+
+        // prologue: RING - 1 frames in flight
+#pragma unroll
+        for (int u = 0; u < EMA_RING - 1; u++) {
+            if (u < batch) ema_issue<PX>(myslot + u * SLOT_STRIDE, rp + (size_t)u * in_fstride, x, w, fast);
+            else va_cp_async_commit();
+        }
 
         float s[PX];
         if (vec_bg && x + PX <= w) {
@@ -86,36 +116,32 @@ ema_diff_thresh_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t i
 
         uint32_t *mrow = mask + (size_t)y * mask_pitch_w + (x >> 5);
         const bool writer = (lane & (32 / PX - 1)) == 0 && x < w;
-        int t = 0;
-        if (first_init) {            // frame 0 initialises the model and gets an empty mask
-            unsigned v0[NW];
-            ema_load<PX>(rp, x, w, vec_in != 0, v0);
-#pragma unroll
-            for (int i = 0; i < PX; i++) s[i] = ema_byte_to_float(v0[i >> 2], i & 3);
-            if (writer) mrow[0] = 0u;
-            t = 1;
-        }
-        // DEPTH frames of loads in flight, then their arithmetic
-        for (; t + DEPTH <= batch; t += DEPTH) {
-            unsigned v[DEPTH][NW];
-#pragma unroll
-            for (int u = 0; u < DEPTH; u++) ema_load<PX>(rp + (size_t)(t + u) * in_fstride, x, w, vec_in != 0, v[u]);
-#pragma unroll
-            for (int u = 0; u < DEPTH; u++) {
-                unsigned m = ema_step<PX>(v[u], s, alpha, thr) & valid;
-#pragma unroll
-                for (int sh = PX, d = 1; sh < 32; sh <<= 1, d <<= 1) m |= __shfl_down_sync(0xffffffffu, m, d) << sh;
-                if (writer) mrow[(size_t)(t + u) * mask_fstride_w] = m;
-            }
-        }
-        for (; t < batch; t++) {
+        for (int t = 0; t < batch; t++) {
+            const int tn = t + EMA_RING - 1;                 // frame to put in flight now
+            if (tn < batch) ema_issue<PX>(myslot + (tn % EMA_RING) * SLOT_STRIDE, rp + (size_t)tn * in_fstride, x, w, fast);
+            else va_cp_async_commit();
+            va_cp_async_wait_group<EMA_RING - 1>();          // frame t has landed
             unsigned v[NW];
-            ema_load<PX>(rp + (size_t)t * in_fstride, x, w, vec_in != 0, v);
-            unsigned m = ema_step<PX>(v, s, alpha, thr) & valid;
+            const unsigned *slot = myslot + (t % EMA_RING) * SLOT_STRIDE;
+            if (PX == 16) {
+                const uint4 q = *reinterpret_cast<const uint4 *>(slot);
+                v[0] = q.x; v[NW > 1 ? 1 : 0] = q.y; v[NW > 2 ? 2 : 0] = q.z; v[NW > 3 ? 3 : 0] = q.w;
+            } else {
+                v[0] = slot[0];
+            }
+            unsigned m;
+            if (t == 0 && first_init) {          // frame 0 initialises the model and gets an empty mask
+#pragma unroll
+                for (int i = 0; i < PX; i++) s[i] = ema_byte_to_float(v[i >> 2], i & 3);
+                m = 0;
+            } else {
+                m = ema_step<PX>(v, s, alpha, thr) & valid;
+            }
 #pragma unroll
             for (int sh = PX, d = 1; sh < 32; sh <<= 1, d <<= 1) m |= __shfl_down_sync(0xffffffffu, m, d) << sh;
             if (writer) mrow[(size_t)t * mask_fstride_w] = m;
         }
+        va_cp_async_wait_group<0>();
 
         if (vec_bg && x + PX <= w) {
 #pragma unroll

@@ -144,26 +144,44 @@ gauss_fast_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fst
             // 8 pixels (24 bytes of RGB) per item -> two staged words, starting at an even word
             const int U0 = WOFS & ~1;
             const int NG = (WOFS - U0 + 32 + NW + 1) >> 1;
-            for (int it = tid; it < R * NG; it += GAUSS_THREADS) {
-                const int tr = it / NG, u = U0 + 2 * (it - tr * NG);
-                const int gy = gauss_reflect_fast(ty0 + tr - r, h);
-                const uint8_t *rp = fin + (size_t)gy * in_pitch;
-                const int gx0 = tx0 - R16 + 4 * u;
-                unsigned lo, hi;
-                if (vec_in && gx0 >= 0 && gx0 + 8 <= w && ((gx0 & 7) == 0)) {
-                    const uint2 *p = reinterpret_cast<const uint2 *>(rp + 3 * (size_t)gx0);
-                    const uint2 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2);
-                    lo = va_luma_x4(q0.x, q0.y, q1.x, mode);
-                    hi = va_luma_x4(q1.y, q2.x, q2.y, mode);
-                } else {
-                    lo = hi = 0;
+            // 4 items per thread per round: all global loads are issued before the first use
+            const int total = R * NG;
+            for (int it0 = tid; it0 < total; it0 += 4 * GAUSS_THREADS) {
+                uint2 q[4][3];
+                bool fastp[4];
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        lo |= va_luma_px(rp + 3 * (size_t)gauss_reflect_fast(gx0 + i, w), mode) << (8 * i);
-                        hi |= va_luma_px(rp + 3 * (size_t)gauss_reflect_fast(gx0 + 4 + i, w), mode) << (8 * i);
+                for (int k = 0; k < 4; k++) {
+                    const int it = it0 + k * GAUSS_THREADS;
+                    const int tr = it / NG, u = U0 + 2 * (it - tr * NG);
+                    const int gx0 = tx0 - R16 + 4 * u;
+                    fastp[k] = it < total && vec_in && gx0 >= 0 && gx0 + 8 <= w && ((gx0 & 7) == 0);
+                    if (fastp[k]) {
+                        const int gy = gauss_reflect_fast(ty0 + tr - r, h);
+                        const uint2 *p = reinterpret_cast<const uint2 *>(fin + (size_t)gy * in_pitch + 3 * (size_t)gx0);
+                        q[k][0] = __ldg(p); q[k][1] = __ldg(p + 1); q[k][2] = __ldg(p + 2);
                     }
                 }
-                *reinterpret_cast<uint2 *>(s8 + tr * SW + 4 * u) = make_uint2(lo, hi);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int it = it0 + k * GAUSS_THREADS;
+                    if (it >= total) break;
+                    const int tr = it / NG, u = U0 + 2 * (it - tr * NG);
+                    unsigned lo, hi;
+                    if (fastp[k]) {
+                        lo = va_luma_x4(q[k][0].x, q[k][0].y, q[k][1].x, mode);
+                        hi = va_luma_x4(q[k][1].y, q[k][2].x, q[k][2].y, mode);
+                    } else {
+                        const int gx0 = tx0 - R16 + 4 * u;
+                        const uint8_t *rp = fin + (size_t)gauss_reflect_fast(ty0 + tr - r, h) * in_pitch;
+                        lo = hi = 0;
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            lo |= va_luma_px(rp + 3 * (size_t)gauss_reflect_fast(gx0 + i, w), mode) << (8 * i);
+                            hi |= va_luma_px(rp + 3 * (size_t)gauss_reflect_fast(gx0 + 4 + i, w), mode) << (8 * i);
+                        }
+                    }
+                    *reinterpret_cast<uint2 *>(s8 + tr * SW + 4 * u) = make_uint2(lo, hi);
+                }
             }
         }
         __syncthreads();
@@ -342,7 +360,7 @@ static int gauss_launch(va_ctx *ctx, va_stream stream, const char *name, bool fu
             for (int th = 32; th <= 192; th += 8) {
                 const int R = th + 2 * r;
                 const size_t sm = (size_t)R * SW + (size_t)(R / 2) * GAUSS_TW * 4;
-                if (sm > (r <= 16 ? 74 : 112) * 1024) break;
+                if (sm > (r <= 16 ? 44 : 112) * 1024) break;   // keep >= 5 CTAs per SM for small radii
                 const int ty = va_div_up(h, th);
                 const double cost = ty * (1.3 * R + 8.0 * ((R / 2 + 7) / 8) * 1.0 + 10.0 * ((th / 2 + 7) / 8));
                 if (cost < best) { best = cost; TH = th; }

@@ -4,24 +4,24 @@
 // per-label areas of regions.py:165-169.
 //
 // Run-based union-find.  The unit of equivalence is a horizontal run of foreground
-// pixels, represented by the pixel index (y * P + x) of its first pixel; the forest
+// pixels, represented by the index (y << LOG) + x of its first pixel; the forest
 // `parent` lives in ctx scratch and is only ever touched at run starts, so its HBM
 // traffic scales with the number of runs, not pixels.  Hooking always points the larger
 // index at the smaller one, hence the root of a component is its first pixel in raster
 // order, and ranking the roots in index order IS the canonical numbering.
 //
 // One warp owns one image row (lane = 32-pixel word); run starts that continue across
-// words are resolved with one ballot + one shuffle per 32 words.
+// words are resolved with one ballot + one shuffle per 32 words, and 1024-pixel chunks
+// without foreground cost one load and one vote.
 //   A init     parent[s] = s for every run start s
 //   B merge    for every maximal overlap segment between a run in row y and one in row
 //              y-1: union(run start, run start)        (atomicMin hooking)
-//   C flatten  parent[s] = root(s); count roots per row
+//   C flatten  parent[s] = root(s) for every other run start; the k-th root of a row
+//              (k = 1, 2, ... in x order) gets parent = -k; roots per row are counted
 //   D scan     exclusive prefix of the per-row root counts (one CTA per frame) -> n
-//   E rank     root s of row y gets label rowoff[y] + (its position among the row's
-//              roots) + 1, stored as parent[s] = -label
-//   F resolve  every other run start copies its root's -label
-//   G write    label image: one coalesced 128-byte store per warp per word; the run start
-//              of each pixel comes from bit scans, its label from one forest lookup
+//   G write    label(run) = rowoff[row of its root] + k; one forest lookup per run, the
+//              labels of a 1024-pixel chunk are assembled in a per-warp shared-memory slab
+//              and leave as 16-byte stores (512 contiguous bytes per warp instruction)
 // Algorithmic HBM bytes per frame: N/8 (mask) + 4N (labels).
 #include "va_device.cuh"
 
@@ -56,10 +56,16 @@ __device__ __forceinline__ int lab_run_start(unsigned wd, int bit, int word_inde
     return z ? 32 * word_index + (32 - __clz((int)z)) : st_in;
 }
 
+// first pixels of the runs of a word; `pbit` = bit 31 of the word to the left
+__device__ __forceinline__ unsigned lab_run_starts(unsigned wd, unsigned pbit) {
+    return wd & ~((wd << 1) | pbit);
+}
+
 // ---- union-find ------------------------------------------------------------------------
+// a node is a root while parent == self; kernel C later marks roots with negative values
 __device__ __forceinline__ int lab_find(const int *parent, int x) {
     int p;
-    while ((p = va_ld_cg(parent + x)) != x) x = p;
+    while ((p = va_ld_cg(parent + x)) != x && p >= 0) x = p;
     return x;
 }
 __device__ __forceinline__ void lab_union(int *parent, int a, int b) {
@@ -77,7 +83,7 @@ __device__ __forceinline__ void lab_union(int *parent, int a, int b) {
 // ---- A: init -----------------------------------------------------------------------------
 __global__ void __launch_bounds__(LAB_THREADS)
 label_init_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
-                  int *__restrict__ parent, size_t P, size_t pf, int w, int h, int batch) {
+                  int *__restrict__ parent, int LOG, size_t pf, int w, int h, int batch) {
     const int lane = threadIdx.x & 31;
     const int wpw = (w + 31) >> 5;
     const unsigned lastmask = (w & 31) ? ((1u << (w & 31)) - 1u) : FULL;
@@ -86,18 +92,18 @@ label_init_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
          row += (long long)gridDim.x * LAB_WARPS) {
         const int b = (int)(row / h), y = (int)(row - (long long)b * h);
         const uint32_t *mr = mask + (size_t)b * mfw + (size_t)y * mpw;
-        int *pr = parent + (size_t)b * pf;
+        int *pr = parent + (size_t)b * pf + ((size_t)y << LOG);
         unsigned prev_top = 0;     // bit 31 of the word before the chunk
         for (int base = 0; base < wpw; base += 32) {
             const unsigned wd = lab_load_word(mr, wpw, base + lane, lastmask);
-            unsigned pw = __shfl_up_sync(FULL, wd, 1);
-            const unsigned pbit = lane ? (pw >> 31) : prev_top;
-            unsigned starts = wd & ~((wd << 1) | pbit);
+            if (!__any_sync(FULL, wd != 0u)) { prev_top = 0; continue; }
+            const unsigned pw = __shfl_up_sync(FULL, wd, 1);
+            unsigned starts = lab_run_starts(wd, lane ? (pw >> 31) : prev_top);
             while (starts) {
                 const int bit = __ffs((int)starts) - 1;
                 starts &= starts - 1;
-                const int idx = (int)((size_t)y * P) + 32 * (base + lane) + bit;
-                pr[idx] = idx;
+                const int x = 32 * (base + lane) + bit;
+                pr[x] = (y << LOG) + x;
             }
             prev_top = __shfl_sync(FULL, wd, 31) >> 31;
         }
@@ -125,7 +131,7 @@ __device__ __forceinline__ void lab_merge_probe(int *pr, unsigned cur, int cur_s
 
 __global__ void __launch_bounds__(LAB_THREADS)
 label_merge_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
-                   int *__restrict__ parent, size_t P, size_t pf, int w, int h, int batch, int conn8) {
+                   int *__restrict__ parent, int LOG, size_t pf, int w, int h, int batch, int conn8) {
     const int lane = threadIdx.x & 31;
     const int wpw = (w + 31) >> 5;
     const unsigned lastmask = (w & 31) ? ((1u << (w & 31)) - 1u) : FULL;
@@ -137,14 +143,56 @@ label_merge_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
         const uint32_t *mc = mask + (size_t)b * mfw + (size_t)y * mpw;
         const uint32_t *mu = mc - mpw;
         int *pr = parent + (size_t)b * pf;
-        const int rowc = (int)((size_t)y * P), rowu = (int)((size_t)(y - 1) * P);
-        const bool up_bit0 = (lab_load_word(mu, wpw, 0, lastmask) & 1u) != 0;
+        const int rowc = y << LOG, rowu = (y - 1) << LOG;
+        bool up_bit0 = false;
         int carry_c = 0, carry_u = 0, carry_l = 0, carry_r = 0;
         unsigned ovp0 = 0, ovpl = 0, ovpr = 0;          // bit 31 of the overlap word before the chunk
         unsigned up_prev_top = 0;                        // bit 31 of the up word before the chunk
         for (int base = 0; base < wpw; base += 32) {
             const unsigned cur = lab_load_word(mc, wpw, base + lane, lastmask);
             const unsigned up = lab_load_word(mu, wpw, base + lane, lastmask);
+            if (base == 0) up_bit0 = (__shfl_sync(FULL, up, 0) & 1u) != 0;
+            // nothing can be merged in this chunk unless both rows have foreground in or next to it
+            // (8-connectivity: the first pixel of the next chunk of the row above also counts)
+            const unsigned nxt = conn8 ? lab_load_word(mu, wpw, base + 32, lastmask) : 0u;
+            const bool any_cur = __any_sync(FULL, cur != 0u);
+            const bool any_up = __any_sync(FULL, up != 0u) || up_prev_top || (nxt & 1u);
+            if (!any_cur || !any_up) {
+                // no overlap segment starts here; carries follow from the words alone
+                int cs, ct, us, ut;
+                if (any_cur) { lab_scan_chunk(cur, lane, base, carry_c, cs, ct); carry_c = __shfl_sync(FULL, ct, 31); }
+                else carry_c = 32 * (base + 32);
+                if (__any_sync(FULL, up != 0u)) {
+                    lab_scan_chunk(up, lane, base, carry_u, us, ut);
+                    carry_u = __shfl_sync(FULL, ut, 31);
+                    if (conn8) {
+                        const unsigned upw = __shfl_up_sync(FULL, up, 1);
+                        const unsigned upl = (up << 1) | (lane ? (upw >> 31) : up_prev_top);
+                        const unsigned upn = __shfl_down_sync(FULL, up, 1);
+                        const unsigned upr = (up >> 1) | ((lane < 31 ? (upn & 1u) : (nxt & 1u)) << 31);
+                        int ls, lt, rs, rt;
+                        lab_scan_chunk(upl, lane, base, carry_l, ls, lt);
+                        lab_scan_chunk(upr, lane, base, carry_r, rs, rt);
+                        carry_l = __shfl_sync(FULL, lt, 31);
+                        carry_r = __shfl_sync(FULL, rt, 31);
+                    }
+                } else {
+                    carry_u = 32 * (base + 32);
+                    if (conn8) {
+                        // shifted rows: only the bits leaking in from the neighbouring chunks can be set
+                        const unsigned upl = lane == 0 ? up_prev_top : 0u;
+                        const unsigned upr = lane == 31 ? ((nxt & 1u) << 31) : 0u;
+                        int ls, lt, rs, rt;
+                        lab_scan_chunk(upl, lane, base, carry_l, ls, lt);
+                        lab_scan_chunk(upr, lane, base, carry_r, rs, rt);
+                        carry_l = __shfl_sync(FULL, lt, 31);
+                        carry_r = __shfl_sync(FULL, rt, 31);
+                    }
+                }
+                ovp0 = ovpl = ovpr = 0;
+                up_prev_top = __shfl_sync(FULL, up, 31) >> 31;
+                continue;
+            }
             int cs, ct, us, ut;
             lab_scan_chunk(cur, lane, base, carry_c, cs, ct);
             lab_scan_chunk(up, lane, base, carry_u, us, ut);
@@ -160,7 +208,6 @@ label_merge_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
                 const unsigned upl = (up << 1) | (lane ? (upw >> 31) : up_prev_top);
                 // upr(x) = up(x + 1): needs bit 0 of the next word (next chunk for lane 31)
                 const unsigned upn = __shfl_down_sync(FULL, up, 1);
-                const unsigned nxt = lab_load_word(mu, wpw, base + 32, lastmask);
                 const unsigned upr = (up >> 1) | ((lane < 31 ? (upn & 1u) : (nxt & 1u)) << 31);
                 int ls, lt, rs, rt;
                 lab_scan_chunk(upl, lane, base, carry_l, ls, lt);
@@ -179,18 +226,18 @@ label_merge_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
                 }
                 carry_l = __shfl_sync(FULL, lt, 31);
                 carry_r = __shfl_sync(FULL, rt, 31);
-                up_prev_top = __shfl_sync(FULL, up, 31) >> 31;
             }
+            up_prev_top = __shfl_sync(FULL, up, 31) >> 31;
             carry_c = __shfl_sync(FULL, ct, 31);
             carry_u = __shfl_sync(FULL, ut, 31);
         }
     }
 }
 
-// ---- C: flatten + count roots per row ------------------------------------------------------
+// ---- C: flatten, rank the roots inside their row, count them ---------------------------------
 __global__ void __launch_bounds__(LAB_THREADS)
 label_flatten_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
-                     int *__restrict__ parent, size_t P, size_t pf, int *__restrict__ rowcnt,
+                     int *__restrict__ parent, int LOG, size_t pf, int *__restrict__ rowcnt,
                      int w, int h, int batch) {
     const int lane = threadIdx.x & 31;
     const int wpw = (w + 31) >> 5;
@@ -202,24 +249,40 @@ label_flatten_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
         const uint32_t *mr = mask + (size_t)b * mfw + (size_t)y * mpw;
         int *pr = parent + (size_t)b * pf;
         unsigned prev_top = 0;
-        int nroots = 0;
+        int nroots = 0;            // roots of this row seen so far (warp-uniform)
         for (int base = 0; base < wpw; base += 32) {
             const unsigned wd = lab_load_word(mr, wpw, base + lane, lastmask);
+            if (!__any_sync(FULL, wd != 0u)) { prev_top = 0; continue; }
             const unsigned pw = __shfl_up_sync(FULL, wd, 1);
-            const unsigned pbit = lane ? (pw >> 31) : prev_top;
-            unsigned starts = wd & ~((wd << 1) | pbit);
-            while (starts) {
-                const int bit = __ffs((int)starts) - 1;
-                starts &= starts - 1;
-                const int idx = (int)((size_t)y * P) + 32 * (base + lane) + bit;
+            const unsigned starts = lab_run_starts(wd, lane ? (pw >> 31) : prev_top);
+            unsigned rootbits = 0;
+            unsigned s = starts;
+            while (s) {
+                const int bit = __ffs((int)s) - 1;
+                s &= s - 1;
+                const int idx = (y << LOG) + 32 * (base + lane) + bit;
                 const int root = lab_find(pr, idx);
-                if (root == idx) nroots++;
+                if (root == idx) rootbits |= 1u << bit;
                 else pr[idx] = root;
             }
+            // rank of my roots among the row's roots, x order
+            const int mine = __popc(rootbits);
+            int incl = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(FULL, incl, d);
+                if (lane >= d) incl += v;
+            }
+            int k = nroots + incl - mine + 1;
+            while (rootbits) {
+                const int bit = __ffs((int)rootbits) - 1;
+                rootbits &= rootbits - 1;
+                pr[(y << LOG) + 32 * (base + lane) + bit] = -k;
+                k++;
+            }
+            nroots += __shfl_sync(FULL, incl, 31);
             prev_top = __shfl_sync(FULL, wd, 31) >> 31;
         }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) nroots += __shfl_xor_sync(FULL, nroots, d);
         if (lane == 0) rowcnt[row] = nroots;
     }
 }
@@ -246,99 +309,17 @@ label_scan_kernel(int *__restrict__ rowcnt, int *__restrict__ counts, int h) {
     for (int i = lo; i < hi; i++) { const int v = rc[i]; rc[i] = run; run += v; }
 }
 
-// ---- E: rank the roots ------------------------------------------------------------------------
-__global__ void __launch_bounds__(LAB_THREADS)
-label_rank_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
-                  int *__restrict__ parent, size_t P, size_t pf, const int *__restrict__ rowoff,
-                  int w, int h, int batch) {
-    const int lane = threadIdx.x & 31;
-    const int wpw = (w + 31) >> 5;
-    const unsigned lastmask = (w & 31) ? ((1u << (w & 31)) - 1u) : FULL;
-    const long long rows = (long long)h * batch;
-    for (long long row = (long long)blockIdx.x * LAB_WARPS + (threadIdx.x >> 5); row < rows;
-         row += (long long)gridDim.x * LAB_WARPS) {
-        const int b = (int)(row / h), y = (int)(row - (long long)b * h);
-        const uint32_t *mr = mask + (size_t)b * mfw + (size_t)y * mpw;
-        int *pr = parent + (size_t)b * pf;
-        unsigned prev_top = 0;
-        int next_label = rowoff[row] + 1;
-        for (int base = 0; base < wpw; base += 32) {
-            const unsigned wd = lab_load_word(mr, wpw, base + lane, lastmask);
-            const unsigned pw = __shfl_up_sync(FULL, wd, 1);
-            const unsigned pbit = lane ? (pw >> 31) : prev_top;
-            const unsigned starts = wd & ~((wd << 1) | pbit);
-            // which of my run starts are roots?
-            unsigned rootbits = 0;
-            unsigned s = starts;
-            while (s) {
-                const int bit = __ffs((int)s) - 1;
-                s &= s - 1;
-                const int idx = (int)((size_t)y * P) + 32 * (base + lane) + bit;
-                if (pr[idx] == idx) rootbits |= 1u << bit;
-            }
-            const int mine = __popc(rootbits);
-            int incl = mine;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int v = __shfl_up_sync(FULL, incl, d);
-                if (lane >= d) incl += v;
-            }
-            int lab = next_label + incl - mine;
-            while (rootbits) {
-                const int bit = __ffs((int)rootbits) - 1;
-                rootbits &= rootbits - 1;
-                const int idx = (int)((size_t)y * P) + 32 * (base + lane) + bit;
-                pr[idx] = -lab;
-                lab++;
-            }
-            next_label += __shfl_sync(FULL, incl, 31);
-            prev_top = __shfl_sync(FULL, wd, 31) >> 31;
-        }
-    }
-}
-
-// ---- F: every run start takes its root's label -------------------------------------------------
-__global__ void __launch_bounds__(LAB_THREADS)
-label_resolve_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
-                     int *__restrict__ parent, size_t P, size_t pf, int w, int h, int batch) {
-    const int lane = threadIdx.x & 31;
-    const int wpw = (w + 31) >> 5;
-    const unsigned lastmask = (w & 31) ? ((1u << (w & 31)) - 1u) : FULL;
-    const long long rows = (long long)h * batch;
-    for (long long row = (long long)blockIdx.x * LAB_WARPS + (threadIdx.x >> 5); row < rows;
-         row += (long long)gridDim.x * LAB_WARPS) {
-        const int b = (int)(row / h), y = (int)(row - (long long)b * h);
-        const uint32_t *mr = mask + (size_t)b * mfw + (size_t)y * mpw;
-        int *pr = parent + (size_t)b * pf;
-        unsigned prev_top = 0;
-        for (int base = 0; base < wpw; base += 32) {
-            const unsigned wd = lab_load_word(mr, wpw, base + lane, lastmask);
-            const unsigned pw = __shfl_up_sync(FULL, wd, 1);
-            const unsigned pbit = lane ? (pw >> 31) : prev_top;
-            unsigned starts = wd & ~((wd << 1) | pbit);
-            while (starts) {
-                const int bit = __ffs((int)starts) - 1;
-                starts &= starts - 1;
-                const int idx = (int)((size_t)y * P) + 32 * (base + lane) + bit;
-                const int p = va_ld_cg(pr + idx);
-                if (p >= 0) pr[idx] = va_ld_cg(pr + p);     // roots already hold -label (kernel E)
-            }
-            prev_top = __shfl_sync(FULL, wd, 31) >> 31;
-        }
-    }
-}
-
 // ---- G: write the label image --------------------------------------------------------------------
 // Two steps per 1024-pixel chunk of a row, both inside one warp (no block barrier):
-//   fill   lane = word: for each run of the word fetch its label once (one forest lookup per
-//          run) and write it to the run's pixels in a per-warp shared-memory slab
+//   fill   lane = word: for each run of the word fetch its label once and write it to the
+//          run's pixels in a per-warp shared-memory slab
 //   store  lane = 4 consecutive pixels: background pixels become 0, foreground pixels read
 //          the slab; one 16-byte store per lane, 512 contiguous bytes per warp instruction
 // The slab index is skewed by one word per 32 pixels so that both steps are conflict-free.
 #define LAB_SKEW(p) ((p) + ((p) >> 5))
 __global__ void __launch_bounds__(LAB_THREADS)
 label_write_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
-                   const int *__restrict__ parent, size_t P, size_t pf,
+                   const int *__restrict__ parent, int LOG, size_t pf, const int *__restrict__ rowoff,
                    int32_t *__restrict__ labels, size_t lpe, size_t lfe, int w, int h, int batch, int vec_out) {
     __shared__ int slab_all[LAB_WARPS][1024 + 32];
     const int lane = threadIdx.x & 31;
@@ -350,11 +331,29 @@ label_write_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
          row += (long long)gridDim.x * LAB_WARPS) {
         const int b = (int)(row / h), y = (int)(row - (long long)b * h);
         const uint32_t *mr = mask + (size_t)b * mfw + (size_t)y * mpw;
-        const int *pr = parent + (size_t)b * pf + (size_t)y * P;
+        const int *pf_ = parent + (size_t)b * pf;
+        const int *pr = pf_ + ((size_t)y << LOG);
+        const int *ro = rowoff + (size_t)b * h;
         int32_t *lr = labels + (size_t)b * lfe + (size_t)y * lpe;
         int carry = 0;
         for (int base = 0; base < wpw; base += 32) {
             const unsigned wd = lab_load_word(mr, wpw, base + lane, lastmask);
+            const int nwords = min(32, wpw - base);
+            if (!__any_sync(FULL, wd != 0u)) {
+                // background only: zeros straight to memory
+                const int4 z = make_int4(0, 0, 0, 0);
+                for (int it = 0; 4 * it < nwords; it++) {
+                    const int x = 32 * base + 128 * it + 4 * lane;
+                    if (vec_out && x + 4 <= w) {
+                        *reinterpret_cast<int4 *>(lr + x) = z;
+                    } else {
+                        for (int k = 0; k < 4; k++)
+                            if (x + k < w) lr[x + k] = 0;
+                    }
+                }
+                carry = 32 * (base + 32);
+                continue;
+            }
             int st_in, top;
             lab_scan_chunk(wd, lane, base, carry, st_in, top);
             // ---- fill: one lookup per run
@@ -364,14 +363,16 @@ label_write_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
                 const unsigned t = ~(wd >> bit);
                 const int ones = t ? __ffs((int)t) - 1 : 32;
                 const int start_x = bit == 0 ? st_in : 32 * (base + lane) + bit;
-                const int lab = -pr[start_x];
+                int p = pr[start_x];
+                int ry = y;
+                if (p >= 0) { ry = p >> LOG; p = pf_[p]; }        // not a root: hop to the root
+                const int lab = ro[ry] - p;                        // p == -k
                 const int p0 = 32 * lane + bit;
                 for (int k = 0; k < ones; k++) slab[LAB_SKEW(p0 + k)] = lab;
                 rem &= ~((ones >= 32 ? FULL : ((1u << ones) - 1u)) << bit);
             }
             __syncwarp();
             // ---- store: 128 pixels per step
-            const int nwords = min(32, wpw - base);
             for (int it = 0; 4 * it < nwords; it++) {
                 const unsigned wi = __shfl_sync(FULL, wd, 4 * it + (lane >> 3));
                 const unsigned nib = (wi >> (4 * (lane & 7))) & 0xFu;
@@ -411,30 +412,26 @@ extern "C" int va_label_bits(va_ctx *ctx, va_stream stream,
     if (w > ctx->max_w || h > ctx->max_h || batch > ctx->max_batch)
         VA_FAIL(ctx, VA_ERR_CAPACITY, "va_label_bits: %dx%dx%d exceeds the ctx capacity %dx%dx%d", w, h, batch,
                 ctx->max_w, ctx->max_h, ctx->max_batch);
-    const size_t P = ctx->lab_pitch;
-    const size_t pf = P * (size_t)ctx->max_h;
+    int LOG = 5;
+    while (((size_t)1 << LOG) < ctx->lab_pitch) LOG++;
+    const size_t pf = ctx->lab_pitch * (size_t)ctx->max_h;
     const long long rows = (long long)h * batch;
     const int grid = va_grid(ctx, (rows + LAB_WARPS - 1) / LAB_WARPS, 8);
     int *parent = ctx->lab_parent;
     int *rowcnt = ctx->lab_rowcnt;
     { auto k = label_init_kernel;
-      VA_LAUNCH(ctx, k, grid, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, parent, P, pf, w, h, batch); }
+      VA_LAUNCH(ctx, k, grid, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, parent, LOG, pf, w, h, batch); }
     { auto k = label_merge_kernel;
-      VA_LAUNCH(ctx, k, grid, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, parent, P, pf, w, h, batch,
+      VA_LAUNCH(ctx, k, grid, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, parent, LOG, pf, w, h, batch,
                 connectivity == 8 ? 1 : 0); }
     { auto k = label_flatten_kernel;
-      VA_LAUNCH(ctx, k, grid, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, parent, P, pf, rowcnt, w, h, batch); }
+      VA_LAUNCH(ctx, k, grid, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, parent, LOG, pf, rowcnt, w, h, batch); }
     { auto k = label_scan_kernel;
       VA_LAUNCH(ctx, k, batch, LAB_THREADS, 0, stream, rowcnt, counts, h); }
-    { auto k = label_rank_kernel;
-      VA_LAUNCH(ctx, k, grid, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, parent, P, pf,
-                (const int *)rowcnt, w, h, batch); }
-    { auto k = label_resolve_kernel;
-      VA_LAUNCH(ctx, k, grid, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, parent, P, pf, w, h, batch); }
     { auto k = label_write_kernel;
       const int vec_out = va_aligned(labels, 16) && labels_pitch_e % 4 == 0 && labels_fstride_e % 4 == 0;
-      VA_LAUNCH(ctx, k, grid, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, (const int *)parent, P, pf,
-                labels, labels_pitch_e, labels_fstride_e, w, h, batch, vec_out); }
+      VA_LAUNCH(ctx, k, grid, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, (const int *)parent, LOG, pf,
+                (const int *)rowcnt, labels, labels_pitch_e, labels_fstride_e, w, h, batch, vec_out); }
     return VA_OK;
 }
 
@@ -454,6 +451,7 @@ region_area_kernel(const int32_t *__restrict__ labels, size_t lpe, size_t lfe,
         const int b = (int)(row / h), y = (int)(row - (long long)b * h);
         const int x = 32 * c + lane;
         const int lab = x < w ? labels[(size_t)b * lfe + (size_t)y * lpe + x] : 0;
+        if (!__any_sync(FULL, lab != 0)) continue;
         // heads of runs of equal labels inside the 32-pixel chunk add the run length once
         const int left = __shfl_up_sync(FULL, lab, 1);
         const bool head = lane == 0 || left != lab;
