@@ -81,14 +81,14 @@ ema_diff_thresh_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t i
     const int warps_per_block = EMA_THREADS >> 5;
     const int span = 32 * PX;                         // pixels per warp step
     const int chunks = (w + span - 1) / span;
-    const long long total = (long long)chunks * h;
+    const unsigned total = (unsigned)((long long)chunks * h);
     unsigned *myslot = &ring[0][threadIdx.x * NW];
     constexpr int SLOT_STRIDE = EMA_THREADS * NW;
 
-    for (long long item = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); item < total;
-         item += (long long)gridDim.x * warps_per_block) {
-        const int y = (int)(item / chunks);
-        const int c = (int)(item - (long long)y * chunks);
+    for (unsigned item = blockIdx.x * warps_per_block + (threadIdx.x >> 5); item < total;
+         item += gridDim.x * warps_per_block) {
+        const int y = (int)(item / (unsigned)chunks);
+        const int c = (int)(item - (unsigned)y * (unsigned)chunks);
         const int x = c * span + lane * PX;
         const uint8_t *rp = in + (size_t)y * in_pitch;
         float *bgp = bg + (size_t)y * bg_pitch_e + x;
@@ -194,11 +194,11 @@ ema_partial_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fs
                    float *__restrict__ S, size_t s_pitch_e, int w, int h, int batch,
                    float alpha, float a, int accumulate, int vec_in) {
     const int groups = (w + 3) >> 2;
-    const long long total = (long long)groups * h;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int y = (int)(i / groups);
-        const int x = 4 * (int)(i - (long long)y * groups);
+    const unsigned total = (unsigned)((long long)groups * h);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += gridDim.x * blockDim.x) {
+        const int y = (int)(i / (unsigned)groups);
+        const int x = 4 * (int)(i - (unsigned)y * (unsigned)groups);
         const uint8_t *rp = in + (size_t)y * in_pitch;
         float *sp = S + (size_t)y * s_pitch_e + x;
         float s[4];
@@ -235,11 +235,11 @@ extern "C" int va_ema_partial(va_ctx *ctx, va_stream stream,
 
 __global__ void __launch_bounds__(256)
 ema_fold_kernel(float *__restrict__ carry, const float *__restrict__ S, size_t pitch_e, int w, int h, float scale) {
-    const long long total = (long long)w * h;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int y = (int)(i / w);
-        const int x = (int)(i - (long long)y * w);
+    const unsigned total = (unsigned)((long long)w * h);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += gridDim.x * blockDim.x) {
+        const int y = (int)(i / (unsigned)w);
+        const int x = (int)(i - (unsigned)y * (unsigned)w);
         const size_t o = (size_t)y * pitch_e + x;
         carry[o] = __fadd_rn(__fmul_rn(scale, carry[o]), S[o]);
     }

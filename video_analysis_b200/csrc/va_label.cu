@@ -87,10 +87,10 @@ label_init_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
     const int lane = threadIdx.x & 31;
     const int wpw = (w + 31) >> 5;
     const unsigned lastmask = (w & 31) ? ((1u << (w & 31)) - 1u) : FULL;
-    const long long rows = (long long)h * batch;
-    for (long long row = (long long)blockIdx.x * LAB_WARPS + (threadIdx.x >> 5); row < rows;
-         row += (long long)gridDim.x * LAB_WARPS) {
-        const int b = (int)(row / h), y = (int)(row - (long long)b * h);
+    const int rows = h * batch;
+    for (int row = blockIdx.x * LAB_WARPS + (threadIdx.x >> 5); row < rows;
+         row += gridDim.x * LAB_WARPS) {
+        const int b = row / h, y = row - b * h;
         const uint32_t *mr = mask + (size_t)b * mfw + (size_t)y * mpw;
         int *pr = parent + (size_t)b * pf + ((size_t)y << LOG);
         unsigned prev_top = 0;     // bit 31 of the word before the chunk
@@ -135,10 +135,10 @@ label_merge_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
     const int lane = threadIdx.x & 31;
     const int wpw = (w + 31) >> 5;
     const unsigned lastmask = (w & 31) ? ((1u << (w & 31)) - 1u) : FULL;
-    const long long rows = (long long)h * batch;
-    for (long long row = (long long)blockIdx.x * LAB_WARPS + (threadIdx.x >> 5); row < rows;
-         row += (long long)gridDim.x * LAB_WARPS) {
-        const int b = (int)(row / h), y = (int)(row - (long long)b * h);
+    const int rows = h * batch;
+    for (int row = blockIdx.x * LAB_WARPS + (threadIdx.x >> 5); row < rows;
+         row += gridDim.x * LAB_WARPS) {
+        const int b = row / h, y = row - b * h;
         if (y == 0) continue;
         const uint32_t *mc = mask + (size_t)b * mfw + (size_t)y * mpw;
         const uint32_t *mu = mc - mpw;
@@ -242,10 +242,10 @@ label_flatten_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
     const int lane = threadIdx.x & 31;
     const int wpw = (w + 31) >> 5;
     const unsigned lastmask = (w & 31) ? ((1u << (w & 31)) - 1u) : FULL;
-    const long long rows = (long long)h * batch;
-    for (long long row = (long long)blockIdx.x * LAB_WARPS + (threadIdx.x >> 5); row < rows;
-         row += (long long)gridDim.x * LAB_WARPS) {
-        const int b = (int)(row / h), y = (int)(row - (long long)b * h);
+    const int rows = h * batch;
+    for (int row = blockIdx.x * LAB_WARPS + (threadIdx.x >> 5); row < rows;
+         row += gridDim.x * LAB_WARPS) {
+        const int b = row / h, y = row - b * h;
         const uint32_t *mr = mask + (size_t)b * mfw + (size_t)y * mpw;
         int *pr = parent + (size_t)b * pf;
         unsigned prev_top = 0;
@@ -326,10 +326,10 @@ label_write_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
     int *slab = slab_all[threadIdx.x >> 5];
     const int wpw = (w + 31) >> 5;
     const unsigned lastmask = (w & 31) ? ((1u << (w & 31)) - 1u) : FULL;
-    const long long rows = (long long)h * batch;
-    for (long long row = (long long)blockIdx.x * LAB_WARPS + (threadIdx.x >> 5); row < rows;
-         row += (long long)gridDim.x * LAB_WARPS) {
-        const int b = (int)(row / h), y = (int)(row - (long long)b * h);
+    const int rows = h * batch;
+    for (int row = blockIdx.x * LAB_WARPS + (threadIdx.x >> 5); row < rows;
+         row += gridDim.x * LAB_WARPS) {
+        const int b = row / h, y = row - b * h;
         const uint32_t *mr = mask + (size_t)b * mfw + (size_t)y * mpw;
         const int *pf_ = parent + (size_t)b * pf;
         const int *pr = pf_ + ((size_t)y << LOG);
@@ -415,7 +415,7 @@ extern "C" int va_label_bits(va_ctx *ctx, va_stream stream,
     int LOG = 5;
     while (((size_t)1 << LOG) < ctx->lab_pitch) LOG++;
     const size_t pf = ctx->lab_pitch * (size_t)ctx->max_h;
-    const long long rows = (long long)h * batch;
+    const int rows = h * batch;
     const int grid = va_grid(ctx, (rows + LAB_WARPS - 1) / LAB_WARPS, 8);
     int *parent = ctx->lab_parent;
     int *rowcnt = ctx->lab_rowcnt;
@@ -443,12 +443,12 @@ region_area_kernel(const int32_t *__restrict__ labels, size_t lpe, size_t lfe,
                    int *__restrict__ areas, int max_labels, int w, int h, int batch) {
     const int lane = threadIdx.x & 31;
     const int chunks = (w + 31) >> 5;
-    const long long total = (long long)chunks * h * batch;
-    for (long long it = (long long)blockIdx.x * LAB_WARPS + (threadIdx.x >> 5); it < total;
-         it += (long long)gridDim.x * LAB_WARPS) {
-        const long long row = it / chunks;
+    const unsigned total = (unsigned)((long long)chunks * h * batch);
+    for (unsigned it = blockIdx.x * LAB_WARPS + (threadIdx.x >> 5); it < total;
+         it += gridDim.x * LAB_WARPS) {
+        const unsigned row = it / (unsigned)chunks;
         const int c = (int)(it - row * chunks);
-        const int b = (int)(row / h), y = (int)(row - (long long)b * h);
+        const int b = row / h, y = row - b * h;
         const int x = 32 * c + lane;
         const int lab = x < w ? labels[(size_t)b * lfe + (size_t)y * lpe + x] : 0;
         if (!__any_sync(FULL, lab != 0)) continue;

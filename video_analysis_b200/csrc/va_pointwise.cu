@@ -83,12 +83,12 @@ luma_fast_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstr
     __shared__ uint4 stage[LUMA_WARPS][96];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint4 *st = stage[warp];
-    const long long total = rows * chunks_per_row;
-    for (long long item = (long long)blockIdx.x * LUMA_WARPS + warp; item < total;
-         item += (long long)gridDim.x * LUMA_WARPS) {
-        const long long row = item / chunks_per_row;
+    const unsigned total = (unsigned)(rows * chunks_per_row);
+    for (unsigned item = blockIdx.x * LUMA_WARPS + warp; item < total;
+         item += gridDim.x * LUMA_WARPS) {
+        const unsigned row = item / (unsigned)chunks_per_row;
         const int px0 = (int)(item - row * chunks_per_row) * 512;
-        const int b = (int)(row / h), y = (int)(row - (long long)b * h);
+        const int b = (int)(row / (unsigned)h), y = (int)(row - (unsigned)b * (unsigned)h);
         const int npx = min(512, w - px0);                 // multiple of 16
         const int n16 = (npx * 3) >> 4;
         const uint8_t *src = in + (size_t)b * in_fstride + (size_t)y * in_pitch + 3 * (size_t)px0;
@@ -167,22 +167,22 @@ copy2d_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstride
     const long long rows = (long long)h * batch;
     if (vec) {
         const int chunks = row_bytes >> 4;
-        const long long total = rows * chunks;
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-             i += (long long)gridDim.x * blockDim.x) {
-            const long long row = i / chunks;
+        const unsigned total = (unsigned)(rows * chunks);
+        for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total;
+             i += gridDim.x * blockDim.x) {
+            const unsigned row = i / (unsigned)chunks;
             const int c = (int)(i - row * chunks);
-            const int b = (int)(row / h), y = (int)(row - (long long)b * h);
+            const int b = (int)(row / (unsigned)h), y = (int)(row - (unsigned)b * (unsigned)h);
             const uint4 v = va_ld_stream16(in + (size_t)b * in_fstride + (size_t)y * in_pitch + 16 * c);
             va_st_stream16(out + (size_t)b * out_fstride + (size_t)y * out_pitch + 16 * c, v);
         }
     } else {
-        const long long total = rows * row_bytes;
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-             i += (long long)gridDim.x * blockDim.x) {
-            const long long row = i / row_bytes;
+        const unsigned total = (unsigned)(rows * row_bytes);
+        for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total;
+             i += gridDim.x * blockDim.x) {
+            const unsigned row = i / (unsigned)row_bytes;
             const int c = (int)(i - row * row_bytes);
-            const int b = (int)(row / h), y = (int)(row - (long long)b * h);
+            const int b = (int)(row / (unsigned)h), y = (int)(row - (unsigned)b * (unsigned)h);
             out[(size_t)b * out_fstride + (size_t)y * out_pitch + c] =
                 in[(size_t)b * in_fstride + (size_t)y * in_pitch + c];
         }
@@ -217,12 +217,12 @@ resize_half_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fs
     // one item = 4 output bytes of one output row (channels == 1, vec) or 1 output byte
     if (vec) {
         const int groups = ow >> 2;
-        const long long total = (long long)groups * oh * batch;
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-             i += (long long)gridDim.x * blockDim.x) {
-            const long long row = i / groups;
+        const unsigned total = (unsigned)((long long)groups * oh * batch);
+        for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total;
+             i += gridDim.x * blockDim.x) {
+            const unsigned row = i / (unsigned)groups;
             const int g = (int)(i - row * groups);
-            const int b = (int)(row / oh), y = (int)(row - (long long)b * oh);
+            const int b = (int)(row / (unsigned)oh), y = (int)(row - (unsigned)b * (unsigned)oh);
             const uint8_t *p = in + (size_t)b * in_fstride + (size_t)(2 * y) * in_pitch + 8 * g;
             const uint2 r0 = *reinterpret_cast<const uint2 *>(p);
             const uint2 r1 = *reinterpret_cast<const uint2 *>(p + in_pitch);
@@ -238,13 +238,13 @@ resize_half_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fs
         }
     } else {
         const int orow = ow * channels;
-        const long long total = (long long)orow * oh * batch;
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-             i += (long long)gridDim.x * blockDim.x) {
-            const long long row = i / orow;
+        const unsigned total = (unsigned)((long long)orow * oh * batch);
+        for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total;
+             i += gridDim.x * blockDim.x) {
+            const unsigned row = i / (unsigned)orow;
             const int xb = (int)(i - row * orow);
             const int x = xb / channels, c = xb - x * channels;
-            const int b = (int)(row / oh), y = (int)(row - (long long)b * oh);
+            const int b = (int)(row / (unsigned)oh), y = (int)(row - (unsigned)b * (unsigned)oh);
             const uint8_t *p = in + (size_t)b * in_fstride + (size_t)(2 * y) * in_pitch + (size_t)(2 * x) * channels + c;
             const unsigned s = (unsigned)p[0] + p[channels] + p[in_pitch] + p[in_pitch + channels] + 2u;
             out[(size_t)b * out_fstride + (size_t)y * out_pitch + xb] = (uint8_t)(s >> 2);
@@ -281,12 +281,12 @@ apply_mask_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fst
                   int w, int h, int channels, int batch, int vec) {
     if (vec) {   // channels == 1: 16 pixels per item
         const int chunks = w >> 4;
-        const long long total = (long long)chunks * h * batch;
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-             i += (long long)gridDim.x * blockDim.x) {
-            const long long row = i / chunks;
+        const unsigned total = (unsigned)((long long)chunks * h * batch);
+        for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total;
+             i += gridDim.x * blockDim.x) {
+            const unsigned row = i / (unsigned)chunks;
             const int c = (int)(i - row * chunks);
-            const int b = (int)(row / h), y = (int)(row - (long long)b * h);
+            const int b = (int)(row / (unsigned)h), y = (int)(row - (unsigned)b * (unsigned)h);
             uint4 v = va_ld_stream16(in + (size_t)b * in_fstride + (size_t)y * in_pitch + 16 * c);
             const uint4 m = *reinterpret_cast<const uint4 *>(mask + (size_t)b * mask_fstride + (size_t)y * mask_pitch + 16 * c);
             // per-byte mask != 0 -> 0xFF: ((m | (0x80 - m)... ) use carry-free trick on 7 low bits
@@ -297,13 +297,13 @@ apply_mask_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fst
         }
     } else {
         const int rowb = w * channels;
-        const long long total = (long long)rowb * h * batch;
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-             i += (long long)gridDim.x * blockDim.x) {
-            const long long row = i / rowb;
+        const unsigned total = (unsigned)((long long)rowb * h * batch);
+        for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total;
+             i += gridDim.x * blockDim.x) {
+            const unsigned row = i / (unsigned)rowb;
             const int xb = (int)(i - row * rowb);
             const int x = xb / channels;
-            const int b = (int)(row / h), y = (int)(row - (long long)b * h);
+            const int b = (int)(row / (unsigned)h), y = (int)(row - (unsigned)b * (unsigned)h);
             const uint8_t m = mask[(size_t)b * mask_fstride + (size_t)y * mask_pitch + x];
             const uint8_t v = in[(size_t)b * in_fstride + (size_t)y * in_pitch + xb];
             out[(size_t)b * out_fstride + (size_t)y * out_pitch + xb] = m ? v : (uint8_t)0;
@@ -359,12 +359,12 @@ threshold_bits_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     const int chunks = (w + 511) >> 9;                       // 512-pixel chunks per row
-    const long long total = (long long)chunks * h * batch;
-    for (long long i = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); i < total;
-         i += (long long)gridDim.x * warps_per_block) {
-        const long long row = i / chunks;
+    const unsigned total = (unsigned)((long long)chunks * h * batch);
+    for (unsigned i = blockIdx.x * warps_per_block + (threadIdx.x >> 5); i < total;
+         i += gridDim.x * warps_per_block) {
+        const unsigned row = i / (unsigned)chunks;
         const int c = (int)(i - row * chunks);
-        const int b = (int)(row / h), y = (int)(row - (long long)b * h);
+        const int b = (int)(row / (unsigned)h), y = (int)(row - (unsigned)b * (unsigned)h);
         const uint8_t *rp = in + (size_t)b * in_fstride + (size_t)y * in_pitch;
         const int x = c * 512 + lane * 16;
         const uint4 v = va_load16_u8(rp, x, w, vec != 0);
@@ -417,12 +417,12 @@ unpack_bits_kernel(const uint32_t *__restrict__ mask, size_t mask_pitch_w, size_
                    int w, int h, int batch, int vec) {
     // one item = 16 pixels
     const int chunks = (w + 15) >> 4;
-    const long long total = (long long)chunks * h * batch;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const long long row = i / chunks;
+    const unsigned total = (unsigned)((long long)chunks * h * batch);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += gridDim.x * blockDim.x) {
+        const unsigned row = i / (unsigned)chunks;
         const int c = (int)(i - row * chunks);
-        const int b = (int)(row / h), y = (int)(row - (long long)b * h);
+        const int b = (int)(row / (unsigned)h), y = (int)(row - (unsigned)b * (unsigned)h);
         const unsigned word = mask[(size_t)b * mask_fstride_w + (size_t)y * mask_pitch_w + (c >> 1)];
         const unsigned m = (word >> ((c & 1) * 16)) & 0xFFFFu;
         unsigned v[4];
@@ -477,11 +477,11 @@ __global__ void __launch_bounds__(256)
 synth_rgb_kernel(uint8_t *__restrict__ out, size_t out_pitch, size_t out_fstride,
                  int w, int h, int t0, int batch, unsigned seed, unsigned kbase, SynthBlobs blobs) {
     // one item = one pixel (3 bytes)
-    const long long total = (long long)w * h * batch;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int b = (int)(i / ((long long)w * h));
-        const int p = (int)(i - (long long)b * w * h);
+    const unsigned total = (unsigned)((long long)w * h * batch);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += gridDim.x * blockDim.x) {
+        const int b = (int)(i / (unsigned)(w * h));
+        const int p = (int)(i - (unsigned)b * (unsigned)(w * h));
         const int y = p / w, x = p - y * w;
         const int t = t0 + b;
         const unsigned kt = va_mix32(seed ^ ((unsigned)(t + 1) * 0x9E3779B9u));
