@@ -68,10 +68,25 @@ __device__ __forceinline__ int lab_find(const int *parent, int x) {
     while ((p = va_ld_cg(parent + x)) != x && p >= 0) x = p;
     return x;
 }
+// find with path halving, used while trees are still being hooked (kernel B).  Rows are
+// merged concurrently in no particular order, which would otherwise grow chains as long as a
+// component is tall.  Halving only rewrites non-root nodes with one of their ancestors
+// (parent values only ever decrease), and a hook is only trusted when atomicMin saw a root,
+// so the plain store cannot lose an equivalence.
+__device__ __forceinline__ int lab_find_halve(int *parent, int x) {
+    int p = va_ld_cg(parent + x);
+    while (p != x) {
+        const int gp = va_ld_cg(parent + p);
+        if (gp != p) parent[x] = gp;
+        x = p;
+        p = gp;
+    }
+    return x;
+}
 __device__ __forceinline__ void lab_union(int *parent, int a, int b) {
     while (true) {
-        a = lab_find(parent, a);
-        b = lab_find(parent, b);
+        a = lab_find_halve(parent, a);
+        b = lab_find_halve(parent, b);
         if (a == b) return;
         if (a < b) { const int t = a; a = b; b = t; }
         const int old = atomicMin(parent + a, b);
