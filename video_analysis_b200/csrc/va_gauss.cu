@@ -92,8 +92,8 @@ template <int RT, bool FUSE_LUMA>
 __global__ void __launch_bounds__(GAUSS_THREADS)
 gauss_fast_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstride,
                   uint8_t *__restrict__ out, size_t out_pitch, size_t out_fstride,
-                  int w, int h, int mode, int TH, int tiles_x, int tiles_y, int n_tiles,
-                  int vec_in, const __grid_constant__ GaussFast g) {
+                  int w, int h, int mode, int TH, int vec_in, const __grid_constant__ GaussFast g) {
+    // grid = (tiles in x, tiles in y, frames): one 128 x TH tile per CTA
     VA_DYN_SMEM(uint8_t, smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int r = RT ? RT : g.r;
@@ -108,143 +108,145 @@ gauss_fast_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fst
     uint8_t *s8 = smem;
     unsigned *hp = reinterpret_cast<unsigned *>(smem + (size_t)R * SW);   // [R/2][TW] u16 pairs
     const bool out_words = (((uintptr_t)out | out_pitch | out_fstride) & 3) == 0;
-    const int tiles_per_frame = tiles_x * tiles_y;
 
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int b = tile / tiles_per_frame;
-        const int rem = tile - b * tiles_per_frame;
-        const int tyi = rem / tiles_x;
-        const int tx0 = (rem - tyi * tiles_x) * GAUSS_TW;
-        const int ty0 = tyi * TH;
-        const uint8_t *fin = in + (size_t)b * in_fstride;
+    const int tx0 = blockIdx.x * GAUSS_TW;
+    const int ty0 = blockIdx.y * TH;
+    const uint8_t *fin = in + (size_t)blockIdx.z * in_fstride;
+    // image columns the row pass really reads for this tile (anything else is staged as 0)
+    const int need_lo = tx0 - r, need_hi = tx0 + GAUSS_TW + r;
 
-        // ---- stage the tile (+ halo): only the staged words the row pass will read
-        if (!FUSE_LUMA) {
-            const int c0 = WOFS >> 2;                              // first / last+1 16-byte chunk
-            const int c1 = (WOFS + NWORDS + 3) >> 2;
-            const int NCH = c1 - c0;
-            for (int it = tid; it < R * NCH; it += GAUSS_THREADS) {
-                const int tr = it / NCH, c = c0 + (it - tr * NCH);
-                const int gy = gauss_reflect_fast(ty0 + tr - r, h);
-                const uint8_t *rp = fin + (size_t)gy * in_pitch;
-                const int gx0 = tx0 - R16 + 16 * c;
-                uint8_t *d = s8 + tr * SW + 16 * c;
-                if (vec_in && gx0 >= 0 && gx0 + 16 <= w) {
-                    va_cp_async16(d, rp + gx0);
-                } else {
-                    unsigned v[4] = {0, 0, 0, 0};
+    // ---- stage the tile (+ halo): only the staged words the row pass will read
+    if (!FUSE_LUMA) {
+        const int c0 = WOFS >> 2;                              // first / last+1 16-byte chunk
+        const int c1 = (WOFS + NWORDS + 3) >> 2;
+        const int NCH = c1 - c0;
+        for (int it = tid; it < R * NCH; it += GAUSS_THREADS) {
+            const int tr = it / NCH, c = c0 + (it - tr * NCH);
+            const int gy = gauss_reflect_fast(ty0 + tr - r, h);
+            const uint8_t *rp = fin + (size_t)gy * in_pitch;
+            const int gx0 = tx0 - R16 + 16 * c;
+            uint8_t *d = s8 + tr * SW + 16 * c;
+            if (vec_in && gx0 >= 0 && gx0 + 16 <= w) {
+                va_cp_async16(d, rp + gx0);
+            } else {
+                unsigned v[4] = {0, 0, 0, 0};
 #pragma unroll
-                    for (int i = 0; i < 16; i++)
-                        v[i >> 2] |= (unsigned)rp[gauss_reflect_fast(gx0 + i, w)] << (8 * (i & 3));
-                    *reinterpret_cast<uint4 *>(d) = make_uint4(v[0], v[1], v[2], v[3]);
+                for (int i = 0; i < 16; i++) {
+                    const int gx = gx0 + i;
+                    if (gx >= need_lo && gx < need_hi)
+                        v[i >> 2] |= (unsigned)rp[gauss_reflect_fast(gx, w)] << (8 * (i & 3));
+                }
+                *reinterpret_cast<uint4 *>(d) = make_uint4(v[0], v[1], v[2], v[3]);
+            }
+        }
+        va_cp_async_wait_all();
+    } else {
+        // 8 pixels (24 bytes of RGB) per item -> two staged words, starting at an even word;
+        // 4 items per thread per round so that all global loads are issued before the first use
+        const int U0 = WOFS & ~1;
+        const int NG = (WOFS - U0 + 32 + NW + 1) >> 1;
+        const int total = R * NG;
+        for (int it0 = tid; it0 < total; it0 += 4 * GAUSS_THREADS) {
+            uint2 q[4][3];
+            bool fastp[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int it = it0 + k * GAUSS_THREADS;
+                const int tr = it / NG, u = U0 + 2 * (it - tr * NG);
+                const int gx0 = tx0 - R16 + 4 * u;
+                fastp[k] = it < total && vec_in && gx0 >= 0 && gx0 + 8 <= w && ((gx0 & 7) == 0);
+                if (fastp[k]) {
+                    const int gy = gauss_reflect_fast(ty0 + tr - r, h);
+                    const uint2 *p = reinterpret_cast<const uint2 *>(fin + (size_t)gy * in_pitch + 3 * (size_t)gx0);
+                    q[k][0] = __ldg(p); q[k][1] = __ldg(p + 1); q[k][2] = __ldg(p + 2);
                 }
             }
-            va_cp_async_wait_all();
-        } else {
-            // 8 pixels (24 bytes of RGB) per item -> two staged words, starting at an even word
-            const int U0 = WOFS & ~1;
-            const int NG = (WOFS - U0 + 32 + NW + 1) >> 1;
-            // 4 items per thread per round: all global loads are issued before the first use
-            const int total = R * NG;
-            for (int it0 = tid; it0 < total; it0 += 4 * GAUSS_THREADS) {
-                uint2 q[4][3];
-                bool fastp[4];
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int it = it0 + k * GAUSS_THREADS;
-                    const int tr = it / NG, u = U0 + 2 * (it - tr * NG);
+            for (int k = 0; k < 4; k++) {
+                const int it = it0 + k * GAUSS_THREADS;
+                if (it >= total) break;
+                const int tr = it / NG, u = U0 + 2 * (it - tr * NG);
+                unsigned lo, hi;
+                if (fastp[k]) {
+                    lo = va_luma_x4(q[k][0].x, q[k][0].y, q[k][1].x, mode);
+                    hi = va_luma_x4(q[k][1].y, q[k][2].x, q[k][2].y, mode);
+                } else {
                     const int gx0 = tx0 - R16 + 4 * u;
-                    fastp[k] = it < total && vec_in && gx0 >= 0 && gx0 + 8 <= w && ((gx0 & 7) == 0);
-                    if (fastp[k]) {
-                        const int gy = gauss_reflect_fast(ty0 + tr - r, h);
-                        const uint2 *p = reinterpret_cast<const uint2 *>(fin + (size_t)gy * in_pitch + 3 * (size_t)gx0);
-                        q[k][0] = __ldg(p); q[k][1] = __ldg(p + 1); q[k][2] = __ldg(p + 2);
-                    }
-                }
+                    const uint8_t *rp = fin + (size_t)gauss_reflect_fast(ty0 + tr - r, h) * in_pitch;
+                    lo = hi = 0;
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int it = it0 + k * GAUSS_THREADS;
-                    if (it >= total) break;
-                    const int tr = it / NG, u = U0 + 2 * (it - tr * NG);
-                    unsigned lo, hi;
-                    if (fastp[k]) {
-                        lo = va_luma_x4(q[k][0].x, q[k][0].y, q[k][1].x, mode);
-                        hi = va_luma_x4(q[k][1].y, q[k][2].x, q[k][2].y, mode);
-                    } else {
-                        const int gx0 = tx0 - R16 + 4 * u;
-                        const uint8_t *rp = fin + (size_t)gauss_reflect_fast(ty0 + tr - r, h) * in_pitch;
-                        lo = hi = 0;
-#pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            lo |= va_luma_px(rp + 3 * (size_t)gauss_reflect_fast(gx0 + i, w), mode) << (8 * i);
-                            hi |= va_luma_px(rp + 3 * (size_t)gauss_reflect_fast(gx0 + 4 + i, w), mode) << (8 * i);
+                    for (int i = 0; i < 8; i++) {
+                        const int gx = gx0 + i;
+                        if (gx >= need_lo && gx < need_hi) {
+                            const unsigned v = va_luma_px(rp + 3 * (size_t)gauss_reflect_fast(gx, w), mode) << (8 * (i & 3));
+                            if (i < 4) lo |= v; else hi |= v;
                         }
                     }
-                    *reinterpret_cast<uint2 *>(s8 + tr * SW + 4 * u) = make_uint2(lo, hi);
                 }
+                *reinterpret_cast<uint2 *>(s8 + tr * SW + 4 * u) = make_uint2(lo, hi);
             }
         }
-        __syncthreads();
+    }
+    __syncthreads();
 
-        // ---- row pass: warp = row pair q, lane = 4-pixel group
-        for (int q = warp; q < (R >> 1); q += GAUSS_THREADS / 32) {
-            const unsigned *r0 = reinterpret_cast<const unsigned *>(s8 + (2 * q) * SW) + WOFS + lane;
-            const unsigned *r1 = reinterpret_cast<const unsigned *>(s8 + (2 * q + 1) * SW) + WOFS + lane;
-            unsigned a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0};
+    // ---- row pass: warp = row pair q, lane = 4-pixel group
+    for (int q = warp; q < (R >> 1); q += GAUSS_THREADS / 32) {
+        const unsigned *r0 = reinterpret_cast<const unsigned *>(s8 + (2 * q) * SW) + WOFS + lane;
+        const unsigned *r1 = reinterpret_cast<const unsigned *>(s8 + (2 * q + 1) * SW) + WOFS + lane;
+        unsigned a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0};
 #pragma unroll
-            for (int j = 0; j < NW; j++) {
-                const unsigned x0 = r0[j], x1 = r1[j];
+        for (int j = 0; j < NW; j++) {
+            const unsigned x0 = r0[j], x1 = r1[j];
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const unsigned c = g.cw[i][j];
-                    a0[i] = __dp4a(x0, c, a0[i]);
-                    a1[i] = __dp4a(x1, c, a1[i]);
-                }
+            for (int i = 0; i < 4; i++) {
+                const unsigned c = g.cw[i][j];
+                a0[i] = __dp4a(x0, c, a0[i]);
+                a1[i] = __dp4a(x1, c, a1[i]);
             }
-            *reinterpret_cast<uint4 *>(hp + q * GAUSS_TW + 4 * lane) =
-                make_uint4(__byte_perm(a0[0], a1[0], 0x5410), __byte_perm(a0[1], a1[1], 0x5410),
-                           __byte_perm(a0[2], a1[2], 0x5410), __byte_perm(a0[3], a1[3], 0x5410));
         }
-        __syncthreads();
+        *reinterpret_cast<uint4 *>(hp + q * GAUSS_TW + 4 * lane) =
+            make_uint4(__byte_perm(a0[0], a1[0], 0x5410), __byte_perm(a0[1], a1[1], 0x5410),
+                       __byte_perm(a0[2], a1[2], 0x5410), __byte_perm(a0[3], a1[3], 0x5410));
+    }
+    __syncthreads();
 
-        // ---- column pass: warp = output row pair yp, lane = 4-column group
-        {
-            const int x = tx0 + 4 * lane;
-            uint8_t *obase = out + (size_t)b * out_fstride + x;
-            for (int yp = warp; yp < (TH >> 1); yp += GAUSS_THREADS / 32) {
-                const int y = ty0 + 2 * yp;
-                if (x >= w || y >= h) continue;
-                unsigned acc[2][4];
+    // ---- column pass: warp = output row pair yp, lane = 4-column group
+    const int x = tx0 + 4 * lane;
+    if (x >= w) return;
+    const bool vec_store = out_words && x + 4 <= w;
+    uint8_t *op = out + (size_t)blockIdx.z * out_fstride + (size_t)(ty0 + 2 * warp) * out_pitch + x;
+    const size_t ostep = (size_t)(GAUSS_THREADS / 32) * 2 * out_pitch;
+    for (int yp = warp; yp < (TH >> 1); yp += GAUSS_THREADS / 32, op += ostep) {
+        const int y = ty0 + 2 * yp;
+        if (y >= h) break;
+        unsigned acc[2][4];
 #pragma unroll
-                for (int i = 0; i < 2; i++)
+        for (int i = 0; i < 2; i++)
 #pragma unroll
-                    for (int k = 0; k < 4; k++) acc[i][k] = 32768u;
-                const uint4 *col = reinterpret_cast<const uint4 *>(hp + yp * GAUSS_TW + 4 * lane);
+            for (int k = 0; k < 4; k++) acc[i][k] = 32768u;
+        const uint4 *col = reinterpret_cast<const uint4 *>(hp + yp * GAUSS_TW + 4 * lane);
 #pragma unroll
-                for (int j = 0; j < NP; j++) {
-                    const uint4 v = col[j * (GAUSS_TW >> 2)];
-                    const unsigned c0 = g.cp[0][j], c1 = g.cp[1][j];
-                    acc[0][0] = __dp2a_lo(v.x, c0, acc[0][0]); acc[1][0] = __dp2a_lo(v.x, c1, acc[1][0]);
-                    acc[0][1] = __dp2a_lo(v.y, c0, acc[0][1]); acc[1][1] = __dp2a_lo(v.y, c1, acc[1][1]);
-                    acc[0][2] = __dp2a_lo(v.z, c0, acc[0][2]); acc[1][2] = __dp2a_lo(v.z, c1, acc[1][2]);
-                    acc[0][3] = __dp2a_lo(v.w, c0, acc[0][3]); acc[1][3] = __dp2a_lo(v.w, c1, acc[1][3]);
-                }
+        for (int j = 0; j < NP; j++) {
+            const uint4 v = col[j * (GAUSS_TW >> 2)];
+            const unsigned c0 = g.cp[0][j], c1 = g.cp[1][j];
+            acc[0][0] = __dp2a_lo(v.x, c0, acc[0][0]); acc[1][0] = __dp2a_lo(v.x, c1, acc[1][0]);
+            acc[0][1] = __dp2a_lo(v.y, c0, acc[0][1]); acc[1][1] = __dp2a_lo(v.y, c1, acc[1][1]);
+            acc[0][2] = __dp2a_lo(v.z, c0, acc[0][2]); acc[1][2] = __dp2a_lo(v.z, c1, acc[1][2]);
+            acc[0][3] = __dp2a_lo(v.w, c0, acc[0][3]); acc[1][3] = __dp2a_lo(v.w, c1, acc[1][3]);
+        }
 #pragma unroll
-                for (int i = 0; i < 2; i++) {
-                    if (y + i >= h) break;
-                    // byte 2 of every accumulator (sum + 32768 < 2^24) is the rounded result
-                    const unsigned res = __byte_perm(__byte_perm(acc[i][0], acc[i][1], 0x0062),
-                                                     __byte_perm(acc[i][2], acc[i][3], 0x0062), 0x5410);
-                    uint8_t *op = obase + (size_t)(y + i) * out_pitch;
-                    if (out_words && x + 4 <= w) {
-                        *reinterpret_cast<unsigned *>(op) = res;
-                    } else {
-                        for (int k = 0; k < 4 && x + k < w; k++) op[k] = (uint8_t)(res >> (8 * k));
-                    }
-                }
+        for (int i = 0; i < 2; i++) {
+            if (y + i >= h) break;
+            // byte 2 of every accumulator (sum + 32768 < 2^24) is the rounded result
+            const unsigned res = __byte_perm(__byte_perm(acc[i][0], acc[i][1], 0x0062),
+                                             __byte_perm(acc[i][2], acc[i][3], 0x0062), 0x5410);
+            uint8_t *o = op + (i ? out_pitch : 0);
+            if (vec_store) {
+                *reinterpret_cast<unsigned *>(o) = res;
+            } else {
+                for (int k = 0; k < 4 && x + k < w; k++) o[k] = (uint8_t)(res >> (8 * k));
             }
         }
-        __syncthreads();
     }
 }
 
@@ -372,11 +374,8 @@ static int gauss_launch(va_ctx *ctx, va_stream stream, const char *name, bool fu
         const size_t smem = (size_t)R * SW + (size_t)(R / 2) * GAUSS_TW * 4;
         VA_REQUIRE(ctx, smem <= 220 * 1024, "%s: tile does not fit in shared memory", name);
         const int tiles_x = va_div_up(w, GAUSS_TW), tiles_y = va_div_up(h, TH);
-        const int n_tiles = tiles_x * tiles_y * batch;
-        int ctas = (int)((220 * 1024) / (smem + 1024));
-        if (ctas > 6) ctas = 6;
-        if (ctas < 1) ctas = 1;
-        const int grid = va_grid(ctx, n_tiles, ctas);
+        VA_REQUIRE(ctx, tiles_y <= 65535 && batch <= 65535, "%s: too many tiles for one launch", name);
+        const dim3 grid(tiles_x, tiles_y, batch);
         const int vec_in = fuse ? (va_aligned(in, 8) && in_pitch % 8 == 0 && in_fstride % 8 == 0)
                                 : (va_aligned(in, 16) && in_pitch % 16 == 0 && in_fstride % 16 == 0);
 #define GAUSS_GO(RT, FUSE)                                                                                       \
@@ -385,7 +384,7 @@ static int gauss_launch(va_ctx *ctx, va_stream stream, const char *name, bool fu
             if (smem > 48 * 1024)                                                                                \
                 VA_CUDA(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             VA_LAUNCH(ctx, kfn, grid, GAUSS_THREADS, smem, stream, in, in_pitch, in_fstride, out, out_pitch,     \
-                      out_fstride, w, h, mode, TH, tiles_x, tiles_y, n_tiles, vec_in, g);                        \
+                      out_fstride, w, h, mode, TH, vec_in, g);                                                   \
         } while (0)
 #define GAUSS_CASE(RT) case RT: if (fuse) GAUSS_GO(RT, true); else GAUSS_GO(RT, false); break;
         switch (r) {

@@ -56,6 +56,15 @@ __device__ __forceinline__ int lab_run_start(unsigned wd, int bit, int word_inde
     return z ? 32 * word_index + (32 - __clz((int)z)) : st_in;
 }
 
+// all words of a row (up to 4096 pixels) are requested before the first one is used, so a
+// warp pays the memory latency once per row instead of once per 1024-pixel chunk
+#define LAB_PREFETCH(pre, row)                                                          \
+    unsigned pre[4];                                                                    \
+    _Pragma("unroll") for (int c_ = 0; c_ < 4; c_++) pre[c_] = lab_load_word(row, wpw, 32 * c_ + lane, lastmask)
+#define LAB_PICK(pre, base, row)                                                                   \
+    ((base) == 0 ? pre[0] : (base) == 32 ? pre[1] : (base) == 64 ? pre[2] : (base) == 96 ? pre[3] \
+                 : lab_load_word(row, wpw, (base) + lane, lastmask))
+
 // first pixels of the runs of a word; `pbit` = bit 31 of the word to the left
 __device__ __forceinline__ unsigned lab_run_starts(unsigned wd, unsigned pbit) {
     return wd & ~((wd << 1) | pbit);
@@ -109,8 +118,9 @@ label_init_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
         const uint32_t *mr = mask + (size_t)b * mfw + (size_t)y * mpw;
         int *pr = parent + (size_t)b * pf + ((size_t)y << LOG);
         unsigned prev_top = 0;     // bit 31 of the word before the chunk
+        LAB_PREFETCH(pre, mr);
         for (int base = 0; base < wpw; base += 32) {
-            const unsigned wd = lab_load_word(mr, wpw, base + lane, lastmask);
+            const unsigned wd = LAB_PICK(pre, base, mr);
             if (!__any_sync(FULL, wd != 0u)) { prev_top = 0; continue; }
             const unsigned pw = __shfl_up_sync(FULL, wd, 1);
             unsigned starts = lab_run_starts(wd, lane ? (pw >> 31) : prev_top);
@@ -163,13 +173,15 @@ label_merge_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
         int carry_c = 0, carry_u = 0, carry_l = 0, carry_r = 0;
         unsigned ovp0 = 0, ovpl = 0, ovpr = 0;          // bit 31 of the overlap word before the chunk
         unsigned up_prev_top = 0;                        // bit 31 of the up word before the chunk
+        LAB_PREFETCH(prec, mc);
+        LAB_PREFETCH(preu, mu);
         for (int base = 0; base < wpw; base += 32) {
-            const unsigned cur = lab_load_word(mc, wpw, base + lane, lastmask);
-            const unsigned up = lab_load_word(mu, wpw, base + lane, lastmask);
+            const unsigned cur = LAB_PICK(prec, base, mc);
+            const unsigned up = LAB_PICK(preu, base, mu);
             if (base == 0) up_bit0 = (__shfl_sync(FULL, up, 0) & 1u) != 0;
             // nothing can be merged in this chunk unless both rows have foreground in or next to it
             // (8-connectivity: the first pixel of the next chunk of the row above also counts)
-            const unsigned nxt = conn8 ? lab_load_word(mu, wpw, base + 32, lastmask) : 0u;
+            const unsigned nxt = conn8 ? __shfl_sync(FULL, LAB_PICK(preu, base + 32, mu), 0) : 0u;
             const bool any_cur = __any_sync(FULL, cur != 0u);
             const bool any_up = __any_sync(FULL, up != 0u) || up_prev_top || (nxt & 1u);
             if (!any_cur || !any_up) {
@@ -265,8 +277,9 @@ label_flatten_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
         int *pr = parent + (size_t)b * pf;
         unsigned prev_top = 0;
         int nroots = 0;            // roots of this row seen so far (warp-uniform)
+        LAB_PREFETCH(pre, mr);
         for (int base = 0; base < wpw; base += 32) {
-            const unsigned wd = lab_load_word(mr, wpw, base + lane, lastmask);
+            const unsigned wd = LAB_PICK(pre, base, mr);
             if (!__any_sync(FULL, wd != 0u)) { prev_top = 0; continue; }
             const unsigned pw = __shfl_up_sync(FULL, wd, 1);
             const unsigned starts = lab_run_starts(wd, lane ? (pw >> 31) : prev_top);
@@ -351,8 +364,9 @@ label_write_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
         const int *ro = rowoff + (size_t)b * h;
         int32_t *lr = labels + (size_t)b * lfe + (size_t)y * lpe;
         int carry = 0;
+        LAB_PREFETCH(pre, mr);
         for (int base = 0; base < wpw; base += 32) {
-            const unsigned wd = lab_load_word(mr, wpw, base + lane, lastmask);
+            const unsigned wd = LAB_PICK(pre, base, mr);
             const int nwords = min(32, wpw - base);
             if (!__any_sync(FULL, wd != 0u)) {
                 // background only: zeros straight to memory
@@ -431,7 +445,7 @@ extern "C" int va_label_bits(va_ctx *ctx, va_stream stream,
     while (((size_t)1 << LOG) < ctx->lab_pitch) LOG++;
     const size_t pf = ctx->lab_pitch * (size_t)ctx->max_h;
     const int rows = h * batch;
-    const int grid = va_grid(ctx, (rows + LAB_WARPS - 1) / LAB_WARPS, 8);
+    const int grid = (int)((rows + LAB_WARPS - 1) / LAB_WARPS);      // one row per warp, scheduled by the hardware
     int *parent = ctx->lab_parent;
     int *rowcnt = ctx->lab_rowcnt;
     { auto k = label_init_kernel;
