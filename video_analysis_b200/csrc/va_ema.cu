@@ -59,7 +59,7 @@ __device__ __forceinline__ void ema_issue(unsigned *slot, const uint8_t *rp, int
     if (fast) {
         if (PX == 16) va_cp_async16(slot, rp + x);
         else va_cp_async4(slot, rp + x);
-    } else {
+    } else if (x < w) {          // ragged row end / unaligned input: bytewise (lanes beyond the row do nothing)
         unsigned v[PX / 4];
         ema_load<PX>(rp, x, w, false, v);
 #pragma unroll

@@ -119,6 +119,7 @@ label_init_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
         int *pr = parent + (size_t)b * pf + ((size_t)y << LOG);
         unsigned prev_top = 0;     // bit 31 of the word before the chunk
         LAB_PREFETCH(pre, mr);
+        if (wpw <= 128 && !__any_sync(FULL, (pre[0] | pre[1] | pre[2] | pre[3]) != 0u)) continue;   // empty row
         for (int base = 0; base < wpw; base += 32) {
             const unsigned wd = LAB_PICK(pre, base, mr);
             if (!__any_sync(FULL, wd != 0u)) { prev_top = 0; continue; }
@@ -175,6 +176,10 @@ label_merge_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
         unsigned up_prev_top = 0;                        // bit 31 of the up word before the chunk
         LAB_PREFETCH(prec, mc);
         LAB_PREFETCH(preu, mu);
+        // a row can only be merged with the one above if both have foreground at all
+        if (wpw <= 128 && (!__any_sync(FULL, (prec[0] | prec[1] | prec[2] | prec[3]) != 0u) ||
+                           !__any_sync(FULL, (preu[0] | preu[1] | preu[2] | preu[3]) != 0u)))
+            continue;
         for (int base = 0; base < wpw; base += 32) {
             const unsigned cur = LAB_PICK(prec, base, mc);
             const unsigned up = LAB_PICK(preu, base, mu);
@@ -278,6 +283,10 @@ label_flatten_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
         unsigned prev_top = 0;
         int nroots = 0;            // roots of this row seen so far (warp-uniform)
         LAB_PREFETCH(pre, mr);
+        if (wpw <= 128 && !__any_sync(FULL, (pre[0] | pre[1] | pre[2] | pre[3]) != 0u)) {   // empty row
+            if (lane == 0) rowcnt[row] = 0;
+            continue;
+        }
         for (int base = 0; base < wpw; base += 32) {
             const unsigned wd = LAB_PICK(pre, base, mr);
             if (!__any_sync(FULL, wd != 0u)) { prev_top = 0; continue; }
