@@ -222,6 +222,7 @@ def gpu_arm(args):
     if world > 1:
         from video_analysis_b200.parallel import ShardedSegmentChain
         sharded = ShardedSegmentChain(chain)
+        sharded.reserve(K)
 
     def run_steps(first, n):
         if world > 1:

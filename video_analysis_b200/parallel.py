@@ -75,6 +75,15 @@ class ShardedSegmentChain(object):
         self._S = None
         self._scratch_mask = None
 
+    def reserve(self, n_batches):
+        """ allocate the blurred-frame storage of pass 1 up front (keeps cudaMalloc out of the hot loop) """
+        ch, rt = self.chain, self.chain.rt
+        while len(self._blurs) < n_batches:
+            self._blurs.append(rt.empty_u8(ch.batch, ch.h, ch.w))
+        if self._S is None:
+            self._S = rt.empty_f32(ch.h, ch.w)
+            self._S.zero_()
+
     def _partial_state(self, blurs):
         """ S of this rank from its blurred batches (device) """
         import torch.distributed as dist
@@ -111,8 +120,7 @@ class ShardedSegmentChain(object):
         labels_ring: list of label DeviceBatches reused round-robin; counts: int32 tensor. """
         ch, rt = self.chain, self.chain.rt
         # pass 1: blur (kept for pass 2) + partial state
-        while len(self._blurs) < len(rgb_batches):
-            self._blurs.append(rt.empty_u8(ch.batch, ch.h, ch.w))
+        self.reserve(len(rgb_batches))
         blurs = []
         for i, rgb in enumerate(rgb_batches):
             out = self._blurs[i] if rgb.n == ch.batch else _slice_batch(self._blurs[i], 0, rgb.n)
