@@ -357,8 +357,15 @@ def instrumented_pass(rt, chain, batch_of, labels, counts, Wm, K, B, N, hbm_peak
     per_kernel = {s: {'ms': round(avg[s], 4), 'share': round(avg[s] / step_ms, 3),
                       'alg_GBps': round(alg_bytes[s] * B / (avg[s] * 1e-3) / 1e9, 1),
                       'frac': round(alg_bytes[s] * B / (avg[s] * 1e-3) / 1e9 / hbm_peak, 3)} for s in stages}
+    traffic = None
+    try:        # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed ncu --set full capture
+        tr = json.load(open(os.path.join(ROOT, 'profiles', 'traffic_r1.json'))).get(dom)
+        if tr and tr.get('batch') == B:
+            traffic = int(tr['dram_bytes_read'] + tr['dram_bytes_write'])
+    except Exception:
+        pass
     return {'bound': 'hbm', 'kernel': dom, 'achieved': round(achieved, 1), 'peak': hbm_peak, 'unit': 'GB/s',
-            'frac': round(achieved / hbm_peak, 3), 'traffic': None, 'peak_source': peak_src,
+            'frac': round(achieved / hbm_peak, 3), 'traffic': traffic, 'peak_source': peak_src,
             'launch_ms': round(avg[dom], 4), 'alg_bytes_per_launch': int(alg_bytes[dom] * B),
             'per_kernel': per_kernel}
 
