@@ -141,50 +141,76 @@ gauss_fast_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fst
         }
         va_cp_async_wait_all();
     } else {
-        // 8 pixels (24 bytes of RGB) per item -> two staged words, starting at an even word;
-        // 4 items per thread per round so that all global loads are issued before the first use
-        const int U0 = WOFS & ~1;
-        const int NG = (WOFS - U0 + 32 + NW + 1) >> 1;
-        const int total = R * NG;
-        for (int it0 = tid; it0 < total; it0 += 4 * GAUSS_THREADS) {
-            uint2 q[4][3];
-            bool fastp[4];
+        // 8 pixels (24 bytes of RGB) per item -> two staged words.
+        // interior (the tile's own 128 columns): half a warp covers one row with 16 coalesced
+        // items, so there is no index arithmetic per item; three passes of loads are in flight
+        const int IW = R16 >> 2;                                  // staged word of tile column 0
+        const int half = lane >> 4, li = lane & 15;
+        const bool tile_inside = vec_in && tx0 + GAUSS_TW <= w;   // warp-uniform
+        const int gxi = tx0 + 8 * li;
+        for (int tr0 = 2 * warp + half; tr0 < R; tr0 += 3 * 2 * (GAUSS_THREADS / 32)) {
+            uint2 q[3][3];
+            if (tile_inside) {
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int it = it0 + k * GAUSS_THREADS;
-                const int tr = it / NG, u = U0 + 2 * (it - tr * NG);
-                const int gx0 = tx0 - R16 + 4 * u;
-                fastp[k] = it < total && vec_in && gx0 >= 0 && gx0 + 8 <= w && ((gx0 & 7) == 0);
-                if (fastp[k]) {
-                    const int gy = gauss_reflect_fast(ty0 + tr - r, h);
-                    const uint2 *p = reinterpret_cast<const uint2 *>(fin + (size_t)gy * in_pitch + 3 * (size_t)gx0);
-                    q[k][0] = __ldg(p); q[k][1] = __ldg(p + 1); q[k][2] = __ldg(p + 2);
+                for (int k = 0; k < 3; k++) {
+                    const int tr = tr0 + k * 2 * (GAUSS_THREADS / 32);
+                    if (tr < R) {
+                        const int gy = gauss_reflect_fast(ty0 + tr - r, h);
+                        const uint2 *p = reinterpret_cast<const uint2 *>(fin + (size_t)gy * in_pitch + 3 * (size_t)gxi);
+                        q[k][0] = __ldg(p); q[k][1] = __ldg(p + 1); q[k][2] = __ldg(p + 2);
+                    }
                 }
             }
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int it = it0 + k * GAUSS_THREADS;
-                if (it >= total) break;
-                const int tr = it / NG, u = U0 + 2 * (it - tr * NG);
+            for (int k = 0; k < 3; k++) {
+                const int tr = tr0 + k * 2 * (GAUSS_THREADS / 32);
+                if (tr >= R) break;
                 unsigned lo, hi;
-                if (fastp[k]) {
+                if (tile_inside) {
                     lo = va_luma_x4(q[k][0].x, q[k][0].y, q[k][1].x, mode);
                     hi = va_luma_x4(q[k][1].y, q[k][2].x, q[k][2].y, mode);
                 } else {
-                    const int gx0 = tx0 - R16 + 4 * u;
                     const uint8_t *rp = fin + (size_t)gauss_reflect_fast(ty0 + tr - r, h) * in_pitch;
                     lo = hi = 0;
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
-                        const int gx = gx0 + i;
-                        if (gx >= need_lo && gx < need_hi) {
+                        const int gx = gxi + i;
+                        if (gx < need_hi) {
                             const unsigned v = va_luma_px(rp + 3 * (size_t)gauss_reflect_fast(gx, w), mode) << (8 * (i & 3));
                             if (i < 4) lo |= v; else hi |= v;
                         }
                     }
                 }
-                *reinterpret_cast<uint2 *>(s8 + tr * SW + 4 * u) = make_uint2(lo, hi);
+                *reinterpret_cast<uint2 *>(s8 + tr * SW + 4 * (IW + 2 * li)) = make_uint2(lo, hi);
             }
+        }
+        // halo: HS items of 8 pixels on either side of every staged row
+        const int HS = (r + 7) >> 3;
+        for (int it = tid; it < R * 2 * HS; it += GAUSS_THREADS) {
+            const int tr = it / (2 * HS), k = it - tr * 2 * HS;
+            const bool right = k >= HS;
+            const int kk = right ? k - HS : k;
+            const int gx0 = right ? tx0 + GAUSS_TW + 8 * kk : tx0 - 8 * (kk + 1);
+            const int word = right ? IW + 32 + 2 * kk : IW - 2 * (kk + 1);
+            const uint8_t *rp = fin + (size_t)gauss_reflect_fast(ty0 + tr - r, h) * in_pitch;
+            unsigned lo, hi;
+            if (vec_in && gx0 >= 0 && gx0 + 8 <= w) {
+                const uint2 *p = reinterpret_cast<const uint2 *>(rp + 3 * (size_t)gx0);
+                const uint2 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2);
+                lo = va_luma_x4(q0.x, q0.y, q1.x, mode);
+                hi = va_luma_x4(q1.y, q2.x, q2.y, mode);
+            } else {
+                lo = hi = 0;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int gx = gx0 + i;
+                    if (gx >= need_lo && gx < need_hi) {
+                        const unsigned v = va_luma_px(rp + 3 * (size_t)gauss_reflect_fast(gx, w), mode) << (8 * (i & 3));
+                        if (i < 4) lo |= v; else hi |= v;
+                    }
+                }
+            }
+            *reinterpret_cast<uint2 *>(s8 + tr * SW + 4 * word) = make_uint2(lo, hi);
         }
     }
     __syncthreads();
@@ -359,12 +385,12 @@ static int gauss_launch(va_ctx *ctx, va_stream stream, const char *name, bool fu
             const char *env = getenv("VA_GAUSS_TH");
             const int forced = env ? atoi(env) : 0;
             double best = 1e30;
-            for (int th = 32; th <= 192; th += 8) {
+            for (int th = 32; th <= 192; th += 2) {
                 const int R = th + 2 * r;
                 const size_t sm = (size_t)R * SW + (size_t)(R / 2) * GAUSS_TW * 4;
                 if (sm > (r <= 16 ? 44 : 112) * 1024) break;   // keep >= 5 CTAs per SM for small radii
                 const int ty = va_div_up(h, th);
-                const double cost = ty * (1.3 * R + 8.0 * ((R / 2 + 7) / 8) * 1.0 + 10.0 * ((th / 2 + 7) / 8));
+                const double cost = ty * (11.0 * 16 * ((R + 15) / 16) + 10.0 * 16 * ((th + 15) / 16));   // staged rows + output rows, 16 per round
                 if (cost < best) { best = cost; TH = th; }
             }
             if (forced >= 8 && forced % 2 == 0) TH = forced;

@@ -83,11 +83,31 @@ __device__ __forceinline__ unsigned morph_hrun(unsigned prev, unsigned cur, unsi
 //   staged band are outside the image (the caller sizes the halo) and never win.
 // RECT: every row of the element has the same run, so the ky rows are combined first
 // (3 words each) and the horizontal run is evaluated once.
-template <bool ERODE, bool RECT>
+// KSQ > 0: odd square K x K element known at compile time (3x3, 5x5, 7x7): everything unrolled.
+// Every row the element touches is inside the staged band (the caller stages the halo, rows
+// outside the image hold the identity), so no range checks are needed.
+template <bool ERODE, bool RECT, int KSQ>
 __device__ __forceinline__ unsigned morph_word(const unsigned *src, int src_rows, int wpw, int sr, int j,
                                                const MorphSE &se) {
     const unsigned ident = ERODE ? 0xffffffffu : 0u;
     const bool has_p = j > 0, has_n = j + 1 < wpw;
+    if (KSQ > 0) {
+        constexpr int H = KSQ / 2;
+        const unsigned *row = src + (sr - H) * wpw + j;
+        unsigned p = ident, c = ident, n = ident;
+#pragma unroll
+        for (int i = 0; i < KSQ; i++, row += wpw) {
+            const unsigned vp = has_p ? row[-1] : ident, vc = row[0], vn = has_n ? row[1] : ident;
+            if (ERODE) { p &= vp; c &= vc; n &= vn; } else { p |= vp; c |= vc; n |= vn; }
+        }
+        unsigned acc = c;
+#pragma unroll
+        for (int d = 1; d <= H; d++) {
+            const unsigned r = __funnelshift_r(c, n, d), l = __funnelshift_l(p, c, d);
+            if (ERODE) acc &= r & l; else acc |= r | l;
+        }
+        return acc;
+    }
     if (RECT) {
         unsigned p = ident, c = ident, n = ident;
         int r0 = sr - se.ay, r1 = r0 + se.ky;
@@ -113,16 +133,16 @@ __device__ __forceinline__ unsigned morph_word(const unsigned *src, int src_rows
     return acc;
 }
 
-template <bool RECT>
+template <bool RECT, int KSQ>
 __device__ __forceinline__ unsigned morph_word_op(int erode, const unsigned *src, int src_rows, int wpw, int sr, int j,
                                                   const MorphSE &se) {
-    return erode ? morph_word<true, RECT>(src, src_rows, wpw, sr, j, se)
-                 : morph_word<false, RECT>(src, src_rows, wpw, sr, j, se);
+    return erode ? morph_word<true, RECT, KSQ>(src, src_rows, wpw, sr, j, se)
+                 : morph_word<false, RECT, KSQ>(src, src_rows, wpw, sr, j, se);
 }
 
 // first  : 0 erode, 1 dilate;  second: -1 none, 0 erode, 1 dilate
 // work split: warp = row of the band, lane = word of the row
-template <bool RECT>
+template <bool RECT, int KSQ>
 __global__ void __launch_bounds__(MORPH_THREADS)
 morph_bits_kernel(const uint32_t *__restrict__ in, size_t in_pitch_w, size_t in_fstride_w,
                   uint32_t *__restrict__ out, size_t out_pitch_w, size_t out_fstride_w,
@@ -170,7 +190,7 @@ morph_bits_kernel(const uint32_t *__restrict__ in, size_t in_pitch_w, size_t in_
             for (int rr = warp; rr < nrows; rr += NWARP) {
                 uint32_t *orow = fout + (size_t)(y0 + rr) * out_pitch_w;
                 for (int j = lane; j < wpw; j += 32) {
-                    unsigned v = morph_word_op<RECT>(first == 0, sa, rows_a, wpw, rr + up, j, se);
+                    unsigned v = morph_word_op<RECT, KSQ>(first == 0, sa, rows_a, wpw, rr + up, j, se);
                     if (j == wpw - 1) v &= lastmask;
                     orow[j] = v;
                 }
@@ -185,7 +205,7 @@ morph_bits_kernel(const uint32_t *__restrict__ in, size_t in_pitch_w, size_t in_
                 for (int j = lane; j < wpw; j += 32) {
                     unsigned v = id2;
                     if (inside) {
-                        v = morph_word_op<RECT>(first == 0, sa, rows_a, wpw, rr + up, j, se);
+                        v = morph_word_op<RECT, KSQ>(first == 0, sa, rows_a, wpw, rr + up, j, se);
                         if (j == wpw - 1) v = second == 0 ? (v | ~lastmask) : (v & lastmask);
                     }
                     sb[rr * wpw + j] = v;
@@ -195,7 +215,7 @@ morph_bits_kernel(const uint32_t *__restrict__ in, size_t in_pitch_w, size_t in_
             for (int rr = warp; rr < nrows; rr += NWARP) {
                 uint32_t *orow = fout + (size_t)(y0 + rr) * out_pitch_w;
                 for (int j = lane; j < wpw; j += 32) {
-                    unsigned v = morph_word_op<RECT>(second == 0, sb, rows_b, wpw, rr + up, j, se);
+                    unsigned v = morph_word_op<RECT, KSQ>(second == 0, sb, rows_b, wpw, rr + up, j, se);
                     if (j == wpw - 1) v &= lastmask;
                     orow[j] = v;
                 }
@@ -234,18 +254,19 @@ extern "C" int va_morph_bits(va_ctx *ctx, va_stream stream,
     bool rect = true;
     for (int i = 1; i < ky; i++) rect = rect && se.a[i] == se.a[0] && se.b[i] == se.b[0];
     const int grid = va_grid(ctx, n_bands, 8);
-    if (rect) {
-        auto kfn = morph_bits_kernel<true>;
-        if (smem > 48 * 1024)
-            VA_CUDA(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        VA_LAUNCH(ctx, kfn, grid, MORPH_THREADS, smem, stream, in, in_pitch_w, in_fstride_w, out, out_pitch_w, out_fstride_w,
-                  w, h, bands_per_frame, n_bands, first, second, se);
-    } else {
-        auto kfn = morph_bits_kernel<false>;
-        if (smem > 48 * 1024)
-            VA_CUDA(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        VA_LAUNCH(ctx, kfn, grid, MORPH_THREADS, smem, stream, in, in_pitch_w, in_fstride_w, out, out_pitch_w, out_fstride_w,
-                  w, h, bands_per_frame, n_bands, first, second, se);
-    }
+#define MORPH_GO(RECT, KSQ)                                                                                       \
+    do {                                                                                                          \
+        auto kfn = morph_bits_kernel<RECT, KSQ>;                                                                  \
+        if (smem > 48 * 1024)                                                                                     \
+            VA_CUDA(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+        VA_LAUNCH(ctx, kfn, grid, MORPH_THREADS, smem, stream, in, in_pitch_w, in_fstride_w, out, out_pitch_w,    \
+                  out_fstride_w, w, h, bands_per_frame, n_bands, first, second, se);                              \
+    } while (0)
+    if (rect && kx == ky && kx == 3) MORPH_GO(true, 3);
+    else if (rect && kx == ky && kx == 5) MORPH_GO(true, 5);
+    else if (rect && kx == ky && kx == 7) MORPH_GO(true, 7);
+    else if (rect) MORPH_GO(true, 0);
+    else MORPH_GO(false, 0);
+#undef MORPH_GO
     return VA_OK;
 }
