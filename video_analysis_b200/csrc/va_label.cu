@@ -16,10 +16,11 @@
 //   A init     parent[s] = s for every run start s
 //   B merge    for every maximal overlap segment between a run in row y and one in row
 //              y-1: union(run start, run start)        (atomicMin hooking)
-//   C flatten  parent[s] = root(s) for every other run start; the k-th root of a row
-//              (k = 1, 2, ... in x order) gets parent = -k; roots per row are counted
+//   C rank     the k-th root of a row (k = 1, 2, ... in x order) gets parent = -k; roots per
+//              row are counted (no pointer chasing here: a root is a run start that is still
+//              its own parent)
 //   D scan     exclusive prefix of the per-row root counts (one CTA per frame) -> n
-//   G write    label(run) = rowoff[row of its root] + k; one forest lookup per run, the
+//   G write    label(run) = rowoff[row of its root] + k; one walk to the root per run, the
 //              labels of a 1024-pixel chunk are assembled in a per-warp shared-memory slab
 //              and leave as 16-byte stores (512 contiguous bytes per warp instruction)
 // Algorithmic HBM bytes per frame: N/8 (mask) + 4N (labels).
@@ -155,7 +156,7 @@ __device__ __forceinline__ void lab_merge_probe(int *pr, unsigned cur, int cur_s
     }
 }
 
-__global__ void __launch_bounds__(LAB_THREADS)
+__global__ void __launch_bounds__(LAB_THREADS, 8)
 label_merge_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
                    int *__restrict__ parent, int LOG, size_t pf, int w, int h, int batch, int conn8) {
     const int lane = threadIdx.x & 31;
@@ -298,9 +299,7 @@ label_flatten_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
                 const int bit = __ffs((int)s) - 1;
                 s &= s - 1;
                 const int idx = (y << LOG) + 32 * (base + lane) + bit;
-                const int root = lab_find(pr, idx);
-                if (root == idx) rootbits |= 1u << bit;
-                else pr[idx] = root;
+                if (pr[idx] == idx) rootbits |= 1u << bit;        // still its own parent after all merges: a root
             }
             // rank of my roots among the row's roots, x order
             const int mine = __popc(rootbits);
@@ -401,10 +400,12 @@ label_write_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
                 const unsigned t = ~(wd >> bit);
                 const int ones = t ? __ffs((int)t) - 1 : 32;
                 const int start_x = bit == 0 ? st_in : 32 * (base + lane) + bit;
+                // walk to the root: every root holds -k (kernel C), nothing else is negative; the
+                // forest is final, so ordinary cached loads are fine and chains are short (halving)
+                int idx = (y << LOG) + start_x;
                 int p = pr[start_x];
-                int ry = y;
-                if (p >= 0) { ry = p >> LOG; p = pf_[p]; }        // not a root: hop to the root
-                const int lab = ro[ry] - p;                        // p == -k
+                while (p >= 0) { idx = p; p = pf_[idx]; }
+                const int lab = ro[idx >> LOG] - p;                // p == -k
                 const int p0 = 32 * lane + bit;
                 for (int k = 0; k < ones; k++) slab[LAB_SKEW(p0 + k)] = lab;
                 rem &= ~((ones >= 32 ? FULL : ((1u << ones) - 1u)) << bit);
