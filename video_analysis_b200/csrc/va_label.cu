@@ -156,19 +156,31 @@ __device__ __forceinline__ void lab_merge_probe(int *pr, unsigned cur, int cur_s
     }
 }
 
-// merges row y (words `prec`, rest of the row at mc) with row y - 1 (`preu`, mu)
-__device__ __forceinline__ void lab_merge_row(const unsigned (&prec)[4], const unsigned (&preu)[4],
-                                              const uint32_t *mc, const uint32_t *mu, int *pr, int y, int LOG,
-                                              int wpw, unsigned lastmask, int lane, int conn8) {
+__global__ void __launch_bounds__(LAB_THREADS, 8)
+label_merge_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
+                   int *__restrict__ parent, int LOG, size_t pf, int w, int h, int batch, int conn8) {
+    const int lane = threadIdx.x & 31;
+    const int wpw = (w + 31) >> 5;
+    const unsigned lastmask = (w & 31) ? ((1u << (w & 31)) - 1u) : FULL;
+    const int rows = h * batch;
+    for (int row = blockIdx.x * LAB_WARPS + (threadIdx.x >> 5); row < rows;
+         row += gridDim.x * LAB_WARPS) {
+        const int b = row / h, y = row - b * h;
+        if (y == 0) continue;
+        const uint32_t *mc = mask + (size_t)b * mfw + (size_t)y * mpw;
+        const uint32_t *mu = mc - mpw;
+        int *pr = parent + (size_t)b * pf;
         const int rowc = y << LOG, rowu = (y - 1) << LOG;
         bool up_bit0 = false;
         int carry_c = 0, carry_u = 0, carry_l = 0, carry_r = 0;
         unsigned ovp0 = 0, ovpl = 0, ovpr = 0;          // bit 31 of the overlap word before the chunk
         unsigned up_prev_top = 0;                        // bit 31 of the up word before the chunk
+        LAB_PREFETCH(prec, mc);
+        LAB_PREFETCH(preu, mu);
         // a row can only be merged with the one above if both have foreground at all
         if (wpw <= 128 && (!__any_sync(FULL, (prec[0] | prec[1] | prec[2] | prec[3]) != 0u) ||
                            !__any_sync(FULL, (preu[0] | preu[1] | preu[2] | preu[3]) != 0u)))
-            return;
+            continue;
         for (int base = 0; base < wpw; base += 32) {
             const unsigned cur = LAB_PICK(prec, base, mc);
             const unsigned up = LAB_PICK(preu, base, mu);
@@ -251,38 +263,6 @@ __device__ __forceinline__ void lab_merge_row(const unsigned (&prec)[4], const u
             up_prev_top = __shfl_sync(FULL, up, 31) >> 31;
             carry_c = __shfl_sync(FULL, ct, 31);
             carry_u = __shfl_sync(FULL, ut, 31);
-        }
-}
-
-// one warp merges LAB_RPW consecutive rows: the words of all LAB_RPW + 1 rows are requested up
-// front (one memory latency per group instead of one per row), then the rows are merged top down
-#define LAB_RPW 4
-__global__ void __launch_bounds__(LAB_THREADS, 4)
-label_merge_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
-                   int *__restrict__ parent, int LOG, size_t pf, int w, int h, int batch, int conn8) {
-    const int lane = threadIdx.x & 31;
-    const int wpw = (w + 31) >> 5;
-    const unsigned lastmask = (w & 31) ? ((1u << (w & 31)) - 1u) : FULL;
-    const int gpf = (h + LAB_RPW - 1) / LAB_RPW;          // row groups per frame
-    const int groups = gpf * batch;
-    for (int grp = blockIdx.x * LAB_WARPS + (threadIdx.x >> 5); grp < groups; grp += gridDim.x * LAB_WARPS) {
-        const int b = grp / gpf, y0 = (grp - b * gpf) * LAB_RPW;
-        const uint32_t *m0 = mask + (size_t)b * mfw + (size_t)y0 * mpw;
-        int *pr = parent + (size_t)b * pf;
-        unsigned rw[LAB_RPW + 1][4];
-#pragma unroll
-        for (int k = 0; k <= LAB_RPW; k++) {
-            const int y = y0 + k - 1;
-#pragma unroll
-            for (int c = 0; c < 4; c++)
-                rw[k][c] = (y >= 0 && y < h) ? lab_load_word(m0 + ((ptrdiff_t)k - 1) * (ptrdiff_t)mpw, wpw, 32 * c + lane, lastmask) : 0u;
-        }
-#pragma unroll
-        for (int k = 0; k < LAB_RPW; k++) {
-            const int y = y0 + k;
-            if (y >= 1 && y < h)
-                lab_merge_row(rw[k + 1], rw[k], m0 + (size_t)k * mpw, m0 + ((ptrdiff_t)k - 1) * (ptrdiff_t)mpw, pr, y, LOG,
-                              wpw, lastmask, lane, conn8);
         }
     }
 }
@@ -481,8 +461,7 @@ extern "C" int va_label_bits(va_ctx *ctx, va_stream stream,
     { auto k = label_init_kernel;
       VA_LAUNCH(ctx, k, grid, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, parent, LOG, pf, w, h, batch); }
     { auto k = label_merge_kernel;
-      const int ggrid = (int)(((long long)((h + 3) / 4) * batch + LAB_WARPS - 1) / LAB_WARPS);
-      VA_LAUNCH(ctx, k, ggrid, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, parent, LOG, pf, w, h, batch,
+      VA_LAUNCH(ctx, k, grid, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, parent, LOG, pf, w, h, batch,
                 connectivity == 8 ? 1 : 0); }
     { auto k = label_flatten_kernel;
       VA_LAUNCH(ctx, k, grid, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, parent, LOG, pf, rowcnt, w, h, batch); }
