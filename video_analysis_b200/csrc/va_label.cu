@@ -105,16 +105,6 @@ __device__ __forceinline__ void lab_union(int *parent, int a, int b) {
     }
 }
 
-// union of a run `a` of the current row with a run `b` of the row above (b < a).  `a` is almost
-// always still its own root, so the hook is attempted without reading parent[a] first: one
-// round trip to L2 less on the critical path of every merge.
-__device__ __forceinline__ void lab_union_down(int *parent, int a, int b) {
-    const int rb = lab_find_halve(parent, b);
-    const int old = atomicMin(parent + a, rb);          // rb <= b < a
-    if (old == a) return;                               // a was a root and now hangs under rb
-    lab_union(parent, old, rb);                         // a already had a parent: merge that tree with rb's
-}
-
 // ---- A: init -----------------------------------------------------------------------------
 __global__ void __launch_bounds__(LAB_THREADS)
 label_init_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
@@ -162,7 +152,7 @@ __device__ __forceinline__ void lab_merge_probe(int *pr, unsigned cur, int cur_s
         // undo the shift: probe(x) = up(x - dx)
         if (dx == 1) bq -= 1;
         else if (dx == -1) bq += (bq == 0 && up_bit0) ? 0 : 1;
-        lab_union_down(pr, rowc + a, rowu + bq);
+        lab_union(pr, rowc + a, rowu + bq);
     }
 }
 
