@@ -199,3 +199,43 @@ def test_full_size_properties_1080p():
     assert np.array_equal(blur.t[5, :, :W].cpu().numpy(), ops.blur(ops.mono(f5), 2))
     rl, rn = ops.label(o_u8[5, :, :W].cpu().numpy())
     assert rn == n and np.array_equal(lab[5].cpu().numpy(), rl)
+
+
+def test_config4_multi_stream_crop_mask_threshold_label():
+    """ BASELINE.json configs[3] at reduced stream count: independent camera streams batched on the
+    leading axis, per-stream crop rectangle and static mask, threshold, label (no background model) """
+    F, VideoMemory = mods()
+    W, H, T = 1280, 720, 6
+    rng = np.random.default_rng(7)
+    for stream in range(3):
+        frames = synth.make_frames(10 + stream, 0, T, W, H, 5)
+        rect = (int(rng.integers(0, 200)), int(rng.integers(0, 100)), 640 + 16 * stream, 360 + 8 * stream)
+        m = np.zeros((rect[3], rect[2]), np.uint8)
+        m[20:-30, 40:-10] = 1
+        chain = F.FilterLabel(F.FilterThreshold(F.FilterApplyMask(
+            F.FilterMonochrome(F.FilterCrop(VideoMemory(frames, copy_data=False), rect, batch=4)), m), 110))
+        got = np.stack(list(chain))
+        for t in range(T):
+            g = ops.apply_mask(ops.mono(ops.crop(frames[t], rect)), m)
+            lab, n = ops.label(g > 110)
+            assert chain.num_features[t] == n and np.array_equal(got[t], lab), (stream, t)
+
+
+def test_config5_stencil_heavy_chain_1080p():
+    """ BASELINE.json configs[4]: blur sigma=15 (91 taps), threshold, 7x7 close then open, resize 0.5x,
+    labelling of large regions -- two 1080p frames against the oracle """
+    F, VideoMemory = mods()
+    frames = synth.make_frames(2, 0, 2, 1920, 1080, 12)
+    v = VideoMemory(frames, copy_data=False)
+    blur = F.FilterBlur(F.FilterMonochrome(v, batch=2), sigma=15)
+    half = F.FilterResize(blur, 0.5)
+    chain = F.FilterLabel(F.FilterMorphology(F.FilterMorphology(F.FilterThreshold(half, 95), 'close', 'rect', 7), 'open', 'rect', 7))
+    got = np.stack(list(chain))
+    for t in range(2):
+        b = ops.resize(ops.blur(ops.mono(frames[t]), 15), 0.5)
+        mask = np.where(b > 95, 255, 0).astype(np.uint8)
+        mo = ops.morph(ops.morph(mask, 'close', 'rect', 7), 'open', 'rect', 7)
+        lab, n = ops.label(mo)
+        assert n >= 1 and chain.num_features[t] == n
+        assert np.array_equal(got[t], lab)
+    assert np.array_equal(np.stack(list(blur)), np.stack([ops.blur(ops.mono(f), 15) for f in frames]))
