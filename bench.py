@@ -229,7 +229,12 @@ def gpu_arm(args):
             sharded.run_device_range([batch_of(first + i) for i in range(n)], labels, counts)
         else:
             for i in range(n):
-                chain.run_device(batch_of(first + i), labels[i & 1], counts)
+                if args.no_overlap:
+                    chain.run_device(batch_of(first + i), labels[i & 1], counts)
+                else:       # front half of batch k+1 overlaps the labelling of batch k (two streams)
+                    chain.run_device_pipelined(batch_of(first + i), labels[i & 1], counts)
+            if not args.no_overlap:
+                chain.pipeline_sync()
 
     def barrier():
         if world > 1:
@@ -300,7 +305,8 @@ def gpu_arm(args):
             'config': {'workload': WORKLOAD, 'frames_per_step': B, 'resident_frames_per_gpu': n_frames,
                        'parallelism': 'frame-range shards x%d, EMA carry via NCCL all-gather' % world if world > 1 else 'single GPU',
                        'l2': 'every step reads a different %d MB batch of the resident video (>> 126 MB L2)' % (B * N * 3 >> 20),
-                       'fused_luma_blur': not args.no_fuse},
+                       'fused_luma_blur': not args.no_fuse,
+                       'two_stream_overlap': (not args.no_overlap) and world == 1},
             'clocks': clocks,
             'e2e': {'value': round(e2e_fps, 1), 'unit': 'frames/s', 'h2d_bytes_per_step': B * N * 3,
                     'd2h_bytes_per_step': B * N * 4 + B * 4, 'steps': Ke,
@@ -380,6 +386,7 @@ def main():
     ap.add_argument('--frames', type=int, default=10000, help='frames of the synthetic video per GPU')
     ap.add_argument('--e2e-steps', type=int, default=30)
     ap.add_argument('--no-fuse', action='store_true')
+    ap.add_argument('--no-overlap', action='store_true', help='one stream, one va_chain_run call per step')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

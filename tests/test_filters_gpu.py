@@ -239,3 +239,25 @@ def test_config5_stencil_heavy_chain_1080p():
         assert n >= 1 and chain.num_features[t] == n
         assert np.array_equal(got[t], lab)
     assert np.array_equal(np.stack(list(blur)), np.stack([ops.blur(ops.mono(f), 15) for f in frames]))
+
+
+def test_two_stream_pipelined_chain_equals_single_stream(frames, ref):
+    mods()
+    import torch
+    from video_analysis_b200.chain import SegmentChain
+    from video_analysis_b200.device import get_runtime
+    rt = get_runtime(0)
+    B = 8
+    ch = SegmentChain((320, 240), batch=B)
+    outs, cnts = [], []
+    for a in range(0, 40, B):
+        rgb = rt.upload(frames[a:a + B])
+        lab, cnt = rt.empty_i32(B, 240, 320), torch.empty((B,), dtype=torch.int32, device=rt.device)
+        ch.run_device_pipelined(rgb, lab, cnt)
+        outs.append(lab); cnts.append(cnt)
+    ch.pipeline_sync()
+    torch.cuda.synchronize()
+    got = np.concatenate([o.t[:, :, :320].cpu().numpy() for o in outs])
+    assert np.array_equal(got, ref['labels'])
+    assert np.array_equal(np.concatenate([c.cpu().numpy() for c in cnts]), ref['counts'])
+    assert np.array_equal(ch.background.view(np.uint32), ref['bg'].view(np.uint32))

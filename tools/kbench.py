@@ -120,6 +120,16 @@ def main():
             ch.run_device(s, l, counts)
         k_chain()
         report('chain fuse=%s' % fuse, (9.5 if fuse else 11.5) * N + 8 * N / B, k_chain)
+    ch = SegmentChain((W, H), sigma=a.sigma, morph_ksize=a.k, batch=B, fuse=True)
+
+    def k_pipe():
+        for _ in range(4):
+            s = rgb(); l = labs[state['i']]
+            ch.run_device_pipelined(s, l, counts)
+        ch.pipeline_sync()
+    k_pipe()
+    med, best = timeit(k_pipe, a.iters)
+    print(json.dumps({'kernel': 'chain two-stream overlap (per step)', 'ms': round(med / 4, 4), 'fps': round(4 * B / (med * 1e-3))}), flush=True)
     print('counts', counts[:8].tolist(), 'launches', rt.launches)
 
 

@@ -132,6 +132,65 @@ class SegmentChain(object):
                                        self.w, self.h, blur.n, self.connectivity))
         return labels, counts
 
+    # ---- two-stream software pipeline over consecutive device batches -----------------------------------
+    def run_device_pipelined(self, rgb, labels, counts):
+        """ Same result as `run_device`, but the chain is split over two internal streams:
+        front = RGB -> luma -> blur -> background/threshold (the sequential state lives here),
+        back  = morphology -> labelling.  The issue-bound front kernels of batch k+1 then share
+        the SMs with the latency-bound union-find kernels of batch k.  Call `pipeline_sync()`
+        (or synchronise the device) before reading `labels` / `counts`. """
+        rt, t = self.rt, torch()
+        n = rgb.n
+        if getattr(self, '_pipe', None) is None:
+            self._pipe = {
+                'front': t.cuda.Stream(device=rt.device), 'back': t.cuda.Stream(device=rt.device), 'k': 0,
+                'blur': rt.empty_u8(self.batch, self.h, self.w),
+                'mask': [rt.empty_bits(self.batch, self.h, self.w) for _ in range(2)],
+                'morph': rt.empty_bits(self.batch, self.h, self.w),
+                'ev_front': [t.cuda.Event(), t.cuda.Event()], 'ev_back': [t.cuda.Event(), t.cuda.Event()],
+            }
+        p = self._pipe
+        k = p['k']
+        p['k'] = k + 1
+        slot = k & 1
+        caller = t.cuda.current_stream(rt.device)
+        ev = t.cuda.Event()
+        ev.record(caller)                                   # inputs / output buffers are ready on the caller's stream
+        rt.ensure(self.w, self.h, n)
+        lib, h = rt.lib, rt._h
+        sub = lambda b: DeviceBatch(b.kind, b.t[:n], n, b.h, b.w, b.channels)
+        blur, mask, morph = sub(p['blur']), sub(p['mask'][slot]), sub(p['morph'])
+        with t.cuda.stream(p['front']):
+            p['front'].wait_event(ev)
+            p['front'].wait_event(p['ev_back'][slot])        # the back half has finished reading this mask slot
+            self.blur_device(rgb, blur)
+            rt._check(lib.va_ema_diff_thresh(h, rt.stream, *blur.img(), self._bg.data_ptr(), self._bg.stride(0),
+                                             *mask.img(), self.w, self.h, n, self.alpha, self.threshold,
+                                             0 if self._started else 1))
+            self._started = True
+            p['ev_front'][slot].record(p['front'])
+        with t.cuda.stream(p['back']):
+            p['back'].wait_event(ev)
+            p['back'].wait_event(p['ev_front'][slot])
+            seg = mask
+            if self.morph_op:
+                rt._check(lib.va_morph_bits(h, rt.stream, *mask.img(), *morph.img(), self.w, self.h, n,
+                                            _lib.MORPH_OPS[self.morph_op], _lib.SE_SHAPES[self.morph_shape],
+                                            int(self.kx), int(self.ky)))
+                seg = morph
+            rt._check(lib.va_label_bits(h, rt.stream, *seg.img(), *labels.img(), counts.data_ptr(),
+                                        self.w, self.h, n, self.connectivity))
+            p['ev_back'][slot].record(p['back'])
+        return labels, counts
+
+    def pipeline_sync(self):
+        """ make the caller's current stream wait for everything `run_device_pipelined` enqueued """
+        p = getattr(self, '_pipe', None)
+        if p is not None:
+            cur = torch().cuda.current_stream(self.rt.device)
+            cur.wait_stream(p['front'])
+            cur.wait_stream(p['back'])
+
     # ---- host frames in, host labels out: pipelined -------------------------------------------------------
     def _make_slots(self):
         t, rt = torch(), self.rt
