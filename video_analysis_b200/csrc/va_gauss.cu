@@ -89,7 +89,7 @@ __device__ __forceinline__ int gauss_reflect_fast(int i, int n) {
 }
 
 template <int RT, bool FUSE_LUMA>
-__global__ void __launch_bounds__(GAUSS_THREADS)
+__global__ void __launch_bounds__(GAUSS_THREADS, (RT > 0 && RT <= 8) ? 6 : 1)
 gauss_fast_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstride,
                   uint8_t *__restrict__ out, size_t out_pitch, size_t out_fstride,
                   int w, int h, int mode, int TH, int vec_in, const __grid_constant__ GaussFast g) {
