@@ -170,6 +170,37 @@ int va_apply_mask_u8(va_ctx *ctx, va_stream stream,
                      uint8_t *out, size_t out_pitch, size_t out_fstride,
                      int w, int h, int channels, int batch);
 
+/* ---- remaining filter bodies and temporal statistics ("next" rows of SURVEY.md 8f) ---- */
+
+/* FilterNormalize._process_frame, video/filters.py:101-135, for uint8 -> uint8 frames: the
+ * clip / scale / cast is applied as a 256-entry table (HOST pointer) computed by the caller with
+ * the reference's expression. */
+int va_lut_u8(va_ctx *ctx, va_stream stream,
+              const uint8_t *in, size_t in_pitch, size_t in_fstride,
+              uint8_t *out, size_t out_pitch, size_t out_fstride,
+              int row_bytes, int h, int batch, const uint8_t *lut256);
+
+/* FilterTimeDifference._compare_frames, video/filters.py:564-568:
+ *    out[t] = int16(in[t + 1]) - in[t], t in [0, batch); `in` holds batch + 1 frames */
+int va_time_diff_i16(va_ctx *ctx, va_stream stream,
+                     const uint8_t *in, size_t in_pitch, size_t in_fstride,
+                     int16_t *out, size_t out_pitch_e, size_t out_fstride_e,
+                     int row_elems, int h, int batch);
+
+/* FilterRotate._process_frame, video/filters.py:338-344: np.rot90(frame, k), k in 0..3
+ * (counter-clockwise).  (w, h) is the input size; the output is (h, w) for odd k. */
+int va_rot90_u8(va_ctx *ctx, va_stream stream,
+                const uint8_t *in, size_t in_pitch, size_t in_fstride,
+                uint8_t *out, size_t out_pitch, size_t out_fstride,
+                int w, int h, int channels, int batch, int k);
+
+/* measure_mean / measure_mean_std, video/analysis/video.py:26-55 (float64 state, reference
+ * operation order).  m2 == NULL: cumulative mean only.  n0 = frames already folded in. */
+int va_mean_update_f64(va_ctx *ctx, va_stream stream,
+                       const uint8_t *in, size_t in_pitch, size_t in_fstride,
+                       double *mean, double *m2, size_t pitch_e,
+                       int row_elems, int h, int batch, long long n0);
+
 /* frame-sharded EMA.  The recurrence is affine,
  *    bg_t = a * bg_{t-1} + alpha * x_t,   a = 1 - alpha,
  * so a rank can fold its frames from a zero state into S and the true state is

@@ -188,8 +188,55 @@ def time_difference(this_frame, prev_frame, dtype=np.int16):
 
 
 # --------------------------------------------------------------------------
+# normalize / rotate -- video/filters.py:76-135, :319-344
+# --------------------------------------------------------------------------
+def normalize(frames, vmin=None, vmax=None, dtype=None):
+    """ FilterNormalize over a sequence: bounds and dtype are fixed by the first frame when not
+    given (filters.py:104-124); clip, scale to the dtype's colour range, cast (filters.py:126-132) """
+    fmin, fmax, tmin, alpha = vmin, vmax, None, None
+    out = []
+    for frame in frames:
+        frame = np.array(frame, copy=True)            # the reference clips its input in place
+        if dtype is None:
+            dtype = frame.dtype
+        if fmin is None:
+            fmin = frame.min()
+        if fmax is None:
+            fmax = frame.max()
+        if tmin is None:
+            if np.issubdtype(dtype, np.integer):
+                tmin, tmax = np.iinfo(dtype).min, np.iinfo(dtype).max
+            else:
+                tmin, tmax = 0, 1
+            alpha = (tmax - tmin) / (fmax - fmin)
+        np.clip(frame, fmin, fmax, out=frame)
+        out.append(((frame - fmin) * alpha + tmin).astype(dtype))
+    return np.stack(out)
+
+
+def rotate(frame, angle):
+    """ filters.py:338-344 """
+    return np.rot90(frame, (angle % 360) // 90)
+
+
+# --------------------------------------------------------------------------
 # temporal folds -- video/analysis/video.py:14-35
 # --------------------------------------------------------------------------
+def measure_mean_std(frames):
+    """ analysis/video.py:39-55 (incremental mean / M2, float64) """
+    mean = np.zeros(np.shape(frames[0]))
+    M2 = np.zeros(np.shape(frames[0]))
+    n = -1
+    for n, frame in enumerate(frames):
+        delta = frame - mean
+        mean = mean + delta / (n + 1)
+        M2 = M2 + delta * (frame - mean)
+    if n < 2:
+        return frames[-1], 0
+    return mean, np.sqrt(M2 / n)
+
+
+
 def measure_mean(frames):
     """ analysis/video.py:26-35 (cumulative mean, float64) """
     mean = np.zeros(np.shape(frames[0]))

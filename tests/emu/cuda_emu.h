@@ -173,6 +173,10 @@ static inline unsigned __dp2a_hi(unsigned a, unsigned b, unsigned c) {
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
+static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
+static inline double __dsub_rn(double a, double b) { volatile double r = a - b; return r; }
+static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
+static inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
 static inline float __uint_as_float(unsigned u) { return emu::from_bits<float>(u); }
 static inline unsigned __float_as_uint(float f) { return (unsigned)emu::to_bits(f); }
 static inline float __int_as_float(int u) { return emu::from_bits<float>((unsigned)u); }

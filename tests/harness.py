@@ -357,6 +357,59 @@ def synth(ctx, seed, t0, n, W, H, blobs):
     return dst.get().reshape(n, H, W, 3)
 
 
+def lut(ctx, frames, table):
+    be = ctx.be
+    B, H = frames.shape[:2]
+    rowb = int(np.prod(frames.shape[2:]))
+    src = Img(be, B, H, rowb, np.uint8, data=frames.reshape(B, H, rowb))
+    dst = Img(be, B, H, rowb, np.uint8)
+    tab = np.ascontiguousarray(table, dtype=np.uint8)
+    ctx.check(ctx.lib.va_lut_u8(ctx.h, be.stream, src.ptr, src.pitch, src.fstride, dst.ptr, dst.pitch, dst.fstride,
+                                rowb, H, B, tab.ctypes.data))
+    return dst.get().reshape(frames.shape)
+
+
+def time_diff(ctx, frames):
+    """ frames (T, H, ...) -> int16 (T-1, H, ...) """
+    be = ctx.be
+    T, H = frames.shape[:2]
+    rowe = int(np.prod(frames.shape[2:]))
+    src = Img(be, T, H, rowe, np.uint8, data=frames.reshape(T, H, rowe))
+    dst = Img(be, T - 1, H, rowe, np.int16)
+    ctx.check(ctx.lib.va_time_diff_i16(ctx.h, be.stream, src.ptr, src.pitch, src.fstride, dst.ptr, dst.pitch, dst.fstride,
+                                       rowe, H, T - 1))
+    return dst.get().reshape((T - 1,) + frames.shape[1:])
+
+
+def rot90(ctx, frames, k):
+    be = ctx.be
+    if frames.ndim == 3:
+        B, H, W = frames.shape
+        ch = 1
+    else:
+        B, H, W, ch = frames.shape
+    oh, ow = (W, H) if k & 1 else (H, W)
+    src = Img(be, B, H, W * ch, np.uint8, data=frames.reshape(B, H, W * ch))
+    dst = Img(be, B, oh, ow * ch, np.uint8)
+    ctx.check(ctx.lib.va_rot90_u8(ctx.h, be.stream, src.ptr, src.pitch, src.fstride, dst.ptr, dst.pitch, dst.fstride,
+                                  W, H, ch, B, k))
+    out = dst.get()
+    return out.reshape(B, oh, ow) if frames.ndim == 3 else out.reshape(B, oh, ow, ch)
+
+
+def mean_update(ctx, frames, mean, m2=None, n0=0):
+    be = ctx.be
+    B, H = frames.shape[:2]
+    rowe = int(np.prod(frames.shape[2:]))
+    src = Img(be, B, H, rowe, np.uint8, data=frames.reshape(B, H, rowe))
+    mu = Img(be, 1, H, rowe, np.float64, data=np.asarray(mean, np.float64).reshape(1, H, rowe))
+    q = None if m2 is None else Img(be, 1, H, rowe, np.float64, data=np.asarray(m2, np.float64).reshape(1, H, rowe))
+    ctx.check(ctx.lib.va_mean_update_f64(ctx.h, be.stream, src.ptr, src.pitch, src.fstride, mu.ptr,
+                                         None if q is None else q.ptr, mu.pitch, rowe, H, B, n0))
+    shape = frames.shape[1:]
+    return mu.get()[0].reshape(shape), (None if q is None else q.get()[0].reshape(shape))
+
+
 def chain(ctx, frames, sigma=2.0, alpha=0.05, thr=25.0, morph_op='open', shape='rect', k=3, connectivity=4,
           bg0=None, fuse=False, want=('mono', 'blur', 'mask', 'morph', 'labels')):
     be = ctx.be

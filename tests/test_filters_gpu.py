@@ -261,3 +261,38 @@ def test_two_stream_pipelined_chain_equals_single_stream(frames, ref):
     assert np.array_equal(got, ref['labels'])
     assert np.array_equal(np.concatenate([c.cpu().numpy() for c in cnts]), ref['counts'])
     assert np.array_equal(ch.background.view(np.uint32), ref['bg'].view(np.uint32))
+
+
+def test_remaining_filter_classes_and_temporal_statistics(frames):
+    F, VideoMemory = mods()
+    from video_analysis_b200.analysis import video as vstat
+    v = VideoMemory(frames[:11], copy_data=False)
+    mono = np.stack([ops.mono(f) for f in frames[:11]])
+    # FilterNormalize: bounds from the first frame / explicit bounds
+    n1 = F.FilterNormalize(F.FilterMonochrome(v, batch=4))
+    assert np.array_equal(np.stack(list(n1)), ops.normalize(list(mono)))
+    n2 = F.FilterNormalize(F.FilterMonochrome(v, batch=4), vmin=70, vmax=180)
+    assert np.array_equal(np.stack(list(n2)), ops.normalize(list(mono), 70, 180))
+    # FilterRotate
+    for angle in (0, 90, 180, 270, 450):
+        r = F.FilterRotate(F.FilterMonochrome(v, batch=4), angle)
+        exp = np.stack([ops.rotate(f, angle) for f in mono])
+        assert r.shape == exp.shape and np.array_equal(np.stack(list(r)), exp), angle
+    rc = F.FilterRotate(F.FilterCrop(v, (8, 4, 100, 60), batch=4), 90)
+    assert np.array_equal(np.stack(list(rc)), np.stack([ops.rotate(ops.crop(f, (8, 4, 100, 60)), 90) for f in frames[:11]]))
+    with pytest.raises(ValueError):
+        F.FilterRotate(v, 45)
+    # FilterTimeDifference
+    td = F.FilterTimeDifference(F.FilterMonochrome(v, batch=4), batch=4)
+    exp = np.stack([ops.time_difference(mono[t + 1], mono[t]) for t in range(10)])
+    got = np.stack(list(td))
+    assert len(td) == 10 and got.dtype == np.int16 and np.array_equal(got, exp)
+    assert np.array_equal(td.get_frame(3), exp[3]) and np.array_equal(td[-1], exp[9])
+    # temporal statistics in float64, bit for bit
+    mv = VideoMemory(mono, copy_data=False)
+    assert np.array_equal(vstat.measure_mean(mv, batch=4).view(np.uint64), ops.measure_mean(list(mono)).view(np.uint64))
+    m, s = vstat.measure_mean_std(mv, batch=4)
+    mr, sr = ops.measure_mean_std(list(mono))
+    assert np.array_equal(m.view(np.uint64), mr.view(np.uint64)) and np.array_equal(s.view(np.uint64), sr.view(np.uint64))
+    acc = vstat.reduce_video(mv, lambda f, r: np.maximum(f, r))
+    assert np.array_equal(acc, mono.max(0))

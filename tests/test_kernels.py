@@ -304,6 +304,39 @@ def test_region_areas_and_largest(be, ctx):
         assert largest[b] == (np.argmax(ra) + 1 if cnt[b] else 0)
 
 
+# ---- remaining filter bodies and temporal statistics -----------------------------------
+def test_normalize_lut_rotate_time_difference(be, ctx):
+    for (H, W) in sizes(be, [(9, 37), (12, 64)], [(480, 640)]):
+        g = rng_frames(H, (3, H, W))
+        c = rng_frames(W, (3, H, W, 3))
+        # FilterNormalize on uint8 is a table: build it with the reference expression, apply on the device
+        for vmin, vmax in ((None, None), (40, 200)):
+            ref = ops.normalize(list(g), vmin, vmax)
+            lo = g[0].min() if vmin is None else vmin
+            hi = g[0].max() if vmax is None else vmax
+            table = ops.normalize([np.arange(256, dtype=np.uint8)], lo, hi)[0]
+            assert np.array_equal(hz.lut(ctx, g, table), ref)
+        for k in range(4):
+            assert np.array_equal(hz.rot90(ctx, g, k), np.stack([ops.rotate(f, 90 * k) for f in g])), k
+            assert np.array_equal(hz.rot90(ctx, c, k), np.stack([ops.rotate(f, 90 * k) for f in c])), k
+        d = hz.time_diff(ctx, g)
+        assert d.dtype == np.int16
+        assert np.array_equal(d, np.stack([ops.time_difference(g[t + 1], g[t]) for t in range(2)]))
+        assert np.array_equal(hz.time_diff(ctx, c), np.stack([ops.time_difference(c[t + 1], c[t]) for t in range(2)]))
+
+
+def test_temporal_mean_and_std_float64(be, ctx):
+    g = rng_frames(11, (9, 10, 33))
+    mean_ref = ops.measure_mean(list(g))
+    mu, _ = hz.mean_update(ctx, g[:4], np.zeros((10, 33)))
+    mu, _ = hz.mean_update(ctx, g[4:], mu, n0=4)                     # continuation
+    assert np.array_equal(mu.view(np.uint64), mean_ref.view(np.uint64))   # float64, bit for bit
+    m_ref, s_ref = ops.measure_mean_std(list(g))
+    mu2, m2 = hz.mean_update(ctx, g, np.zeros((10, 33)), np.zeros((10, 33)))
+    assert np.array_equal(mu2.view(np.uint64), m_ref.view(np.uint64))
+    assert np.array_equal(np.sqrt(m2 / 8).view(np.uint64), s_ref.view(np.uint64))
+
+
 # ---- the whole chain ---------------------------------------------------------------------------------
 @pytest.mark.parametrize('fuse', [False, True])
 def test_chain_run_matches_oracle_stagewise_and_end_to_end(be, ctx, fuse):

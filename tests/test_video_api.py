@@ -169,6 +169,31 @@ def test_new_operator_constructors_validate():
     assert filters.get_color_range(np.uint8) == (0, 255) and filters.get_color_range(np.float32) == (0, 1)
 
 
+def test_replicate_and_drop_frames_index_logic():
+    v = video(t=5)
+    r = filters.FilterReplicate(v, 3)
+    assert len(r) == 15 and [f[0, 0, 0] for f in r] == [v.data[i % 5][0, 0, 0] for i in range(15)]
+    assert np.array_equal(r.get_frame(7), v.data[2]) and np.array_equal(r[-1], v.data[4])
+    r.set_frame_pos(6)
+    assert np.array_equal(r.get_next_frame(), v.data[1])
+    with pytest.raises(IndexError):
+        r.set_frame_pos(15)
+    v = video(t=10)
+    d = filters.FilterDropFrames(v, 3)
+    assert len(d) == 4 and d.fps == 25 / 3
+    assert [f[0, 0, 0] for f in d] == [v.data[i][0, 0, 0] for i in (0, 3, 6, 9)]
+    assert np.array_equal(d.get_frame(-1), v.data[9])
+    d2 = filters.FilterDropFrames(v, 2.5)
+    assert len(d2) == 4 and [f[0, 0, 0] for f in d2] == [v.data[int(i * 2.5)][0, 0, 0] for i in range(4)]
+    t = filters.FilterTimeDifference(video(t=6, color=False))
+    assert len(t) == 5 and t.shape == (5, 12, 16)
+    with pytest.raises(NotImplementedError):
+        filters.FilterTimeDifference(v, dtype=np.float32)
+    with pytest.raises(ValueError):
+        filters.FilterRotate(v, 30)
+    assert filters.FilterRotate(v, 270).size == (12, 16)
+
+
 def test_device_filters_fail_loudly_without_gpu():
     import torch
     if torch.cuda.is_available():

@@ -1,0 +1,186 @@
+// va_extra.cu -- the remaining per-frame filter bodies of video/filters.py and the temporal
+// statistics of video/analysis/video.py ("next" rows of SURVEY.md 8f).  Simple HBM-streaming
+// kernels; none of them is on the benchmarked chain.
+#include "va_device.cuh"
+
+// =================================================================================
+// FilterNormalize._process_frame (video/filters.py:101-135) for uint8 -> uint8: the clip /
+// scale / cast is a 256-entry table that the host computes with the reference's expression
+// =================================================================================
+struct Lut256 { unsigned char v[256]; };
+
+__global__ void __launch_bounds__(256)
+lut_u8_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstride,
+              uint8_t *__restrict__ out, size_t out_pitch, size_t out_fstride,
+              int row_bytes, int h, int batch, int vec, const __grid_constant__ Lut256 lut) {
+    __shared__ unsigned char s[256];
+    s[threadIdx.x] = lut.v[threadIdx.x];
+    __syncthreads();
+    const unsigned rows = (unsigned)(h * batch);
+    if (vec) {
+        const unsigned chunks = (unsigned)row_bytes >> 4;
+        const unsigned total = rows * chunks;
+        for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+            const unsigned row = i / chunks, c = i - row * chunks;
+            const int b = (int)(row / (unsigned)h), y = (int)(row - (unsigned)b * (unsigned)h);
+            uint4 q = va_ld_stream16(in + (size_t)b * in_fstride + (size_t)y * in_pitch + 16 * c);
+            unsigned *w = reinterpret_cast<unsigned *>(&q);
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                w[k] = s[w[k] & 0xff] | (s[(w[k] >> 8) & 0xff] << 8) | (s[(w[k] >> 16) & 0xff] << 16) | (s[w[k] >> 24] << 24);
+            va_st_stream16(out + (size_t)b * out_fstride + (size_t)y * out_pitch + 16 * c, q);
+        }
+    } else {
+        const unsigned total = rows * (unsigned)row_bytes;
+        for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+            const unsigned row = i / (unsigned)row_bytes, c = i - row * (unsigned)row_bytes;
+            const int b = (int)(row / (unsigned)h), y = (int)(row - (unsigned)b * (unsigned)h);
+            out[(size_t)b * out_fstride + (size_t)y * out_pitch + c] = s[in[(size_t)b * in_fstride + (size_t)y * in_pitch + c]];
+        }
+    }
+}
+
+extern "C" int va_lut_u8(va_ctx *ctx, va_stream stream,
+                         const uint8_t *in, size_t in_pitch, size_t in_fstride,
+                         uint8_t *out, size_t out_pitch, size_t out_fstride,
+                         int row_bytes, int h, int batch, const uint8_t *lut256) {
+    VA_CHECK_CTX(ctx);
+    VA_REQUIRE(ctx, in && out && lut256, "va_lut_u8: null pointer");
+    VA_REQUIRE(ctx, row_bytes > 0 && h > 0 && batch > 0, "va_lut_u8: bad size");
+    Lut256 lut;
+    memcpy(lut.v, lut256, 256);
+    const int vec = row_bytes % 16 == 0 && va_aligned(in, 16) && va_aligned(out, 16) && in_pitch % 16 == 0 &&
+                    out_pitch % 16 == 0 && in_fstride % 16 == 0 && out_fstride % 16 == 0;
+    const long long items = (long long)h * batch * (vec ? row_bytes / 16 : row_bytes);
+    VA_REQUIRE(ctx, items < (1ll << 31), "va_lut_u8: batch too large for one launch");
+    const int grid = va_grid(ctx, (items + 255) / 256, 8);
+    auto kfn = lut_u8_kernel;
+    VA_LAUNCH(ctx, kfn, grid, 256, 0, stream, in, in_pitch, in_fstride, out, out_pitch, out_fstride, row_bytes, h, batch, vec, lut);
+    return VA_OK;
+}
+
+// =================================================================================
+// FilterTimeDifference._compare_frames (video/filters.py:564-568):
+//   out[t] = int16(frame[t + 1]) - frame[t]      for t in [0, batch)   (in holds batch + 1 frames)
+// =================================================================================
+__global__ void __launch_bounds__(256)
+time_diff_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstride,
+                 int16_t *__restrict__ out, size_t out_pitch_e, size_t out_fstride_e,
+                 int row_elems, int h, int batch) {
+    const unsigned total = (unsigned)row_elems * (unsigned)h * (unsigned)batch;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned row = i / (unsigned)row_elems, x = i - row * (unsigned)row_elems;
+        const int t = (int)(row / (unsigned)h), y = (int)(row - (unsigned)t * (unsigned)h);
+        const uint8_t *p = in + (size_t)t * in_fstride + (size_t)y * in_pitch + x;
+        out[(size_t)t * out_fstride_e + (size_t)y * out_pitch_e + x] = (int16_t)((int)p[in_fstride] - (int)p[0]);
+    }
+}
+
+extern "C" int va_time_diff_i16(va_ctx *ctx, va_stream stream,
+                                const uint8_t *in, size_t in_pitch, size_t in_fstride,
+                                int16_t *out, size_t out_pitch_e, size_t out_fstride_e,
+                                int row_elems, int h, int batch) {
+    VA_CHECK_CTX(ctx);
+    VA_REQUIRE(ctx, in && out, "va_time_diff_i16: null pointer");
+    VA_REQUIRE(ctx, row_elems > 0 && h > 0 && batch > 0, "va_time_diff_i16: bad size");
+    const long long items = (long long)row_elems * h * batch;
+    VA_REQUIRE(ctx, items < (1ll << 31), "va_time_diff_i16: batch too large for one launch");
+    const int grid = va_grid(ctx, (items + 255) / 256, 8);
+    auto kfn = time_diff_kernel;
+    VA_LAUNCH(ctx, kfn, grid, 256, 0, stream, in, in_pitch, in_fstride, out, out_pitch_e, out_fstride_e, row_elems, h, batch);
+    return VA_OK;
+}
+
+// =================================================================================
+// FilterRotate._process_frame (video/filters.py:338-344): np.rot90(frame, k), counter-clockwise
+//   (w, h) is the INPUT size; output is (h, w) for odd k
+// =================================================================================
+__global__ void __launch_bounds__(256)
+rot90_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstride,
+             uint8_t *__restrict__ out, size_t out_pitch, size_t out_fstride,
+             int w, int h, int channels, int batch, int k) {
+    const int ow = (k & 1) ? h : w, oh = (k & 1) ? w : h;
+    const unsigned total = (unsigned)ow * (unsigned)oh * (unsigned)batch;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned row = i / (unsigned)ow;
+        const int j = (int)(i - row * (unsigned)ow);                       // output column
+        const int b = (int)(row / (unsigned)oh), r = (int)(row - (unsigned)b * (unsigned)oh);   // output row
+        int sy, sx;                                                        // source pixel
+        if (k == 0) { sy = r; sx = j; }
+        else if (k == 1) { sy = j; sx = w - 1 - r; }
+        else if (k == 2) { sy = h - 1 - r; sx = w - 1 - j; }
+        else { sy = h - 1 - j; sx = r; }
+        const uint8_t *p = in + (size_t)b * in_fstride + (size_t)sy * in_pitch + (size_t)sx * channels;
+        uint8_t *o = out + (size_t)b * out_fstride + (size_t)r * out_pitch + (size_t)j * channels;
+        for (int c = 0; c < channels; c++) o[c] = p[c];
+    }
+}
+
+extern "C" int va_rot90_u8(va_ctx *ctx, va_stream stream,
+                           const uint8_t *in, size_t in_pitch, size_t in_fstride,
+                           uint8_t *out, size_t out_pitch, size_t out_fstride,
+                           int w, int h, int channels, int batch, int k) {
+    VA_CHECK_CTX(ctx);
+    VA_REQUIRE(ctx, in && out && in != out, "va_rot90_u8: null or aliased pointers");
+    VA_REQUIRE(ctx, w > 0 && h > 0 && batch > 0 && (channels == 1 || channels == 3), "va_rot90_u8: bad size");
+    VA_REQUIRE(ctx, k >= 0 && k <= 3, "va_rot90_u8: k must be 0..3");
+    const long long items = (long long)w * h * batch;
+    VA_REQUIRE(ctx, items < (1ll << 31), "va_rot90_u8: batch too large for one launch");
+    const int grid = va_grid(ctx, (items + 255) / 256, 8);
+    auto kfn = rot90_kernel;
+    VA_LAUNCH(ctx, kfn, grid, 256, 0, stream, in, in_pitch, in_fstride, out, out_pitch, out_fstride, w, h, channels, batch, k);
+    return VA_OK;
+}
+
+// =================================================================================
+// measure_mean / measure_mean_std (video/analysis/video.py:26-55), float64 state, the
+// reference's operation order (no FMA contraction):
+//   mean only:  mean = mean * n / (n + 1) + frame / (n + 1)
+//   with M2:    delta = frame - mean;  mean = mean + delta / (n + 1);  M2 = M2 + delta * (frame - mean)
+// n0 = number of frames already folded into the state.
+// =================================================================================
+__global__ void __launch_bounds__(256)
+mean_update_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstride,
+                   double *__restrict__ mean, double *__restrict__ m2, size_t pitch_e,
+                   int row_elems, int h, int batch, long long n0) {
+    const unsigned total = (unsigned)row_elems * (unsigned)h;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned y = i / (unsigned)row_elems, x = i - y * (unsigned)row_elems;
+        const uint8_t *p = in + (size_t)y * in_pitch + x;
+        const size_t o = (size_t)y * pitch_e + x;
+        double mu = mean[o];
+        if (m2) {
+            double q = m2[o];
+            for (int t = 0; t < batch; t++) {
+                const double f = (double)p[(size_t)t * in_fstride];
+                const double np1 = (double)(n0 + t + 1);
+                const double delta = __dsub_rn(f, mu);
+                mu = __dadd_rn(mu, __ddiv_rn(delta, np1));
+                q = __dadd_rn(q, __dmul_rn(delta, __dsub_rn(f, mu)));
+            }
+            m2[o] = q;
+        } else {
+            for (int t = 0; t < batch; t++) {
+                const double f = (double)p[(size_t)t * in_fstride];
+                const double n = (double)(n0 + t), np1 = (double)(n0 + t + 1);
+                mu = __dadd_rn(__ddiv_rn(__dmul_rn(mu, n), np1), __ddiv_rn(f, np1));
+            }
+        }
+        mean[o] = mu;
+    }
+}
+
+extern "C" int va_mean_update_f64(va_ctx *ctx, va_stream stream,
+                                  const uint8_t *in, size_t in_pitch, size_t in_fstride,
+                                  double *mean, double *m2, size_t pitch_e,
+                                  int row_elems, int h, int batch, long long n0) {
+    VA_CHECK_CTX(ctx);
+    VA_REQUIRE(ctx, in && mean, "va_mean_update_f64: null pointer");
+    VA_REQUIRE(ctx, row_elems > 0 && h > 0 && batch > 0 && n0 >= 0, "va_mean_update_f64: bad size");
+    const long long items = (long long)row_elems * h;
+    VA_REQUIRE(ctx, items < (1ll << 31), "va_mean_update_f64: frame too large");
+    const int grid = va_grid(ctx, (items + 255) / 256, 8);
+    auto kfn = mean_update_kernel;
+    VA_LAUNCH(ctx, kfn, grid, 256, 0, stream, in, in_pitch, in_fstride, mean, m2, pitch_e, row_elems, h, batch, n0);
+    return VA_OK;
+}

@@ -282,6 +282,42 @@ class DeviceRuntime(object):
                                              labels.w, labels.h, labels.n))
         return areas, largest
 
+    def lut(self, src, table):
+        """ out = table[in] for uint8 frames (FilterNormalize) """
+        tab = np.ascontiguousarray(table, dtype=np.uint8)
+        self.ensure(src.w, src.h, src.n)
+        out = self.empty_u8(src.n, src.h, src.w, src.channels)
+        self._check(self.lib.va_lut_u8(self._h, self.stream, src.ptr, src.pitch, src.fstride,
+                                       out.ptr, out.pitch, out.fstride, src.w * src.channels, src.h, src.n,
+                                       tab.ctypes.data))
+        return out
+
+    def rot90(self, src, k):
+        self.ensure(max(src.w, src.h), max(src.w, src.h), src.n)
+        ow, oh = (src.h, src.w) if k & 1 else (src.w, src.h)
+        out = self.empty_u8(src.n, oh, ow, src.channels)
+        self._check(self.lib.va_rot90_u8(self._h, self.stream, src.ptr, src.pitch, src.fstride,
+                                         out.ptr, out.pitch, out.fstride, src.w, src.h, src.channels, src.n, int(k)))
+        return out
+
+    def time_diff(self, src):
+        """ src holds n + 1 frames -> int16 tensor (n, h, w * channels) of consecutive differences """
+        t = torch()
+        n = src.n - 1
+        self.ensure(src.w, src.h, src.n)
+        out = t.empty((n, src.h, src.w * src.channels), dtype=t.int16, device=self.device)
+        self._check(self.lib.va_time_diff_i16(self._h, self.stream, src.ptr, src.pitch, src.fstride,
+                                              out.data_ptr(), out.stride(1), out.stride(0),
+                                              src.w * src.channels, src.h, n))
+        return out
+
+    def mean_update(self, src, mean, m2, n0):
+        """ fold a batch of uint8 frames into float64 running statistics (in place) """
+        self.ensure(src.w, src.h, src.n)
+        self._check(self.lib.va_mean_update_f64(self._h, self.stream, src.ptr, src.pitch, src.fstride,
+                                                mean.data_ptr(), None if m2 is None else m2.data_ptr(),
+                                                mean.stride(0), src.w * src.channels, src.h, src.n, int(n0)))
+
     def ema_partial(self, src, S, alpha, accumulate):
         self.ensure(src.w, src.h, src.n)
         self._check(self.lib.va_ema_partial(self._h, self.stream, src.ptr, src.pitch, src.fstride,

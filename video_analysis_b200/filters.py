@@ -480,6 +480,186 @@ class FilterResize(DeviceFilterBase):
                                   '(%dx%d -> %dx%d with %s requested)' % (batch.w, batch.h, w, h, self.interpolation))
 
 
+class FilterNormalize(DeviceFilterBase):
+    """ clips to [vmin, vmax] and rescales to the colour range of `dtype` (filters.py:76-135).
+    Bounds / dtype that are not given are taken from the first frame, as in the reference.
+    The device path covers uint8 -> uint8 (one table look-up per byte, the table being the
+    reference's own expression evaluated on 0..255); other dtypes raise NotImplementedError. """
+
+    def __init__(self, source, vmin=None, vmax=None, dtype=None, **kwargs):
+        self._fmin, self._fmax, self._dtype = vmin, vmax, dtype
+        self._table = None
+        super(FilterNormalize, self).__init__(source, **kwargs)
+
+    def _build_table(self, first_frame):
+        if self._dtype is None:
+            self._dtype = first_frame.dtype
+        if np.dtype(self._dtype) != np.uint8 or first_frame.dtype != np.uint8:
+            raise NotImplementedError('FilterNormalize on the device handles uint8 frames and dtype=uint8')
+        if self._fmin is None:
+            self._fmin = first_frame.min()
+        if self._fmax is None:
+            self._fmax = first_frame.max()
+        tmin, tmax = get_color_range(self._dtype)
+        alpha = (tmax - tmin) / (self._fmax - self._fmin)
+        ramp = np.arange(256, dtype=np.uint8)
+        np.clip(ramp, self._fmin, self._fmax, out=ramp)
+        self._table = ((ramp - self._fmin) * alpha + tmin).astype(self._dtype)     # filters.py:126-132
+
+    def _device_process(self, rt, batch):
+        if self._table is None:
+            t = torch()
+            first = batch.t[0, :, :batch.w * batch.channels].cpu().numpy()         # bounds come from the first frame
+            self._build_table(first)
+        return rt.lut(batch, self._table)
+
+
+class FilterRotate(DeviceFilterBase):
+    """ rotates the video counter-clockwise by 0 / 90 / 180 / 270 degrees (filters.py:319-344) """
+
+    def __init__(self, source, angle=0, **kwargs):
+        angle = angle % 360
+        if angle in (0, 180):
+            size = source.size
+        elif angle in (90, 270):
+            size = (source.size[1], source.size[0])
+        else:
+            raise ValueError('angle must be from [0, 90, 180, 270] but was %s' % angle)
+        self.angle = angle
+        super(FilterRotate, self).__init__(source, size=size, **kwargs)
+
+    def _device_process(self, rt, batch):
+        return rt.rot90(batch, self.angle // 90) if self.angle else batch
+
+
+class FilterReplicate(VideoFilterBase):
+    """ replicates the video `count` times (filters.py:396-430); pure index logic """
+
+    def __init__(self, source, count=1):
+        self.count = count
+        super(FilterReplicate, self).__init__(source, frame_count=source.frame_count * count)
+
+    def get_frame_pos(self):
+        return self._frame_pos
+
+    def set_frame_pos(self, index):
+        if index < 0:
+            index += self.frame_count
+        if not 0 <= index < self.frame_count:
+            raise IndexError('Cannot access frame %d.' % index)
+        self._source.set_frame_pos(index % self._source.frame_count)
+        self._frame_pos = index
+
+    def get_frame(self, index):
+        if index < 0:
+            index += self.frame_count
+        if not 0 <= index < self.frame_count:
+            raise IndexError('Cannot access frame %d.' % index)
+        return self._source.get_frame(index % self._source.frame_count)
+
+    def get_next_frame(self):
+        if self._frame_pos >= self.frame_count:
+            raise StopIteration
+        if self._frame_pos % self._source.frame_count == 0:
+            self._source.set_frame_pos(0)
+        frame = self._source.get_next_frame()
+        self._frame_pos += 1
+        return frame
+
+
+class FilterDropFrames(VideoFilterBase):
+    """ keeps every `compression`-th frame (filters.py:434-483); pure index logic """
+
+    def __init__(self, source, compression=1):
+        self._compression = compression
+        frame_count = int((source.frame_count - 1) / compression) + 1
+        super(FilterDropFrames, self).__init__(source, frame_count=frame_count, fps=source.fps / compression)
+
+    def _source_index(self, index):
+        return int(index * self._compression)
+
+    def get_frame_pos(self):
+        return self._frame_pos
+
+    def set_frame_pos(self, index):
+        if index < 0:
+            index += self.frame_count
+        if not 0 <= index < self.frame_count:
+            raise IndexError('Cannot access frame %d.' % index)
+        self._source.set_frame_pos(self._source_index(index))
+        self._frame_pos = index
+
+    def get_frame(self, index):
+        if index < 0:
+            index += self.frame_count
+        frame = self._source[self._source_index(index)]
+        self._frame_pos = index + 1
+        return frame
+
+    def get_next_frame(self):
+        if self._frame_pos >= self.frame_count:
+            raise StopIteration
+        frame = self._source[self._source_index(self._frame_pos)]
+        self._frame_pos += 1
+        return frame
+
+
+class FilterTimeDifference(VideoFilterBase):
+    """ differences between consecutive frames, int16 by default (filters.py:492-568).
+    Frame t of this video is source[t + 1] - source[t]; one frame shorter than the source.
+    Iterating pulls `batch` + 1 source frames at a time and differences them on the GPU. """
+
+    def __init__(self, source, dtype=np.int16, batch=DEFAULT_BATCH, device=None):
+        if dtype is not None and np.dtype(dtype) != np.int16:
+            raise NotImplementedError('FilterTimeDifference on the device produces int16 differences')
+        self._dtype = dtype
+        self.batch = batch
+        self._device = device
+        self._ready = collections.deque()
+        self._last = None                      # last source frame of the previous block
+        super(FilterTimeDifference, self).__init__(source, frame_count=source.frame_count - 1)
+
+    def get_frame_pos(self):
+        return self._frame_pos
+
+    def set_frame_pos(self, index):
+        if index < 0:
+            index += self.frame_count
+        self._source.set_frame_pos(index)
+        self._ready.clear()
+        self._last = None
+        self._frame_pos = index
+
+    def _diff(self, block):
+        t = torch()
+        rt = get_runtime(self._device)
+        with t.cuda.device(rt.device):
+            out = rt.time_diff(rt.upload(block))
+            host = out.cpu().numpy()
+        return host.reshape((len(block) - 1,) + block.shape[1:])
+
+    def get_frame(self, index):
+        if index < 0:
+            index += self.frame_count
+        pair = np.stack([np.asarray(self._source.get_frame(index)), np.asarray(self._source.get_frame(index + 1))])
+        return self._process_frame(self._diff(pair)[0])
+
+    def get_next_frame(self):
+        if not self._ready:
+            frames = [] if self._last is None else [self._last]
+            try:
+                while len(frames) < self.batch + 1:
+                    frames.append(np.asarray(self._source.get_next_frame()))
+            except StopIteration:
+                pass
+            if len(frames) < 2:
+                raise StopIteration
+            self._last = frames[-1]
+            self._ready.extend(self._diff(np.stack(frames)))
+        self._frame_pos += 1
+        return self._process_frame(self._ready.popleft())
+
+
 # =========================================================================================
 # operators named by the north star that the reference does not ship
 # =========================================================================================
