@@ -10,9 +10,11 @@
 // index at the smaller one, hence the root of a component is its first pixel in raster
 // order, and ranking the roots in index order IS the canonical numbering.
 //
-// Kernels A-C walk the mask with one LANE per image row (most rows are empty: a few
-// instructions per word); kernel G owns one row per warp (lane = 32-pixel word) and resolves
-// run starts that continue across words with one ballot + one shuffle per 32 words.
+// Kernels A and C walk the mask with one LANE per image row (most rows are empty: a few
+// instructions per word).  Kernels B and G own one row per warp (lane = 32-pixel word); run
+// starts that continue across words are resolved with one ballot + one shuffle per 32 words.
+// (A lane-per-row merge was measured slower: rows of one blob then hook in lock step and the
+// concurrent finds walk the chain that is being built.)
 //   A init     parent[s] = s for every run start s
 //   B merge    for every maximal overlap segment between a run in row y and one in row
 //              y-1: union(run start, run start)        (atomicMin hooking)
@@ -106,7 +108,7 @@ __device__ __forceinline__ void lab_union(int *parent, int a, int b) {
 }
 
 // =====================================================================================
-// Kernels A, B, C walk the mask with lane = ROW (32 rows per warp) and a sequential loop over
+// Kernels A and C walk the mask with lane = ROW (32 rows per warp) and a sequential loop over
 // the words of the row.  Most rows of a real mask are empty, and with one lane per row an
 // empty row costs a few instructions per word instead of a whole warp; run continuation
 // across words is a carried register instead of a warp scan.
@@ -166,84 +168,131 @@ label_init_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
 }
 
 // ---- B: merge with the row above -----------------------------------------------------------
-// Lane l of a warp holds row y0 - 1 + l: lanes 1..31 merge their row with the row held by the
-// lane below them (31 merges per warp).  Per word, a lane needs the word of the row above and
-// the start of the run that reaches into it from the left; both come from one shuffle each.
-// 8-connectivity probes the row above shifted by one pixel to either side as well.
-__device__ __forceinline__ void lab_probe(int *pf_, unsigned cur, int cs, unsigned pu, int us, unsigned &ovp,
-                                          int word, int rowc, int rowu, int dx, bool up_bit0, bool active) {
-    const unsigned ov = active ? (cur & pu) : 0u;
-    unsigned ss = ov & ~((ov << 1) | ovp);             // first pixel of every overlap segment
-    ovp = ov >> 31;
+// one "probe" row: the row above shifted by dx in {-1, 0, +1} (dx != 0 only for 8-connectivity)
+__device__ __forceinline__ void lab_merge_probe(int *pr, unsigned cur, int cur_stin, unsigned pu, int pu_stin,
+                                                unsigned ov_prev_bit, int lane, int base, int rowc, int rowu,
+                                                int dx, bool up_bit0) {
+    const unsigned ov = cur & pu;
+    unsigned ss = ov & ~((ov << 1) | ov_prev_bit);     // first pixel of every overlap segment
     while (ss) {
         const int bit = __ffs((int)ss) - 1;
         ss &= ss - 1;
-        const int a = lab_run_start(cur, bit, word, cs);
-        int bq = lab_run_start(pu, bit, word, us);      // in the (shifted) row above
-        if (dx == 1) bq -= 1;                           // undo the shift: probe(x) = up(x - dx)
+        const int a = lab_run_start(cur, bit, base + lane, cur_stin);
+        int bq = lab_run_start(pu, bit, base + lane, pu_stin);      // in the shifted row
+        // undo the shift: probe(x) = up(x - dx)
+        if (dx == 1) bq -= 1;
         else if (dx == -1) bq += (bq == 0 && up_bit0) ? 0 : 1;
-        lab_union(pf_, rowc + a, rowu + bq);
+        lab_union(pr, rowc + a, rowu + bq);
     }
 }
 
-__global__ void __launch_bounds__(LAB_THREADS, 3)
+__global__ void __launch_bounds__(LAB_THREADS, 8)
 label_merge_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
-                   int *__restrict__ parent, int LOG, size_t pf, int w, int h, int batch, int conn8, int vec) {
+                   int *__restrict__ parent, int LOG, size_t pf, int w, int h, int batch, int conn8) {
     const int lane = threadIdx.x & 31;
     const int wpw = (w + 31) >> 5;
     const unsigned lastmask = (w & 31) ? ((1u << (w & 31)) - 1u) : FULL;
-    const int wpf = (h - 1 + 30) / 31;                // warps per frame: 31 merged rows each
-    const int total = wpf * batch;
-    for (int wi = blockIdx.x * LAB_WARPS + (threadIdx.x >> 5); wi < total; wi += gridDim.x * LAB_WARPS) {
-        const int b = wi / wpf, y = (wi - b * wpf) * 31 + lane;       // lane 0: the row above the first merged row
-        const bool valid = y < h;
-        const bool active = valid && lane > 0;
-        const uint32_t *row = mask + (size_t)b * mfw + (size_t)(valid ? y : 0) * mpw;
-        int *pf_ = parent + (size_t)b * pf;
+    const int rows = h * batch;
+    for (int row = blockIdx.x * LAB_WARPS + (threadIdx.x >> 5); row < rows;
+         row += gridDim.x * LAB_WARPS) {
+        const int b = row / h, y = row - b * h;
+        if (y == 0) continue;
+        const uint32_t *mc = mask + (size_t)b * mfw + (size_t)y * mpw;
+        const uint32_t *mu = mc - mpw;
+        int *pr = parent + (size_t)b * pf;
         const int rowc = y << LOG, rowu = (y - 1) << LOG;
-        // carried per row: start of the run reaching into the next word from the left, for the row
-        // itself (cs) and, for 8-connectivity, for the row shifted right / left by one pixel
-        int cs = 0, cl = 0, cr = 0;
-        unsigned ovp0 = 0, ovpl = 0, ovpr = 0, my_prev_top = 0;
-        bool my_bit0 = false;
-        unsigned nxt[LAB_GROUP];
-        lab_load_group(row, 0, wpw, lastmask, vec != 0, valid, nxt);
-        for (int j = 0; j < wpw; j += LAB_GROUP) {
-            unsigned wd[LAB_GROUP + 1];
-#pragma unroll
-            for (int k = 0; k < LAB_GROUP; k++) wd[k] = nxt[k];
-            lab_load_group(row, j + LAB_GROUP, wpw, lastmask, vec != 0, valid && j + LAB_GROUP < wpw, nxt);
-            wd[LAB_GROUP] = nxt[0];                                  // look-ahead word for the >> 1 shift
-            if (j == 0) my_bit0 = (wd[0] & 1u) != 0;
-            // nothing to do in this group for the whole warp?
-            if (!__any_sync(FULL, (wd[0] | wd[1] | wd[2] | wd[3]) != 0u)) {
-                cs = cl = cr = 32 * (j + LAB_GROUP);
+        bool up_bit0 = false;
+        int carry_c = 0, carry_u = 0, carry_l = 0, carry_r = 0;
+        unsigned ovp0 = 0, ovpl = 0, ovpr = 0;          // bit 31 of the overlap word before the chunk
+        unsigned up_prev_top = 0;                        // bit 31 of the up word before the chunk
+        LAB_PREFETCH(prec, mc);
+        LAB_PREFETCH(preu, mu);
+        // a row can only be merged with the one above if both have foreground at all
+        if (wpw <= 128 && (!__any_sync(FULL, (prec[0] | prec[1] | prec[2] | prec[3]) != 0u) ||
+                           !__any_sync(FULL, (preu[0] | preu[1] | preu[2] | preu[3]) != 0u)))
+            continue;
+        for (int base = 0; base < wpw; base += 32) {
+            const unsigned cur = LAB_PICK(prec, base, mc);
+            const unsigned up = LAB_PICK(preu, base, mu);
+            if (base == 0) up_bit0 = (__shfl_sync(FULL, up, 0) & 1u) != 0;
+            // nothing can be merged in this chunk unless both rows have foreground in or next to it
+            // (8-connectivity: the first pixel of the next chunk of the row above also counts)
+            const unsigned nxt = conn8 ? __shfl_sync(FULL, LAB_PICK(preu, base + 32, mu), 0) : 0u;
+            const bool any_cur = __any_sync(FULL, cur != 0u);
+            const bool any_up = __any_sync(FULL, up != 0u) || up_prev_top || (nxt & 1u);
+            if (!any_cur || !any_up) {
+                // no overlap segment starts here; carries follow from the words alone
+                int cs, ct, us, ut;
+                if (any_cur) { lab_scan_chunk(cur, lane, base, carry_c, cs, ct); carry_c = __shfl_sync(FULL, ct, 31); }
+                else carry_c = 32 * (base + 32);
+                if (__any_sync(FULL, up != 0u)) {
+                    lab_scan_chunk(up, lane, base, carry_u, us, ut);
+                    carry_u = __shfl_sync(FULL, ut, 31);
+                    if (conn8) {
+                        const unsigned upw = __shfl_up_sync(FULL, up, 1);
+                        const unsigned upl = (up << 1) | (lane ? (upw >> 31) : up_prev_top);
+                        const unsigned upn = __shfl_down_sync(FULL, up, 1);
+                        const unsigned upr = (up >> 1) | ((lane < 31 ? (upn & 1u) : (nxt & 1u)) << 31);
+                        int ls, lt, rs, rt;
+                        lab_scan_chunk(upl, lane, base, carry_l, ls, lt);
+                        lab_scan_chunk(upr, lane, base, carry_r, rs, rt);
+                        carry_l = __shfl_sync(FULL, lt, 31);
+                        carry_r = __shfl_sync(FULL, rt, 31);
+                    }
+                } else {
+                    carry_u = 32 * (base + 32);
+                    if (conn8) {
+                        // shifted rows: only the bits leaking in from the neighbouring chunks can be set
+                        const unsigned upl = lane == 0 ? up_prev_top : 0u;
+                        const unsigned upr = lane == 31 ? ((nxt & 1u) << 31) : 0u;
+                        int ls, lt, rs, rt;
+                        lab_scan_chunk(upl, lane, base, carry_l, ls, lt);
+                        lab_scan_chunk(upr, lane, base, carry_r, rs, rt);
+                        carry_l = __shfl_sync(FULL, lt, 31);
+                        carry_r = __shfl_sync(FULL, rt, 31);
+                    }
+                }
                 ovp0 = ovpl = ovpr = 0;
-                my_prev_top = 0;
+                up_prev_top = __shfl_sync(FULL, up, 31) >> 31;
                 continue;
             }
-#pragma unroll
-            for (int k = 0; k < LAB_GROUP; k++) {
-                const int word = j + k;
-                const unsigned cur = wd[k];
-                const unsigned up = __shfl_up_sync(FULL, cur, 1);
-                const int us = __shfl_up_sync(FULL, cs, 1);
-                lab_probe(pf_, cur, cs, up, us, ovp0, word, rowc, rowu, 0, false, active);
-                if (conn8) {
-                    // my own row shifted by one pixel either way; the lane above probes them
-                    const unsigned myl = (cur << 1) | my_prev_top;                    // myl(x) = row(x - 1)
-                    const unsigned myr = (cur >> 1) | ((wd[k + 1] & 1u) << 31);       // myr(x) = row(x + 1)
-                    const unsigned upl = __shfl_up_sync(FULL, myl, 1), upr = __shfl_up_sync(FULL, myr, 1);
-                    const int ls = __shfl_up_sync(FULL, cl, 1), rs = __shfl_up_sync(FULL, cr, 1);
-                    const bool up_bit0 = __shfl_up_sync(FULL, (int)my_bit0, 1) != 0;
-                    lab_probe(pf_, cur, cs, upl, ls, ovpl, word, rowc, rowu, 1, up_bit0, active);
-                    lab_probe(pf_, cur, cs, upr, rs, ovpr, word, rowc, rowu, -1, up_bit0, active);
-                    cl = myl != FULL ? 32 * word + (32 - __clz((int)~myl)) : cl;
-                    cr = myr != FULL ? 32 * word + (32 - __clz((int)~myr)) : cr;
-                }
-                cs = cur != FULL ? 32 * word + (32 - __clz((int)~cur)) : cs;
-                my_prev_top = cur >> 31;
+            int cs, ct, us, ut;
+            lab_scan_chunk(cur, lane, base, carry_c, cs, ct);
+            lab_scan_chunk(up, lane, base, carry_u, us, ut);
+            {
+                const unsigned ov = cur & up;
+                const unsigned pv = __shfl_up_sync(FULL, ov, 1);
+                lab_merge_probe(pr, cur, cs, up, us, lane ? (pv >> 31) : ovp0, lane, base, rowc, rowu, 0, up_bit0);
+                ovp0 = __shfl_sync(FULL, ov, 31) >> 31;
             }
+            if (conn8) {
+                // upl(x) = up(x - 1)
+                const unsigned upw = __shfl_up_sync(FULL, up, 1);
+                const unsigned upl = (up << 1) | (lane ? (upw >> 31) : up_prev_top);
+                // upr(x) = up(x + 1): needs bit 0 of the next word (next chunk for lane 31)
+                const unsigned upn = __shfl_down_sync(FULL, up, 1);
+                const unsigned upr = (up >> 1) | ((lane < 31 ? (upn & 1u) : (nxt & 1u)) << 31);
+                int ls, lt, rs, rt;
+                lab_scan_chunk(upl, lane, base, carry_l, ls, lt);
+                lab_scan_chunk(upr, lane, base, carry_r, rs, rt);
+                {
+                    const unsigned ov = cur & upl;
+                    const unsigned pv = __shfl_up_sync(FULL, ov, 1);
+                    lab_merge_probe(pr, cur, cs, upl, ls, lane ? (pv >> 31) : ovpl, lane, base, rowc, rowu, 1, up_bit0);
+                    ovpl = __shfl_sync(FULL, ov, 31) >> 31;
+                }
+                {
+                    const unsigned ov = cur & upr;
+                    const unsigned pv = __shfl_up_sync(FULL, ov, 1);
+                    lab_merge_probe(pr, cur, cs, upr, rs, lane ? (pv >> 31) : ovpr, lane, base, rowc, rowu, -1, up_bit0);
+                    ovpr = __shfl_sync(FULL, ov, 31) >> 31;
+                }
+                carry_l = __shfl_sync(FULL, lt, 31);
+                carry_r = __shfl_sync(FULL, rt, 31);
+            }
+            up_prev_top = __shfl_sync(FULL, up, 31) >> 31;
+            carry_c = __shfl_sync(FULL, ct, 31);
+            carry_u = __shfl_sync(FULL, ut, 31);
         }
     }
 }
@@ -418,18 +467,16 @@ extern "C" int va_label_bits(va_ctx *ctx, va_stream stream,
     while (((size_t)1 << LOG) < ctx->lab_pitch) LOG++;
     const size_t pf = ctx->lab_pitch * (size_t)ctx->max_h;
     const int rows = h * batch;
-    const int grid = (int)((rows + LAB_WARPS - 1) / LAB_WARPS);      // write kernel: one row per warp
-    const int vec = va_aligned(mask, 16) && mask_pitch_w % 4 == 0 && mask_fstride_w % 4 == 0;
-    const int grid_a = va_div_up((long long)((h + 31) / 32) * batch, LAB_WARPS);
-    const int grid_b = va_div_up((long long)((h - 1 + 30) / 31) * batch, LAB_WARPS);
+    const int grid = (int)((rows + LAB_WARPS - 1) / LAB_WARPS);      // one row per warp, scheduled by the hardware
     int *parent = ctx->lab_parent;
     int *rowcnt = ctx->lab_rowcnt;
+    const int vec = va_aligned(mask, 16) && mask_pitch_w % 4 == 0 && mask_fstride_w % 4 == 0;
+    const int grid_a = va_div_up((long long)((h + 31) / 32) * batch, LAB_WARPS);        // lane-per-row kernels
     { auto k = label_init_kernel;
       VA_LAUNCH(ctx, k, grid_a, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, parent, LOG, pf, w, h, batch, vec); }
-    if (h > 1) {
-      auto k = label_merge_kernel;
-      VA_LAUNCH(ctx, k, grid_b, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, parent, LOG, pf, w, h, batch,
-                connectivity == 8 ? 1 : 0, vec); }
+    { auto k = label_merge_kernel;
+      VA_LAUNCH(ctx, k, grid, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, parent, LOG, pf, w, h, batch,
+                connectivity == 8 ? 1 : 0); }
     { auto k = label_flatten_kernel;
       VA_LAUNCH(ctx, k, grid_a, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, parent, LOG, pf, rowcnt, w, h, batch, vec); }
     { auto k = label_scan_kernel;
