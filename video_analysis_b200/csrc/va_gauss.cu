@@ -88,6 +88,14 @@ __device__ __forceinline__ int gauss_reflect_fast(int i, int n) {
     return i;
 }
 
+// one bounce is enough when the halo is shorter than the image (r < n); `tiny` selects the
+// general form for images smaller than the halo
+__device__ __forceinline__ int gauss_reflect_row(int i, int n, bool tiny) {
+    if (tiny) return va_reflect101(i, n);
+    i = i < 0 ? -i : i;
+    return i >= n ? 2 * n - 2 - i : i;
+}
+
 template <int RT, bool FUSE_LUMA>
 __global__ void __launch_bounds__(GAUSS_THREADS, (RT > 0 && RT <= 8) ? 6 : 1)
 gauss_fast_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstride,
@@ -148,6 +156,10 @@ gauss_fast_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fst
         const int half = lane >> 4, li = lane & 15;
         const bool tile_inside = vec_in && tx0 + GAUSS_TW <= w;   // warp-uniform
         const int gxi = tx0 + 8 * li;
+        const bool tiny = h <= r;                                 // image shorter than the halo
+        const uint8_t *colp = fin + 3 * (size_t)gxi;              // this lane's column in every row
+        const unsigned pitch32 = (unsigned)in_pitch;
+        uint8_t *sdst = s8 + 4 * (IW + 2 * li);
         for (int tr0 = 2 * warp + half; tr0 < R; tr0 += 3 * 2 * (GAUSS_THREADS / 32)) {
             uint2 q[3][3];
             if (tile_inside) {
@@ -155,8 +167,8 @@ gauss_fast_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fst
                 for (int k = 0; k < 3; k++) {
                     const int tr = tr0 + k * 2 * (GAUSS_THREADS / 32);
                     if (tr < R) {
-                        const int gy = gauss_reflect_fast(ty0 + tr - r, h);
-                        const uint2 *p = reinterpret_cast<const uint2 *>(fin + (size_t)gy * in_pitch + 3 * (size_t)gxi);
+                        const int gy = gauss_reflect_row(ty0 + tr - r, h, tiny);
+                        const uint2 *p = reinterpret_cast<const uint2 *>(colp + (size_t)((unsigned)gy * pitch32));
                         q[k][0] = __ldg(p); q[k][1] = __ldg(p + 1); q[k][2] = __ldg(p + 2);
                     }
                 }
@@ -181,7 +193,7 @@ gauss_fast_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fst
                         }
                     }
                 }
-                *reinterpret_cast<uint2 *>(s8 + tr * SW + 4 * (IW + 2 * li)) = make_uint2(lo, hi);
+                *reinterpret_cast<uint2 *>(sdst + tr * SW) = make_uint2(lo, hi);
             }
         }
         // halo: HS items of 8 pixels on either side of every staged row
@@ -340,6 +352,7 @@ static int gauss_launch(va_ctx *ctx, va_stream stream, const char *name, bool fu
     VA_REQUIRE(ctx, w > 0 && h > 0 && batch > 0, "%s: bad size %dx%dx%d", name, w, h, batch);
     VA_REQUIRE(ctx, channels == 1 || channels == 3, "%s: channels must be 1 or 3", name);
     VA_REQUIRE(ctx, sigma > 0, "%s: sigma must be positive", name);
+    VA_REQUIRE(ctx, (unsigned long long)h * in_pitch < (1ull << 32), "%s: frame larger than 4 GiB", name);
     VA_REQUIRE(ctx, mode >= -1 && mode <= 2, "%s: unsupported conversion method to monochrome: %d", name, mode);
     int taps[GAUSS_MAX_TAPS];
     const int ksize = va_gauss_build_taps(sigma, taps, GAUSS_MAX_TAPS);
