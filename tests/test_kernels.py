@@ -100,9 +100,10 @@ def test_gauss_golden(be, ctx):
 
 
 def test_luma_gauss_fused_equals_two_step(be, ctx):
-    for (H, W) in sizes(be, [(33, 150)], [(1080, 1920), (480, 640)]):
+    # widths that are multiples of 16 take the software-pipelined kernel (radius <= 10), others the plain one
+    for (H, W) in sizes(be, [(33, 150), (33, 160), (9, 16), (5, 144)], [(1080, 1920), (480, 640), (271, 1008)]):
         fr = rng_frames(5, (2, H, W, 3))
-        for s in (1, 2, 5):
+        for s in (1, 2, 3.3, 5):
             assert np.array_equal(hz.luma_gauss(ctx, fr, s), np.stack([ops.blur(ops.mono(f), s) for f in fr]))
     fr = rng_frames(6, (1, 20, 40, 3))
     assert np.array_equal(hz.luma_gauss(ctx, fr, 2, mode=1), np.stack([ops.blur(f[..., 1], 2) for f in fr]))
