@@ -292,191 +292,6 @@ gauss_fast_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fst
 }
 
 // ---------------------------------------------------------------------------------
-// Fused RGB -> luma -> blur, software pipelined (the kernel the chain uses).
-// Ablation of the kernel above showed the three phases of a tile simply add up: fetching
-// the RGB tile (HBM latency / bandwidth), row pass, column pass.  Here a persistent CTA
-// requests the raw RGB bytes of its NEXT tile with cp.async (no registers, no waiting) right
-// after it has converted the current tile to luma, so the fetch overlaps both filter passes.
-//   smem: rgb[R][448] raw bytes (16-byte chunks; covers 10 halo pixels on either side)
-//         s8[R][SW] luma, hp[R/2][128] row-pass pairs   -- as in gauss_fast_kernel
-// Preconditions (checked by the launcher, otherwise gauss_fast_kernel<.., true> is used):
-//   radius <= 10, width a multiple of 16, 16-byte aligned rows.
-// ---------------------------------------------------------------------------------
-#define GPIPE_RGBW 448          // staged RGB bytes per row: 3 * (128 + 2 * 10.67)
-#define GPIPE_HALO_BYTES 32     // bytes staged to the left of the tile's first pixel
-
-template <int RT>
-__global__ void __launch_bounds__(GAUSS_THREADS)
-gauss_pipe_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstride,
-                  uint8_t *__restrict__ out, size_t out_pitch, size_t out_fstride,
-                  int w, int h, int mode, int TH, int tiles_x, int tiles_y, int n_tiles,
-                  const __grid_constant__ GaussFast g) {
-    VA_DYN_SMEM(uint8_t, smem);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int r = RT;
-    constexpr int R16 = (r + 15) & ~15;
-    constexpr int SW = GAUSS_TW + 2 * R16 + 16;
-    constexpr int O = (4 - (r & 3)) & 3;
-    constexpr int NW = (O + 2 * r + 4 + 3) >> 2;
-    constexpr int NP = r + 1;
-    constexpr int WOFS = (R16 >> 2) - ((r + 3) >> 2);
-    constexpr int IW = R16 >> 2;
-    constexpr int NCHUNK = GPIPE_RGBW / 16;
-    const int R = TH + 2 * r;
-    uint8_t *rgb = smem;
-    uint8_t *s8 = smem + (size_t)R * GPIPE_RGBW;
-    unsigned *hp = reinterpret_cast<unsigned *>(s8 + (size_t)R * SW);
-    const bool out_words = (((uintptr_t)out | out_pitch | out_fstride) & 3) == 0;
-    const int tiles_per_frame = tiles_x * tiles_y;
-    const int row_bytes = 3 * w;
-    const bool tiny = h <= r;
-
-    // request the raw RGB bytes of a tile; chunks outside the row are zero-filled
-    auto prefetch = [&](int tile) {
-        const int b = tile / tiles_per_frame;
-        const int rem = tile - b * tiles_per_frame;
-        const int tyi = rem / tiles_x;
-        const int tx0 = (rem - tyi * tiles_x) * GAUSS_TW, ty0 = tyi * TH;
-        const uint8_t *fin = in + (size_t)b * in_fstride;
-        for (int it = tid; it < R * NCHUNK; it += GAUSS_THREADS) {
-            const int tr = it / NCHUNK, c = it - tr * NCHUNK;
-            const int off = 3 * tx0 - GPIPE_HALO_BYTES + 16 * c;
-            uint8_t *d = rgb + tr * GPIPE_RGBW + 16 * c;
-            if (off >= 0 && off + 16 <= row_bytes) {
-                const int gy = gauss_reflect_row(ty0 + tr - r, h, tiny);
-                va_cp_async16(d, fin + (size_t)((unsigned)gy * (unsigned)in_pitch) + off);
-            } else {
-                *reinterpret_cast<uint4 *>(d) = make_uint4(0, 0, 0, 0);
-            }
-        }
-        va_cp_async_commit();
-    };
-
-    int tile = blockIdx.x;
-    if (tile < n_tiles) prefetch(tile);
-    for (; tile < n_tiles; tile += gridDim.x) {
-        const int b = tile / tiles_per_frame;
-        const int rem = tile - b * tiles_per_frame;
-        const int tyi = rem / tiles_x;
-        const int tx0 = (rem - tyi * tiles_x) * GAUSS_TW, ty0 = tyi * TH;
-        va_cp_async_wait_group<0>();
-        __syncthreads();                       // rgb(tile) has landed; everyone is done with hp of the previous tile
-
-        // ---- convert: staged RGB -> staged luma, 8 pixels per item.  Staged luma word u holds
-        // pixels tx0 - R16 + 4u ..; RGB byte of pixel x sits at 3 (x - tx0) + 32.
-        {
-            const int half = lane >> 4, li = lane & 15;
-            const bool inside = tx0 + GAUSS_TW <= w;                 // interior needs no bounds checks
-            for (int tr = 2 * warp + half; tr < R; tr += 2 * (GAUSS_THREADS / 32)) {
-                const uint8_t *rrow = rgb + tr * GPIPE_RGBW + GPIPE_HALO_BYTES;
-                unsigned lo, hi;
-                if (inside) {
-                    const uint2 *p = reinterpret_cast<const uint2 *>(rrow + 24 * li);
-                    const uint2 q0 = p[0], q1 = p[1], q2 = p[2];
-                    lo = va_luma_x4(q0.x, q0.y, q1.x, mode);
-                    hi = va_luma_x4(q1.y, q2.x, q2.y, mode);
-                } else {
-                    lo = hi = 0;
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const int gx = tx0 + 8 * li + i;
-                        if (gx < tx0 + GAUSS_TW + r && gx < w + r) {             // beyond that nothing reads it
-                            const int sx = gauss_reflect_fast(gx, w) - tx0;          // column relative to the tile
-                            const unsigned v = va_luma_px(rrow + 3 * sx, mode) << (8 * (i & 3));
-                            if (i < 4) lo |= v; else hi |= v;
-                        }
-                    }
-                }
-                *reinterpret_cast<uint2 *>(s8 + tr * SW + 4 * (IW + 2 * li)) = make_uint2(lo, hi);
-            }
-            // halo: 8-pixel items left and right of the tile (two of each cover r <= 10 and the
-            // words the row pass touches beyond it)
-            for (int it = tid; it < R * 4; it += GAUSS_THREADS) {
-                const int tr = it >> 2, k = it & 3;
-                const bool right = k >= 2;
-                const int kk = k & 1;
-                const int gx0 = right ? tx0 + GAUSS_TW + 8 * kk : tx0 - 8 * (kk + 1);
-                const int word = right ? IW + 32 + 2 * kk : IW - 2 * (kk + 1);
-                const uint8_t *rrow = rgb + tr * GPIPE_RGBW + GPIPE_HALO_BYTES;
-                unsigned lo = 0, hi = 0;
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const int gx = gx0 + i;
-                    if (gx >= tx0 - r && gx < tx0 + GAUSS_TW + r && gx < w + r) {
-                        const int sx = gauss_reflect_fast(gx, w) - tx0;
-                        const unsigned v = va_luma_px(rrow + 3 * sx, mode) << (8 * (i & 3));
-                        if (i < 4) lo |= v; else hi |= v;
-                    }
-                }
-                *reinterpret_cast<uint2 *>(s8 + tr * SW + 4 * word) = make_uint2(lo, hi);
-            }
-        }
-        __syncthreads();                       // luma staged; rgb is free again
-        if (tile + (int)gridDim.x < n_tiles) prefetch(tile + gridDim.x);
-
-        // ---- row pass: warp = row pair q, lane = 4-pixel group
-        for (int q = warp; q < (R >> 1); q += GAUSS_THREADS / 32) {
-            const unsigned *r0 = reinterpret_cast<const unsigned *>(s8 + (2 * q) * SW) + WOFS + lane;
-            const unsigned *r1 = reinterpret_cast<const unsigned *>(s8 + (2 * q + 1) * SW) + WOFS + lane;
-            unsigned a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0};
-#pragma unroll
-            for (int j = 0; j < NW; j++) {
-                const unsigned x0 = r0[j], x1 = r1[j];
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const unsigned c = g.cw[i][j];
-                    a0[i] = __dp4a(x0, c, a0[i]);
-                    a1[i] = __dp4a(x1, c, a1[i]);
-                }
-            }
-            *reinterpret_cast<uint4 *>(hp + q * GAUSS_TW + 4 * lane) =
-                make_uint4(__byte_perm(a0[0], a1[0], 0x5410), __byte_perm(a0[1], a1[1], 0x5410),
-                           __byte_perm(a0[2], a1[2], 0x5410), __byte_perm(a0[3], a1[3], 0x5410));
-        }
-        __syncthreads();
-
-        // ---- column pass: warp = output row pair yp, lane = 4-column group
-        const int x = tx0 + 4 * lane;
-        if (x < w) {
-            const bool vec_store = out_words && x + 4 <= w;
-            uint8_t *op = out + (size_t)b * out_fstride + (size_t)(ty0 + 2 * warp) * out_pitch + x;
-            const size_t ostep = (size_t)(GAUSS_THREADS / 32) * 2 * out_pitch;
-            for (int yp = warp; yp < (TH >> 1); yp += GAUSS_THREADS / 32, op += ostep) {
-                const int y = ty0 + 2 * yp;
-                if (y >= h) break;
-                unsigned acc[2][4];
-#pragma unroll
-                for (int i = 0; i < 2; i++)
-#pragma unroll
-                    for (int k = 0; k < 4; k++) acc[i][k] = 32768u;
-                const uint4 *col = reinterpret_cast<const uint4 *>(hp + yp * GAUSS_TW + 4 * lane);
-#pragma unroll
-                for (int j = 0; j < NP; j++) {
-                    const uint4 v = col[j * (GAUSS_TW >> 2)];
-                    const unsigned c0 = g.cp[0][j], c1 = g.cp[1][j];
-                    acc[0][0] = __dp2a_lo(v.x, c0, acc[0][0]); acc[1][0] = __dp2a_lo(v.x, c1, acc[1][0]);
-                    acc[0][1] = __dp2a_lo(v.y, c0, acc[0][1]); acc[1][1] = __dp2a_lo(v.y, c1, acc[1][1]);
-                    acc[0][2] = __dp2a_lo(v.z, c0, acc[0][2]); acc[1][2] = __dp2a_lo(v.z, c1, acc[1][2]);
-                    acc[0][3] = __dp2a_lo(v.w, c0, acc[0][3]); acc[1][3] = __dp2a_lo(v.w, c1, acc[1][3]);
-                }
-#pragma unroll
-                for (int i = 0; i < 2; i++) {
-                    if (y + i >= h) break;
-                    const unsigned res = __byte_perm(__byte_perm(acc[i][0], acc[i][1], 0x0062),
-                                                     __byte_perm(acc[i][2], acc[i][3], 0x0062), 0x5410);
-                    uint8_t *o = op + (i ? out_pitch : 0);
-                    if (vec_store) {
-                        *reinterpret_cast<unsigned *>(o) = res;
-                    } else {
-                        for (int k = 0; k < 4 && x + k < w; k++) o[k] = (uint8_t)(res >> (8 * k));
-                    }
-                }
-            }
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------
 // generic kernel: any channel count, taps up to 256, scalar arithmetic
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GAUSS_THREADS)
@@ -578,36 +393,6 @@ static int gauss_launch(va_ctx *ctx, va_stream stream, const char *name, bool fu
                 if (k1 >= 0 && k1 < ksize) wd |= (unsigned)taps[k1] << 8;
                 g.cp[i][j] = wd;
             }
-        // software-pipelined fused kernel when its preconditions hold
-        if (fuse && r <= 10 && w % 16 == 0 && va_aligned(in, 16) && in_pitch % 16 == 0 && in_fstride % 16 == 0 &&
-            !(getenv("VA_GAUSS_NOPIPE") && atoi(getenv("VA_GAUSS_NOPIPE")))) {
-            int TH = getenv("VA_GAUSS_TH") ? atoi(getenv("VA_GAUSS_TH")) : 52;
-            if (TH < 8 || (TH & 1)) TH = 52;
-            const int R = TH + 2 * r;
-            const int R16p = (r + 15) & ~15;
-            const size_t smem = (size_t)R * GPIPE_RGBW + (size_t)R * (GAUSS_TW + 2 * R16p + 16) + (size_t)(R / 2) * GAUSS_TW * 4;
-            const int tiles_x = va_div_up(w, GAUSS_TW), tiles_y = va_div_up(h, TH);
-            const int n_tiles = tiles_x * tiles_y * batch;
-            int ctas = (int)((224 * 1024) / (smem + 1024));
-            if (ctas < 1) ctas = 1;
-            if (ctas > 6) ctas = 6;
-            const int grid = va_grid(ctx, n_tiles, ctas);
-#define GPIPE_GO(RT)                                                                                             \
-            do {                                                                                                 \
-                auto kfn = gauss_pipe_kernel<RT>;                                                                \
-                VA_CUDA(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-                VA_LAUNCH(ctx, kfn, grid, GAUSS_THREADS, smem, stream, in, in_pitch, in_fstride, out, out_pitch,  \
-                          out_fstride, w, h, mode, TH, tiles_x, tiles_y, n_tiles, g);                            \
-            } while (0)
-            switch (r) {
-                case 1: GPIPE_GO(1); break; case 2: GPIPE_GO(2); break; case 3: GPIPE_GO(3); break;
-                case 4: GPIPE_GO(4); break; case 5: GPIPE_GO(5); break; case 6: GPIPE_GO(6); break;
-                case 7: GPIPE_GO(7); break; case 8: GPIPE_GO(8); break; case 9: GPIPE_GO(9); break;
-                default: GPIPE_GO(10); break;
-            }
-#undef GPIPE_GO
-            return VA_OK;
-        }
         // tile height: minimise staged rows + idle warp rounds + rows wasted below the image
         const int R16 = (r + 15) & ~15;
         const int SW = GAUSS_TW + 2 * R16 + 16;
