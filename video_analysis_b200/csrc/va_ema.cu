@@ -155,56 +155,6 @@ ema_diff_thresh_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t i
     }
 }
 
-// Small frames (VGA and below) do not offer enough 4- or 16-pixel threads to fill 148 SMs;
-// this variant gives every pixel its own thread (one warp = one mask word, assembled by a
-// single ballot) and keeps 8 frames of byte loads in flight per thread in registers.
-#define EMA1_DEPTH 8
-__global__ void __launch_bounds__(EMA_THREADS)
-ema_diff_thresh_px1_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstride,
-                           float *__restrict__ bg, size_t bg_pitch_e,
-                           uint32_t *__restrict__ mask, size_t mask_pitch_w, size_t mask_fstride_w,
-                           int w, int h, int batch, float alpha, float thr, int first_init) {
-    const int lane = threadIdx.x & 31;
-    const int warps_per_block = EMA_THREADS >> 5;
-    const int chunks = (w + 31) >> 5;
-    const unsigned total = (unsigned)chunks * (unsigned)h;
-    for (unsigned item = blockIdx.x * warps_per_block + (threadIdx.x >> 5); item < total;
-         item += gridDim.x * warps_per_block) {
-        const int y = (int)(item / (unsigned)chunks);
-        const int c = (int)(item - (unsigned)y * (unsigned)chunks);
-        const int x = 32 * c + lane;
-        const bool active = x < w;
-        const uint8_t *rp = in + (size_t)y * in_pitch + x;
-        float *bgp = bg + (size_t)y * bg_pitch_e + x;
-        uint32_t *mrow = mask + (size_t)y * mask_pitch_w + c;
-        float s = active ? *bgp : 0.0f;
-        unsigned v[EMA1_DEPTH];
-#pragma unroll
-        for (int u = 0; u < EMA1_DEPTH; u++) v[u] = (active && u < batch) ? rp[(size_t)u * in_fstride] : 0u;
-        for (int t0 = 0; t0 < batch; t0 += EMA1_DEPTH) {
-#pragma unroll
-            for (int u = 0; u < EMA1_DEPTH; u++) {
-                const int t = t0 + u;
-                if (t >= batch) break;
-                const float xf = (float)v[u];
-                const int tn = t + EMA1_DEPTH;
-                v[u] = (active && tn < batch) ? rp[(size_t)tn * in_fstride] : 0u;
-                bool bit = false;
-                if (t == 0 && first_init) {
-                    s = xf;
-                } else {
-                    const float d = __fadd_rn(xf, -s);
-                    bit = active && fabsf(d) > thr;
-                    s = __fadd_rn(s, __fmul_rn(alpha, d));
-                }
-                const unsigned m = __ballot_sync(0xffffffffu, bit);
-                if (lane == 0) mrow[(size_t)t * mask_fstride_w] = m;
-            }
-        }
-        if (active) *bgp = s;
-    }
-}
-
 extern "C" int va_ema_diff_thresh(va_ctx *ctx, va_stream stream,
                                   const uint8_t *in, size_t in_pitch, size_t in_fstride,
                                   float *bg, size_t bg_pitch_e,
@@ -218,15 +168,7 @@ extern "C" int va_ema_diff_thresh(va_ctx *ctx, va_stream stream,
     // 16 pixels per thread when that still fills the machine, else 4
     const long long threads16 = (long long)((w + 511) / 512) * 32 * h;
     const bool use16 = threads16 >= (long long)ctx->sm_count * 512;
-    const long long threads4 = (long long)((w + 127) / 128) * 32 * h;
-    if (threads4 < (long long)ctx->sm_count * 1024) {
-        // small frames: one thread per pixel
-        const long long warps = (long long)((w + 31) / 32) * h;
-        const int grid = va_grid(ctx, (warps + 7) / 8, 8);
-        auto kfn = ema_diff_thresh_px1_kernel;
-        VA_LAUNCH(ctx, kfn, grid, EMA_THREADS, 0, stream, in, in_pitch, in_fstride, bg, bg_pitch_e, mask, mask_pitch_w,
-                  mask_fstride_w, w, h, batch, alpha, thr, first_frame_inits);
-    } else if (use16) {
+    if (use16) {
         const int vec_in = va_aligned(in, 16) && in_pitch % 16 == 0 && in_fstride % 16 == 0;
         const long long warps = (long long)((w + 511) / 512) * h;
         const int grid = va_grid(ctx, (warps + 7) / 8, 8);
