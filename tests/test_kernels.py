@@ -100,7 +100,7 @@ def test_gauss_golden(be, ctx):
 
 
 def test_luma_gauss_fused_equals_two_step(be, ctx):
-    # widths that are multiples of 16 take the software-pipelined kernel (radius <= 10), others the plain one
+    # aligned and ragged widths, tiles cut by the right / bottom image edge, images smaller than a tile
     for (H, W) in sizes(be, [(33, 150), (33, 160), (9, 16), (5, 144)], [(1080, 1920), (480, 640), (271, 1008)]):
         fr = rng_frames(5, (2, H, W, 3))
         for s in (1, 2, 3.3, 5):

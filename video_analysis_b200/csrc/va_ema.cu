@@ -75,7 +75,8 @@ ema_diff_thresh_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t i
                        uint32_t *__restrict__ mask, size_t mask_pitch_w, size_t mask_fstride_w,
                        int w, int h, int batch, float alpha, float thr, int first_init, int vec_in, int vec_bg) {
     constexpr int NW = PX / 4;
-    __shared__ uint4 ring_raw[EMA_RING * EMA_THREADS * NW / 4];      // uint4: 16-byte aligned slots
+    constexpr int RING = PX == 16 ? 8 : 16;                            // frames in flight per thread
+    __shared__ uint4 ring_raw[RING * EMA_THREADS * NW / 4];            // uint4: 16-byte aligned slots
     unsigned(*ring)[EMA_THREADS * NW] = reinterpret_cast<unsigned(*)[EMA_THREADS * NW]>(ring_raw);
     const int lane = threadIdx.x & 31;
     const int warps_per_block = EMA_THREADS >> 5;
@@ -97,7 +98,7 @@ ema_diff_thresh_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t i
 
         // prologue: RING - 1 frames in flight
 #pragma unroll
-        for (int u = 0; u < EMA_RING - 1; u++) {
+        for (int u = 0; u < RING - 1; u++) {
             if (u < batch) ema_issue<PX>(myslot + u * SLOT_STRIDE, rp + (size_t)u * in_fstride, x, w, fast);
             else va_cp_async_commit();
         }
@@ -117,12 +118,12 @@ ema_diff_thresh_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t i
         uint32_t *mrow = mask + (size_t)y * mask_pitch_w + (x >> 5);
         const bool writer = (lane & (32 / PX - 1)) == 0 && x < w;
         for (int t = 0; t < batch; t++) {
-            const int tn = t + EMA_RING - 1;                 // frame to put in flight now
-            if (tn < batch) ema_issue<PX>(myslot + (tn % EMA_RING) * SLOT_STRIDE, rp + (size_t)tn * in_fstride, x, w, fast);
+            const int tn = t + RING - 1;                 // frame to put in flight now
+            if (tn < batch) ema_issue<PX>(myslot + (tn % RING) * SLOT_STRIDE, rp + (size_t)tn * in_fstride, x, w, fast);
             else va_cp_async_commit();
-            va_cp_async_wait_group<EMA_RING - 1>();          // frame t has landed
+            va_cp_async_wait_group<RING - 1>();          // frame t has landed
             unsigned v[NW];
-            const unsigned *slot = myslot + (t % EMA_RING) * SLOT_STRIDE;
+            const unsigned *slot = myslot + (t % RING) * SLOT_STRIDE;
             if (PX == 16) {
                 const uint4 q = *reinterpret_cast<const uint4 *>(slot);
                 v[0] = q.x; v[NW > 1 ? 1 : 0] = q.y; v[NW > 2 ? 2 : 0] = q.z; v[NW > 3 ? 3 : 0] = q.w;
