@@ -28,6 +28,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__ static

@@ -292,6 +292,205 @@ gauss_fast_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fst
 }
 
 // ---------------------------------------------------------------------------------
+// streaming kernel (radius < 16, 16-byte aligned frames, w % 16 == 0): a CTA owns a strip of
+// 4 * blockDim.x columns and walks down a segment of rows.  Thread t owns columns 4t .. 4t+3 for the
+// whole walk and keeps the last RT + 1 row pairs of the row pass in registers, so the 16-bit
+// intermediate image never exists in memory and no row of the segment is staged twice.
+// A step is RT + 1 row pairs = one turn of the register window, so every slot index is static.
+// Per pair of step s:
+//   stage     one 16-pixel item of step s + 1: raw bytes (cp.async'ed into a private ring slot a few
+//             pairs ago) -> luma words in the row buffer of step s + 1; the slot is refilled at once
+//   rows      dp4a on 2 rows x 4 pixels from the row buffer of step s -> window slot
+//   cols      dp2a over the window -> 2 output rows x 4 pixels, one 4-byte store each
+// and one barrier per step.
+// ---------------------------------------------------------------------------------
+#define GS_MAX_THREADS 256
+#define GS_MAX_R 16
+#define GS_DEPTH 3                       // raw ring slots per thread
+#define GS_HW 4                          // halo words (16 pixels) on either side of a staged row
+
+// luma of four interleaved RGB pixels with the channel pick expressed as two PRMT selectors
+__device__ __forceinline__ unsigned gs_luma_x4(unsigned w0, unsigned w1, unsigned w2, bool mean, unsigned sel_a, unsigned sel_b) {
+    if (mean) return va_mean3_x4(w0, w1, w2);
+    return __byte_perm(__byte_perm(w0, w1, sel_a), w2, sel_b);
+}
+
+template <int RT, bool FUSE_LUMA>
+__global__ void __launch_bounds__(GS_MAX_THREADS, 3)
+gauss_stream_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstride,
+                    uint8_t *__restrict__ out, size_t out_pitch, size_t out_fstride,
+                    int w, int h, int mode, int SH, const __grid_constant__ GaussFast g) {
+    // grid = (strips in x, segments in y, frames)
+    constexpr int r = RT, NP = RT + 1;
+    constexpr int O = (4 - (r & 3)) & 3;
+    constexpr int NW = (O + 2 * r + 4 + 3) >> 2;             // staged words feeding one 4-pixel group
+    constexpr int WOFS = GS_HW - ((r + 3) >> 2);             // first staged word needed by group 0
+    constexpr int NQ = FUSE_LUMA ? 3 : 1;                    // 16-byte chunks per 16-pixel item
+    constexpr int ROWS = 2 * NP;                             // image rows per step (one turn of the window)
+    constexpr int IPT = (ROWS + 3) / 4;                      // interior items per thread and step
+    constexpr int NI = IPT + 1;                              // + the halo item
+    constexpr int D = GS_DEPTH;                              // raw ring slots per thread
+    static_assert(NI <= NP || NP == 1, "one item per pair");
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NT = blockDim.x;
+    const int RW = NT + 2 * GS_HW;                           // words per staged row
+    VA_DYN_SMEM(uint4, smem);
+    uint4 *raw = smem;                                       // [D][NQ][NT] private raw bytes
+    unsigned *lbuf = reinterpret_cast<unsigned *>(smem + D * NQ * NT);   // [2][ROWS][RW] luma words
+    const int x0 = blockIdx.x * 4 * NT;
+    const int y0 = blockIdx.y * SH;
+    const int rows = min(SH, h - y0);
+    const int npairs = ((rows + 1) >> 1) + r;
+    const int nsteps = (npairs + NP - 1) / NP;
+    const uint8_t *fin = in + (size_t)blockIdx.z * in_fstride;
+    const unsigned pitch32 = (unsigned)in_pitch;
+    const bool mean = mode < 0;
+    const unsigned sel_a = mode == 0 ? 0x0630u : mode == 1 ? 0x0741u : 0x0052u;
+    const unsigned sel_b = mode == 0 ? 0x5210u : mode == 1 ? 0x6210u : 0x7410u;
+
+    // staging duty of this thread: NI items per step -- up to IPT interior items (a quarter warp covers
+    // 128 columns of one row; rows frow, frow + 4, ...) and one halo item for the first 2 * ROWS threads.
+    // Items travel through a private ring of D raw slots: item n is converted while items n + 1 ..
+    // n + D - 1 are in flight, and its slot is refilled with item n + D at once.
+    // Columns outside the image (w % 16 == 0, so an item is inside or outside as a whole): the item
+    // next to the left / right border is the mirrored neighbour item (BORDER_REFLECT_101, radius < 16),
+    // anything further out is never read and staged as 0.
+    const int frow = lane >> 3;
+    const int fcol = warp * 8 + (lane & 7);
+    const int fgx = x0 + 16 * fcol;
+    const int hrow = tid >> 1;
+    const bool hside = tid & 1;
+    const int hgx = hside ? x0 + 4 * NT : x0 - 16;
+    enum { IN = 0, MIRROR_L = 1, MIRROR_R = 2, ZERO = 3 };
+    const int fkind = fgx < w ? IN : fgx == w ? MIRROR_R : ZERO;
+    const int hkind = tid >= 2 * ROWS ? ZERO : hgx < 0 ? MIRROR_L : hgx < w ? IN : hgx == w ? MIRROR_R : ZERO;
+    const uint8_t *fcolp = fin + (FUSE_LUMA ? 3 : 1) * (size_t)(fkind == MIRROR_R ? w - 16 : fgx);
+    const uint8_t *hcolp = fin + (FUSE_LUMA ? 3 : 1) * (size_t)(hkind == MIRROR_L ? 0 : hkind == MIRROR_R ? w - 16 : hgx);
+    uint4 *rb = raw + tid;
+
+    auto issue = [&](int st, int i, int slot) {             // i static
+        if (st < nsteps) {
+            const bool halo = i == IPT;
+            const int row = halo ? hrow : frow + 4 * i;
+            if ((halo ? hkind : fkind) != ZERO && row < ROWS) {
+                const unsigned gy = (unsigned)gauss_reflect_row(y0 - r + ROWS * st + row, h, false);
+                const uint8_t *p = (halo ? hcolp : fcolp) + (size_t)(gy * pitch32);
+#pragma unroll
+                for (int k = 0; k < NQ; k++) va_cp_async16(rb + (slot * NQ + k) * NT, p + 16 * k);
+            }
+        }
+        va_cp_async_commit();
+    };
+    auto convert = [&](int st, int i, int slot) {           // i static
+        if (st >= nsteps) return;
+        const bool halo = i == IPT;
+        const int row = halo ? hrow : frow + 4 * i;
+        if (row >= ROWS) return;
+        const int kind = halo ? hkind : fkind;
+        if (halo && tid >= 2 * ROWS) return;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (kind != ZERO) {
+            const uint4 *q = rb + slot * NQ * NT;
+            if (FUSE_LUMA) {
+                const uint4 a = q[0], b = q[NT], c = q[2 * NT];
+                val = make_uint4(gs_luma_x4(a.x, a.y, a.z, mean, sel_a, sel_b), gs_luma_x4(a.w, b.x, b.y, mean, sel_a, sel_b),
+                                 gs_luma_x4(b.z, b.w, c.x, mean, sel_a, sel_b), gs_luma_x4(c.y, c.z, c.w, mean, sel_a, sel_b));
+            } else {
+                val = q[0];
+            }
+            if (kind == MIRROR_L)        // columns -16 .. -1 <- columns 16 .. 1 (column 16 is never read)
+                val = make_uint4(__byte_perm(val.w, 0, 0x1234), __byte_perm(val.z, val.w, 0x1234),
+                                 __byte_perm(val.y, val.z, 0x1234), __byte_perm(val.x, val.y, 0x1234));
+            else if (kind == MIRROR_R)   // columns w .. w + 15 <- columns w - 2 .. w - 17 (the last one is never read)
+                val = make_uint4(__byte_perm(val.z, val.w, 0x3456), __byte_perm(val.y, val.z, 0x3456),
+                                 __byte_perm(val.x, val.y, 0x3456), __byte_perm(0, val.x, 0x3456));
+        }
+        unsigned *lb = lbuf + (st & 1) * ROWS * RW + row * RW;
+        *reinterpret_cast<uint4 *>(lb + (halo ? (hside ? GS_HW + NT : 0) : GS_HW + 4 * fcol)) = val;
+    };
+
+    const int x = x0 + 4 * tid;
+    const bool active = x < w;
+    uint8_t *orow = out + (size_t)blockIdx.z * out_fstride + (size_t)y0 * out_pitch + x;
+    unsigned win[NP][4];
+#pragma unroll
+    for (int u = 0; u < NP; u++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) win[u][k] = 0;
+
+    // prologue: fill the ring, then stage all of step 0
+#pragma unroll
+    for (int n = 0; n < D; n++) issue(n / NI, n % NI, n);
+#pragma unroll
+    for (int i = 0; i < NI; i++) {
+        va_cp_async_wait_group<D - 1>();
+        convert(0, i, i % D);
+        issue((i + D) / NI, (i + D) % NI, i % D);
+    }
+    __syncthreads();
+    int bslot = NI % D;                                     // ring slot of item 0 of the step being staged
+    for (int s = 0; s < nsteps; s++) {
+        const unsigned *lb = lbuf + (s & 1) * ROWS * RW + WOFS + tid;
+#pragma unroll
+        for (int gg = 0; gg < NP; gg++) {              // pair j lives in window slot gg
+            // ---- stage one item of step s + 1 (into the other row buffer), refill its ring slot
+            if (gg < NI) {
+                int slot = bslot + gg % D;
+                slot = slot >= D ? slot - D : slot;
+                va_cp_async_wait_group<D - 1>();
+                convert(s + 1, gg, slot);
+                issue(s + 1 + (gg + D) / NI, (gg + D) % NI, slot);
+            }
+            const int j = s * NP + gg;
+            if (!active || j >= npairs) continue;
+            // ---- row pass of pair j
+            const unsigned *r0 = lb + 2 * gg * RW;
+            const unsigned *r1 = r0 + RW;
+            unsigned a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int jw = 0; jw < NW; jw++) {
+                const unsigned xa = r0[jw], xb = r1[jw];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (4 * jw + 3 < O + i || 4 * jw > O + i + 2 * r) continue;   // no tap of pixel i in this word
+                    const unsigned c = g.cw[i][jw];
+                    a0[i] = __dp4a(xa, c, a0[i]);
+                    a1[i] = __dp4a(xb, c, a1[i]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) win[gg][k] = __byte_perm(a0[k], a1[k], 0x5410);
+            if (s == 0 && gg < r) continue;
+            // ---- column pass: output rows 2 (j - r) + {0, 1} of the segment from pairs j - r .. j,
+            // i.e. window slots gg + 1, gg + 2, ... (mod NP)
+            unsigned acc[2][4];
+#pragma unroll
+            for (int i = 0; i < 2; i++)
+#pragma unroll
+                for (int k = 0; k < 4; k++) acc[i][k] = 32768u;
+#pragma unroll
+            for (int t = 0; t < NP; t++) {
+                const unsigned c0 = g.cp[0][t], c1 = g.cp[1][t];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const unsigned v = win[(gg + 1 + t) % NP][k];
+                    acc[0][k] = __dp2a_lo(v, c0, acc[0][k]);
+                    acc[1][k] = __dp2a_lo(v, c1, acc[1][k]);
+                }
+            }
+            // byte 2 of every accumulator (sum + 32768 < 2^24) is the rounded result
+            *reinterpret_cast<unsigned *>(orow) =
+                __byte_perm(__byte_perm(acc[0][0], acc[0][1], 0x0062), __byte_perm(acc[0][2], acc[0][3], 0x0062), 0x5410);
+            if (2 * (j - r) + 1 < rows)
+                *reinterpret_cast<unsigned *>(orow + out_pitch) =
+                    __byte_perm(__byte_perm(acc[1][0], acc[1][1], 0x0062), __byte_perm(acc[1][2], acc[1][3], 0x0062), 0x5410);
+            orow += 2 * out_pitch;
+        }
+        bslot = (bslot + NI) % D;
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // generic kernel: any channel count, taps up to 256, scalar arithmetic
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GAUSS_THREADS)
@@ -393,6 +592,53 @@ static int gauss_launch(va_ctx *ctx, va_stream stream, const char *name, bool fu
                 if (k1 >= 0 && k1 < ksize) wd |= (unsigned)taps[k1] << 8;
                 g.cp[i][j] = wd;
             }
+        // streaming kernel for small radii on aligned frames
+        {
+            const char *env = getenv("VA_GAUSS_STREAM");
+            const int stream_mode = env ? atoi(env) : 1;          // 0: tile kernel only (tuning / A-B checks)
+            const bool in16 = va_aligned(in, 16) && in_pitch % 16 == 0 && in_fstride % 16 == 0;
+            const bool out4 = va_aligned(out, 4) && out_pitch % 4 == 0 && out_fstride % 4 == 0;
+            if (stream_mode && r <= 8 && h >= r + 2 && w % 16 == 0 && in16 && out4 && batch <= 65535) {
+                // strip width: least idle columns, then the widest strip (fewest halo columns)
+                int NT = 64;
+                long long best = 1ll << 60;
+                for (int nt = 64; nt <= GS_MAX_THREADS; nt += 32) {
+                    const long long cover = (long long)va_div_up(w, 4 * nt) * nt;
+                    if (cover <= best) { best = cover; NT = nt; }
+                }
+                if (getenv("VA_GS_NT")) NT = atoi(getenv("VA_GS_NT"));
+                const int strips = va_div_up(w, 4 * NT);
+                // segments in y: enough CTAs for a few waves, each segment re-stages 2 r rows
+                int segs = va_div_up((long long)ctx->sm_count * 24, (long long)strips * batch);
+                const int max_segs = h / (8 * r) > 0 ? h / (8 * r) : 1;
+                if (segs > max_segs) segs = max_segs;
+                if (getenv("VA_GS_SEGS")) segs = atoi(getenv("VA_GS_SEGS"));
+                if (segs < 1) segs = 1;
+                const int SH = 2 * va_div_up(h, 2 * segs);
+                const int segs_y = va_div_up(h, SH);
+                if (segs_y <= 65535) {
+                    const int NQ = fuse ? 3 : 1;
+                    const int ROWS = 2 * (r + 1);
+                    const size_t smem = (size_t)GS_DEPTH * NQ * NT * 16 + (size_t)2 * ROWS * (NT + 2 * GS_HW) * 4;
+                    const dim3 grid(strips, segs_y, batch);
+#define GS_GO(RT, FUSE)                                                                                       \
+                    do {                                                                                      \
+                        auto kfn = gauss_stream_kernel<RT, FUSE>;                                             \
+                        if (smem > 48 * 1024)                                                                 \
+                            VA_CUDA(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                        VA_LAUNCH(ctx, kfn, grid, NT, smem, stream, in, in_pitch, in_fstride, out, out_pitch, \
+                                  out_fstride, w, h, mode, SH, g);                                            \
+                    } while (0)
+#define GS_CASE(RT) case RT: if (fuse) GS_GO(RT, true); else GS_GO(RT, false); break;
+                    switch (r) {
+                        GS_CASE(1) GS_CASE(2) GS_CASE(3) GS_CASE(4) GS_CASE(5) GS_CASE(6) GS_CASE(7) GS_CASE(8)
+                    }
+#undef GS_CASE
+#undef GS_GO
+                    return VA_OK;
+                }
+            }
+        }
         // tile height: minimise staged rows + idle warp rounds + rows wasted below the image
         const int R16 = (r + 15) & ~15;
         const int SW = GAUSS_TW + 2 * R16 + 16;
