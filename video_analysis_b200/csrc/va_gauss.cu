@@ -292,17 +292,18 @@ gauss_fast_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fst
 }
 
 // ---------------------------------------------------------------------------------
-// streaming kernel (radius < 16, 16-byte aligned frames, w % 16 == 0): a CTA owns a strip of
-// 4 * blockDim.x columns and walks down a segment of rows.  Thread t owns columns 4t .. 4t+3 for the
-// whole walk and keeps the last RT + 1 row pairs of the row pass in registers, so the 16-bit
+// streaming kernel (radius < 16, 16-byte aligned frames, w % 16 == 0): a warp owns a strip of 128
+// columns and walks down a segment of rows.  Lane t owns columns 4t .. 4t+3 for the whole walk and
+// keeps the last RT + 1 row pairs of the row pass in registers, so the 16-bit
 // intermediate image never exists in memory and no row of the segment is staged twice.
-// A step is RT + 1 row pairs = one turn of the register window, so every slot index is static.
-// Per pair of step s:
+// Warps are independent (each stages its own 128 columns plus a 16-column halo on either side), so
+// there is no CTA barrier.  A step is RT + 1 row pairs = one turn of the register window, so every
+// slot index is static.  Per pair of step s:
 //   stage     one 16-pixel item of step s + 1: raw bytes (cp.async'ed into a private ring slot a few
 //             pairs ago) -> luma words in the row buffer of step s + 1; the slot is refilled at once
 //   rows      dp4a on 2 rows x 4 pixels from the row buffer of step s -> window slot
 //   cols      dp2a over the window -> 2 output rows x 4 pixels, one 4-byte store each
-// and one barrier per step.
+// and one __syncwarp per step.
 // ---------------------------------------------------------------------------------
 #define GS_MAX_THREADS 256
 #define GS_MAX_R 16
@@ -320,23 +321,25 @@ __global__ void __launch_bounds__(GS_MAX_THREADS, 3)
 gauss_stream_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstride,
                     uint8_t *__restrict__ out, size_t out_pitch, size_t out_fstride,
                     int w, int h, int mode, int SH, const __grid_constant__ GaussFast g) {
-    // grid = (strips in x, segments in y, frames)
+    // grid = (groups of strips in x, segments in y, frames); every warp works on its own
     constexpr int r = RT, NP = RT + 1;
     constexpr int O = (4 - (r & 3)) & 3;
     constexpr int NW = (O + 2 * r + 4 + 3) >> 2;             // staged words feeding one 4-pixel group
     constexpr int WOFS = GS_HW - ((r + 3) >> 2);             // first staged word needed by group 0
     constexpr int NQ = FUSE_LUMA ? 3 : 1;                    // 16-byte chunks per 16-pixel item
     constexpr int ROWS = 2 * NP;                             // image rows per step (one turn of the window)
-    constexpr int IPT = (ROWS + 3) / 4;                      // interior items per thread and step
-    constexpr int NI = IPT + 1;                              // + the halo item
-    constexpr int D = GS_DEPTH;                              // raw ring slots per thread
-    static_assert(NI <= NP || NP == 1, "one item per pair");
+    constexpr int IPT = (ROWS + 3) / 4;                      // interior items per lane and step
+    constexpr int HPT = (2 * ROWS + 31) / 32;                // halo items per lane and step
+    constexpr int NI = IPT + HPT;
+    constexpr int D = GS_DEPTH;                              // raw ring slots per lane
+    constexpr int RW = 32 + 2 * GS_HW;                       // words per staged row
+    static_assert(NI <= NP, "one item per pair");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NT = blockDim.x;
-    const int RW = NT + 2 * GS_HW;                           // words per staged row
     VA_DYN_SMEM(uint4, smem);
-    uint4 *raw = smem;                                       // [D][NQ][NT] private raw bytes
-    unsigned *lbuf = reinterpret_cast<unsigned *>(smem + D * NQ * NT);   // [2][ROWS][RW] luma words
-    const int x0 = blockIdx.x * 4 * NT;
+    uint4 *rb = smem + tid;                                  // [D][NQ][NT] private raw bytes
+    unsigned *lbuf = reinterpret_cast<unsigned *>(smem + D * NQ * NT) + warp * (2 * ROWS * RW);   // [warp][2][ROWS][RW] luma words
+    const int x0 = (blockIdx.x * (NT >> 5) + warp) * 128;
+    if (x0 >= w) return;
     const int y0 = blockIdx.y * SH;
     const int rows = min(SH, h - y0);
     const int npairs = ((rows + 1) >> 1) + r;
@@ -347,30 +350,28 @@ gauss_stream_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_f
     const unsigned sel_a = mode == 0 ? 0x0630u : mode == 1 ? 0x0741u : 0x0052u;
     const unsigned sel_b = mode == 0 ? 0x5210u : mode == 1 ? 0x6210u : 0x7410u;
 
-    // staging duty of this thread: NI items per step -- up to IPT interior items (a quarter warp covers
-    // 128 columns of one row; rows frow, frow + 4, ...) and one halo item for the first 2 * ROWS threads.
+    // staging duty of this lane: NI items of 16 pixels per step -- IPT of the strip's own 128 columns (a
+    // quarter warp covers one row; rows frow, frow + 4, ...) and HPT of the 16-column halos on either side.
     // Items travel through a private ring of D raw slots: item n is converted while items n + 1 ..
     // n + D - 1 are in flight, and its slot is refilled with item n + D at once.
     // Columns outside the image (w % 16 == 0, so an item is inside or outside as a whole): the item
     // next to the left / right border is the mirrored neighbour item (BORDER_REFLECT_101, radius < 16),
     // anything further out is never read and staged as 0.
-    const int frow = lane >> 3;
-    const int fcol = warp * 8 + (lane & 7);
-    const int fgx = x0 + 16 * fcol;
-    const int hrow = tid >> 1;
-    const bool hside = tid & 1;
-    const int hgx = hside ? x0 + 4 * NT : x0 - 16;
     enum { IN = 0, MIRROR_L = 1, MIRROR_R = 2, ZERO = 3 };
+    const int frow = lane >> 3;
+    const int fcol = lane & 7;
+    const int fgx = x0 + 16 * fcol;
     const int fkind = fgx < w ? IN : fgx == w ? MIRROR_R : ZERO;
-    const int hkind = tid >= 2 * ROWS ? ZERO : hgx < 0 ? MIRROR_L : hgx < w ? IN : hgx == w ? MIRROR_R : ZERO;
     const uint8_t *fcolp = fin + (FUSE_LUMA ? 3 : 1) * (size_t)(fkind == MIRROR_R ? w - 16 : fgx);
+    const bool hside = lane & 1;
+    const int hgx = hside ? x0 + 128 : x0 - 16;
+    const int hkind = hgx < 0 ? MIRROR_L : hgx < w ? IN : hgx == w ? MIRROR_R : ZERO;
     const uint8_t *hcolp = fin + (FUSE_LUMA ? 3 : 1) * (size_t)(hkind == MIRROR_L ? 0 : hkind == MIRROR_R ? w - 16 : hgx);
-    uint4 *rb = raw + tid;
 
     auto issue = [&](int st, int i, int slot) {             // i static
         if (st < nsteps) {
-            const bool halo = i == IPT;
-            const int row = halo ? hrow : frow + 4 * i;
+            const bool halo = i >= IPT;
+            const int row = halo ? (lane >> 1) + 16 * (i - IPT) : frow + 4 * i;
             if ((halo ? hkind : fkind) != ZERO && row < ROWS) {
                 const unsigned gy = (unsigned)gauss_reflect_row(y0 - r + ROWS * st + row, h, false);
                 const uint8_t *p = (halo ? hcolp : fcolp) + (size_t)(gy * pitch32);
@@ -382,11 +383,10 @@ gauss_stream_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_f
     };
     auto convert = [&](int st, int i, int slot) {           // i static
         if (st >= nsteps) return;
-        const bool halo = i == IPT;
-        const int row = halo ? hrow : frow + 4 * i;
+        const bool halo = i >= IPT;
+        const int row = halo ? (lane >> 1) + 16 * (i - IPT) : frow + 4 * i;
         if (row >= ROWS) return;
         const int kind = halo ? hkind : fkind;
-        if (halo && tid >= 2 * ROWS) return;
         uint4 val = make_uint4(0, 0, 0, 0);
         if (kind != ZERO) {
             const uint4 *q = rb + slot * NQ * NT;
@@ -405,10 +405,10 @@ gauss_stream_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_f
                                  __byte_perm(val.x, val.y, 0x3456), __byte_perm(0, val.x, 0x3456));
         }
         unsigned *lb = lbuf + (st & 1) * ROWS * RW + row * RW;
-        *reinterpret_cast<uint4 *>(lb + (halo ? (hside ? GS_HW + NT : 0) : GS_HW + 4 * fcol)) = val;
+        *reinterpret_cast<uint4 *>(lb + (halo ? (hside ? GS_HW + 32 : 0) : GS_HW + 4 * fcol)) = val;
     };
 
-    const int x = x0 + 4 * tid;
+    const int x = x0 + 4 * lane;
     const bool active = x < w;
     uint8_t *orow = out + (size_t)blockIdx.z * out_fstride + (size_t)y0 * out_pitch + x;
     unsigned win[NP][4];
@@ -426,10 +426,10 @@ gauss_stream_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_f
         convert(0, i, i % D);
         issue((i + D) / NI, (i + D) % NI, i % D);
     }
-    __syncthreads();
+    __syncwarp();
     int bslot = NI % D;                                     // ring slot of item 0 of the step being staged
     for (int s = 0; s < nsteps; s++) {
-        const unsigned *lb = lbuf + (s & 1) * ROWS * RW + WOFS + tid;
+        const unsigned *lb = lbuf + (s & 1) * ROWS * RW + WOFS + lane;
 #pragma unroll
         for (int gg = 0; gg < NP; gg++) {              // pair j lives in window slot gg
             // ---- stage one item of step s + 1 (into the other row buffer), refill its ring slot
@@ -486,7 +486,7 @@ gauss_stream_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_f
             orow += 2 * out_pitch;
         }
         bslot = (bslot + NI) % D;
-        __syncthreads();
+        __syncwarp();
     }
 }
 
@@ -619,7 +619,7 @@ static int gauss_launch(va_ctx *ctx, va_stream stream, const char *name, bool fu
                 if (segs_y <= 65535) {
                     const int NQ = fuse ? 3 : 1;
                     const int ROWS = 2 * (r + 1);
-                    const size_t smem = (size_t)GS_DEPTH * NQ * NT * 16 + (size_t)2 * ROWS * (NT + 2 * GS_HW) * 4;
+                    const size_t smem = (size_t)GS_DEPTH * NQ * NT * 16 + (size_t)(NT / 32) * 2 * ROWS * (32 + 2 * GS_HW) * 4;
                     const dim3 grid(strips, segs_y, batch);
 #define GS_GO(RT, FUSE)                                                                                       \
                     do {                                                                                      \
