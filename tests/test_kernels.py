@@ -68,6 +68,17 @@ def test_crop_by_pointer_offset(be, ctx):
         assert np.array_equal(hz.copy2d(ctx, mono, (16, 2, 32, 8)), mono[:, 2:10, 16:48])
 
 
+def test_luma_every_channel_sum(be, ctx):
+    # all 766 sums, at every position of a 4-pixel group and through the fused blur's converter
+    s = np.arange(768 * 4) % 766
+    px = np.zeros((1, 16, 192, 3), np.uint8)
+    px[0, :, :, 0] = np.minimum(s, 255).reshape(16, 192)
+    px[0, :, :, 1] = np.clip(s - 255, 0, 255).reshape(16, 192)
+    px[0, :, :, 2] = np.clip(s - 510, 0, 255).reshape(16, 192)
+    assert np.array_equal(hz.luma(ctx, px)[0], (s // 3).reshape(16, 192))
+    assert np.array_equal(hz.luma_gauss(ctx, px, 0.5), np.stack([ops.blur(ops.mono(f), 0.5) for f in px]))
+
+
 def test_luma_rejects_bad_arguments(be, ctx):
     fr = rng_frames(1, (1, 4, 8, 3))
     with pytest.raises(ValueError):

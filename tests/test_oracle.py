@@ -66,6 +66,19 @@ def test_mono_is_integer_division():
         assert np.array_equal(ops.mono(f, name), f[:, :, c])
 
 
+def test_div3_by_half_precision_fma():
+    # the kernels divide the channel sum by 3 with one fp16 fused multiply-add (csrc/va_device.cuh:
+    # va_div3_h2): RN_fp16((1024 + s) * 0x3555 + 682.5) == 1024 + s // 3 for every sum s <= 765
+    from fractions import Fraction
+    c = Fraction(float(np.uint16(0x3555).view(np.float16)))
+    b = Fraction(float(np.uint16(0x6155).view(np.float16)))
+    for s in range(766):
+        v = (1024 + s) * c + b
+        f = np.float64(v.numerator) / np.float64(v.denominator)
+        assert Fraction(float(f)) == v                      # exact in double, so one rounding to fp16
+        assert int(np.float16(f).view(np.uint16)) == 0x6400 + s // 3
+
+
 @pytest.mark.parametrize('sigma', [0.05, 0.3, 0.5, 1, 2, 3, 5, 15, 21])
 @pytest.mark.parametrize('shape', [(37, 53), (120, 160)])
 def test_integer_gaussian_equals_cv2(sigma, shape):

@@ -74,16 +74,29 @@ __device__ __forceinline__ int va_reflect101(int i, int n) {
     return i < n ? i : p - i;
 }
 
+// floor(s / 3) for two sums s <= 765 held as the halves 0x6400 + s (fp16 1024 + s): one fp16 FMA with
+// c = 0x3555 (1365 / 4096) and b = 682.5 rounds 1023.75 + s c to 1024 + floor(s / 3) for every such s
+// (checked exhaustively; tests/test_oracle.py repeats the check), so the low byte of each half is the
+// quotient
+__device__ __forceinline__ unsigned va_div3_h2(unsigned p) {
+#ifdef VA_EMU
+    return (0x6400u + ((p & 0xffffu) - 0x6400u) / 3u) | ((0x6400u + ((p >> 16) - 0x6400u) / 3u) << 16);
+#else
+    unsigned d;
+    asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(p), "r"(0x35553555u), "r"(0x61556155u));
+    return d;
+#endif
+}
+
 // (c0 + c1 + c2) / 3 for four interleaved RGB pixels held in three words
 __device__ __forceinline__ unsigned va_mean3_x4(unsigned w0, unsigned w1, unsigned w2) {
-    unsigned s0 = __dp4a(w0, 0x00010101u, 0u);
-    unsigned s1 = __dp4a(w0, 0x01000000u, __dp4a(w1, 0x00000101u, 0u));
-    unsigned s2 = __dp4a(w1, 0x01010000u, __dp4a(w2, 0x00000001u, 0u));
-    unsigned s3 = __dp4a(w2, 0x01010100u, 0u);
-    // floor(s / 3) == umulhi(s, (2^32 + 2) / 3) for s < 2^31
-    unsigned q0 = __umulhi(s0, 0x55555556u), q1 = __umulhi(s1, 0x55555556u);
-    unsigned q2 = __umulhi(s2, 0x55555556u), q3 = __umulhi(s3, 0x55555556u);
-    return q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
+    const unsigned s0 = __dp4a(w0, 0x00010101u, 0x6400u);
+    const unsigned s1 = __dp4a(w0, 0x01000000u, __dp4a(w1, 0x00000101u, 0x6400u));
+    const unsigned s2 = __dp4a(w1, 0x01010000u, __dp4a(w2, 0x00000001u, 0x6400u));
+    const unsigned s3 = __dp4a(w2, 0x01010100u, 0x6400u);
+    const unsigned q01 = va_div3_h2(__byte_perm(s0, s1, 0x5410));
+    const unsigned q23 = va_div3_h2(__byte_perm(s2, s3, 0x5410));
+    return __byte_perm(q01, q23, 0x6420);
 }
 // channel c of four interleaved RGB pixels held in three words
 __device__ __forceinline__ unsigned va_pick3_x4(unsigned w0, unsigned w1, unsigned w2, int c) {

@@ -599,12 +599,14 @@ static int gauss_launch(va_ctx *ctx, va_stream stream, const char *name, bool fu
             const bool in16 = va_aligned(in, 16) && in_pitch % 16 == 0 && in_fstride % 16 == 0;
             const bool out4 = va_aligned(out, 4) && out_pitch % 4 == 0 && out_fstride % 4 == 0;
             if (stream_mode && r <= 8 && h >= r + 2 && w % 16 == 0 && in16 && out4 && batch <= 65535) {
-                // strip width: least idle columns, then the widest strip (fewest halo columns)
-                int NT = 64;
+                // warps per CTA: least idle warps at the right image edge, then the size closest to 3 warps
+                // (warps are independent; small CTAs pack the SMs better)
+                int NT = 96;
                 long long best = 1ll << 60;
-                for (int nt = 64; nt <= GS_MAX_THREADS; nt += 32) {
+                for (int nt = 32; nt <= GS_MAX_THREADS; nt += 32) {
                     const long long cover = (long long)va_div_up(w, 4 * nt) * nt;
-                    if (cover <= best) { best = cover; NT = nt; }
+                    const int dist = nt > 96 ? nt - 96 : 96 - nt, bdist = NT > 96 ? NT - 96 : 96 - NT;
+                    if (cover < best || (cover == best && dist < bdist)) { best = cover; NT = nt; }
                 }
                 if (getenv("VA_GS_NT")) NT = atoi(getenv("VA_GS_NT"));
                 const int strips = va_div_up(w, 4 * NT);
