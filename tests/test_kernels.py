@@ -182,6 +182,20 @@ def test_ema_diff_threshold_bit_exact(be, ctx):
         assert np.array_equal(bg2.view(np.uint32), bg2_ref.view(np.uint32))
 
 
+def test_ema_threshold_edge_cases(be, ctx):
+    # differences that hit the threshold exactly (alpha = 0.5 keeps the state on a dyadic grid), zero,
+    # negative and signed-zero thresholds; a non-finite threshold is rejected
+    rng = np.random.default_rng(11)
+    g = rng.integers(0, 8, (9, 6, 64), dtype=np.uint8) * 4
+    for alpha, thr in ((0.5, 2.0), (0.5, 1.0), (0.25, 3.0), (0.05, 0.0), (0.05, -0.0), (0.5, -1.0), (1.0, 4.0)):
+        m_ref, bg_ref = ops.background_ema(list(g), alpha, thr)
+        m, bg = hz.ema_diff_thresh(ctx, g, alpha, thr)
+        assert np.array_equal(m, ops.pack_bits(m_ref)), (alpha, thr)
+        assert np.array_equal(bg.view(np.uint32), bg_ref.view(np.uint32))
+    with pytest.raises(ValueError):
+        hz.ema_diff_thresh(ctx, g, 0.05, float('inf'))
+
+
 def test_ema_golden(be, ctx):
     m, bg = hz.ema_diff_thresh(ctx, GOLD['s_blur'], 0.05, 25)
     assert np.array_equal(m, ops.pack_bits(GOLD['s_mask']))

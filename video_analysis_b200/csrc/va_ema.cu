@@ -35,15 +35,18 @@ __device__ __forceinline__ float ema_byte_to_float(unsigned word, int i) {
     return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540u + i)) - 8388608.0f;
 }
 
-// one frame for the PX pixels of a thread: returns the PX mask bits, updates the state
+// one frame for the PX pixels of a thread: returns the PX mask bits, updates the state.
+// |d| > thr is read off the sign of thr - |d| (negative exactly when the comparison holds: a
+// float subtraction never rounds across zero, and thr == |d| gives +0) and shifted into the mask
+// by one funnel shift per pixel, highest pixel first.  thr is finite and not -0 (checked by the host).
 template <int PX>
 __device__ __forceinline__ unsigned ema_step(const unsigned (&v)[PX / 4], float (&s)[PX], float alpha, float thr) {
     unsigned m = 0;
 #pragma unroll
-    for (int i = 0; i < PX; i++) {
+    for (int i = PX - 1; i >= 0; i--) {
         const float xf = ema_byte_to_float(v[i >> 2], i & 3);
         const float d = __fadd_rn(xf, -s[i]);
-        if (fabsf(d) > thr) m |= 1u << i;
+        m = __funnelshift_l(__float_as_uint(__fadd_rn(thr, -fabsf(d))), m, 1);
         s[i] = __fadd_rn(s[i], __fmul_rn(alpha, d));
     }
     return m;
@@ -97,10 +100,12 @@ ema_diff_thresh_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t i
         const bool fast = vec_in && x + PX <= w;
 
         // prologue: RING - 1 frames in flight
+        const uint8_t *rnext = rp;                     // row y of the next frame to put in flight
 #pragma unroll
         for (int u = 0; u < RING - 1; u++) {
-            if (u < batch) ema_issue<PX>(myslot + u * SLOT_STRIDE, rp + (size_t)u * in_fstride, x, w, fast);
+            if (u < batch) ema_issue<PX>(myslot + u * SLOT_STRIDE, rnext, x, w, fast);
             else va_cp_async_commit();
+            rnext += in_fstride;
         }
 
         float s[PX];
@@ -119,8 +124,9 @@ ema_diff_thresh_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t i
         const bool writer = (lane & (32 / PX - 1)) == 0 && x < w;
         for (int t = 0; t < batch; t++) {
             const int tn = t + RING - 1;                 // frame to put in flight now
-            if (tn < batch) ema_issue<PX>(myslot + (tn % RING) * SLOT_STRIDE, rp + (size_t)tn * in_fstride, x, w, fast);
+            if (tn < batch) ema_issue<PX>(myslot + (tn % RING) * SLOT_STRIDE, rnext, x, w, fast);
             else va_cp_async_commit();
+            rnext += in_fstride;
             va_cp_async_wait_group<RING - 1>();          // frame t has landed
             unsigned v[NW];
             const unsigned *slot = myslot + (t % RING) * SLOT_STRIDE;
@@ -140,7 +146,8 @@ ema_diff_thresh_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t i
             }
 #pragma unroll
             for (int sh = PX, d = 1; sh < 32; sh <<= 1, d <<= 1) m |= __shfl_down_sync(0xffffffffu, m, d) << sh;
-            if (writer) mrow[(size_t)t * mask_fstride_w] = m;
+            if (writer) *mrow = m;
+            mrow += mask_fstride_w;
         }
         va_cp_async_wait_group<0>();
 
@@ -165,6 +172,8 @@ extern "C" int va_ema_diff_thresh(va_ctx *ctx, va_stream stream,
     VA_REQUIRE(ctx, in && bg && mask, "va_ema_diff_thresh: null pointer");
     VA_REQUIRE(ctx, w > 0 && h > 0 && batch > 0, "va_ema_diff_thresh: bad size");
     VA_REQUIRE(ctx, mask_pitch_w >= (size_t)((w + 31) / 32) && bg_pitch_e >= (size_t)w, "va_ema_diff_thresh: pitch smaller than a row");
+    VA_REQUIRE(ctx, thr - thr == 0.0f, "va_ema_diff_thresh: threshold must be finite");
+    thr += 0.0f;                                        // -0 -> +0 (the kernel tests the sign of thr - |d|)
     const int vec_bg = va_aligned(bg, 16) && bg_pitch_e % 4 == 0;
     // 16 pixels per thread when that still fills the machine, else 4
     const long long threads16 = (long long)((w + 511) / 512) * 32 * h;
