@@ -297,6 +297,23 @@ def gpu_arm(args):
         e2e_s = float(tmax.item())
     e2e_fps = world * Ke * B / e2e_s
 
+    # ---- e2e with the region table as the result: same chain, same host input, but
+    # per-region moments / boxes come back instead of the 4-bytes-per-pixel label image
+    MAXR = 256
+    for st, cnt, big in e2e_chain.process_blocks(blocks(max(3, min(Wm, 5))), max_regions=MAXR):
+        sink += int(cnt[0])
+    barrier()
+    t0 = time.perf_counter()
+    for st, cnt, big in e2e_chain.process_blocks(blocks(Ke), max_regions=MAXR):
+        sink += int(cnt[-1]) + int(st[0, 0, 0]) + int(big[0])
+    torch.cuda.synchronize()
+    reg_s = time.perf_counter() - t0
+    if world > 1:
+        tmax = torch.tensor([reg_s], device=rt.device)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        reg_s = float(tmax.item())
+    reg_fps = world * Ke * B / reg_s
+
     if rank == 0:
         line = {
             'metric': 'frames/sec full filter+segment chain', 'value': round(fps, 1), 'unit': 'frames/s',
@@ -311,6 +328,10 @@ def gpu_arm(args):
             'e2e': {'value': round(e2e_fps, 1), 'unit': 'frames/s', 'h2d_bytes_per_step': B * N * 3,
                     'd2h_bytes_per_step': B * N * 4 + B * 4, 'steps': Ke,
                     'api': 'SegmentChain.process_blocks (pinned host frames in, int32 labels + counts out)'},
+            'e2e_region_table': {'value': round(reg_fps, 1), 'unit': 'frames/s', 'h2d_bytes_per_step': B * N * 3,
+                                 'd2h_bytes_per_step': B * (MAXR * 80 + 8), 'steps': Ke,
+                                 'api': 'SegmentChain.process_blocks(max_regions=%d): pinned host frames in, per-region '
+                                        'moments + bounding boxes + counts out (no label image crosses PCIe)' % MAXR},
             'gpu_launches': int(launches),
             'roofline': roof,
         }

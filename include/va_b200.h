@@ -161,6 +161,20 @@ int va_region_areas(va_ctx *ctx, va_stream stream,
                     int32_t *areas, int max_labels, int32_t *largest,
                     int w, int h, int batch);
 
+/* per-region statistics straight from a packed mask -- the label image is never written (nor
+ * copied to the host).  Regions are numbered like va_label_bits numbers them.  For region l of
+ * frame b, stats[(b * max_regions + l - 1) * VA_REGION_FIELDS + k] holds, as exact integers,
+ *   k = 0..5  raw moments m00 m10 m01 m20 m11 m02 of cv2.moments(region.astype(uint8)), the input
+ *             of regionprops (video/analysis/image.py:347-352; m00 = area of regions.py:165-166)
+ *   k = 6..9  xmin ymin xmax ymax (find_bounding_box, video/analysis/regions.py:113-149)
+ * counts[b] = number of regions of frame b (rows of regions beyond max_regions are not written);
+ * largest[b] = label of the largest region (regions.py:169), may be NULL. */
+#define VA_REGION_FIELDS 10
+int va_region_stats(va_ctx *ctx, va_stream stream,
+                    const uint32_t *mask, size_t mask_pitch_w, size_t mask_fstride_w,
+                    int64_t *stats, int max_regions, int32_t *counts, int32_t *largest,
+                    int w, int h, int batch, int connectivity);
+
 /* K6 apply-mask: out = mask != 0 ? in : 0 (not in the reference; idioms
  * video/io/composer.py:154,186,208).  mask is u8 (H, W); mask_fstride = 0
  * broadcasts one static mask over the batch. */

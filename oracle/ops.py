@@ -336,6 +336,68 @@ def get_largest_region(mask, ret_area=False):
     return labels == label_max
 
 
+def find_bounding_box(mask):
+    """ regions.py:113-149: (left, top, width, height) of the first block of non-empty rows and the
+    first block of non-empty columns (the bounding box when the mask holds one connected region) """
+    rows = np.any(mask, axis=1)
+    cols = np.any(mask, axis=0)
+    top = 0
+    while not rows[top]:
+        top += 1
+    bottom = top + 1
+    while bottom < mask.shape[0] and rows[bottom]:
+        bottom += 1
+    left = 0
+    while not cols[left]:
+        left += 1
+    right = left + 1
+    while right < mask.shape[1] and cols[right]:
+        right += 1
+    return (left, top, right - left, bottom - top)
+
+
+def region_moments(labels, n):
+    """ image.py:350: cv2.moments(mask.astype(np.uint8)) for every region of a label image """
+    return [cv2.moments((labels == l).astype(np.uint8)) for l in range(1, n + 1)]
+
+
+class regionprops(object):
+    """ image.py:310-405, the properties derived from the moments (same formulae, same order) """
+
+    def __init__(self, mask=None, moments=None):
+        self.moments = moments if moments is not None else cv2.moments(mask.astype(np.uint8))
+
+    @property
+    def area(self):
+        return self.moments['m00']
+
+    @property
+    def centroid(self):
+        m = self.moments
+        return (m['m10'] / m['m00'], m['m01'] / m['m00'])
+
+    @property
+    def orientation(self):
+        m = self.moments
+        a, b, c = m['mu20'], m['mu11'], m['mu02']
+        if a - c == 0:
+            return -np.pi / 4 if b > 0 else np.pi / 4
+        return -np.arctan2(2 * b, (a - c)) / 2
+
+    @property
+    def inertia_tensor_eigvals(self):
+        m = self.moments
+        a, b, c = m['mu20'] / m['m00'], -m['mu11'] / m['m00'], m['mu02'] / m['m00']
+        e1 = (a + c) + np.sqrt(4 * b ** 2 + (a - c) ** 2)
+        e2 = (a + c) - np.sqrt(4 * b ** 2 + (a - c) ** 2)
+        return e1, e2
+
+    @property
+    def eccentricity(self):
+        e1, e2 = self.inertia_tensor_eigvals
+        return 0 if e1 == 0 else np.sqrt(1 - e2 / e1)
+
+
 # --------------------------------------------------------------------------
 # packed bit masks (device layout): 32-bit words, LSB = lowest x
 # --------------------------------------------------------------------------

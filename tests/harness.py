@@ -313,6 +313,19 @@ def region_areas(ctx, labels, max_labels):
     return areas.get()[0], largest.get()[0, 0]
 
 
+def region_stats(ctx, words, W, max_regions, connectivity=4):
+    """ returns (stats int64 [B, max_regions, 10], counts int32 [B], largest int32 [B]) """
+    be = ctx.be
+    B, H, Wp = words.shape
+    src = Img(be, B, H, Wp, np.uint32, data=words)
+    st = Img(be, 1, B, max_regions * 10, np.int64, fill=0x5A)
+    cnt = Img(be, 1, 1, B, np.int32)
+    largest = Img(be, 1, 1, B, np.int32)
+    ctx.check(ctx.lib.va_region_stats(ctx.h, be.stream, src.ptr, src.pitch, src.fstride, st.ptr, max_regions, cnt.ptr,
+                                      largest.ptr, W, H, B, connectivity))
+    return st.get()[0].reshape(B, max_regions, 10), cnt.get()[0, 0], largest.get()[0, 0]
+
+
 def apply_mask(ctx, frames, mask):
     be = ctx.be
     if frames.ndim == 3:

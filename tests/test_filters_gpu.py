@@ -125,6 +125,28 @@ def test_segment_chain_host_pipeline(frames, ref):
         assert np.array_equal(np.concatenate([l1, l2]), ref['labels'])
 
 
+def test_segment_chain_region_tables(frames, ref):
+    # same chain, per-region statistics as the result: equal to statistics of the oracle's label images
+    mods()
+    from video_analysis_b200.chain import SegmentChain
+    ch = SegmentChain((320, 240), sigma=2, alpha=0.05, threshold=25, morph_op='open', morph_ksize=3, batch=8)
+    regs = ch.process_regions(frames, max_regions=64)
+    assert len(regs) == len(frames)
+    assert np.array_equal(ch.background.view(np.uint32), ref['bg'].view(np.uint32))
+    for t in range(len(frames)):
+        lab, n = ref['labels'][t], ref['counts'][t]
+        assert len(regs[t]) == n
+        areas = ops.region_areas(lab, n)
+        for reg in regs[t]:
+            ys, xs = np.nonzero(lab == reg['label'])
+            assert reg['area'] == areas[reg['label'] - 1]
+            assert reg['bbox'] == (xs.min(), ys.min(), xs.max() - xs.min() + 1, ys.max() - ys.min() + 1)
+            assert reg['moments']['m10'] == xs.sum() and reg['moments']['m02'] == (ys.astype(np.int64) ** 2).sum()
+    ch.reset()
+    with pytest.raises(MemoryError):
+        ch.process_regions(frames[:30], max_regions=1)
+
+
 def test_config5_like_chain(frames):
     """ stencil-heavy variant: sigma 5, 7x7 close then labelling with 8-connectivity """
     mods()
@@ -153,6 +175,35 @@ def test_analysis_helpers(frames, ref):
     assert np.array_equal(image.opening(ref['mask'][20]), ops.morph(ref['mask'][20], 'open'))
     assert np.array_equal(image.erode(ref['mask'][20]), ops.morph(ref['mask'][20], 'erode', 'cross', 3))
     assert np.array_equal(image.closing(ref['mask'][20], 'ellipse', 5), ops.morph(ref['mask'][20], 'close', 'ellipse', 5))
+
+
+def test_region_statistics_and_regionprops(frames, ref):
+    mods()
+    from video_analysis_b200.analysis import image, regions
+    m = ref['morph'][25]
+    lab, n = ops.label(m)
+    regs = regions.region_stats(m)
+    assert len(regs) == n and n >= 2
+    for reg, mom in zip(regs, ops.region_moments(lab, n)):
+        for key in ('m00', 'm10', 'm01', 'm20', 'm11', 'm02', 'mu20', 'mu11', 'mu02', 'nu20', 'nu11', 'nu02'):
+            assert reg['moments'][key] == pytest.approx(mom[key], rel=1e-12, abs=1e-14 * mom['m20'] + 1e-12), key
+        mask_l = lab == reg['label']
+        assert reg['bbox'] == ops.find_bounding_box(mask_l) and reg['area'] == mask_l.sum()
+        got, want = image.regionprops(moments=reg['moments']), ops.regionprops(mask=mask_l)
+        assert got.centroid == pytest.approx(want.centroid, rel=1e-12)
+        assert got.orientation == pytest.approx(want.orientation, rel=1e-9, abs=1e-12)
+        assert got.eccentricity == pytest.approx(want.eccentricity, rel=1e-9, abs=1e-9)
+        assert image.regionprops(mask=mask_l).moments['mu11'] == pytest.approx(want.moments['mu11'], rel=1e-12, abs=1e-14 * mom['m20'] + 1e-12)
+    # the reference's bounding box of a mask with several regions: first block of rows / columns
+    assert regions.find_bounding_box(m) == ops.find_bounding_box(m)
+    two = np.zeros((40, 60), np.uint8)
+    two[3:9, 30:41] = 1
+    two[20:30, 5:12] = 1
+    assert regions.find_bounding_box(two) == ops.find_bounding_box(two) == (5, 3, 7, 6)
+    with pytest.raises(IndexError):
+        regions.find_bounding_box(np.zeros((8, 8), np.uint8))
+    with pytest.raises(MemoryError):
+        regions.region_stats((np.indices((16, 64)).sum(0) & 1), max_regions=16)
 
 
 def test_synthetic_video_source():

@@ -319,6 +319,11 @@ def test_label_capacity_error(be, ctx):
         hz.label(ctx, ops.pack_bits(m), 40)
 
 
+def synth_masks(n, H, W):
+    fr = synth.make_frames(0, 0, n, W, H, 6)
+    return ops.chain(fr)['morph'].astype(bool)
+
+
 def test_region_areas_and_largest(be, ctx):
     fr = synth.make_frames(0, 0, 6, 200, 120, 6)
     r = ops.chain(fr)
@@ -328,6 +333,36 @@ def test_region_areas_and_largest(be, ctx):
         ra = ops.region_areas(lab[b], cnt[b])
         assert np.array_equal(areas[b, :cnt[b]], ra)
         assert largest[b] == (np.argmax(ra) + 1 if cnt[b] else 0)
+
+
+def test_region_stats_match_cv2_moments_and_bounding_boxes(be, ctx):
+    # raw moments are exact integers; cv2.moments returns the same numbers as doubles
+    rng = np.random.default_rng(5)
+    cases = [(synth_masks(6, 120, 200), 200), ((rng.random((3, 40, 70)) < 0.4), 70),
+             (np.ones((1, 33, 97), bool), 97), (np.zeros((2, 9, 40), bool), 40)]
+    for masks, W in cases:
+        for conn in (4, 8):
+            B = masks.shape[0]
+            cap = 2048
+            st, cnt, largest = hz.region_stats(ctx, ops.pack_bits(masks), W, cap, conn)
+            for b in range(B):
+                lab, n = ops.label(masks[b], conn)
+                assert cnt[b] == n
+                moms = ops.region_moments(lab, n)
+                for l in range(n):
+                    got = st[b, l]
+                    for k, key in enumerate(('m00', 'm10', 'm01', 'm20', 'm11', 'm02')):
+                        assert float(got[k]) == moms[l][key], (b, l, key)
+                    ys, xs = np.nonzero(lab == l + 1)
+                    assert tuple(got[6:10]) == (xs.min(), ys.min(), xs.max(), ys.max())
+                    assert ops.find_bounding_box(lab == l + 1) == (got[6], got[7], got[8] - got[6] + 1, got[9] - got[7] + 1)
+                areas = ops.region_areas(lab, n)
+                assert largest[b] == (np.argmax(areas) + 1 if n else 0)
+                assert (st[b, n:].view(np.uint8) == 0x5A).all()        # rows of absent regions are not touched
+    # more regions than the caller's capacity: counts still report all of them
+    checker = (np.indices((1, 16, 64)).sum(0) & 1).astype(bool)
+    st, cnt, _ = hz.region_stats(ctx, ops.pack_bits(checker), 64, 8, 4)
+    assert cnt[0] == 512 and (st[0, :, 0] == 1).all()
 
 
 # ---- remaining filter bodies and temporal statistics -----------------------------------

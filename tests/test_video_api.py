@@ -201,3 +201,22 @@ def test_device_filters_fail_loudly_without_gpu():
     from video_analysis_b200._lib import VAError
     with pytest.raises(VAError):
         next(iter(filters.FilterMonochrome(video())))
+
+
+def test_central_moments_are_derived_like_cv2():
+    # host half of regions.region_stats: integer raw moments -> cv2.moments' second-order entries
+    import cv2
+    from video_analysis_b200.analysis.regions import moments_from_raw
+    rng = np.random.default_rng(3)
+    for shape, p in (((40, 70), 0.5), ((300, 500), 0.3), ((7, 9), 0.9), ((1080, 1920), 0.6)):
+        mask = (rng.random(shape) < p).astype(np.uint8)
+        ys, xs = np.nonzero(mask)
+        xs, ys = xs.astype(np.int64), ys.astype(np.int64)
+        raw = [len(xs), xs.sum(), ys.sum(), (xs * xs).sum(), (xs * ys).sum(), (ys * ys).sum()]
+        got, want = moments_from_raw(raw), cv2.moments(mask)
+        # raw moments are exact; the central ones are differences of numbers as large as the raw
+        # moments, so they agree to a few ulp of THOSE (cv2 itself rounds there)
+        scale = {'m': 0.0, 'mu': 1e-15 * max(want['m20'], want['m11'], want['m02']),
+                 'nu': 1e-15 * max(want['m20'], want['m11'], want['m02']) / want['m00'] ** 2}
+        for key in got:
+            assert got[key] == pytest.approx(want[key], rel=1e-13, abs=scale[key.rstrip('0123456789')]), key

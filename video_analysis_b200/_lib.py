@@ -69,6 +69,7 @@ SIGNATURES = {
     'va_morph_bits': (c_int, [c_void_p, c_void_p] + _IMG + _IMG + [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
     'va_label_bits': (c_int, [c_void_p, c_void_p] + _IMG + _IMG + [c_void_p, c_int, c_int, c_int, c_int]),
     'va_region_areas': (c_int, [c_void_p, c_void_p] + _IMG + [c_void_p, c_int, c_void_p, c_int, c_int, c_int]),
+    'va_region_stats': (c_int, [c_void_p, c_void_p] + _IMG + [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int]),
     'va_apply_mask_u8': (c_int, [c_void_p, c_void_p] + _IMG + _IMG + _IMG + [c_int, c_int, c_int, c_int]),
     'va_ema_partial': (c_int, [c_void_p, c_void_p] + _IMG + [c_void_p, c_size_t, c_int, c_int, c_int, c_float, c_int]),
     'va_ema_fold': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_float]),

@@ -36,3 +36,61 @@ def opening(mask, shape='rect', ksize=3, device=None):
 
 def closing(mask, shape='rect', ksize=3, device=None):
     return morphology(mask, 'close', shape, ksize, device)
+
+
+class regionprops(object):
+    """ properties of a region in a binary image from its moments (reference: image.py:310-405,
+    which credits scikit-image for the formulae).  `mask` is reduced to moments on the device
+    (`regions.region_stats`: all foreground pixels of the mask count as one region, as in
+    cv2.moments(mask)); `moments` takes a cv2.moments-style dict, e.g. one entry of
+    `regions.region_stats(...)`. """
+
+    def __init__(self, mask=None, contour=None, moments=None, device=None):
+        if moments is not None:
+            self.moments = moments
+        elif mask is not None:
+            from .regions import RAW_KEYS, moments_from_raw, region_stats
+            parts = region_stats(mask, connectivity=8, device=device)
+            raw = [sum(int(p['moments'][k]) for p in parts) for k in RAW_KEYS]
+            self.moments = moments_from_raw(raw)
+        elif contour is not None:
+            raise NotImplementedError('contour moments are outside the filter -> segment path')
+        else:
+            raise ValueError('Either the mask or the moments must be given')
+
+    @property
+    def area(self):
+        return self.moments['m00']
+
+    @property
+    def centroid(self):
+        m = self.moments
+        return (m['m10'] / m['m00'], m['m01'] / m['m00'])
+
+    @property
+    def orientation(self):
+        m = self.moments
+        a, b, c = m['mu20'], m['mu11'], m['mu02']
+        if a - c == 0:
+            return -np.pi / 4 if b > 0 else np.pi / 4
+        return -np.arctan2(2 * b, (a - c)) / 2
+
+    @property
+    def inertia_tensor_eigvals(self):
+        m = self.moments
+        a, b, c = m['mu20'] / m['m00'], -m['mu11'] / m['m00'], m['mu02'] / m['m00']
+        root = np.sqrt(4 * b ** 2 + (a - c) ** 2)
+        return (a + c) + root, (a + c) - root
+
+    @property
+    def eccentricity(self):
+        e1, e2 = self.inertia_tensor_eigvals
+        return 0 if e1 == 0 else np.sqrt(1 - e2 / e1)
+
+    @property
+    def major_axis_length(self):
+        return 4 * np.sqrt(self.inertia_tensor_eigvals[0])
+
+    @property
+    def minor_axis_length(self):
+        return 4 * np.sqrt(self.inertia_tensor_eigvals[1])

@@ -132,6 +132,44 @@ class SegmentChain(object):
                                        self.w, self.h, blur.n, self.connectivity))
         return labels, counts
 
+    def regions_device(self, rgb, stats=None, counts=None, largest=None, max_regions=256):
+        """ the chain with per-region statistics as its result instead of a label image (SURVEY 8f
+        rank 1): -> (stats int64 (n, max_regions, 10), counts int32 (n,), largest int32 (n,)) device
+        tensors; rows as documented for va_region_stats in include/va_b200.h """
+        rt, t = self.rt, torch()
+        n = rgb.n
+        if (rgb.w, rgb.h, rgb.channels) != (self.w, self.h, 3):
+            raise ValueError('chain built for %dx%d colour frames, got %dx%dx%d' % (self.w, self.h, rgb.w, rgb.h, rgb.channels))
+        if not self.connectivity:
+            raise ValueError('region statistics need a connectivity of 4 or 8')
+        p = getattr(self, '_reg', None)
+        if p is None:
+            p = self._reg = {'blur': rt.empty_u8(self.batch, self.h, self.w), 'mask': rt.empty_bits(self.batch, self.h, self.w),
+                             'morph': rt.empty_bits(self.batch, self.h, self.w)}
+        sub = lambda b: DeviceBatch(b.kind, b.t[:n], n, b.h, b.w, b.channels)
+        blur, mask, morph = sub(p['blur']), sub(p['mask']), sub(p['morph'])
+        if stats is None:
+            stats = t.empty((n, int(max_regions), 10), dtype=t.int64, device=rt.device)
+        if counts is None:
+            counts = t.empty((n,), dtype=t.int32, device=rt.device)
+        if largest is None:
+            largest = t.empty((n,), dtype=t.int32, device=rt.device)
+        lib, h = rt.lib, rt._h
+        self.blur_device(rgb, blur)
+        rt._check(lib.va_ema_diff_thresh(h, rt.stream, *blur.img(), self._bg.data_ptr(), self._bg.stride(0),
+                                         *mask.img(), self.w, self.h, n, self.alpha, self.threshold,
+                                         0 if self._started else 1))
+        self._started = True
+        seg = mask
+        if self.morph_op:
+            rt._check(lib.va_morph_bits(h, rt.stream, *mask.img(), *morph.img(), self.w, self.h, n,
+                                        _lib.MORPH_OPS[self.morph_op], _lib.SE_SHAPES[self.morph_shape],
+                                        int(self.kx), int(self.ky)))
+            seg = morph
+        rt._check(lib.va_region_stats(h, rt.stream, *seg.img(), stats.data_ptr(), int(stats.shape[1]), counts.data_ptr(),
+                                      largest.data_ptr(), self.w, self.h, n, self.connectivity))
+        return stats, counts, largest
+
     # ---- two-stream software pipeline over consecutive device batches -----------------------------------
     def run_device_pipelined(self, rgb, labels, counts):
         """ Same result as `run_device`, but the chain is split over two internal streams:
@@ -198,11 +236,9 @@ class SegmentChain(object):
         for _ in range(self.depth):
             s = {
                 'in': t.empty((self.batch, self.h, self.w * 3), dtype=t.uint8, device=rt.device),
-                'labels': rt.empty_i32(self.batch, self.h, self.w),
                 'counts': t.empty((self.batch,), dtype=t.int32, device=rt.device),
                 'ev_in': t.cuda.Event(), 'ev_run': t.cuda.Event(), 'ev_out': t.cuda.Event(),
             }
-            s['labels_host'] = t.empty(tuple(s['labels'].t.shape), dtype=t.int32, pin_memory=True)
             s['counts_host'] = t.empty((self.batch,), dtype=t.int32, pin_memory=True)
             slots.append(s)
         self._slots = slots
@@ -210,12 +246,31 @@ class SegmentChain(object):
         self._s_run = t.cuda.Stream(device=rt.device)
         self._s_out = t.cuda.Stream(device=rt.device)
 
-    def process_blocks(self, blocks):
+    def _slot_outputs(self, s, max_regions):
+        """ result buffers of a slot, made on first use: the label image (max_regions is None) or the
+        region table """
+        t, rt = torch(), self.rt
+        if max_regions is None:
+            if 'labels' not in s:
+                s['labels'] = rt.empty_i32(self.batch, self.h, self.w)
+                s['labels_host'] = t.empty(tuple(s['labels'].t.shape), dtype=t.int32, pin_memory=True)
+        elif s.get('stats') is None or s['stats'].shape[1] != max_regions:
+            s['stats'] = t.empty((self.batch, max_regions, 10), dtype=t.int64, device=rt.device)
+            s['largest'] = t.empty((self.batch,), dtype=t.int32, device=rt.device)
+            s['stats_host'] = t.empty((self.batch, max_regions, 10), dtype=t.int64, pin_memory=True)
+            s['largest_host'] = t.empty((self.batch,), dtype=t.int32, pin_memory=True)
+
+    def process_blocks(self, blocks, max_regions=None):
         """ blocks: iterable of host arrays (m, h, w, 3) uint8 with m <= batch (page-locked memory
         gives asynchronous copies).  Yields (labels (m, h, w) int32, counts (m,) int32) per block,
-        in order.  The yielded arrays are views of a ring of pinned buffers: they are valid until
-        the next block is requested (copy them if you keep them, as `process` does). """
+        in order -- or, with `max_regions`, (stats (m, max_regions, 10) int64, counts, largest): the
+        per-region table of `regions_device` instead of the label image, a few kilobytes per frame
+        over PCIe instead of 4 bytes per pixel.  The yielded arrays are views of a ring of pinned
+        buffers: they are valid until the next block is requested (copy them if you keep them, as
+        `process` does). """
         t, rt = torch(), self.rt
+        if max_regions is not None:
+            max_regions = int(max_regions)
         if self._slots is None:
             self._make_slots()
         pending = collections.deque()
@@ -230,6 +285,7 @@ class SegmentChain(object):
                 s = self._slots[k % self.depth]
                 if len(pending) == self.depth:             # the slot is still owned by an unyielded block
                     yield self._finish(pending.popleft())
+                self._slot_outputs(s, max_regions)
                 with t.cuda.stream(self._s_in):
                     self._s_in.wait_event(s['ev_run'])     # previous kernels that read this input are done
                     s['in'][:m].copy_(t.from_numpy(block.reshape(m, self.h, self.w * 3)), non_blocking=True)
@@ -238,22 +294,31 @@ class SegmentChain(object):
                     self._s_run.wait_event(s['ev_in'])
                     self._s_run.wait_event(s['ev_out'])    # previous download of this slot's labels is done
                     rgb = DeviceBatch('u8', s['in'][:m], m, self.h, self.w, 3)
-                    lab = DeviceBatch('i32', s['labels'].t[:m], m, self.h, self.w)
-                    self.run_device(rgb, lab, s['counts'][:m])
+                    if max_regions is None:
+                        lab = DeviceBatch('i32', s['labels'].t[:m], m, self.h, self.w)
+                        self.run_device(rgb, lab, s['counts'][:m])
+                    else:
+                        self.regions_device(rgb, s['stats'][:m], s['counts'][:m], s['largest'][:m])
                     s['ev_run'].record(self._s_run)
                 with t.cuda.stream(self._s_out):
                     self._s_out.wait_event(s['ev_run'])
-                    s['labels_host'][:m].copy_(s['labels'].t[:m], non_blocking=True)
+                    if max_regions is None:
+                        s['labels_host'][:m].copy_(s['labels'].t[:m], non_blocking=True)
+                    else:
+                        s['stats_host'][:m].copy_(s['stats'][:m], non_blocking=True)
+                        s['largest_host'][:m].copy_(s['largest'][:m], non_blocking=True)
                     s['counts_host'][:m].copy_(s['counts'][:m], non_blocking=True)
                     s['ev_out'].record(self._s_out)
-                pending.append((s, m))
+                pending.append((s, m, max_regions))
             while pending:
                 yield self._finish(pending.popleft())
 
     def _finish(self, item):
-        s, m = item
+        s, m, max_regions = item
         s['ev_out'].synchronize()
-        return s['labels_host'].numpy()[:m, :, :self.w], s['counts_host'].numpy()[:m]
+        if max_regions is None:
+            return s['labels_host'].numpy()[:m, :, :self.w], s['counts_host'].numpy()[:m]
+        return s['stats_host'].numpy()[:m], s['counts_host'].numpy()[:m], s['largest_host'].numpy()[:m]
 
     def process(self, frames):
         """ frames: ndarray (n, h, w, 3) uint8 or a video object -> (labels (n, h, w) int32,
@@ -274,3 +339,22 @@ class SegmentChain(object):
             counts[k:k + len(cnt)] = cnt
             k += len(lab)
         return labels[:k], counts[:k]
+
+    def process_regions(self, frames, max_regions=256):
+        """ like `process`, but returns for every frame the list of its regions (`label`, `area`,
+        `bbox`, `moments`: see analysis.regions.stats_to_regions) instead of a label image """
+        from .analysis.regions import stats_to_regions
+        if hasattr(frames, 'frame_block'):
+            video = frames
+            n = video.frame_count
+            blocks = (video.frame_block(a, min(a + self.batch, n)) for a in range(0, n, self.batch))
+        else:
+            frames = np.asarray(frames)
+            blocks = (frames[a:a + self.batch] for a in range(0, len(frames), self.batch))
+        out = []
+        for stats, counts, _ in self.process_blocks(blocks, max_regions=max_regions):
+            for st, c in zip(stats, counts):
+                if c > max_regions:
+                    raise MemoryError('a frame has %d regions, max_regions is %d' % (c, max_regions))
+                out.append(stats_to_regions(st, int(c)))
+        return out

@@ -610,8 +610,9 @@ static int gauss_launch(va_ctx *ctx, va_stream stream, const char *name, bool fu
                 }
                 if (getenv("VA_GS_NT")) NT = atoi(getenv("VA_GS_NT"));
                 const int strips = va_div_up(w, 4 * NT);
-                // segments in y: enough CTAs for a few waves, each segment re-stages 2 r rows
-                int segs = va_div_up((long long)ctx->sm_count * 24, (long long)strips * batch);
+                // segments in y: about 12 CTAs per SM (measured optimum at 1080p: fewer leave SMs idle at the
+                // end, more re-stage too many halo rows -- each segment stages 2 r extra rows)
+                int segs = va_div_up((long long)ctx->sm_count * 12, (long long)strips * batch);
                 const int max_segs = h / (8 * r) > 0 ? h / (8 * r) : 1;
                 if (segs > max_segs) segs = max_segs;
                 if (getenv("VA_GS_SEGS")) segs = atoi(getenv("VA_GS_SEGS"));

@@ -451,17 +451,16 @@ label_write_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
     }
 }
 
-extern "C" int va_label_bits(va_ctx *ctx, va_stream stream,
-                             const uint32_t *mask, size_t mask_pitch_w, size_t mask_fstride_w,
-                             int32_t *labels, size_t labels_pitch_e, size_t labels_fstride_e,
-                             int32_t *counts, int w, int h, int batch, int connectivity) {
-    VA_CHECK_CTX(ctx);
-    VA_REQUIRE(ctx, mask && labels, "va_label_bits: null pointer");
-    VA_REQUIRE(ctx, w > 0 && h > 0 && batch > 0, "va_label_bits: bad size");
-    VA_REQUIRE(ctx, connectivity == 4 || connectivity == 8, "va_label_bits: connectivity must be 4 or 8");
-    VA_REQUIRE(ctx, mask_pitch_w >= (size_t)((w + 31) / 32) && labels_pitch_e >= (size_t)w, "va_label_bits: pitch smaller than a row");
+// phases A-D: afterwards every root holds -(rank in its row), rowcnt holds the exclusive prefix of
+// the per-row root counts and counts[b] the number of components
+static int label_forest(va_ctx *ctx, va_stream stream, const char *name,
+                        const uint32_t *mask, size_t mask_pitch_w, size_t mask_fstride_w,
+                        int32_t *counts, int w, int h, int batch, int connectivity, int *LOG_out, size_t *pf_out) {
+    VA_REQUIRE(ctx, w > 0 && h > 0 && batch > 0, "%s: bad size", name);
+    VA_REQUIRE(ctx, connectivity == 4 || connectivity == 8, "%s: connectivity must be 4 or 8", name);
+    VA_REQUIRE(ctx, mask_pitch_w >= (size_t)((w + 31) / 32), "%s: pitch smaller than a row", name);
     if (w > ctx->max_w || h > ctx->max_h || batch > ctx->max_batch)
-        VA_FAIL(ctx, VA_ERR_CAPACITY, "va_label_bits: %dx%dx%d exceeds the ctx capacity %dx%dx%d", w, h, batch,
+        VA_FAIL(ctx, VA_ERR_CAPACITY, "%s: %dx%dx%d exceeds the ctx capacity %dx%dx%d", name, w, h, batch,
                 ctx->max_w, ctx->max_h, ctx->max_batch);
     int LOG = 5;
     while (((size_t)1 << LOG) < ctx->lab_pitch) LOG++;
@@ -481,10 +480,154 @@ extern "C" int va_label_bits(va_ctx *ctx, va_stream stream,
       VA_LAUNCH(ctx, k, grid_a, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, parent, LOG, pf, rowcnt, w, h, batch, vec); }
     { auto k = label_scan_kernel;
       VA_LAUNCH(ctx, k, batch, LAB_THREADS, 0, stream, rowcnt, counts, h); }
+    *LOG_out = LOG;
+    *pf_out = pf;
+    return VA_OK;
+}
+
+extern "C" int va_label_bits(va_ctx *ctx, va_stream stream,
+                             const uint32_t *mask, size_t mask_pitch_w, size_t mask_fstride_w,
+                             int32_t *labels, size_t labels_pitch_e, size_t labels_fstride_e,
+                             int32_t *counts, int w, int h, int batch, int connectivity) {
+    VA_CHECK_CTX(ctx);
+    VA_REQUIRE(ctx, mask && labels, "va_label_bits: null pointer");
+    VA_REQUIRE(ctx, w <= 0 || labels_pitch_e >= (size_t)w, "va_label_bits: pitch smaller than a row");
+    int LOG;
+    size_t pf;
+    const int rc = label_forest(ctx, stream, "va_label_bits", mask, mask_pitch_w, mask_fstride_w, counts, w, h, batch,
+                                connectivity, &LOG, &pf);
+    if (rc != VA_OK) return rc;
+    const int grid = (int)((h * batch + LAB_WARPS - 1) / LAB_WARPS);
     { auto k = label_write_kernel;
       const int vec_out = va_aligned(labels, 16) && labels_pitch_e % 4 == 0 && labels_fstride_e % 4 == 0;
-      VA_LAUNCH(ctx, k, grid, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, (const int *)parent, LOG, pf,
-                (const int *)rowcnt, labels, labels_pitch_e, labels_fstride_e, w, h, batch, vec_out); }
+      VA_LAUNCH(ctx, k, grid, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, (const int *)ctx->lab_parent, LOG, pf,
+                (const int *)ctx->lab_rowcnt, labels, labels_pitch_e, labels_fstride_e, w, h, batch, vec_out); }
+    return VA_OK;
+}
+
+// =====================================================================================
+// per-region statistics straight from the mask: the label image is never written.
+// Row-run form of the raw moments of cv2.moments(region.astype(uint8)) (video/analysis/image.py:350)
+// and the bounding box of regions.py:113-149, exact in 64-bit integers:
+//   a run x0..x1 of row y adds  n = x1-x0+1,  sx = n (x0+x1) / 2,  sxx = sum x^2,
+//   m00 += n  m10 += sx  m01 += n y  m20 += sxx  m11 += y sx  m02 += n y^2
+// =====================================================================================
+__global__ void __launch_bounds__(LAB_THREADS)
+region_stats_init_kernel(long long *__restrict__ stats, int max_regions, const int *__restrict__ counts) {
+    const int b = blockIdx.y;
+    const int n = min(counts[b], max_regions);
+    for (int l = blockIdx.x * LAB_THREADS + threadIdx.x; l < n; l += gridDim.x * LAB_THREADS) {
+        long long *s = stats + ((size_t)b * max_regions + l) * VA_REGION_FIELDS;
+#pragma unroll
+        for (int k = 0; k < 6; k++) s[k] = 0;
+        s[6] = s[7] = 0x7fffffff;        // xmin, ymin
+        s[8] = s[9] = -1;                // xmax, ymax
+    }
+}
+
+__global__ void __launch_bounds__(LAB_THREADS)
+region_stats_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
+                    const int *__restrict__ parent, int LOG, size_t pf, const int *__restrict__ rowoff,
+                    long long *__restrict__ stats, int max_regions, int w, int h, int batch) {
+    const int lane = threadIdx.x & 31;
+    const int wpw = (w + 31) >> 5;
+    const unsigned lastmask = (w & 31) ? ((1u << (w & 31)) - 1u) : FULL;
+    const int rows = h * batch;
+    for (int row = blockIdx.x * LAB_WARPS + (threadIdx.x >> 5); row < rows;
+         row += gridDim.x * LAB_WARPS) {
+        const int b = row / h, y = row - b * h;
+        const uint32_t *mr = mask + (size_t)b * mfw + (size_t)y * mpw;
+        const int *pf_ = parent + (size_t)b * pf;
+        const int *pr = pf_ + ((size_t)y << LOG);
+        const int *ro = rowoff + (size_t)b * h;
+        long long *sb = stats + (size_t)b * max_regions * VA_REGION_FIELDS;
+        int carry = 0;
+        LAB_PREFETCH(pre, mr);
+        for (int base = 0; base < wpw; base += 32) {
+            const unsigned wd = LAB_PICK(pre, base, mr);
+            if (!__any_sync(FULL, wd != 0u)) { carry = 32 * (base + 32); continue; }
+            int st_in, top;
+            lab_scan_chunk(wd, lane, base, carry, st_in, top);
+            // the part of every run that lies in this word is one contribution
+            unsigned rem = wd;
+            while (rem) {
+                const int bit = __ffs((int)rem) - 1;
+                const unsigned t = ~(wd >> bit);
+                const int ones = t ? __ffs((int)t) - 1 : 32;
+                const int start_x = bit == 0 ? st_in : 32 * (base + lane) + bit;
+                int idx = (y << LOG) + start_x;
+                int p = pr[start_x];
+                while (p >= 0) { idx = p; p = pf_[idx]; }
+                const int lab = ro[idx >> LOG] - p;                // 1 .. n
+                rem &= ~((ones >= 32 ? FULL : ((1u << ones) - 1u)) << bit);
+                if (lab > max_regions) continue;
+                const long long x0 = 32 * (base + lane) + bit, x1 = x0 + ones - 1, n = ones;
+                const long long sx = n * (x0 + x1) / 2;
+                // sum_{x=x0}^{x1} x^2 = F(x1) - F(x0 - 1), F(k) = k (k + 1) (2k + 1) / 6
+                const long long f1 = x1 * (x1 + 1) * (2 * x1 + 1) / 6, f0 = (x0 - 1) * x0 * (2 * x0 - 1) / 6;
+                unsigned long long *s = reinterpret_cast<unsigned long long *>(sb + (size_t)(lab - 1) * VA_REGION_FIELDS);
+                atomicAdd(s + 0, (unsigned long long)n);
+                atomicAdd(s + 1, (unsigned long long)sx);
+                atomicAdd(s + 2, (unsigned long long)(n * y));
+                atomicAdd(s + 3, (unsigned long long)(f1 - f0));
+                atomicAdd(s + 4, (unsigned long long)(sx * y));
+                atomicAdd(s + 5, (unsigned long long)(n * y * y));
+                long long *sl = reinterpret_cast<long long *>(s);
+                atomicMin(sl + 6, x0);
+                atomicMin(sl + 7, (long long)y);
+                atomicMax(sl + 8, x1);
+                atomicMax(sl + 9, (long long)y);
+            }
+            carry = __shfl_sync(FULL, top, 31);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(LAB_THREADS)
+region_largest64_kernel(const long long *__restrict__ stats, int max_regions, const int *__restrict__ counts,
+                        int *__restrict__ largest) {
+    __shared__ long long best_a[LAB_THREADS];
+    __shared__ int best_l[LAB_THREADS];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int n = min(counts[b], max_regions);
+    long long ba = 0;
+    int bl = 0;
+    for (int l = tid; l < n; l += LAB_THREADS) {
+        const long long a = stats[((size_t)b * max_regions + l) * VA_REGION_FIELDS];
+        if (a > ba) { ba = a; bl = l + 1; }
+    }
+    best_a[tid] = ba; best_l[tid] = bl;
+    __syncthreads();
+    if (tid == 0) {
+        for (int i = 1; i < LAB_THREADS; i++)
+            if (best_a[i] > ba || (best_a[i] == ba && best_a[i] > 0 && best_l[i] < bl)) { ba = best_a[i]; bl = best_l[i]; }
+        largest[b] = bl;      // np.argmax(areas) + 1 (regions.py:169); 0 when the frame has no region
+    }
+}
+
+extern "C" int va_region_stats(va_ctx *ctx, va_stream stream,
+                               const uint32_t *mask, size_t mask_pitch_w, size_t mask_fstride_w,
+                               int64_t *stats, int max_regions, int32_t *counts, int32_t *largest,
+                               int w, int h, int batch, int connectivity) {
+    VA_CHECK_CTX(ctx);
+    VA_REQUIRE(ctx, mask && stats && counts, "va_region_stats: null pointer");
+    VA_REQUIRE(ctx, max_regions > 0, "va_region_stats: max_regions must be positive");
+    int LOG;
+    size_t pf;
+    const int rc = label_forest(ctx, stream, "va_region_stats", mask, mask_pitch_w, mask_fstride_w, counts, w, h, batch,
+                                connectivity, &LOG, &pf);
+    if (rc != VA_OK) return rc;
+    { auto k = region_stats_init_kernel;
+      const dim3 grid(va_div_up(max_regions, LAB_THREADS) < 64 ? va_div_up(max_regions, LAB_THREADS) : 64, batch);
+      VA_LAUNCH(ctx, k, grid, LAB_THREADS, 0, stream, (long long *)stats, max_regions, (const int *)counts); }
+    { auto k = region_stats_kernel;
+      const int grid = (int)((h * batch + LAB_WARPS - 1) / LAB_WARPS);
+      VA_LAUNCH(ctx, k, grid, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, (const int *)ctx->lab_parent, LOG, pf,
+                (const int *)ctx->lab_rowcnt, (long long *)stats, max_regions, w, h, batch); }
+    if (largest) {
+        auto k = region_largest64_kernel;
+        VA_LAUNCH(ctx, k, batch, LAB_THREADS, 0, stream, (const long long *)stats, max_regions, (const int *)counts, largest);
+    }
     return VA_OK;
 }
 

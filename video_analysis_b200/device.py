@@ -29,6 +29,9 @@ def _round_up(v, m):
     return (v + m - 1) // m * m
 
 
+REGION_FIELDS = 10          # VA_REGION_FIELDS of include/va_b200.h: m00 m10 m01 m20 m11 m02 xmin ymin xmax ymax
+
+
 class DeviceBatch(object):
     """ a batch of images resident on the GPU.
 
@@ -281,6 +284,19 @@ class DeviceRuntime(object):
                                              areas.data_ptr(), int(max_labels), largest.data_ptr(),
                                              labels.w, labels.h, labels.n))
         return areas, largest
+
+    def region_stats(self, mask, connectivity=4, max_regions=1024):
+        """ per-region raw moments and bounding boxes straight from a packed mask (no label image):
+        -> (stats int64 device tensor (n, max_regions, 10), counts int32 (n,), largest int32 (n,)) """
+        t = torch()
+        self.ensure(mask.w, mask.h, mask.n)
+        stats = t.empty((mask.n, int(max_regions), REGION_FIELDS), dtype=t.int64, device=self.device)
+        counts = t.empty((mask.n,), dtype=t.int32, device=self.device)
+        largest = t.empty((mask.n,), dtype=t.int32, device=self.device)
+        self._check(self.lib.va_region_stats(self._h, self.stream, mask.ptr, mask.pitch, mask.fstride,
+                                             stats.data_ptr(), int(max_regions), counts.data_ptr(), largest.data_ptr(),
+                                             mask.w, mask.h, mask.n, int(connectivity)))
+        return stats, counts, largest
 
     def lut(self, src, table):
         """ out = table[in] for uint8 frames (FilterNormalize) """
