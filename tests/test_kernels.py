@@ -234,6 +234,17 @@ def test_morphology_bit_exact(be, ctx):
                     assert np.array_equal(hz.morph(ctx, packed, W, op, shape, k), ops.pack_bits(ref)), (H, W, p, op, shape, k)
 
 
+def test_morphology_square_elements_strips_and_segments(be, ctx):
+    # the register-streaming kernel: several word strips per row (ragged last word), several row
+    # segments per frame, images shorter than the element
+    for (H, W) in ((100, 1003), (67, 1920), (2, 40), (1, 33), (5, 961)):
+        m = rmask(H + W, (2, H, W), 0.8)
+        for op in ('erode', 'dilate', 'open', 'close'):
+            for k in (3, 5, 7):
+                ref = np.stack([ops.morph(f, op, 'rect', k) for f in m])
+                assert np.array_equal(hz.morph(ctx, ops.pack_bits(m), W, op, 'rect', k), ops.pack_bits(ref)), (H, W, op, k)
+
+
 def test_morphology_large_elements(be, ctx):
     m = rmask(9, (1, 50, 90), 0.9)
     for k in (9, 15, 31):

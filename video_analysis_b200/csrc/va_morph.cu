@@ -14,7 +14,9 @@
 //     out(y) = AND/OR_j  hrun_j( in(y + j - ay) ).
 // OPEN / CLOSE run both passes in one CTA on a band of rows; the intermediate stays
 // in shared memory.  Algorithmic HBM bytes: N/8 in + N/8 out per frame.
+// Odd square RECT elements up to 7x7 (the common case) take the register-only streaming kernel below.
 #include <cmath>
+#include <cstdlib>
 
 #include "va_device.cuh"
 
@@ -225,6 +227,96 @@ morph_bits_kernel(const uint32_t *__restrict__ in, size_t in_pitch_w, size_t in_
     }
 }
 
+// ---------------------------------------------------------------------------------
+// streaming kernel for odd square RECT elements (3x3, 5x5, 7x7): a warp owns a strip of words and
+// walks down a segment of rows with everything in registers -- lane = word, horizontal neighbours
+// by shuffle, the last K horizontally reduced rows in a register window.  Erosion is dilation of the
+// complement, so both passes of an OPEN / CLOSE are dilations on data XORed with an all-ones / zero
+// mask; "outside the image never wins" and the bits beyond the row end are then plain zeros.
+// The second pass consumes the first one's rows as they appear (lag K/2 rows).  A pass spoils one
+// word at either end of the strip, so strips overlap by `passes` words on each side.
+// ---------------------------------------------------------------------------------
+#define MORPH_S_THREADS 128
+#define MORPH_S_PREFETCH 8
+
+template <int K>
+__device__ __forceinline__ unsigned morph_dilate_h(unsigned c) {
+    const unsigned p = __shfl_up_sync(0xffffffffu, c, 1), n = __shfl_down_sync(0xffffffffu, c, 1);
+    unsigned acc = c;
+#pragma unroll
+    for (int d = 1; d <= K / 2; d++) acc |= __funnelshift_r(c, n, d) | __funnelshift_l(p, c, d);
+    return acc;
+}
+
+template <int K>
+__global__ void __launch_bounds__(MORPH_S_THREADS)
+morph_stream_kernel(const uint32_t *__restrict__ in, size_t in_pitch_w, size_t in_fstride_w,
+                    uint32_t *__restrict__ out, size_t out_pitch_w, size_t out_fstride_w,
+                    int w, int h, int strips, int segs, int SH, int n_warps, int first, int second) {
+    constexpr int H = K / 2;
+    const int lane = threadIdx.x & 31;
+    const int wid = blockIdx.x * (MORPH_S_THREADS / 32) + (threadIdx.x >> 5);
+    if (wid >= n_warps) return;
+    const int passes = second >= 0 ? 2 : 1;
+    const int usable = 32 - 2 * passes;
+    const int b = wid / (strips * segs);
+    const int rem = wid - b * strips * segs;
+    const int seg = rem / strips, strip = rem - seg * strips;
+    const int wpw = (w + 31) >> 5;
+    const unsigned lastmask = (w & 31) ? ((1u << (w & 31)) - 1u) : 0xffffffffu;
+    const int j = strip * usable - passes + lane;              // word of this lane
+    const bool jin = j >= 0 && j < wpw;
+    const unsigned keep = !jin ? 0u : (j == wpw - 1 ? lastmask : 0xffffffffu);   // bits of the row in this word
+    const bool writer = jin && lane >= passes && lane < 32 - passes;
+    const unsigned m1 = first == 0 ? 0xffffffffu : 0u;         // complement masks: erode = ~dilate(~x)
+    const unsigned m2 = second == 0 ? 0xffffffffu : 0u;
+    const int ys = seg * SH, ye = min(ys + SH, h);             // output rows of this warp
+    const int y_first = ys - passes * H;                       // first input row needed
+    const int n_in = (ye - ys) + 2 * passes * H;
+    const uint32_t *col = in + (size_t)b * in_fstride_w + (jin ? j : 0);
+    uint32_t *ocol = out + (size_t)b * out_fstride_w + (jin ? j : 0);
+
+    unsigned hw[K], ew[K];                                     // windows of horizontally reduced rows
+#pragma unroll
+    for (int k = 0; k < K; k++) hw[k] = ew[k] = 0u;
+    for (int i0 = 0; i0 < n_in; i0 += MORPH_S_PREFETCH) {
+        unsigned raw[MORPH_S_PREFETCH];
+#pragma unroll
+        for (int u = 0; u < MORPH_S_PREFETCH; u++) {
+            const int y = y_first + i0 + u;
+            raw[u] = (jin && y >= 0 && y < h && i0 + u < n_in) ? __ldg(col + (size_t)y * in_pitch_w) : m1;   // complemented below: 0
+        }
+#pragma unroll
+        for (int u = 0; u < MORPH_S_PREFETCH; u++) {
+            const int i = i0 + u;
+            if (i >= n_in) break;
+            // ---- pass 1 on input row y_first + i; its result is row yc = y_first + i - H
+#pragma unroll
+            for (int k = 0; k < K - 1; k++) hw[k] = hw[k + 1];
+            hw[K - 1] = morph_dilate_h<K>((raw[u] ^ m1) & keep);
+            if (i < 2 * H) continue;
+            unsigned e = hw[0];
+#pragma unroll
+            for (int k = 1; k < K; k++) e |= hw[k];
+            const int yc = y_first + i - H;
+            if (passes == 1) {
+                if (writer) ocol[(size_t)yc * out_pitch_w] = (e ^ m1) & keep;
+                continue;
+            }
+            // ---- pass 2 on row yc of the intermediate (rows outside the image never win)
+            const unsigned mid = (yc >= 0 && yc < h) ? ((e ^ m1 ^ m2) & keep) : 0u;
+#pragma unroll
+            for (int k = 0; k < K - 1; k++) ew[k] = ew[k + 1];
+            ew[K - 1] = morph_dilate_h<K>(mid);
+            if (i < 4 * H) continue;
+            unsigned o = ew[0];
+#pragma unroll
+            for (int k = 1; k < K; k++) o |= ew[k];
+            if (writer) ocol[(size_t)(yc - H) * out_pitch_w] = (o ^ m2) & keep;
+        }
+    }
+}
+
 extern "C" int va_morph_bits(va_ctx *ctx, va_stream stream,
                              const uint32_t *in, size_t in_pitch_w, size_t in_fstride_w,
                              uint32_t *out, size_t out_pitch_w, size_t out_fstride_w,
@@ -246,6 +338,34 @@ extern "C" int va_morph_bits(va_ctx *ctx, va_stream stream,
         default: first = 1; second = 0; break;
     }
     const int passes = second >= 0 ? 2 : 1;
+    {
+        bool sq = shape == VA_SE_RECT && kx == ky && (kx == 3 || kx == 5 || kx == 7);
+        const char *env = getenv("VA_MORPH_STREAM");
+        if (env && atoi(env) == 0) sq = false;                   // A-B checks against the band kernel
+        if (sq) {
+            const int usable = 32 - 2 * passes;
+            const int strips = va_div_up((long long)wpw, usable);
+            // rows per segment: the walk is a chain of load latencies, so many short segments (about 48
+            // warps per SM, at least 24 rows; each segment re-reads passes * (k - 1) rows)
+            int segs = va_div_up((long long)ctx->sm_count * 48, (long long)strips * batch);
+            if (segs > h / 24) segs = h / 24;
+            if (segs < 1) segs = 1;
+            const int SH = va_div_up(h, segs);
+            segs = va_div_up(h, SH);
+            const long long n_warps = (long long)strips * segs * batch;
+            VA_REQUIRE(ctx, n_warps < (1ll << 31), "va_morph_bits: too many strips");
+            const int grid = va_div_up(n_warps, MORPH_S_THREADS / 32);
+#define MORPH_SGO(KK)                                                                                      \
+            do {                                                                                           \
+                auto kfn = morph_stream_kernel<KK>;                                                        \
+                VA_LAUNCH(ctx, kfn, grid, MORPH_S_THREADS, 0, stream, in, in_pitch_w, in_fstride_w, out,   \
+                          out_pitch_w, out_fstride_w, w, h, strips, segs, SH, (int)n_warps, first, second); \
+            } while (0)
+            if (kx == 3) MORPH_SGO(3); else if (kx == 5) MORPH_SGO(5); else MORPH_SGO(7);
+#undef MORPH_SGO
+            return VA_OK;
+        }
+    }
     const int halo = ky - 1;
     const size_t smem = ((size_t)(MORPH_BAND + passes * halo) + (passes == 2 ? (size_t)(MORPH_BAND + halo) : 0)) * wpw * 4;
     VA_REQUIRE(ctx, smem <= 200 * 1024, "va_morph_bits: %d-pixel rows with a %d-row element do not fit in shared memory", w, ky);
