@@ -237,7 +237,7 @@ def test_morphology_bit_exact(be, ctx):
 def test_morphology_square_elements_strips_and_segments(be, ctx):
     # the register-streaming kernel: several word strips per row (ragged last word), several row
     # segments per frame, images shorter than the element
-    for (H, W) in ((100, 1003), (67, 1920), (2, 40), (1, 33), (5, 961)):
+    for (H, W) in ((100, 1003), (67, 1920), (2, 40), (1, 33), (5, 961), (37, 2200), (9, 4001)):
         m = rmask(H + W, (2, H, W), 0.8)
         for op in ('erode', 'dilate', 'open', 'close'):
             for k in (3, 5, 7):

@@ -10,7 +10,7 @@
 // index at the smaller one, hence the root of a component is its first pixel in raster
 // order, and ranking the roots in index order IS the canonical numbering.
 //
-// Kernels A and C walk the mask with one LANE per image row (most rows are empty: a few
+// Kernels A and C walk the mask with four LANES per image row (most rows are empty: a few
 // instructions per word).  Kernels B and G own one row per warp (lane = 32-pixel word); run
 // starts that continue across words are resolved with one ballot + one shuffle per 32 words.
 // (A lane-per-row merge was measured slower: rows of one blob then hook in lock step and the
@@ -108,29 +108,32 @@ __device__ __forceinline__ void lab_union(int *parent, int a, int b) {
 }
 
 // =====================================================================================
-// Kernels A and C walk the mask with lane = ROW (32 rows per warp) and a sequential loop over
-// the words of the row.  Most rows of a real mask are empty, and with one lane per row an
-// empty row costs a few instructions per word instead of a whole warp; run continuation
-// across words is a carried register instead of a warp scan.
+// Kernels A and C walk the mask with four lanes per image row (8 rows per warp): each lane owns a
+// quarter of the row's words, fetches them 16 at a time with 16-byte loads that are all in flight
+// together, and scans them sequentially.  Most rows of a real mask are empty, and with a lane per
+// quarter row an empty stretch costs a few instructions per word instead of a whole warp; run
+// continuation across words is a carried bit instead of a warp scan.
 // =====================================================================================
-#define LAB_GROUP 4            // words fetched per step (one 16-byte load when the row is aligned)
+#define LAB_GROUP 4            // words per 16-byte load
+#define LAB_BATCH 4            // loads in flight per lane
 
-__device__ __forceinline__ void lab_load_group(const uint32_t *row, int j, int wpw, unsigned lastmask, bool vec,
-                                               bool valid, unsigned (&wd)[LAB_GROUP]) {
+// words [j, j + 16) of a row (0 beyond the part / row end, last word masked)
+__device__ __forceinline__ void lab_load_batch(const uint32_t *row, int j, int jend, int wpw, unsigned lastmask, bool vec,
+                                               bool valid, unsigned (&wd)[LAB_GROUP * LAB_BATCH]) {
 #pragma unroll
-    for (int k = 0; k < LAB_GROUP; k++) wd[k] = 0u;
-    if (!valid) return;
-    if (vec && j + LAB_GROUP <= wpw) {
-        const uint4 q = *reinterpret_cast<const uint4 *>(row + j);
-        wd[0] = q.x; wd[1] = q.y; wd[2] = q.z; wd[3] = q.w;
-    } else {
+    for (int g = 0; g < LAB_BATCH; g++) {
+        const int jg = j + LAB_GROUP * g;
+        if (valid && vec && jg + LAB_GROUP <= jend) {
+            const uint4 q = *reinterpret_cast<const uint4 *>(row + jg);
+            wd[4 * g] = q.x; wd[4 * g + 1] = q.y; wd[4 * g + 2] = q.z; wd[4 * g + 3] = q.w;
+        } else {
 #pragma unroll
-        for (int k = 0; k < LAB_GROUP; k++)
-            if (j + k < wpw) wd[k] = row[j + k];
+            for (int k = 0; k < LAB_GROUP; k++) wd[4 * g + k] = (valid && jg + k < jend) ? row[jg + k] : 0u;
+        }
     }
     const int last = wpw - 1 - j;
 #pragma unroll
-    for (int k = 0; k < LAB_GROUP; k++)
+    for (int k = 0; k < LAB_GROUP * LAB_BATCH; k++)
         if (k == last) wd[k] &= lastmask;
 }
 
@@ -141,19 +144,21 @@ label_init_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
     const int lane = threadIdx.x & 31;
     const int wpw = (w + 31) >> 5;
     const unsigned lastmask = (w & 31) ? ((1u << (w & 31)) - 1u) : FULL;
-    const int wpf = (h + 31) >> 5;                    // warps per frame
+    const int ppw = ((wpw + 15) >> 4) << 2;           // words per quarter row, a multiple of 4
+    const int wpf = (h + 7) >> 3;                     // warps per frame
     const int total = wpf * batch;
     for (int wi = blockIdx.x * LAB_WARPS + (threadIdx.x >> 5); wi < total; wi += gridDim.x * LAB_WARPS) {
-        const int b = wi / wpf, y = (wi - b * wpf) * 32 + lane;
-        const bool valid = y < h;
-        const uint32_t *row = mask + (size_t)b * mfw + (size_t)(valid ? y : 0) * mpw;
+        const int b = wi / wpf, y = (wi - b * wpf) * 8 + (lane >> 2);
+        const int j0 = (lane & 3) * ppw, jend = min(j0 + ppw, wpw);
+        const bool valid = y < h && j0 < wpw;
+        const uint32_t *row = mask + (size_t)b * mfw + (size_t)(y < h ? y : 0) * mpw;
         int *pr = parent + (size_t)b * pf + ((size_t)y << LOG);
-        unsigned prev_top = 0;
-        for (int j = 0; j < wpw; j += LAB_GROUP) {
-            unsigned wd[LAB_GROUP];
-            lab_load_group(row, j, wpw, lastmask, vec != 0, valid, wd);
+        unsigned prev_top = (valid && j0 > 0) ? (row[j0 - 1] >> 31) : 0u;
+        for (int j = j0; j < jend; j += LAB_GROUP * LAB_BATCH) {
+            unsigned wd[LAB_GROUP * LAB_BATCH];
+            lab_load_batch(row, j, jend, wpw, lastmask, vec != 0, valid, wd);
 #pragma unroll
-            for (int k = 0; k < LAB_GROUP; k++) {
+            for (int k = 0; k < LAB_GROUP * LAB_BATCH; k++) {
                 unsigned starts = lab_run_starts(wd[k], prev_top);
                 while (starts) {
                     const int bit = __ffs((int)starts) - 1;
@@ -299,7 +304,8 @@ label_merge_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
 
 // ---- C: rank the roots inside their row, count them -------------------------------------------
 // A root is a run start that is still its own parent after all merges.  The k-th root of a row
-// in x order gets parent = -k (no pointer chasing here).
+// in x order gets parent = -k (no pointer chasing here).  Four lanes per row: every lane counts the
+// roots of its quarter, a 4-lane prefix gives its first rank, a second sweep assigns.
 __global__ void __launch_bounds__(LAB_THREADS)
 label_flatten_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
                      int *__restrict__ parent, int LOG, size_t pf, int *__restrict__ rowcnt,
@@ -307,31 +313,48 @@ label_flatten_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
     const int lane = threadIdx.x & 31;
     const int wpw = (w + 31) >> 5;
     const unsigned lastmask = (w & 31) ? ((1u << (w & 31)) - 1u) : FULL;
-    const int wpf = (h + 31) >> 5;
+    const int ppw = ((wpw + 15) >> 4) << 2;
+    const int wpf = (h + 7) >> 3;
     const int total = wpf * batch;
     for (int wi = blockIdx.x * LAB_WARPS + (threadIdx.x >> 5); wi < total; wi += gridDim.x * LAB_WARPS) {
-        const int b = wi / wpf, y = (wi - b * wpf) * 32 + lane;
-        const bool valid = y < h;
-        const uint32_t *row = mask + (size_t)b * mfw + (size_t)(valid ? y : 0) * mpw;
+        const int b = wi / wpf, y = (wi - b * wpf) * 8 + (lane >> 2);
+        const int j0 = (lane & 3) * ppw, jend = min(j0 + ppw, wpw);
+        const bool valid = y < h && j0 < wpw;
+        const uint32_t *row = mask + (size_t)b * mfw + (size_t)(y < h ? y : 0) * mpw;
         int *pr = parent + (size_t)b * pf + ((size_t)y << LOG);
-        unsigned prev_top = 0;
-        int nroots = 0;
-        for (int j = 0; j < wpw; j += LAB_GROUP) {
-            unsigned wd[LAB_GROUP];
-            lab_load_group(row, j, wpw, lastmask, vec != 0, valid, wd);
+        const unsigned top0 = (valid && j0 > 0) ? (row[j0 - 1] >> 31) : 0u;
+        int rank = 0;
+        for (int sweep = 0; sweep < 2; sweep++) {
+            unsigned prev_top = top0;
+            int nroots = 0;
+            for (int j = j0; j < jend; j += LAB_GROUP * LAB_BATCH) {
+                unsigned wd[LAB_GROUP * LAB_BATCH];
+                lab_load_batch(row, j, jend, wpw, lastmask, vec != 0, valid, wd);
 #pragma unroll
-            for (int k = 0; k < LAB_GROUP; k++) {
-                unsigned starts = lab_run_starts(wd[k], prev_top);
-                while (starts) {
-                    const int bit = __ffs((int)starts) - 1;
-                    starts &= starts - 1;
-                    const int x = 32 * (j + k) + bit;
-                    if (pr[x] == (y << LOG) + x) pr[x] = -(++nroots);
+                for (int k = 0; k < LAB_GROUP * LAB_BATCH; k++) {
+                    unsigned starts = lab_run_starts(wd[k], prev_top);
+                    while (starts) {
+                        const int bit = __ffs((int)starts) - 1;
+                        starts &= starts - 1;
+                        const int x = 32 * (j + k) + bit;
+                        if (pr[x] == (y << LOG) + x) {
+                            nroots++;
+                            if (sweep) pr[x] = -(rank + nroots);
+                        }
+                    }
+                    prev_top = wd[k] >> 31;
                 }
-                prev_top = wd[k] >> 31;
             }
+            if (sweep) break;
+            // inclusive prefix over the four lanes of the row
+            int inc = nroots;
+            const int q = lane & 3;
+            int v = __shfl_up_sync(FULL, inc, 1); if (q >= 1) inc += v;
+            v = __shfl_up_sync(FULL, inc, 2); if (q >= 2) inc += v;
+            rank = inc - nroots;
+            if (q == 3 && y < h) rowcnt[(size_t)b * h + y] = inc;
+            if (!__any_sync(FULL, nroots != 0)) break;         // nothing to rank in these 8 rows
         }
-        if (valid) rowcnt[(size_t)b * h + y] = nroots;
     }
 }
 
@@ -470,7 +493,7 @@ static int label_forest(va_ctx *ctx, va_stream stream, const char *name,
     int *parent = ctx->lab_parent;
     int *rowcnt = ctx->lab_rowcnt;
     const int vec = va_aligned(mask, 16) && mask_pitch_w % 4 == 0 && mask_fstride_w % 4 == 0;
-    const int grid_a = va_div_up((long long)((h + 31) / 32) * batch, LAB_WARPS);        // lane-per-row kernels
+    const int grid_a = va_div_up((long long)((h + 7) / 8) * batch, LAB_WARPS);          // four-lanes-per-row kernels
     { auto k = label_init_kernel;
       VA_LAUNCH(ctx, k, grid_a, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, parent, LOG, pf, w, h, batch, vec); }
     { auto k = label_merge_kernel;

@@ -228,9 +228,9 @@ morph_bits_kernel(const uint32_t *__restrict__ in, size_t in_pitch_w, size_t in_
 }
 
 // ---------------------------------------------------------------------------------
-// streaming kernel for odd square RECT elements (3x3, 5x5, 7x7): a warp owns a strip of words and
-// walks down a segment of rows with everything in registers -- lane = word, horizontal neighbours
-// by shuffle, the last K horizontally reduced rows in a register window.  Erosion is dilation of the
+// streaming kernel for odd square RECT elements (3x3, 5x5, 7x7): a warp owns a strip of 64 words and
+// walks down a segment of rows with everything in registers -- lane = two adjacent words, horizontal
+// neighbours by shuffle, the last K horizontally reduced rows in a register window.  Erosion is dilation of the
 // complement, so both passes of an OPEN / CLOSE are dilations on data XORed with an all-ones / zero
 // mask; "outside the image never wins" and the bits beyond the row end are then plain zeros.
 // The second pass consumes the first one's rows as they appear (lag K/2 rows).  A pass spoils one
@@ -239,80 +239,115 @@ morph_bits_kernel(const uint32_t *__restrict__ in, size_t in_pitch_w, size_t in_
 #define MORPH_S_THREADS 128
 #define MORPH_S_PREFETCH 8
 
+// horizontal dilation of the two adjacent words (a, b) of every lane; words of neighbouring lanes
+// arrive by shuffle (the end lanes get their own word back: they are halo lanes, see above)
 template <int K>
-__device__ __forceinline__ unsigned morph_dilate_h(unsigned c) {
-    const unsigned p = __shfl_up_sync(0xffffffffu, c, 1), n = __shfl_down_sync(0xffffffffu, c, 1);
-    unsigned acc = c;
+__device__ __forceinline__ void morph_dilate_h2(unsigned &a, unsigned &b) {
+    const unsigned p = __shfl_up_sync(0xffffffffu, b, 1), n = __shfl_down_sync(0xffffffffu, a, 1);
+    unsigned ra = a, rb = b;
 #pragma unroll
-    for (int d = 1; d <= K / 2; d++) acc |= __funnelshift_r(c, n, d) | __funnelshift_l(p, c, d);
-    return acc;
+    for (int d = 1; d <= K / 2; d++) {
+        ra |= __funnelshift_r(a, b, d) | __funnelshift_l(p, a, d);
+        rb |= __funnelshift_r(b, n, d) | __funnelshift_l(a, b, d);
+    }
+    a = ra;
+    b = rb;
 }
 
-template <int K>
+template <int K, int PASSES>
 __global__ void __launch_bounds__(MORPH_S_THREADS)
 morph_stream_kernel(const uint32_t *__restrict__ in, size_t in_pitch_w, size_t in_fstride_w,
                     uint32_t *__restrict__ out, size_t out_pitch_w, size_t out_fstride_w,
-                    int w, int h, int strips, int segs, int SH, int n_warps, int first, int second) {
+                    int w, int h, int strips, int segs, int SH, int n_warps, int first, int second, int vec) {
     constexpr int H = K / 2;
+    constexpr int USABLE = 64 - 2 * PASSES;                    // words of a strip that are written
     const int lane = threadIdx.x & 31;
     const int wid = blockIdx.x * (MORPH_S_THREADS / 32) + (threadIdx.x >> 5);
     if (wid >= n_warps) return;
-    const int passes = second >= 0 ? 2 : 1;
-    const int usable = 32 - 2 * passes;
     const int b = wid / (strips * segs);
     const int rem = wid - b * strips * segs;
     const int seg = rem / strips, strip = rem - seg * strips;
     const int wpw = (w + 31) >> 5;
     const unsigned lastmask = (w & 31) ? ((1u << (w & 31)) - 1u) : 0xffffffffu;
-    const int j = strip * usable - passes + lane;              // word of this lane
-    const bool jin = j >= 0 && j < wpw;
-    const unsigned keep = !jin ? 0u : (j == wpw - 1 ? lastmask : 0xffffffffu);   // bits of the row in this word
-    const bool writer = jin && lane >= passes && lane < 32 - passes;
+    // lane = two adjacent words ja, ja + 1; strips start PASSES words early (even, so that pairs stay 8-byte aligned)
+    const int ja = strip * USABLE - PASSES + 2 * lane;
+    const bool ina = ja >= 0 && ja < wpw, inb = ja + 1 >= 0 && ja + 1 < wpw;
+    const unsigned keepa = !ina ? 0u : (ja == wpw - 1 ? lastmask : 0xffffffffu);       // bits of the row in each word
+    const unsigned keepb = !inb ? 0u : (ja + 1 == wpw - 1 ? lastmask : 0xffffffffu);
+    const bool wra = ina && 2 * lane >= PASSES && 2 * lane < 64 - PASSES;
+    const bool wrb = inb && 2 * lane + 1 >= PASSES && 2 * lane + 1 < 64 - PASSES;
+    const bool pair = vec && ina && inb;                                                // one 8-byte access
     const unsigned m1 = first == 0 ? 0xffffffffu : 0u;         // complement masks: erode = ~dilate(~x)
     const unsigned m2 = second == 0 ? 0xffffffffu : 0u;
+    const unsigned m12 = m1 ^ m2;
     const int ys = seg * SH, ye = min(ys + SH, h);             // output rows of this warp
-    const int y_first = ys - passes * H;                       // first input row needed
-    const int n_in = (ye - ys) + 2 * passes * H;
-    const uint32_t *col = in + (size_t)b * in_fstride_w + (jin ? j : 0);
-    uint32_t *ocol = out + (size_t)b * out_fstride_w + (jin ? j : 0);
+    const int y_first = ys - PASSES * H;                       // first input row needed
+    const int n_in = (ye - ys) + 2 * PASSES * H;
+    // row pointers run along with the walk (the ones outside the image are never dereferenced)
+    const uint32_t *src = in + (size_t)b * in_fstride_w + (ptrdiff_t)ja + (ptrdiff_t)y_first * (ptrdiff_t)in_pitch_w;
+    uint32_t *dst = out + (size_t)b * out_fstride_w + (ptrdiff_t)ja + (ptrdiff_t)(y_first - PASSES * H) * (ptrdiff_t)out_pitch_w;
 
-    unsigned hw[K], ew[K];                                     // windows of horizontally reduced rows
+    unsigned hwa[K], hwb[K], ewa[K], ewb[K];                   // windows of horizontally reduced rows
 #pragma unroll
-    for (int k = 0; k < K; k++) hw[k] = ew[k] = 0u;
+    for (int k = 0; k < K; k++) hwa[k] = hwb[k] = ewa[k] = ewb[k] = 0u;
+    // every lane runs the same instruction stream (the shuffles need the whole warp); rows beyond the
+    // segment in the last batch are loaded like any other and their results are not stored
     for (int i0 = 0; i0 < n_in; i0 += MORPH_S_PREFETCH) {
-        unsigned raw[MORPH_S_PREFETCH];
+        unsigned ra[MORPH_S_PREFETCH], rb[MORPH_S_PREFETCH];
 #pragma unroll
         for (int u = 0; u < MORPH_S_PREFETCH; u++) {
-            const int y = y_first + i0 + u;
-            raw[u] = (jin && y >= 0 && y < h && i0 + u < n_in) ? __ldg(col + (size_t)y * in_pitch_w) : m1;   // complemented below: 0
+            const bool yin = (unsigned)(y_first + i0 + u) < (unsigned)h;
+            ra[u] = rb[u] = m1;                                 // complemented to 0 below
+            if (yin && pair) {
+                const uint2 q = __ldg(reinterpret_cast<const uint2 *>(src));
+                ra[u] = q.x; rb[u] = q.y;
+            } else if (yin) {
+                if (ina) ra[u] = __ldg(src);
+                if (inb) rb[u] = __ldg(src + 1);
+            }
+            src += in_pitch_w;
         }
 #pragma unroll
         for (int u = 0; u < MORPH_S_PREFETCH; u++) {
             const int i = i0 + u;
-            if (i >= n_in) break;
             // ---- pass 1 on input row y_first + i; its result is row yc = y_first + i - H
 #pragma unroll
-            for (int k = 0; k < K - 1; k++) hw[k] = hw[k + 1];
-            hw[K - 1] = morph_dilate_h<K>((raw[u] ^ m1) & keep);
-            if (i < 2 * H) continue;
-            unsigned e = hw[0];
+            for (int k = 0; k < K - 1; k++) { hwa[k] = hwa[k + 1]; hwb[k] = hwb[k + 1]; }
+            unsigned xa = (ra[u] ^ m1) & keepa, xb = (rb[u] ^ m1) & keepb;
+            morph_dilate_h2<K>(xa, xb);
+            hwa[K - 1] = xa; hwb[K - 1] = xb;
+            unsigned ea = hwa[0], eb = hwb[0];
 #pragma unroll
-            for (int k = 1; k < K; k++) e |= hw[k];
+            for (int k = 1; k < K; k++) { ea |= hwa[k]; eb |= hwb[k]; }
             const int yc = y_first + i - H;
-            if (passes == 1) {
-                if (writer) ocol[(size_t)yc * out_pitch_w] = (e ^ m1) & keep;
-                continue;
+            unsigned oa, ob;
+            bool store;
+            if (PASSES == 1) {
+                oa = (ea ^ m1) & keepa; ob = (eb ^ m1) & keepb;
+                store = i >= 2 * H && yc < ye;
+            } else {
+                // ---- pass 2 on row yc of the intermediate (rows outside the image never win)
+                const bool cin = (unsigned)yc < (unsigned)h;
+                unsigned ma = cin ? ((ea ^ m12) & keepa) : 0u, mb = cin ? ((eb ^ m12) & keepb) : 0u;
+#pragma unroll
+                for (int k = 0; k < K - 1; k++) { ewa[k] = ewa[k + 1]; ewb[k] = ewb[k + 1]; }
+                morph_dilate_h2<K>(ma, mb);
+                ewa[K - 1] = ma; ewb[K - 1] = mb;
+                oa = ewa[0]; ob = ewb[0];
+#pragma unroll
+                for (int k = 1; k < K; k++) { oa |= ewa[k]; ob |= ewb[k]; }
+                oa = (oa ^ m2) & keepa; ob = (ob ^ m2) & keepb;
+                store = i >= 4 * H && yc - H < ye;
             }
-            // ---- pass 2 on row yc of the intermediate (rows outside the image never win)
-            const unsigned mid = (yc >= 0 && yc < h) ? ((e ^ m1 ^ m2) & keep) : 0u;
-#pragma unroll
-            for (int k = 0; k < K - 1; k++) ew[k] = ew[k + 1];
-            ew[K - 1] = morph_dilate_h<K>(mid);
-            if (i < 4 * H) continue;
-            unsigned o = ew[0];
-#pragma unroll
-            for (int k = 1; k < K; k++) o |= ew[k];
-            if (writer) ocol[(size_t)(yc - H) * out_pitch_w] = (o ^ m2) & keep;
+            if (store) {
+                if (wra && wrb && pair) {
+                    *reinterpret_cast<uint2 *>(dst) = make_uint2(oa, ob);
+                } else {
+                    if (wra) dst[0] = oa;
+                    if (wrb) dst[1] = ob;
+                }
+            }
+            dst += out_pitch_w;
         }
     }
 }
@@ -343,25 +378,34 @@ extern "C" int va_morph_bits(va_ctx *ctx, va_stream stream,
         const char *env = getenv("VA_MORPH_STREAM");
         if (env && atoi(env) == 0) sq = false;                   // A-B checks against the band kernel
         if (sq) {
-            const int usable = 32 - 2 * passes;
+            const int usable = 64 - 2 * passes;
             const int strips = va_div_up((long long)wpw, usable);
-            // rows per segment: the walk is a chain of load latencies, so many short segments (about 48
-            // warps per SM, at least 24 rows; each segment re-reads passes * (k - 1) rows)
-            int segs = va_div_up((long long)ctx->sm_count * 48, (long long)strips * batch);
-            if (segs > h / 24) segs = h / 24;
+            // rows per segment: the walk is a chain of load latencies, so many short segments (about 24
+            // warps per SM, at least 16 rows; each segment re-reads passes * (k - 1) rows), sized so that
+            // the rows a warp reads fill whole prefetch batches
+            const int halo_rows = passes * (kx - 1);
+            int segs = va_div_up((long long)ctx->sm_count * 24, (long long)strips * batch);
+            if (segs > h / 16) segs = h / 16;
             if (segs < 1) segs = 1;
-            const int SH = va_div_up(h, segs);
+            int SH = va_div_up(h, segs);
+            SH = va_div_up(SH + halo_rows, MORPH_S_PREFETCH) * MORPH_S_PREFETCH - halo_rows;
+            if (SH < 1) SH = MORPH_S_PREFETCH;
             segs = va_div_up(h, SH);
+            // 8-byte accesses need even word offsets: rows start 8-byte aligned and strips start at even words
+            const int vec = va_aligned(in, 8) && va_aligned(out, 8) && in_pitch_w % 2 == 0 && out_pitch_w % 2 == 0 &&
+                            in_fstride_w % 2 == 0 && out_fstride_w % 2 == 0 && passes % 2 == 0;
             const long long n_warps = (long long)strips * segs * batch;
             VA_REQUIRE(ctx, n_warps < (1ll << 31), "va_morph_bits: too many strips");
             const int grid = va_div_up(n_warps, MORPH_S_THREADS / 32);
-#define MORPH_SGO(KK)                                                                                      \
+#define MORPH_SGO(KK, PP)                                                                                  \
             do {                                                                                           \
-                auto kfn = morph_stream_kernel<KK>;                                                        \
+                auto kfn = morph_stream_kernel<KK, PP>;                                                    \
                 VA_LAUNCH(ctx, kfn, grid, MORPH_S_THREADS, 0, stream, in, in_pitch_w, in_fstride_w, out,   \
-                          out_pitch_w, out_fstride_w, w, h, strips, segs, SH, (int)n_warps, first, second); \
+                          out_pitch_w, out_fstride_w, w, h, strips, segs, SH, (int)n_warps, first, second, vec); \
             } while (0)
-            if (kx == 3) MORPH_SGO(3); else if (kx == 5) MORPH_SGO(5); else MORPH_SGO(7);
+#define MORPH_SK(KK) do { if (passes == 2) MORPH_SGO(KK, 2); else MORPH_SGO(KK, 1); } while (0)
+            if (kx == 3) MORPH_SK(3); else if (kx == 5) MORPH_SK(5); else MORPH_SK(7);
+#undef MORPH_SK
 #undef MORPH_SGO
             return VA_OK;
         }
