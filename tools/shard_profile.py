@@ -24,12 +24,11 @@ def t(fn, name):
 
 for rep in range(2):
     t(lambda: sh.run_device_range(batches, labels, counts), 'run_device_range (%d steps)' % K)
-blurs = t(lambda: [ch.blur_device(b, sh._blurs[i]) for i, b in enumerate(batches)], 'pass1 blur')
-t(lambda: sh._partial_state(blurs), 'partial state')
-S, n = sh._partial_state(blurs)
-t(lambda: parallel.exchange_carry(S, n, ch.alpha, lambda c, s, sc: rt.ema_fold(c, s, sc, W, H)), 'exchange')
-ch.reset()
-t(lambda: [ch.segment_device(b, labels[i & 1], counts) for i, b in enumerate(blurs)], 'pass2 segment')
+m = sh.tail_batches(K)
+blurs = t(lambda: [ch.blur_device(b, sh._blurs[i]) for i, b in enumerate(batches[K - m:])], 'pass1 blur (%d tail batches)' % m)
+t(lambda: sh._partial_state(blurs, m == K), 'partial state')
+S = sh._partial_state(blurs, m == K)
+t(lambda: parallel.exchange_carry(S, K * B, ch.alpha, lambda c, s, sc: rt.ema_fold(c, s, sc, W, H)), 'exchange')
 ch.reset()
 t(lambda: [ch.run_device(b, labels[i & 1], counts) for i, b in enumerate(batches)], 'fused chain (reference)')
 dist.destroy_process_group()

@@ -171,12 +171,13 @@ class SegmentChain(object):
         return stats, counts, largest
 
     # ---- two-stream software pipeline over consecutive device batches -----------------------------------
-    def run_device_pipelined(self, rgb, labels, counts):
+    def run_device_pipelined(self, rgb, labels, counts, blur=None):
         """ Same result as `run_device`, but the chain is split over two internal streams:
         front = RGB -> luma -> blur -> background/threshold (the sequential state lives here),
         back  = morphology -> labelling.  The issue-bound front kernels of batch k+1 then share
         the SMs with the latency-bound union-find kernels of batch k.  Call `pipeline_sync()`
-        (or synchronise the device) before reading `labels` / `counts`. """
+        (or synchronise the device) before reading `labels` / `counts`.  `blur`: the already blurred
+        batch (DeviceBatch 'u8'), when the caller has it. """
         rt, t = self.rt, torch()
         n = rgb.n
         if getattr(self, '_pipe', None) is None:
@@ -197,11 +198,13 @@ class SegmentChain(object):
         rt.ensure(self.w, self.h, n)
         lib, h = rt.lib, rt._h
         sub = lambda b: DeviceBatch(b.kind, b.t[:n], n, b.h, b.w, b.channels)
-        blur, mask, morph = sub(p['blur']), sub(p['mask'][slot]), sub(p['morph'])
+        have_blur = blur is not None
+        blur, mask, morph = (blur if have_blur else sub(p['blur'])), sub(p['mask'][slot]), sub(p['morph'])
         with t.cuda.stream(p['front']):
             p['front'].wait_event(ev)
             p['front'].wait_event(p['ev_back'][slot])        # the back half has finished reading this mask slot
-            self.blur_device(rgb, blur)
+            if not have_blur:
+                self.blur_device(rgb, blur)
             rt._check(lib.va_ema_diff_thresh(h, rt.stream, *blur.img(), self._bg.data_ptr(), self._bg.stride(0),
                                              *mask.img(), self.w, self.h, n, self.alpha, self.threshold,
                                              0 if self._started else 1))

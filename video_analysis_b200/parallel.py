@@ -13,13 +13,13 @@ that crosses GPUs; rank r then combines
 
     carry_r = sum_{j<r} a^(n_{j+1} + ... + n_{r-1}) * S_j
 
-locally (at most R-1 AXPYs, va_ema_fold) and pass 2 runs the ordinary K3/K4/K5 kernels from
-that state.  Rank 0 is bit-identical to the single-GPU run; later ranks differ by the
+locally (at most R-1 AXPYs, va_ema_fold) and pass 2 runs the ordinary chain from that state.  Rank 0 is bit-identical to the single-GPU run; later ranks differ by the
 re-association of the recurrence (<= 1e-5 relative on the background), which
 decays as a^k into their chunk.
 
 Terms older than `tail` frames are below float32 resolution (a^tail < 2^-30) and are not
-folded: S_r only reads the last `tail` blurred frames of a shard.
+folded: S_r only reads the last `tail` blurred frames of a shard, so pass 1 only blurs those
+(and keeps them for pass 2).
 """
 
 import math
@@ -75,22 +75,25 @@ class ShardedSegmentChain(object):
         self._S = None
         self._scratch_mask = None
 
+    def tail_batches(self, n_batches):
+        """ how many of the last batches of a shard carry weight into the next shard """
+        return min(n_batches, -(-self.tail // self.chain.batch) + 1)
+
     def reserve(self, n_batches):
         """ allocate the blurred-frame storage of pass 1 up front (keeps cudaMalloc out of the hot loop) """
         ch, rt = self.chain, self.chain.rt
-        while len(self._blurs) < n_batches:
+        while len(self._blurs) < self.tail_batches(n_batches):
             self._blurs.append(rt.empty_u8(ch.batch, ch.h, ch.w))
         if self._S is None:
             self._S = rt.empty_f32(ch.h, ch.w)
-            self._S.zero_()
 
-    def _partial_state(self, blurs):
-        """ S of this rank from its blurred batches (device) """
+    def _partial_state(self, blurs, covers_shard):
+        """ S of this rank from (the last of) its blurred batches (device) """
         import torch.distributed as dist
         ch, rt = self.chain, self.chain.rt
         if self._S is None:
             self._S = rt.empty_f32(ch.h, ch.w)
-            self._S.zero_()
+        self._S.zero_()
         n = sum(b.n for b in blurs)
         rank = dist.get_rank(self.group)
         # only the last `tail` frames matter
@@ -103,7 +106,7 @@ class ShardedSegmentChain(object):
             if lo >= b.n:
                 continue
             part = b if lo == 0 else _slice_batch(b, lo, b.n)
-            if first and rank == 0 and skip == 0:
+            if first and rank == 0 and skip == 0 and covers_shard:
                 # the sequential model starts from its first frame: S = float(x_0)
                 if self._scratch_mask is None:
                     self._scratch_mask = rt.empty_bits(1, ch.h, ch.w)
@@ -113,27 +116,36 @@ class ShardedSegmentChain(object):
             else:
                 rt.ema_partial(part, self._S, ch.alpha, not first)
             first = False
-        return self._S, n
+        return self._S
 
     def run_device_range(self, rgb_batches, labels_ring, counts):
         """ rgb_batches: this rank's frames as a list of DeviceBatch (n, h, w, 3), in order.
-        labels_ring: list of label DeviceBatches reused round-robin; counts: int32 tensor. """
+        labels_ring: list of label DeviceBatches reused round-robin; counts: int32 tensor (batch,)
+        shared by all batches, or (len(rgb_batches), batch) with one row per batch.
+        Results are complete once the caller's stream has passed `chain.pipeline_sync()` (done here). """
         ch, rt = self.chain, self.chain.rt
-        # pass 1: blur (kept for pass 2) + partial state
-        self.reserve(len(rgb_batches))
+        nb = len(rgb_batches)
+        # pass 1: blur the last batches of the shard -- the only frames whose weight a^k reaches the
+        # next rank -- and fold them into the partial state; the blurred frames are kept for pass 2
+        m = self.tail_batches(nb)
+        self.reserve(nb)
         blurs = []
-        for i, rgb in enumerate(rgb_batches):
-            out = self._blurs[i] if rgb.n == ch.batch else _slice_batch(self._blurs[i], 0, rgb.n)
-            blurs.append(ch.blur_device(rgb, out))
-        S, n = self._partial_state(blurs)
-        carry = exchange_carry(S, n, ch.alpha, lambda c, s, sc: rt.ema_fold(c, s, sc, ch.w, ch.h), self.group)
-        # pass 2: background / threshold / morphology / labels from the exact incoming state
+        for i in range(nb - m, nb):
+            rgb = rgb_batches[i]
+            buf = self._blurs[i - (nb - m)]
+            blurs.append(ch.blur_device(rgb, buf if rgb.n == ch.batch else _slice_batch(buf, 0, rgb.n)))
+        S = self._partial_state(blurs, covers_shard=(m == nb))
+        n_total = sum(b.n for b in rgb_batches)
+        carry = exchange_carry(S, n_total, ch.alpha, lambda c, s, sc: rt.ema_fold(c, s, sc, ch.w, ch.h), self.group)
+        # pass 2: the ordinary two-stream chain from the exact incoming state
         if carry is None:
             ch.reset()
         else:
             ch.set_background(carry)
-        for i, blur in enumerate(blurs):
-            ch.segment_device(blur, labels_ring[i % len(labels_ring)], counts)
+        for i, rgb in enumerate(rgb_batches):
+            ch.run_device_pipelined(rgb, labels_ring[i % len(labels_ring)], counts[i] if counts.dim() == 2 else counts,
+                                    blur=blurs[i - (nb - m)] if i >= nb - m else None)
+        ch.pipeline_sync()
 
 
 def _slice_batch(b, lo, hi):
