@@ -40,7 +40,7 @@ extern "C" int va_create(va_ctx **out, int device, int max_w, int max_h, int max
     if (ctx->lab_pitch * (size_t)max_h >= ((size_t)1 << 31)) { free(ctx); return VA_ERR_CAPACITY; }
     const size_t n_parent = ctx->lab_pitch * (size_t)max_h * (size_t)max_batch;
     if (cudaMalloc((void **)&ctx->lab_parent, n_parent * sizeof(int32_t)) != cudaSuccess ||
-        cudaMalloc((void **)&ctx->lab_rowcnt, (size_t)max_h * max_batch * sizeof(int32_t)) != cudaSuccess) {
+        cudaMalloc((void **)&ctx->lab_rowcnt, (size_t)2 * max_h * max_batch * sizeof(int32_t)) != cudaSuccess) {
         cudaGetLastError();
         va_destroy(ctx);
         return VA_ERR_NOMEM;

@@ -140,7 +140,7 @@ __device__ __forceinline__ void lab_load_batch(const uint32_t *row, int j, int j
 // ---- A: init -----------------------------------------------------------------------------
 __global__ void __launch_bounds__(LAB_THREADS)
 label_init_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
-                  int *__restrict__ parent, int LOG, size_t pf, int w, int h, int batch, int vec) {
+                  int *__restrict__ parent, int LOG, size_t pf, int *__restrict__ rowflag, int w, int h, int batch, int vec) {
     const int lane = threadIdx.x & 31;
     const int wpw = (w + 31) >> 5;
     const unsigned lastmask = (w & 31) ? ((1u << (w & 31)) - 1u) : FULL;
@@ -154,12 +154,14 @@ label_init_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
         const uint32_t *row = mask + (size_t)b * mfw + (size_t)(y < h ? y : 0) * mpw;
         int *pr = parent + (size_t)b * pf + ((size_t)y << LOG);
         unsigned prev_top = (valid && j0 > 0) ? (row[j0 - 1] >> 31) : 0u;
+        unsigned any = 0;
         for (int j = j0; j < jend; j += LAB_GROUP * LAB_BATCH) {
             unsigned wd[LAB_GROUP * LAB_BATCH];
             lab_load_batch(row, j, jend, wpw, lastmask, vec != 0, valid, wd);
 #pragma unroll
             for (int k = 0; k < LAB_GROUP * LAB_BATCH; k++) {
                 unsigned starts = lab_run_starts(wd[k], prev_top);
+                any |= wd[k];
                 while (starts) {
                     const int bit = __ffs((int)starts) - 1;
                     starts &= starts - 1;
@@ -169,6 +171,10 @@ label_init_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
                 prev_top = wd[k] >> 31;
             }
         }
+        // does the row have foreground at all?  (kernel B skips the others without touching the mask)
+        any |= __shfl_xor_sync(FULL, any, 1);
+        any |= __shfl_xor_sync(FULL, any, 2);
+        if ((lane & 3) == 0 && y < h) rowflag[(size_t)b * h + y] = any != 0u;
     }
 }
 
@@ -193,15 +199,18 @@ __device__ __forceinline__ void lab_merge_probe(int *pr, unsigned cur, int cur_s
 
 __global__ void __launch_bounds__(LAB_THREADS, 8)
 label_merge_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
-                   int *__restrict__ parent, int LOG, size_t pf, int w, int h, int batch, int conn8) {
+                   int *__restrict__ parent, int LOG, size_t pf, const int *__restrict__ rowflag,
+                   int w, int h, int batch, int conn8) {
+    // grid = (groups of 8 rows, frames): one row per warp
     const int lane = threadIdx.x & 31;
     const int wpw = (w + 31) >> 5;
     const unsigned lastmask = (w & 31) ? ((1u << (w & 31)) - 1u) : FULL;
-    const int rows = h * batch;
-    for (int row = blockIdx.x * LAB_WARPS + (threadIdx.x >> 5); row < rows;
-         row += gridDim.x * LAB_WARPS) {
-        const int b = row / h, y = row - b * h;
-        if (y == 0) continue;
+    {
+        const int b = blockIdx.y, y = blockIdx.x * LAB_WARPS + (threadIdx.x >> 5);
+        if (y == 0 || y >= h) return;
+        // a row can only be merged with the one above if both have foreground at all (flags of kernel A)
+        const int f = rowflag[(size_t)b * h + y - (lane & 1)];
+        if (!__all_sync(FULL, f != 0)) return;
         const uint32_t *mc = mask + (size_t)b * mfw + (size_t)y * mpw;
         const uint32_t *mu = mc - mpw;
         int *pr = parent + (size_t)b * pf;
@@ -212,10 +221,6 @@ label_merge_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
         unsigned up_prev_top = 0;                        // bit 31 of the up word before the chunk
         LAB_PREFETCH(prec, mc);
         LAB_PREFETCH(preu, mu);
-        // a row can only be merged with the one above if both have foreground at all
-        if (wpw <= 128 && (!__any_sync(FULL, (prec[0] | prec[1] | prec[2] | prec[3]) != 0u) ||
-                           !__any_sync(FULL, (preu[0] | preu[1] | preu[2] | preu[3]) != 0u)))
-            continue;
         for (int base = 0; base < wpw; base += 32) {
             const unsigned cur = LAB_PICK(prec, base, mc);
             const unsigned up = LAB_PICK(preu, base, mu);
@@ -391,21 +396,35 @@ label_scan_kernel(int *__restrict__ rowcnt, int *__restrict__ counts, int h) {
 __global__ void __launch_bounds__(LAB_THREADS)
 label_write_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
                    const int *__restrict__ parent, int LOG, size_t pf, const int *__restrict__ rowoff,
+                   const int *__restrict__ rowflag,
                    int32_t *__restrict__ labels, size_t lpe, size_t lfe, int w, int h, int batch, int vec_out) {
+    // grid = (groups of 8 rows, frames): one row per warp
     __shared__ int slab_all[LAB_WARPS][1024 + 32];
     const int lane = threadIdx.x & 31;
     int *slab = slab_all[threadIdx.x >> 5];
     const int wpw = (w + 31) >> 5;
     const unsigned lastmask = (w & 31) ? ((1u << (w & 31)) - 1u) : FULL;
-    const int rows = h * batch;
-    for (int row = blockIdx.x * LAB_WARPS + (threadIdx.x >> 5); row < rows;
-         row += gridDim.x * LAB_WARPS) {
-        const int b = row / h, y = row - b * h;
+    {
+        const int b = blockIdx.y, y = blockIdx.x * LAB_WARPS + (threadIdx.x >> 5);
+        if (y >= h) return;
+        int32_t *lr = labels + (size_t)b * lfe + (size_t)y * lpe;
+        if (rowflag[(size_t)b * h + y] == 0) {
+            // background row (flag of kernel A): zeros straight to memory, the mask is not even read
+            const int4 z = make_int4(0, 0, 0, 0);
+            for (int x = 4 * lane; x < w; x += 128) {
+                if (vec_out && x + 4 <= w) {
+                    *reinterpret_cast<int4 *>(lr + x) = z;
+                } else {
+                    for (int k = 0; k < 4; k++)
+                        if (x + k < w) lr[x + k] = 0;
+                }
+            }
+            return;
+        }
         const uint32_t *mr = mask + (size_t)b * mfw + (size_t)y * mpw;
         const int *pf_ = parent + (size_t)b * pf;
         const int *pr = pf_ + ((size_t)y << LOG);
         const int *ro = rowoff + (size_t)b * h;
-        int32_t *lr = labels + (size_t)b * lfe + (size_t)y * lpe;
         int carry = 0;
         LAB_PREFETCH(pre, mr);
         for (int base = 0; base < wpw; base += 32) {
@@ -488,17 +507,18 @@ static int label_forest(va_ctx *ctx, va_stream stream, const char *name,
     int LOG = 5;
     while (((size_t)1 << LOG) < ctx->lab_pitch) LOG++;
     const size_t pf = ctx->lab_pitch * (size_t)ctx->max_h;
-    const int rows = h * batch;
-    const int grid = (int)((rows + LAB_WARPS - 1) / LAB_WARPS);      // one row per warp, scheduled by the hardware
     int *parent = ctx->lab_parent;
     int *rowcnt = ctx->lab_rowcnt;
+    int *rowflag = ctx->lab_rowcnt + (size_t)ctx->max_h * ctx->max_batch;      // does the row have foreground?
     const int vec = va_aligned(mask, 16) && mask_pitch_w % 4 == 0 && mask_fstride_w % 4 == 0;
     const int grid_a = va_div_up((long long)((h + 7) / 8) * batch, LAB_WARPS);          // four-lanes-per-row kernels
     { auto k = label_init_kernel;
-      VA_LAUNCH(ctx, k, grid_a, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, parent, LOG, pf, w, h, batch, vec); }
+      VA_LAUNCH(ctx, k, grid_a, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, parent, LOG, pf, rowflag, w, h, batch, vec); }
     { auto k = label_merge_kernel;
-      VA_LAUNCH(ctx, k, grid, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, parent, LOG, pf, w, h, batch,
-                connectivity == 8 ? 1 : 0); }
+      VA_REQUIRE(ctx, batch <= 65535, "%s: more than 65535 frames in one call", name);
+      const dim3 grid_b(va_div_up(h, LAB_WARPS), batch);
+      VA_LAUNCH(ctx, k, grid_b, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, parent, LOG, pf, (const int *)rowflag,
+                w, h, batch, connectivity == 8 ? 1 : 0); }
     { auto k = label_flatten_kernel;
       VA_LAUNCH(ctx, k, grid_a, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, parent, LOG, pf, rowcnt, w, h, batch, vec); }
     { auto k = label_scan_kernel;
@@ -520,11 +540,12 @@ extern "C" int va_label_bits(va_ctx *ctx, va_stream stream,
     const int rc = label_forest(ctx, stream, "va_label_bits", mask, mask_pitch_w, mask_fstride_w, counts, w, h, batch,
                                 connectivity, &LOG, &pf);
     if (rc != VA_OK) return rc;
-    const int grid = (int)((h * batch + LAB_WARPS - 1) / LAB_WARPS);
     { auto k = label_write_kernel;
       const int vec_out = va_aligned(labels, 16) && labels_pitch_e % 4 == 0 && labels_fstride_e % 4 == 0;
+      const dim3 grid(va_div_up(h, LAB_WARPS), batch);
       VA_LAUNCH(ctx, k, grid, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, (const int *)ctx->lab_parent, LOG, pf,
-                (const int *)ctx->lab_rowcnt, labels, labels_pitch_e, labels_fstride_e, w, h, batch, vec_out); }
+                (const int *)ctx->lab_rowcnt, (const int *)(ctx->lab_rowcnt + (size_t)ctx->max_h * ctx->max_batch),
+                labels, labels_pitch_e, labels_fstride_e, w, h, batch, vec_out); }
     return VA_OK;
 }
 
