@@ -1,7 +1,8 @@
 """
 Launches every kernel of the chain exactly once (after a warm-up of 19 launches) so that
-`ncu -s 19 -c 10` captures one profile per kernel:
-  luma, gauss, luma_gauss, ema_diff_thresh, morph, label x5 (init merge flatten scan write)
+`ncu -s 19 -c 13` captures one profile per kernel:
+  luma, gauss, luma_gauss, ema_diff_thresh, morph, label x5 (init merge flatten scan write),
+  region statistics x3 (init stats largest; their forest kernels come first and are skipped by -k)
 """
 import os
 import sys
@@ -30,5 +31,6 @@ bg.copy_(ch._bg)
 mask = rt.ema_diff_thresh(blur, bg, 0.05, 25.0, False)
 mo = rt.morph(mask, 'open', 'rect', 3)
 lab, cnt = rt.label(mo, 4)
+stats, cnt2, big = rt.region_stats(mo, 4, 256)
 torch.cuda.synchronize()
 print('ok', cnt[:4].tolist(), rt.launches)

@@ -572,14 +572,15 @@ region_stats_init_kernel(long long *__restrict__ stats, int max_regions, const i
 __global__ void __launch_bounds__(LAB_THREADS)
 region_stats_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
                     const int *__restrict__ parent, int LOG, size_t pf, const int *__restrict__ rowoff,
+                    const int *__restrict__ rowflag,
                     long long *__restrict__ stats, int max_regions, int w, int h, int batch) {
+    // grid = (groups of 8 rows, frames): one row per warp; background rows (flag of kernel A) have nothing to add
     const int lane = threadIdx.x & 31;
     const int wpw = (w + 31) >> 5;
     const unsigned lastmask = (w & 31) ? ((1u << (w & 31)) - 1u) : FULL;
-    const int rows = h * batch;
-    for (int row = blockIdx.x * LAB_WARPS + (threadIdx.x >> 5); row < rows;
-         row += gridDim.x * LAB_WARPS) {
-        const int b = row / h, y = row - b * h;
+    {
+        const int b = blockIdx.y, y = blockIdx.x * LAB_WARPS + (threadIdx.x >> 5);
+        if (y >= h || rowflag[(size_t)b * h + y] == 0) return;
         const uint32_t *mr = mask + (size_t)b * mfw + (size_t)y * mpw;
         const int *pf_ = parent + (size_t)b * pf;
         const int *pr = pf_ + ((size_t)y << LOG);
@@ -642,11 +643,16 @@ region_largest64_kernel(const long long *__restrict__ stats, int max_regions, co
     }
     best_a[tid] = ba; best_l[tid] = bl;
     __syncthreads();
-    if (tid == 0) {
-        for (int i = 1; i < LAB_THREADS; i++)
-            if (best_a[i] > ba || (best_a[i] == ba && best_a[i] > 0 && best_l[i] < bl)) { ba = best_a[i]; bl = best_l[i]; }
-        largest[b] = bl;      // np.argmax(areas) + 1 (regions.py:169); 0 when the frame has no region
+    // tree reduction; ties go to the smaller label (np.argmax returns the first maximum)
+    for (int s = LAB_THREADS / 2; s > 0; s >>= 1) {
+        if (tid < s) {
+            const long long oa = best_a[tid + s];
+            const int ol = best_l[tid + s];
+            if (oa > best_a[tid] || (oa == best_a[tid] && oa > 0 && ol < best_l[tid])) { best_a[tid] = oa; best_l[tid] = ol; }
+        }
+        __syncthreads();
     }
+    if (tid == 0) largest[b] = best_l[0];      // np.argmax(areas) + 1 (regions.py:169); 0 when the frame has no region
 }
 
 extern "C" int va_region_stats(va_ctx *ctx, va_stream stream,
@@ -665,9 +671,10 @@ extern "C" int va_region_stats(va_ctx *ctx, va_stream stream,
       const dim3 grid(va_div_up(max_regions, LAB_THREADS) < 64 ? va_div_up(max_regions, LAB_THREADS) : 64, batch);
       VA_LAUNCH(ctx, k, grid, LAB_THREADS, 0, stream, (long long *)stats, max_regions, (const int *)counts); }
     { auto k = region_stats_kernel;
-      const int grid = (int)((h * batch + LAB_WARPS - 1) / LAB_WARPS);
+      const dim3 grid(va_div_up(h, LAB_WARPS), batch);
       VA_LAUNCH(ctx, k, grid, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, (const int *)ctx->lab_parent, LOG, pf,
-                (const int *)ctx->lab_rowcnt, (long long *)stats, max_regions, w, h, batch); }
+                (const int *)ctx->lab_rowcnt, (const int *)(ctx->lab_rowcnt + (size_t)ctx->max_h * ctx->max_batch),
+                (long long *)stats, max_regions, w, h, batch); }
     if (largest) {
         auto k = region_largest64_kernel;
         VA_LAUNCH(ctx, k, batch, LAB_THREADS, 0, stream, (const long long *)stats, max_regions, (const int *)counts, largest);
@@ -716,11 +723,15 @@ region_largest_kernel(const int *__restrict__ areas, int max_labels, int *__rest
     }
     best_a[tid] = ba; best_l[tid] = bl;
     __syncthreads();
-    if (tid == 0) {
-        for (int i = 1; i < LAB_THREADS; i++)
-            if (best_a[i] > ba || (best_a[i] == ba && best_a[i] > 0 && best_l[i] < bl)) { ba = best_a[i]; bl = best_l[i]; }
-        largest[b] = bl;      // np.argmax(areas) + 1; 0 when the frame has no region
+    // tree reduction; ties go to the smaller label (np.argmax returns the first maximum)
+    for (int s = LAB_THREADS / 2; s > 0; s >>= 1) {
+        if (tid < s) {
+            const int oa = best_a[tid + s], ol = best_l[tid + s];
+            if (oa > best_a[tid] || (oa == best_a[tid] && oa > 0 && ol < best_l[tid])) { best_a[tid] = oa; best_l[tid] = ol; }
+        }
+        __syncthreads();
     }
+    if (tid == 0) largest[b] = best_l[0];      // np.argmax(areas) + 1; 0 when the frame has no region
 }
 
 extern "C" int va_region_areas(va_ctx *ctx, va_stream stream,
