@@ -8,6 +8,8 @@
 //   d = float(x) - bg;  bit = |d| > thr;  bg = bg + alpha * d     (mul and add rounded
 // separately: __fmul_rn / __fadd_rn keep the compiler from contracting to an FMA, so the
 // result is bit-identical to the NumPy float32 oracle).
+#include <cstdlib>
+
 #include "va_device.cuh"
 
 #define EMA_THREADS 256
@@ -175,9 +177,10 @@ extern "C" int va_ema_diff_thresh(va_ctx *ctx, va_stream stream,
     VA_REQUIRE(ctx, thr - thr == 0.0f, "va_ema_diff_thresh: threshold must be finite");
     thr += 0.0f;                                        // -0 -> +0 (the kernel tests the sign of thr - |d|)
     const int vec_bg = va_aligned(bg, 16) && bg_pitch_e % 4 == 0;
-    // 16 pixels per thread when that still fills the machine, else 4
+    // 16 pixels per thread unless that leaves most SMs without a warp (measured: faster down to VGA), else 4
     const long long threads16 = (long long)((w + 511) / 512) * 32 * h;
-    const bool use16 = threads16 >= (long long)ctx->sm_count * 512;
+    bool use16 = threads16 >= (long long)ctx->sm_count * 128;
+    if (getenv("VA_EMA_PX")) use16 = atoi(getenv("VA_EMA_PX")) == 16;     // tuning only
     if (use16) {
         const int vec_in = va_aligned(in, 16) && in_pitch % 16 == 0 && in_fstride % 16 == 0;
         const long long warps = (long long)((w + 511) / 512) * h;
