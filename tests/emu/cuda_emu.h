@@ -63,6 +63,7 @@ struct Warp {
 };
 struct Block {
     std::barrier<> bar;
+    std::atomic<int> vote{0};
     std::vector<std::unique_ptr<Warp>> warps;
     explicit Block(int n) : bar(n) {
         for (int i = 0; i < n; i += 32) warps.emplace_back(new Warp(std::min(32, n - i)));
@@ -77,6 +78,16 @@ inline thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 static const int warpSize = 32;
 
 static inline void __syncthreads() { emu::cur_block->bar.arrive_and_wait(); }
+static inline int __syncthreads_or(int pred) {
+    emu::Block *b = emu::cur_block;
+    if (pred) b->vote.store(1);
+    b->bar.arrive_and_wait();
+    const int r = b->vote.load();
+    b->bar.arrive_and_wait();
+    b->vote.store(0);
+    b->bar.arrive_and_wait();
+    return r;
+}
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu::cur_block->warps[emu::warp]->bar.arrive_and_wait(); }
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
