@@ -334,11 +334,13 @@ class SegmentChain(object):
             frames = np.asarray(frames)
             n = len(frames)
             blocks = (frames[a:a + self.batch] for a in range(0, n, self.batch))
-        labels = np.empty((n, self.h, self.w), np.int32)
+        t = torch()
+        labels_t = t.empty((n, self.h, self.w), dtype=t.int32)       # filled by torch's multi-threaded host copy
+        labels = labels_t.numpy()
         counts = np.empty((n,), np.int32)
         k = 0
         for lab, cnt in self.process_blocks(blocks):
-            labels[k:k + len(lab)] = lab
+            labels_t[k:k + len(lab)].copy_(t.from_numpy(lab))
             counts[k:k + len(cnt)] = cnt
             k += len(lab)
         return labels[:k], counts[:k]
