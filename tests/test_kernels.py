@@ -94,6 +94,31 @@ def test_gauss_bit_exact(be, ctx):
         assert np.array_equal(hz.gauss(ctx, g, 2, in_pad=3, out_pad=5), np.stack([ops.blur(f, 2) for f in g]))
 
 
+def test_gauss_streaming_kernel(be, ctx, monkeypatch):
+    # 16-byte aligned frames with W % 16 == 0 take the register-window kernel (radius <= 9): every radius,
+    # strips cut by the right image edge, several row segments, images barely taller than the window,
+    # fused and unfused, mean and single-channel luma
+    cases = sizes(be, [(33, 160), (12, 16), (40, 640), (21, 336)], [(480, 640), (271, 1008), (67, 2064)])
+    for (H, W) in cases:
+        fr = rng_frames(H * W, (2, H, W, 3))
+        g = fr[..., 1].copy()
+        for s in (0.3, 0.5, 0.7, 0.9, 1.1, 1.3, 1.5, 2, 2.6, 3):
+            want = np.stack([ops.blur(f, s) for f in g])
+            for segs, nt in ((None, None), (1, 64), (3, 96), (2, 256)):
+                for key, val in (('VA_GS_SEGS', segs), ('VA_GS_NT', nt)):
+                    if val is None:
+                        monkeypatch.delenv(key, raising=False)
+                    else:
+                        monkeypatch.setenv(key, str(val))
+                assert np.array_equal(hz.gauss(ctx, g, s), want), (H, W, s, segs, nt)
+                if segs is None or s == 2:
+                    assert np.array_equal(hz.luma_gauss(ctx, fr, s, mode=1), want), (H, W, s, segs, nt)
+                    assert np.array_equal(hz.luma_gauss(ctx, fr, s),
+                                          np.stack([ops.blur(ops.mono(f), s) for f in fr])), (H, W, s, segs, nt)
+    monkeypatch.setenv('VA_GAUSS_STREAM', '0')           # and the tile kernel on the same inputs
+    assert np.array_equal(hz.gauss(ctx, g, 2), np.stack([ops.blur(f, 2) for f in g]))
+
+
 def test_gauss_large_sigma_identity_and_generic_paths(be, ctx):
     g = rng_frames(3, (1, 50, 70))
     for s in (0.05, 0.2, 10, 15, 21):          # ksize 1 (copy), tap 256 (generic), wide (TH=96)

@@ -292,7 +292,8 @@ gauss_fast_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fst
 }
 
 // ---------------------------------------------------------------------------------
-// streaming kernel (radius < 16, 16-byte aligned frames, w % 16 == 0): a warp owns a strip of 128
+// streaming kernel (radius <= 9: sigma <= 3; wider windows cost too many registers and the tile kernel
+// wins again; 16-byte aligned frames, w % 16 == 0): a warp owns a strip of 128
 // columns and walks down a segment of rows.  Lane t owns columns 4t .. 4t+3 for the whole walk and
 // keeps the last RT + 1 row pairs of the row pass in registers, so the 16-bit
 // intermediate image never exists in memory and no row of the segment is staged twice.
@@ -317,7 +318,7 @@ __device__ __forceinline__ unsigned gs_luma_x4(unsigned w0, unsigned w1, unsigne
 }
 
 template <int RT, bool FUSE_LUMA>
-__global__ void __launch_bounds__(GS_MAX_THREADS, 3)
+__global__ void __launch_bounds__(GS_MAX_THREADS, RT <= 8 ? 3 : 2)
 gauss_stream_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstride,
                     uint8_t *__restrict__ out, size_t out_pitch, size_t out_fstride,
                     int w, int h, int mode, int SH, const __grid_constant__ GaussFast g) {
@@ -598,7 +599,7 @@ static int gauss_launch(va_ctx *ctx, va_stream stream, const char *name, bool fu
             const int stream_mode = env ? atoi(env) : 1;          // 0: tile kernel only (tuning / A-B checks)
             const bool in16 = va_aligned(in, 16) && in_pitch % 16 == 0 && in_fstride % 16 == 0;
             const bool out4 = va_aligned(out, 4) && out_pitch % 4 == 0 && out_fstride % 4 == 0;
-            if (stream_mode && r <= 8 && h >= r + 2 && w % 16 == 0 && in16 && out4 && batch <= 65535) {
+            if (stream_mode && r <= 9 && h >= r + 2 && w % 16 == 0 && in16 && out4 && batch <= 65535) {
                 // warps per CTA: least idle warps at the right image edge, then the size closest to 3 warps
                 // (warps are independent; small CTAs pack the SMs better)
                 int NT = 96;
@@ -635,6 +636,7 @@ static int gauss_launch(va_ctx *ctx, va_stream stream, const char *name, bool fu
 #define GS_CASE(RT) case RT: if (fuse) GS_GO(RT, true); else GS_GO(RT, false); break;
                     switch (r) {
                         GS_CASE(1) GS_CASE(2) GS_CASE(3) GS_CASE(4) GS_CASE(5) GS_CASE(6) GS_CASE(7) GS_CASE(8)
+                        GS_CASE(9)
                     }
 #undef GS_CASE
 #undef GS_GO
