@@ -342,6 +342,22 @@ def test_label_adversarial(be, ctx):
             check_labels(ctx, m[None])
 
 
+def test_label_noise_next_to_blobs(be, ctx):
+    # rows with hundreds of runs next to rows with a few, components that cross from one kind into the other,
+    # widths with several 32-word chunks
+    rng = np.random.default_rng(21)
+    for (H, W) in sizes(be, [(70, 1300)], [(400, 1920), (90, 4000)]):
+        m = np.zeros((2, H, W), np.uint8)
+        m[0, :H // 3] = rng.random((H // 3, W)) < 0.5                      # noise on top
+        m[0, H // 3 - 2:, W // 4:W // 4 + 70] = 1                          # a bar growing out of the noise
+        m[0, H // 2:H // 2 + 11, 5:W - 5] = 1                              # a wide slab
+        m[0, H // 2 + 10:, W - 40:W - 8] = 1
+        m[1, 3::8] = rng.random((len(range(3, H, 8)), W)) < 0.5            # one noisy row per band
+        m[1, :, ::97] = 1                                                  # vertical lines through all bands
+        m[1, H - 9:, :] |= (rng.random((9, W)) < 0.55).astype(np.uint8)
+        check_labels(ctx, m)
+
+
 def test_label_golden_and_pitch(be, ctx):
     lab, cnt = hz.label(ctx, ops.pack_bits(GOLD['s_morph']), 64, 4, lab_pad=4)
     assert np.array_equal(lab, GOLD['s_labels']) and np.array_equal(cnt, GOLD['s_counts'])
