@@ -105,6 +105,21 @@ int va_resize_half_u8(va_ctx *ctx, va_stream stream,
                       uint8_t *out, size_t out_pitch, size_t out_fstride,
                       int w, int h, int channels, int batch);
 
+/* FilterResize._process_frame, video/filters.py:308-315, cv2.resize(INTER_AREA) when both scale factors
+ * are integers (OpenCV's ResizeAreaFast): out = round_half_even(float(sum over kx x ky) * (1.f / (kx ky))),
+ * and (sum + 2) >> 2 for 2 x 2.  (w, h) is the INPUT size, a multiple of (kx, ky); output (w / kx, h / ky). */
+int va_resize_area_u8(va_ctx *ctx, va_stream stream,
+                      const uint8_t *in, size_t in_pitch, size_t in_fstride,
+                      uint8_t *out, size_t out_pitch, size_t out_fstride,
+                      int w, int h, int channels, int batch, int kx, int ky);
+
+/* the same call site with cv2.INTER_NEAREST, any output size (dw, dh):
+ * out(x, y) = in(min(floor(x * (1 / (dw / w))), w - 1), min(floor(y * (1 / (dh / h))), h - 1)), in doubles */
+int va_resize_nearest_u8(va_ctx *ctx, va_stream stream,
+                         const uint8_t *in, size_t in_pitch, size_t in_fstride,
+                         uint8_t *out, size_t out_pitch, size_t out_fstride,
+                         int w, int h, int dw, int dh, int channels, int batch);
+
 /* K3 running-average background + |difference| > thr -> packed mask bits.
  * Not in the reference; fold shape follows
  * video/analysis/video.py:14-35, signed difference video/filters.py:564-568:

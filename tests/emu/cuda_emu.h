@@ -183,6 +183,7 @@ static inline unsigned __dp2a_hi(unsigned a, unsigned b, unsigned c) {
     return c + (a & 0xFFFF) * ((b >> 16) & 0xFF) + (a >> 16) * ((b >> 24) & 0xFF);
 }
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+static inline int __float2int_rn(float a) { return (int)std::nearbyintf(a); }
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }

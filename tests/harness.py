@@ -227,6 +227,31 @@ def resize_half(ctx, frames, in_pad=0):
     return out if frames.ndim == 3 else out.reshape(B, H // 2, W // 2, ch)
 
 
+def resize_area(ctx, frames, kx, ky):
+    be = ctx.be
+    B, H, W = frames.shape[:3]
+    ch = 1 if frames.ndim == 3 else frames.shape[3]
+    src = Img(be, B, H, W * ch, np.uint8, W * ch + 5, frames.reshape(B, H, W * ch))
+    dst = Img(be, B, H // ky, (W // kx) * ch, np.uint8, (W // kx) * ch + 3)
+    ctx.check(ctx.lib.va_resize_area_u8(ctx.h, be.stream, src.ptr, src.pitch, src.fstride, dst.ptr, dst.pitch, dst.fstride,
+                                        W, H, ch, B, kx, ky))
+    assert (dst.raw()[:, :, (W // kx) * ch:] == 0xCD).all()
+    out = dst.get()
+    return out if frames.ndim == 3 else out.reshape(B, H // ky, W // kx, ch)
+
+
+def resize_nearest(ctx, frames, dw, dh):
+    be = ctx.be
+    B, H, W = frames.shape[:3]
+    ch = 1 if frames.ndim == 3 else frames.shape[3]
+    src = Img(be, B, H, W * ch, np.uint8, data=frames.reshape(B, H, W * ch))
+    dst = Img(be, B, dh, dw * ch, np.uint8)
+    ctx.check(ctx.lib.va_resize_nearest_u8(ctx.h, be.stream, src.ptr, src.pitch, src.fstride, dst.ptr, dst.pitch, dst.fstride,
+                                           W, H, dw, dh, ch, B))
+    out = dst.get()
+    return out if frames.ndim == 3 else out.reshape(B, dh, dw, ch)
+
+
 def mask_words(W):
     return (W + 31) // 32
 

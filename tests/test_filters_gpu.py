@@ -79,8 +79,16 @@ def test_crop_resize_applymask_and_random_access(frames):
     assert np.array_equal(np.stack(list(red)), np.stack([ops.crop(f, rect, 'red') for f in frames[:9]]))
     half = F.FilterResize(cm, 0.5)
     assert np.array_equal(np.stack(list(half)), np.stack([ops.resize(f, 0.5) for f in exp]))
+    quarter = F.FilterResize(cm, 0.25)                                    # 160x120 -> 40x30: INTER_AREA by 4
+    assert np.array_equal(np.stack(list(quarter)), np.stack([ops.resize(f, 0.25) for f in exp]))
+    third = F.FilterResize(crop, (32, 40))                                # colour, factors 5 and 3
+    assert np.array_equal(np.stack(list(third)), np.stack([ops.resize(ops.crop(f, rect), (32, 40)) for f in frames[:9]]))
+    near = F.FilterResize(cm, (57, 201), interpolation='nearest')         # any size, also enlarging
+    assert np.array_equal(np.stack(list(near)), np.stack([ops.resize(f, (57, 201), 'nearest') for f in exp]))
     with pytest.raises(NotImplementedError):
-        next(iter(F.FilterResize(cm, 0.3)))
+        next(iter(F.FilterResize(cm, 0.3)))                               # 48x36: not an integer factor
+    with pytest.raises(NotImplementedError):
+        next(iter(F.FilterResize(cm, 2.0)))                               # 'auto' enlarges with INTER_CUBIC
     m = np.zeros((120, 160), bool)
     m[20:90, 30:140] = True
     masked = F.FilterApplyMask(cm, m)

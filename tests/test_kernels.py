@@ -187,6 +187,25 @@ def test_synth_equals_numpy_generator(be, ctx):
     assert np.array_equal(hz.synth(ctx, 0, 0, 6, 64, 48, synth.blob_table(0, 64, 48, 4)), GOLD['s_frames'])
 
 
+def test_resize_area_integer_factors_and_nearest(be, ctx):
+    rng = np.random.default_rng(8)
+    for (H, W) in sizes(be, [(24, 60), (36, 48)], [(1080, 1920), (720, 1280)]):
+        g = rng_frames(H, (2, H, W))
+        c = rng_frames(W, (2, H, W, 3))
+        for kx, ky in ((3, 3), (4, 4), (2, 3), (6, 2), (3, 1), (1, 2), (2, 2), (12, 12)):
+            if W % kx or H % ky:
+                continue
+            for fr in (g, c):
+                ref = np.stack([ops.resize(f, (W // kx, H // ky), 'area') for f in fr])
+                assert np.array_equal(hz.resize_area(ctx, fr, kx, ky), ref), (H, W, kx, ky, fr.ndim)
+        for dw, dh in ((W // 2, H // 2), (W // 3 + 1, H // 5 + 2), (W + 7, H + 3), (1, 1), (2 * W, 3)):
+            for fr in (g, c):
+                ref = np.stack([ops.resize(f, (dw, dh), 'nearest') for f in fr])
+                assert np.array_equal(hz.resize_nearest(ctx, fr, dw, dh), ref), (H, W, dw, dh, fr.ndim)
+    with pytest.raises(ValueError):
+        hz.resize_area(ctx, rng_frames(1, (1, 10, 10)), 3, 3)
+
+
 # ---- K3 -----------------------------------------------------------------------------------------
 def noisy_video(seed, shape):
     rng = np.random.default_rng(seed)

@@ -184,3 +184,86 @@ extern "C" int va_mean_update_f64(va_ctx *ctx, va_stream stream,
     VA_LAUNCH(ctx, kfn, grid, 256, 0, stream, in, in_pitch, in_fstride, mean, m2, pitch_e, row_elems, h, batch, n0);
     return VA_OK;
 }
+
+
+// ---------------------------------------------------------------------------------
+// FilterResize beyond the 1/2 case (video/filters.py:308-315): INTER_AREA with integer scale factors
+// and INTER_NEAREST.  One thread per output byte (plain gathers; these are not on the bench path).
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+resize_area_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstride,
+                   uint8_t *__restrict__ out, size_t out_pitch, size_t out_fstride,
+                   int ow, int oh, int cs, int batch, int kx, int ky, float scale) {
+    const unsigned rowb = (unsigned)(ow * cs);
+    const unsigned long long total = (unsigned long long)rowb * oh * batch;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned xb = (unsigned)(i % rowb);
+        const unsigned long long rest = i / rowb;
+        const unsigned y = (unsigned)(rest % oh), b = (unsigned)(rest / oh);
+        const unsigned x = xb / cs, c = xb - x * cs;
+        const uint8_t *p = in + (size_t)b * in_fstride + (size_t)(y * ky) * in_pitch + (size_t)(x * kx) * cs + c;
+        int sum = 0;
+        for (int j = 0; j < ky; j++, p += in_pitch)
+            for (int k = 0; k < kx; k++) sum += p[k * cs];
+        // OpenCV: 2 x 2 has its own integer form, everything else goes through float(sum) * scale, cvRound
+        const int v = (kx == 2 && ky == 2) ? (sum + 2) >> 2 : __float2int_rn(__fmul_rn((float)sum, scale));
+        out[(size_t)b * out_fstride + (size_t)y * out_pitch + xb] = (uint8_t)v;
+    }
+}
+
+extern "C" int va_resize_area_u8(va_ctx *ctx, va_stream stream,
+                                 const uint8_t *in, size_t in_pitch, size_t in_fstride,
+                                 uint8_t *out, size_t out_pitch, size_t out_fstride,
+                                 int w, int h, int channels, int batch, int kx, int ky) {
+    VA_CHECK_CTX(ctx);
+    VA_REQUIRE(ctx, in && out && in != out, "va_resize_area_u8: null or aliased pointers");
+    VA_REQUIRE(ctx, w > 0 && h > 0 && batch > 0 && (channels == 1 || channels == 3), "va_resize_area_u8: bad size");
+    VA_REQUIRE(ctx, kx >= 1 && ky >= 1 && kx * ky > 1 && kx <= 64 && ky <= 64, "va_resize_area_u8: bad factors %d x %d", kx, ky);
+    VA_REQUIRE(ctx, w % kx == 0 && h % ky == 0, "va_resize_area_u8: %dx%d is not a multiple of %dx%d", w, h, kx, ky);
+    const int ow = w / kx, oh = h / ky;
+    VA_REQUIRE(ctx, in_pitch >= (size_t)w * channels && out_pitch >= (size_t)ow * channels, "va_resize_area_u8: pitch smaller than a row");
+    const long long items = (long long)ow * channels * oh * batch;
+    const int grid = va_grid(ctx, (items + 255) / 256, 16);
+    auto kfn = resize_area_kernel;
+    VA_LAUNCH(ctx, kfn, grid, 256, 0, stream, in, in_pitch, in_fstride, out, out_pitch, out_fstride, ow, oh, channels, batch,
+              kx, ky, 1.f / (float)(kx * ky));
+    return VA_OK;
+}
+
+__global__ void __launch_bounds__(256)
+resize_nearest_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstride,
+                      uint8_t *__restrict__ out, size_t out_pitch, size_t out_fstride,
+                      int w, int h, int ow, int oh, int cs, int batch, double ifx, double ify) {
+    const unsigned rowb = (unsigned)(ow * cs);
+    const unsigned long long total = (unsigned long long)rowb * oh * batch;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned xb = (unsigned)(i % rowb);
+        const unsigned long long rest = i / rowb;
+        const unsigned y = (unsigned)(rest % oh), b = (unsigned)(rest / oh);
+        const unsigned x = xb / cs, c = xb - x * cs;
+        const int sx = min((int)floor(__dmul_rn((double)x, ifx)), w - 1);
+        const int sy = min((int)floor(__dmul_rn((double)y, ify)), h - 1);
+        out[(size_t)b * out_fstride + (size_t)y * out_pitch + xb] =
+            in[(size_t)b * in_fstride + (size_t)sy * in_pitch + (size_t)sx * cs + c];
+    }
+}
+
+extern "C" int va_resize_nearest_u8(va_ctx *ctx, va_stream stream,
+                                    const uint8_t *in, size_t in_pitch, size_t in_fstride,
+                                    uint8_t *out, size_t out_pitch, size_t out_fstride,
+                                    int w, int h, int dw, int dh, int channels, int batch) {
+    VA_CHECK_CTX(ctx);
+    VA_REQUIRE(ctx, in && out && in != out, "va_resize_nearest_u8: null or aliased pointers");
+    VA_REQUIRE(ctx, w > 0 && h > 0 && dw > 0 && dh > 0 && batch > 0 && (channels == 1 || channels == 3), "va_resize_nearest_u8: bad size");
+    VA_REQUIRE(ctx, in_pitch >= (size_t)w * channels && out_pitch >= (size_t)dw * channels, "va_resize_nearest_u8: pitch smaller than a row");
+    // cv::resize: inv_scale = dsize / ssize, ifx = 1 / inv_scale (doubles), x_ofs[x] = min(cvFloor(x * ifx), ssize - 1)
+    const double ifx = 1.0 / ((double)dw / (double)w), ify = 1.0 / ((double)dh / (double)h);
+    const long long items = (long long)dw * channels * dh * batch;
+    const int grid = va_grid(ctx, (items + 255) / 256, 16);
+    auto kfn = resize_nearest_kernel;
+    VA_LAUNCH(ctx, kfn, grid, 256, 0, stream, in, in_pitch, in_fstride, out, out_pitch, out_fstride, w, h, dw, dh, channels, batch,
+              ifx, ify);
+    return VA_OK;
+}

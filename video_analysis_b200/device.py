@@ -213,6 +213,26 @@ class DeviceRuntime(object):
                                                out.ptr, out.pitch, out.fstride, src.w, src.h, src.channels, src.n))
         return out
 
+    def resize_area(self, src, kx, ky):
+        """ cv2.resize(INTER_AREA) by the integer factors 1/kx, 1/ky """
+        if kx == 2 and ky == 2:
+            return self.resize_half(src)
+        self.ensure(src.w, src.h, src.n)
+        out = self.empty_u8(src.n, src.h // ky, src.w // kx, src.channels)
+        self._check(self.lib.va_resize_area_u8(self._h, self.stream, src.ptr, src.pitch, src.fstride,
+                                               out.ptr, out.pitch, out.fstride, src.w, src.h, src.channels, src.n,
+                                               int(kx), int(ky)))
+        return out
+
+    def resize_nearest(self, src, dw, dh):
+        """ cv2.resize(INTER_NEAREST) to (dw, dh) """
+        self.ensure(max(src.w, dw), max(src.h, dh), src.n)
+        out = self.empty_u8(src.n, dh, dw, src.channels)
+        self._check(self.lib.va_resize_nearest_u8(self._h, self.stream, src.ptr, src.pitch, src.fstride,
+                                                  out.ptr, out.pitch, out.fstride, src.w, src.h, int(dw), int(dh),
+                                                  src.channels, src.n))
+        return out
+
     def apply_mask(self, src, mask_dev):
         """ mask_dev: uint8 device tensor (h, w) """
         self.ensure(src.w, src.h, src.n)

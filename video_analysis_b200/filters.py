@@ -441,9 +441,10 @@ class FilterBlur(DeviceFilterBase):
 
 
 class FilterResize(DeviceFilterBase):
-    """ resizes the video (filters.py:252-315).  The device path implements the exact integer
-    case -- shrinking to half size with INTER_AREA ('auto' picks that when shrinking); other
-    factors / interpolations raise NotImplementedError rather than silently running on the CPU. """
+    """ resizes the video (filters.py:252-315).  The device path implements INTER_AREA for integer
+    shrink factors (OpenCV's exact integer / single-rounding form; 'auto' picks INTER_AREA when shrinking)
+    and INTER_NEAREST for any size; other combinations raise NotImplementedError rather than silently
+    running on the CPU. """
 
     def __init__(self, source, size=None, interpolation='auto', even_dimensions=False, **kwargs):
         if hasattr(size, '__iter__'):
@@ -474,10 +475,13 @@ class FilterResize(DeviceFilterBase):
         if self.interpolation is None:
             return batch
         w, h = self.size
-        if self.interpolation == 'area' and batch.w == 2 * w and batch.h == 2 * h:
-            return rt.resize_half(batch)
-        raise NotImplementedError('FilterResize on the device supports INTER_AREA by exactly 1/2 '
-                                  '(%dx%d -> %dx%d with %s requested)' % (batch.w, batch.h, w, h, self.interpolation))
+        if self.interpolation == 'area' and batch.w % w == 0 and batch.h % h == 0:
+            return rt.resize_area(batch, batch.w // w, batch.h // h)
+        if self.interpolation == 'nearest':
+            return rt.resize_nearest(batch, w, h)
+        raise NotImplementedError('FilterResize on the device supports INTER_AREA by integer factors and '
+                                  'INTER_NEAREST (%dx%d -> %dx%d with %s requested)'
+                                  % (batch.w, batch.h, w, h, self.interpolation))
 
 
 class FilterNormalize(DeviceFilterBase):
