@@ -226,6 +226,26 @@ def test_ema_diff_threshold_bit_exact(be, ctx):
         assert np.array_equal(bg2.view(np.uint32), bg2_ref.view(np.uint32))
 
 
+def test_ema_flat_group_mapping(be, ctx, monkeypatch):
+    # widths that are multiples of 32 but not of a whole warp step take the raster-order group mapping
+    # (warps straddle rows, the last warp has idle lanes); both pixels-per-thread variants, and the
+    # row-chunk mapping on the same input as the cross-check
+    for px in ('4', '16'):
+        monkeypatch.setenv('VA_EMA_PX', px)
+        for (B, H, W) in sizes(be, [(5, 9, 96), (4, 7, 160), (3, 5, 1056), (6, 1, 32)], [(5, 1080, 1920), (4, 720, 1280)]):
+            g = noisy_video(W, (B, H, W))
+            m_ref, bg_ref = ops.background_ema(list(g), 0.05, 25)
+            for noflat in (False, True):
+                if noflat:
+                    monkeypatch.setenv('VA_EMA_NOFLAT', '1')
+                else:
+                    monkeypatch.delenv('VA_EMA_NOFLAT', raising=False)
+                m, bg = hz.ema_diff_thresh(ctx, g, 0.05, 25)
+                assert np.array_equal(m, ops.pack_bits(m_ref)), (px, B, H, W, noflat)
+                assert np.array_equal(bg.view(np.uint32), bg_ref.view(np.uint32))
+    monkeypatch.delenv('VA_EMA_NOFLAT', raising=False)
+
+
 def test_ema_threshold_edge_cases(be, ctx):
     # differences that hit the threshold exactly (alpha = 0.5 keeps the state on a dyadic grid), zero,
     # negative and signed-zero thresholds; a non-finite threshold is rejected

@@ -73,29 +73,42 @@ __device__ __forceinline__ void ema_issue(unsigned *slot, const uint8_t *rp, int
     va_cp_async_commit();
 }
 
-template <int PX>
-__global__ void __launch_bounds__(EMA_THREADS, PX == 16 ? 4 : 5)
+// NT = threads per block.  The 16-pixel variant runs one warp per block: a warp's work (its pixels through the whole
+// batch) is long and indivisible, so the block scheduler has to be able to even the warps out over the SMs -- with
+// 8-warp blocks a 1080p launch (4050 warps, 27.4 per SM) left some SMs with 32 warps and others with 24 and ran
+// as long as the fullest one.
+template <int PX, int NT>
+__global__ void __launch_bounds__(NT, NT == 32 ? 32 : PX == 16 ? 4 : 5)
 ema_diff_thresh_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstride,
                        float *__restrict__ bg, size_t bg_pitch_e,
                        uint32_t *__restrict__ mask, size_t mask_pitch_w, size_t mask_fstride_w,
-                       int w, int h, int batch, float alpha, float thr, int first_init, int vec_in, int vec_bg) {
+                       int w, int h, int batch, float alpha, float thr, int first_init, int vec_in, int vec_bg, int flat) {
     constexpr int NW = PX / 4;
     constexpr int RING = PX == 16 ? 8 : 16;                            // frames in flight per thread
-    __shared__ uint4 ring_raw[RING * EMA_THREADS * NW / 4];            // uint4: 16-byte aligned slots
-    unsigned(*ring)[EMA_THREADS * NW] = reinterpret_cast<unsigned(*)[EMA_THREADS * NW]>(ring_raw);
+    __shared__ uint4 ring_raw[RING * NT * NW / 4];                     // uint4: 16-byte aligned slots
+    unsigned(*ring)[NT * NW] = reinterpret_cast<unsigned(*)[NT * NW]>(ring_raw);
     const int lane = threadIdx.x & 31;
-    const int warps_per_block = EMA_THREADS >> 5;
+    constexpr int warps_per_block = NT >> 5;
     const int span = 32 * PX;                         // pixels per warp step
     const int chunks = (w + span - 1) / span;
-    const unsigned total = (unsigned)((long long)chunks * h);
+    // flat: w % (2 PX) == 0, so a warp takes 32 consecutive PX-pixel groups of the image in raster order (they may
+    // straddle rows; lanes that share a mask word stay in one row) and no lane idles beyond the row end
+    const int groups = w / PX;                                         // flat only
+    const unsigned total = flat ? (unsigned)(((long long)groups * h + 31) >> 5) : (unsigned)((long long)chunks * h);
     unsigned *myslot = &ring[0][threadIdx.x * NW];
-    constexpr int SLOT_STRIDE = EMA_THREADS * NW;
+    constexpr int SLOT_STRIDE = NT * NW;
 
     for (unsigned item = blockIdx.x * warps_per_block + (threadIdx.x >> 5); item < total;
          item += gridDim.x * warps_per_block) {
-        const int y = (int)(item / (unsigned)chunks);
-        const int c = (int)(item - (unsigned)y * (unsigned)chunks);
-        const int x = c * span + lane * PX;
+        int y, x;
+        if (flat) {
+            const unsigned g = item * 32u + lane;
+            y = (int)(g / (unsigned)groups);
+            x = y < h ? (int)(g - (unsigned)y * (unsigned)groups) * PX : w;       // beyond the image: an idle lane
+        } else {
+            y = (int)(item / (unsigned)chunks);
+            x = (int)(item - (unsigned)y * (unsigned)chunks) * span + lane * PX;
+        }
         const uint8_t *rp = in + (size_t)y * in_pitch;
         float *bgp = bg + (size_t)y * bg_pitch_e + x;
         const unsigned valid = x >= w ? 0u : (x + PX <= w ? ((1u << PX) - 1u) : ((1u << (w - x)) - 1u));
@@ -183,18 +196,29 @@ extern "C" int va_ema_diff_thresh(va_ctx *ctx, va_stream stream,
     if (getenv("VA_EMA_PX")) use16 = atoi(getenv("VA_EMA_PX")) == 16;     // tuning only
     if (use16) {
         const int vec_in = va_aligned(in, 16) && in_pitch % 16 == 0 && in_fstride % 16 == 0;
-        const long long warps = (long long)((w + 511) / 512) * h;
-        const int grid = va_grid(ctx, (warps + 7) / 8, 8);
-        auto kfn = ema_diff_thresh_kernel<16>;
-        VA_LAUNCH(ctx, kfn, grid, EMA_THREADS, 0, stream, in, in_pitch, in_fstride, bg, bg_pitch_e, mask, mask_pitch_w,
-                  mask_fstride_w, w, h, batch, alpha, thr, first_frame_inits, vec_in, vec_bg);
+        const int flat = w % 32 == 0 && w % 512 != 0 && !getenv("VA_EMA_NOFLAT");
+        const long long warps = flat ? ((long long)(w / 16) * h + 31) / 32 : (long long)((w + 511) / 512) * h;
+        VA_REQUIRE(ctx, warps < (1ll << 31), "va_ema_diff_thresh: frame too large");
+        const int nt = getenv("VA_EMA_NT") ? atoi(getenv("VA_EMA_NT")) : 32;                // tuning only
+        if (nt == 256) {
+            const int grid = va_grid(ctx, (warps + 7) / 8, 8);
+            auto kfn = ema_diff_thresh_kernel<16, 256>;
+            VA_LAUNCH(ctx, kfn, grid, 256, 0, stream, in, in_pitch, in_fstride, bg, bg_pitch_e, mask, mask_pitch_w,
+                      mask_fstride_w, w, h, batch, alpha, thr, first_frame_inits, vec_in, vec_bg, flat);
+            return VA_OK;
+        }
+        const int grid = (int)warps;                      // one warp per block, no grid-stride rounds
+        auto kfn = ema_diff_thresh_kernel<16, 32>;
+        VA_LAUNCH(ctx, kfn, grid, 32, 0, stream, in, in_pitch, in_fstride, bg, bg_pitch_e, mask, mask_pitch_w,
+                  mask_fstride_w, w, h, batch, alpha, thr, first_frame_inits, vec_in, vec_bg, flat);
     } else {
         const int vec_in = va_aligned(in, 4) && in_pitch % 4 == 0 && in_fstride % 4 == 0;
-        const long long warps = (long long)((w + 127) / 128) * h;
+        const int flat = w % 32 == 0 && w % 128 != 0 && !getenv("VA_EMA_NOFLAT");
+        const long long warps = flat ? ((long long)(w / 4) * h + 31) / 32 : (long long)((w + 127) / 128) * h;
         const int grid = va_grid(ctx, (warps + 7) / 8, 8);
-        auto kfn = ema_diff_thresh_kernel<4>;
+        auto kfn = ema_diff_thresh_kernel<4, EMA_THREADS>;
         VA_LAUNCH(ctx, kfn, grid, EMA_THREADS, 0, stream, in, in_pitch, in_fstride, bg, bg_pitch_e, mask, mask_pitch_w,
-                  mask_fstride_w, w, h, batch, alpha, thr, first_frame_inits, vec_in, vec_bg);
+                  mask_fstride_w, w, h, batch, alpha, thr, first_frame_inits, vec_in, vec_bg, flat);
     }
     return VA_OK;
 }
