@@ -120,6 +120,23 @@ int va_resize_nearest_u8(va_ctx *ctx, va_stream stream,
                          uint8_t *out, size_t out_pitch, size_t out_fstride,
                          int w, int h, int dw, int dh, int channels, int batch);
 
+/* the same call site with cv2.INTER_AREA shrinking by any (non-integer) factors to (dw, dh): OpenCV's
+ * computeResizeAreaTab / resizeArea_<uchar, float> -- cell tables in doubles, weights and sums in float32
+ * with every operation rounded on its own, round half to even.  Integer factors dispatch to the calls above.
+ * Enlarging in either direction returns VA_ERR_UNSUPPORTED (OpenCV then interpolates linearly). */
+int va_resize_area_any_u8(va_ctx *ctx, va_stream stream,
+                          const uint8_t *in, size_t in_pitch, size_t in_fstride,
+                          uint8_t *out, size_t out_pitch, size_t out_fstride,
+                          int w, int h, int dw, int dh, int channels, int batch);
+
+/* the same call site with cv2.INTER_LINEAR, any output size (OpenCV's 8-bit fixed-point path: 11-bit
+ * coefficients, out = (((b0 (H0 >> 4)) >> 16) + ((b1 (H1 >> 4)) >> 16) + 2) >> 2 with H = S[sx] a0 + S[sx+1] a1;
+ * shrinking by exactly 2 x 2 is INTER_AREA, as in cv2) */
+int va_resize_linear_u8(va_ctx *ctx, va_stream stream,
+                        const uint8_t *in, size_t in_pitch, size_t in_fstride,
+                        uint8_t *out, size_t out_pitch, size_t out_fstride,
+                        int w, int h, int dw, int dh, int channels, int batch);
+
 /* K3 running-average background + |difference| > thr -> packed mask bits.
  * Not in the reference; fold shape follows
  * video/analysis/video.py:14-35, signed difference video/filters.py:564-568:

@@ -252,6 +252,20 @@ def resize_nearest(ctx, frames, dw, dh):
     return out if frames.ndim == 3 else out.reshape(B, dh, dw, ch)
 
 
+def resize_to(ctx, frames, dw, dh, how):
+    """ how: 'area_any' | 'linear' """
+    be = ctx.be
+    B, H, W = frames.shape[:3]
+    ch = 1 if frames.ndim == 3 else frames.shape[3]
+    src = Img(be, B, H, W * ch, np.uint8, W * ch + 5, frames.reshape(B, H, W * ch))
+    dst = Img(be, B, dh, dw * ch, np.uint8, dw * ch + 3)
+    fn = getattr(ctx.lib, 'va_resize_%s_u8' % how)
+    ctx.check(fn(ctx.h, be.stream, src.ptr, src.pitch, src.fstride, dst.ptr, dst.pitch, dst.fstride, W, H, dw, dh, ch, B))
+    assert (dst.raw()[:, :, dw * ch:] == 0xCD).all()
+    out = dst.get()
+    return out if frames.ndim == 3 else out.reshape(B, dh, dw, ch)
+
+
 def mask_words(W):
     return (W + 31) // 32
 

@@ -85,8 +85,10 @@ def test_crop_resize_applymask_and_random_access(frames):
     assert np.array_equal(np.stack(list(third)), np.stack([ops.resize(ops.crop(f, rect), (32, 40)) for f in frames[:9]]))
     near = F.FilterResize(cm, (57, 201), interpolation='nearest')         # any size, also enlarging
     assert np.array_equal(np.stack(list(near)), np.stack([ops.resize(f, (57, 201), 'nearest') for f in exp]))
-    with pytest.raises(NotImplementedError):
-        next(iter(F.FilterResize(cm, 0.3)))                               # 48x36: not an integer factor
+    frac = F.FilterResize(cm, 0.3)                                        # 48x36: INTER_AREA by 10/3
+    assert np.array_equal(np.stack(list(frac)), np.stack([ops.resize(f, 0.3) for f in exp]))
+    lin = F.FilterResize(crop, (201, 57), interpolation='linear')         # colour, enlarging x, shrinking y
+    assert np.array_equal(np.stack(list(lin)), np.stack([ops.resize(ops.crop(f, rect), (201, 57), 'linear') for f in frames[:9]]))
     with pytest.raises(NotImplementedError):
         next(iter(F.FilterResize(cm, 2.0)))                               # 'auto' enlarges with INTER_CUBIC
     m = np.zeros((120, 160), bool)

@@ -206,6 +206,24 @@ def test_resize_area_integer_factors_and_nearest(be, ctx):
         hz.resize_area(ctx, rng_frames(1, (1, 10, 10)), 3, 3)
 
 
+def test_resize_area_any_factor_and_linear(be, ctx):
+    for (H, W) in sizes(be, [(24, 60), (37, 53)], [(1080, 1920), (271, 1003)]):
+        g = rng_frames(H + 1, (2, H, W))
+        c = rng_frames(W + 1, (2, H, W, 3))
+        for dw, dh in ((W * 3 // 10, H * 3 // 10), (W - 1, H - 1), (W // 2 + 1, H // 3), (7, 5), (W, H // 2), (W // 3, H),
+                       (W // 2, H // 2), (W * 2 // 3, H * 2 // 3), (1, 1)):
+            for fr in (g, c):
+                ref = np.stack([ops.resize(f, (dw, dh), 'area') for f in fr]).reshape((2, dh, dw) + fr.shape[3:])
+                assert np.array_equal(hz.resize_to(ctx, fr, dw, dh, 'area_any'), ref), (H, W, dw, dh, fr.ndim)
+        for dw, dh in ((W * 3 // 10, H * 3 // 10), (W - 1, H - 1), (W + 7, H + 3), (2 * W, 2 * H), (W // 2, H // 2), (7, 5),
+                       (1, 1), (W + W // 2 + 1, H // 2), (W, H * 2)):
+            for fr in (g, c):
+                ref = np.stack([ops.resize(f, (dw, dh), 'linear') for f in fr]).reshape((2, dh, dw) + fr.shape[3:])
+                assert np.array_equal(hz.resize_to(ctx, fr, dw, dh, 'linear'), ref), (H, W, dw, dh, fr.ndim)
+    with pytest.raises(NotImplementedError):
+        hz.resize_to(ctx, rng_frames(1, (1, 10, 10)), 12, 5, 'area_any')        # INTER_AREA enlarging = linear in cv2
+
+
 # ---- K3 -----------------------------------------------------------------------------------------
 def noisy_video(seed, shape):
     rng = np.random.default_rng(seed)

@@ -219,7 +219,7 @@ extern "C" int va_resize_area_u8(va_ctx *ctx, va_stream stream,
     VA_CHECK_CTX(ctx);
     VA_REQUIRE(ctx, in && out && in != out, "va_resize_area_u8: null or aliased pointers");
     VA_REQUIRE(ctx, w > 0 && h > 0 && batch > 0 && (channels == 1 || channels == 3), "va_resize_area_u8: bad size");
-    VA_REQUIRE(ctx, kx >= 1 && ky >= 1 && kx * ky > 1 && kx <= 64 && ky <= 64, "va_resize_area_u8: bad factors %d x %d", kx, ky);
+    VA_REQUIRE(ctx, kx >= 1 && ky >= 1 && kx * ky > 1 && (long long)kx * ky <= 8000000, "va_resize_area_u8: bad factors %d x %d", kx, ky);   // sums stay in 31 bits
     VA_REQUIRE(ctx, w % kx == 0 && h % ky == 0, "va_resize_area_u8: %dx%d is not a multiple of %dx%d", w, h, kx, ky);
     const int ow = w / kx, oh = h / ky;
     VA_REQUIRE(ctx, in_pitch >= (size_t)w * channels && out_pitch >= (size_t)ow * channels, "va_resize_area_u8: pitch smaller than a row");
@@ -265,5 +265,174 @@ extern "C" int va_resize_nearest_u8(va_ctx *ctx, va_stream stream,
     auto kfn = resize_nearest_kernel;
     VA_LAUNCH(ctx, kfn, grid, 256, 0, stream, in, in_pitch, in_fstride, out, out_pitch, out_fstride, w, h, dw, dh, channels, batch,
               ifx, ify);
+    return VA_OK;
+}
+
+
+// ---------------------------------------------------------------------------------
+// INTER_AREA shrinking by non-integer factors (OpenCV's computeResizeAreaTab + resizeArea_<uchar, float>):
+// destination cell dx covers source [dx s, dx s + s), s = 1 / (dsize / ssize) in doubles; the cell's table is
+// an optional partial pixel on the left (if it covers more than 1e-3), the whole pixels with weight
+// float(1 / cell width), an optional partial pixel on the right.  A destination value is
+//     sum over rows in table order of  beta * (sum over columns in table order of  S * alpha)
+// in float32, every product and every sum rounded on its own (this is what the x86 build of cv2 4.13 does;
+// checked bit for bit), then rounded half to even.  One thread per output byte; the table of its cell is
+// recomputed in registers with the same double operations, so nothing is staged.
+// ---------------------------------------------------------------------------------
+struct AreaCell {
+    int s0;                  // first source index of the table
+    int n;                   // entries
+    float a_first, a_mid, a_last;
+    int has_first, has_last;
+};
+
+__device__ __forceinline__ AreaCell area_cell(int d, double scale, int ssize) {
+    AreaCell c;
+    const double f1 = __dmul_rn((double)d, scale);
+    const double f2 = __dadd_rn(f1, scale);
+    const double cell = fmin(scale, (double)ssize - f1);
+    int s1 = (int)ceil(f1), s2 = (int)floor(f2);
+    s2 = min(s2, ssize - 1);
+    s1 = min(s1, s2);
+    c.has_first = (double)s1 - f1 > 1e-3;
+    c.has_last = f2 - (double)s2 > 1e-3;
+    c.a_first = (float)__ddiv_rn((double)s1 - f1, cell);
+    c.a_mid = (float)__ddiv_rn(1.0, cell);
+    c.a_last = (float)__ddiv_rn(fmin(fmin(f2 - (double)s2, 1.0), cell), cell);
+    c.s0 = c.has_first ? s1 - 1 : s1;
+    c.n = (s2 - s1) + c.has_first + c.has_last;
+    return c;
+}
+
+__device__ __forceinline__ float area_weight(const AreaCell &c, int i) {
+    if (i == 0 && c.has_first) return c.a_first;
+    if (i == c.n - 1 && c.has_last) return c.a_last;
+    return c.a_mid;
+}
+
+__global__ void __launch_bounds__(256)
+resize_area_any_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstride,
+                       uint8_t *__restrict__ out, size_t out_pitch, size_t out_fstride,
+                       int w, int h, int ow, int oh, int cs, int batch, double scale_x, double scale_y) {
+    const unsigned rowb = (unsigned)(ow * cs);
+    const unsigned long long total = (unsigned long long)rowb * oh * batch;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned xb = (unsigned)(i % rowb);
+        const unsigned long long rest = i / rowb;
+        const unsigned y = (unsigned)(rest % oh), b = (unsigned)(rest / oh);
+        const unsigned x = xb / cs, c = xb - x * cs;
+        const AreaCell cx = area_cell((int)x, scale_x, w), cy = area_cell((int)y, scale_y, h);
+        const uint8_t *p = in + (size_t)b * in_fstride + (size_t)cy.s0 * in_pitch + (size_t)cx.s0 * cs + c;
+        float sum = 0.f;
+        for (int j = 0; j < cy.n; j++, p += in_pitch) {
+            float buf = 0.f;
+            for (int k = 0; k < cx.n; k++) buf = __fadd_rn(buf, __fmul_rn((float)p[k * cs], area_weight(cx, k)));
+            const float t = __fmul_rn(area_weight(cy, j), buf);
+            sum = j == 0 ? t : __fadd_rn(sum, t);
+        }
+        const int v = __float2int_rn(sum);
+        out[(size_t)b * out_fstride + (size_t)y * out_pitch + xb] = (uint8_t)min(max(v, 0), 255);
+    }
+}
+
+// cv::resize's test for the integer-factor INTER_AREA path (both |scale - round(scale)| < DBL_EPSILON)
+static bool resize_area_is_fast(int w, int h, int dw, int dh, double *sx, double *sy, int *kx, int *ky) {
+    *sx = 1.0 / ((double)dw / (double)w);
+    *sy = 1.0 / ((double)dh / (double)h);
+    *kx = (int)nearbyint(*sx);
+    *ky = (int)nearbyint(*sy);
+    return fabs(*sx - *kx) < 2.220446049250313e-16 && fabs(*sy - *ky) < 2.220446049250313e-16;
+}
+
+extern "C" int va_resize_area_any_u8(va_ctx *ctx, va_stream stream,
+                                     const uint8_t *in, size_t in_pitch, size_t in_fstride,
+                                     uint8_t *out, size_t out_pitch, size_t out_fstride,
+                                     int w, int h, int dw, int dh, int channels, int batch) {
+    VA_CHECK_CTX(ctx);
+    VA_REQUIRE(ctx, in && out && in != out, "va_resize_area_any_u8: null or aliased pointers");
+    VA_REQUIRE(ctx, w > 0 && h > 0 && dw > 0 && dh > 0 && batch > 0 && (channels == 1 || channels == 3), "va_resize_area_any_u8: bad size");
+    if (dw > w || dh > h)
+        VA_FAIL(ctx, VA_ERR_UNSUPPORTED, "va_resize_area_any_u8: %dx%d -> %dx%d enlarges (INTER_AREA then interpolates linearly)", w, h, dw, dh);
+    double sx, sy;
+    int kx, ky;
+    if (resize_area_is_fast(w, h, dw, dh, &sx, &sy, &kx, &ky)) {
+        if (kx == 1 && ky == 1)
+            return va_copy2d_u8(ctx, stream, in, in_pitch, in_fstride, out, out_pitch, out_fstride, w * channels, h, batch);
+        if (kx == 2 && ky == 2)
+            return va_resize_half_u8(ctx, stream, in, in_pitch, in_fstride, out, out_pitch, out_fstride, w, h, channels, batch);
+        return va_resize_area_u8(ctx, stream, in, in_pitch, in_fstride, out, out_pitch, out_fstride, w, h, channels, batch, kx, ky);
+    }
+    VA_REQUIRE(ctx, in_pitch >= (size_t)w * channels && out_pitch >= (size_t)dw * channels, "va_resize_area_any_u8: pitch smaller than a row");
+    const long long items = (long long)dw * channels * dh * batch;
+    const int grid = va_grid(ctx, (items + 255) / 256, 16);
+    auto kfn = resize_area_any_kernel;
+    VA_LAUNCH(ctx, kfn, grid, 256, 0, stream, in, in_pitch, in_fstride, out, out_pitch, out_fstride, w, h, dw, dh, channels, batch,
+              sx, sy);
+    return VA_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// INTER_LINEAR (OpenCV's 8-bit fixed-point path: 11-bit coefficients, HResizeLinear then VResizeLinear):
+//     fx = float((dx + .5) scale - .5), sx = floor(fx), fx -= sx; columns left of the image use sx = 0, fx = 0,
+//     columns at or beyond the last source pixel use that pixel alone; a = (rint((1 - fx) 2048), rint(fx 2048))
+//     rows: the same without the reset, row indices clipped instead
+//     H(row) = S[sx] a0 + S[sx + 1] a1;   out = (((b0 (H0 >> 4)) >> 16) + ((b1 (H1 >> 4)) >> 16) + 2) >> 2
+// Shrinking by exactly 2 x 2 is INTER_AREA in OpenCV ((a + b + c + d + 2) >> 2): the host dispatches it.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void linear_coef(int d, double scale, float &f, int &s) {
+    f = (float)__dadd_rn(__dmul_rn((double)d + 0.5, scale), -0.5);
+    s = (int)floorf(f);
+    f = __fadd_rn(f, -(float)s);
+}
+
+__global__ void __launch_bounds__(256)
+resize_linear_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstride,
+                     uint8_t *__restrict__ out, size_t out_pitch, size_t out_fstride,
+                     int w, int h, int ow, int oh, int cs, int batch, double scale_x, double scale_y) {
+    const unsigned rowb = (unsigned)(ow * cs);
+    const unsigned long long total = (unsigned long long)rowb * oh * batch;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned xb = (unsigned)(i % rowb);
+        const unsigned long long rest = i / rowb;
+        const unsigned y = (unsigned)(rest % oh), b = (unsigned)(rest / oh);
+        const unsigned x = xb / cs, c = xb - x * cs;
+        float fx, fy;
+        int sx, sy;
+        linear_coef((int)x, scale_x, fx, sx);
+        linear_coef((int)y, scale_y, fy, sy);
+        if (sx < 0) { sx = 0; fx = 0.f; }
+        if (sx >= w - 1) { sx = w - 1; fx = 0.f; }
+        const int a0 = __float2int_rn(__fmul_rn(__fadd_rn(1.f, -fx), 2048.f)), a1 = __float2int_rn(__fmul_rn(fx, 2048.f));
+        const int b0 = __float2int_rn(__fmul_rn(__fadd_rn(1.f, -fy), 2048.f)), b1 = __float2int_rn(__fmul_rn(fy, 2048.f));
+        const int y0 = min(max(sy, 0), h - 1), y1 = min(max(sy + 1, 0), h - 1);
+        const int x1 = sx < w - 1 ? sx + 1 : sx;                   // its weight is 0 at the last pixel
+        const uint8_t *f0 = in + (size_t)b * in_fstride + (size_t)y0 * in_pitch + c;
+        const uint8_t *f1 = in + (size_t)b * in_fstride + (size_t)y1 * in_pitch + c;
+        const int h0 = f0[(size_t)sx * cs] * a0 + (sx < w - 1 ? f0[(size_t)x1 * cs] * a1 : 0);
+        const int h1 = f1[(size_t)sx * cs] * a0 + (sx < w - 1 ? f1[(size_t)x1 * cs] * a1 : 0);
+        const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+        out[(size_t)b * out_fstride + (size_t)y * out_pitch + xb] = (uint8_t)v;
+    }
+}
+
+extern "C" int va_resize_linear_u8(va_ctx *ctx, va_stream stream,
+                                   const uint8_t *in, size_t in_pitch, size_t in_fstride,
+                                   uint8_t *out, size_t out_pitch, size_t out_fstride,
+                                   int w, int h, int dw, int dh, int channels, int batch) {
+    VA_CHECK_CTX(ctx);
+    VA_REQUIRE(ctx, in && out && in != out, "va_resize_linear_u8: null or aliased pointers");
+    VA_REQUIRE(ctx, w > 0 && h > 0 && dw > 0 && dh > 0 && batch > 0 && (channels == 1 || channels == 3), "va_resize_linear_u8: bad size");
+    double sx, sy;
+    int kx, ky;
+    if (resize_area_is_fast(w, h, dw, dh, &sx, &sy, &kx, &ky) && kx == 2 && ky == 2)
+        return va_resize_half_u8(ctx, stream, in, in_pitch, in_fstride, out, out_pitch, out_fstride, w, h, channels, batch);
+    VA_REQUIRE(ctx, in_pitch >= (size_t)w * channels && out_pitch >= (size_t)dw * channels, "va_resize_linear_u8: pitch smaller than a row");
+    const long long items = (long long)dw * channels * dh * batch;
+    const int grid = va_grid(ctx, (items + 255) / 256, 16);
+    auto kfn = resize_linear_kernel;
+    VA_LAUNCH(ctx, kfn, grid, 256, 0, stream, in, in_pitch, in_fstride, out, out_pitch, out_fstride, w, h, dw, dh, channels, batch,
+              sx, sy);
     return VA_OK;
 }

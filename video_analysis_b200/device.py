@@ -233,6 +233,24 @@ class DeviceRuntime(object):
                                                   src.channels, src.n))
         return out
 
+    def resize_area_any(self, src, dw, dh):
+        """ cv2.resize(INTER_AREA) shrinking to (dw, dh), any factors """
+        self.ensure(src.w, src.h, src.n)
+        out = self.empty_u8(src.n, dh, dw, src.channels)
+        self._check(self.lib.va_resize_area_any_u8(self._h, self.stream, src.ptr, src.pitch, src.fstride,
+                                                   out.ptr, out.pitch, out.fstride, src.w, src.h, int(dw), int(dh),
+                                                   src.channels, src.n))
+        return out
+
+    def resize_linear(self, src, dw, dh):
+        """ cv2.resize(INTER_LINEAR) to (dw, dh) """
+        self.ensure(max(src.w, dw), max(src.h, dh), src.n)
+        out = self.empty_u8(src.n, dh, dw, src.channels)
+        self._check(self.lib.va_resize_linear_u8(self._h, self.stream, src.ptr, src.pitch, src.fstride,
+                                                 out.ptr, out.pitch, out.fstride, src.w, src.h, int(dw), int(dh),
+                                                 src.channels, src.n))
+        return out
+
     def apply_mask(self, src, mask_dev):
         """ mask_dev: uint8 device tensor (h, w) """
         self.ensure(src.w, src.h, src.n)

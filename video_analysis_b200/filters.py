@@ -441,9 +441,10 @@ class FilterBlur(DeviceFilterBase):
 
 
 class FilterResize(DeviceFilterBase):
-    """ resizes the video (filters.py:252-315).  The device path implements INTER_AREA for integer
-    shrink factors (OpenCV's exact integer / single-rounding form; 'auto' picks INTER_AREA when shrinking)
-    and INTER_NEAREST for any size; other combinations raise NotImplementedError rather than silently
+    """ resizes the video (filters.py:252-315).  The device path implements INTER_AREA for any shrink
+    factors ('auto' picks INTER_AREA when shrinking; integer factors take OpenCV's exact integer /
+    single-rounding form, the others its float32 area tables), INTER_LINEAR (OpenCV's 11-bit fixed point)
+    and INTER_NEAREST for any size; cubic / Lanczos raise NotImplementedError rather than silently
     running on the CPU. """
 
     def __init__(self, source, size=None, interpolation='auto', even_dimensions=False, **kwargs):
@@ -477,9 +478,15 @@ class FilterResize(DeviceFilterBase):
         w, h = self.size
         if self.interpolation == 'area' and batch.w % w == 0 and batch.h % h == 0:
             return rt.resize_area(batch, batch.w // w, batch.h // h)
+        if self.interpolation == 'area' and w <= batch.w and h <= batch.h:
+            return rt.resize_area_any(batch, w, h)
+        if self.interpolation == 'linear':
+            return rt.resize_linear(batch, w, h)
+        # (INTER_AREA that enlarges in either direction interpolates linearly in cv2, with its own coefficient
+        # rule; the device path does not restate that one)
         if self.interpolation == 'nearest':
             return rt.resize_nearest(batch, w, h)
-        raise NotImplementedError('FilterResize on the device supports INTER_AREA by integer factors and '
+        raise NotImplementedError('FilterResize on the device supports INTER_AREA (shrinking), INTER_LINEAR and '
                                   'INTER_NEAREST (%dx%d -> %dx%d with %s requested)'
                                   % (batch.w, batch.h, w, h, self.interpolation))
 
