@@ -137,6 +137,15 @@ int va_resize_linear_u8(va_ctx *ctx, va_stream stream,
                         uint8_t *out, size_t out_pitch, size_t out_fstride,
                         int w, int h, int dw, int dh, int channels, int batch);
 
+/* the same call site with cv2.INTER_CUBIC ('auto' when enlarging, video/filters.py:282-284), any output size:
+ * OpenCV's own 8-bit path (a = -0.75, 11-bit coefficients, float32 column pass on the 8-lane vector body of a
+ * row, (sum + 2^21) >> 22 on its tail).  Bit-exact against cv2 with cv2.ipp.setUseIPP(False); the cv2 wheel's
+ * default routes this interpolation through Intel IPP, whose result differs by at most 1 LSB. */
+int va_resize_cubic_u8(va_ctx *ctx, va_stream stream,
+                       const uint8_t *in, size_t in_pitch, size_t in_fstride,
+                       uint8_t *out, size_t out_pitch, size_t out_fstride,
+                       int w, int h, int dw, int dh, int channels, int batch);
+
 /* K3 running-average background + |difference| > thr -> packed mask bits.
  * Not in the reference; fold shape follows
  * video/analysis/video.py:14-35, signed difference video/filters.py:564-568:
@@ -176,6 +185,16 @@ int va_morph_bits(va_ctx *ctx, va_stream stream,
                   const uint32_t *in, size_t in_pitch_w, size_t in_fstride_w,
                   uint32_t *out, size_t out_pitch_w, size_t out_fstride_w,
                   int w, int h, int batch, int op, int shape, int kx, int ky);
+
+/* VideoComposer.highlight_mask, video/io/composer.py:131-154: where the mask is set,
+ * frame[mask, channel] = uint8(strength + (255 - strength) / 255 * frame[mask, channel]).  lut256 (HOST pointer,
+ * copied into the launch) is that expression on 0..255; channel -1 = all channels, 0..2 = one channel of an
+ * interleaved colour frame.  The mask is the packed-bit image K3 / K4 produce (LSB = lowest x). */
+int va_highlight_mask_u8(va_ctx *ctx, va_stream stream,
+                         const uint8_t *in, size_t in_pitch, size_t in_fstride,
+                         const uint32_t *mask, size_t mask_pitch_w, size_t mask_fstride_w,
+                         uint8_t *out, size_t out_pitch, size_t out_fstride,
+                         int w, int h, int channels, int batch, int channel, const uint8_t *lut256);
 
 /* K5 connected-component labelling; replaces
  * ndimage.measurements.label(mask) at video/analysis/regions.py:162.

@@ -453,3 +453,31 @@ def chain(frames, sigma=2, alpha=0.05, thr=25, morph_op='open', morph_shape='rec
     res['counts'] = np.array(counts, dtype=np.int32)
     res['bg'] = bg
     return res
+
+
+# --------------------------------------------------------------------------
+# annotated output -- video/io/composer.py:131-154 (VideoComposer.highlight_mask, zoom factor 1)
+# --------------------------------------------------------------------------
+_CHANNEL_NAMES = {0: 0, 'r': 0, 'red': 0, 1: 1, 'g': 1, 'green': 1, 2: 2, 'b': 2, 'blue': 2}   # composer.py:43-45
+
+
+def highlight_mask(frame, mask, channel='all', strength=128):
+    """ returns a copy of `frame` with the non-zero entries of `mask` highlighted """
+    frame = frame.copy()
+    is_color = frame.ndim == 3
+    if channel is None or channel == 'all':
+        channel = slice(0, 3) if is_color else 0
+    elif is_color:
+        try:
+            channel = _CHANNEL_NAMES[channel]
+        except KeyError:
+            raise ValueError('Unknown value `%s` for channel.' % channel)
+    else:
+        raise ValueError('Highlighting a specific channel is only supported for color videos.')
+    mask = np.asarray(mask).astype(bool)
+    factor = (255 - strength) / 255                                   # composer.py:153 (true division)
+    if is_color:
+        frame[mask, channel] = strength + factor * frame[mask, channel]
+    else:
+        frame[mask] = strength + factor * frame[mask]                 # a monochrome _frame has no channel axis
+    return frame

@@ -266,6 +266,31 @@ def resize_to(ctx, frames, dw, dh, how):
     return out if frames.ndim == 3 else out.reshape(B, dh, dw, ch)
 
 
+def pack_bits_np(masks):
+    """ (B, H, W) nonzero = set -> (B, H, ceil(W / 32)) uint32 words, bit i of word j = pixel 32 j + i """
+    B, H, W = masks.shape
+    Wp = (W + 31) // 32
+    m = np.zeros((B, H, Wp * 32), np.uint8)
+    m[:, :, :W] = masks != 0
+    by = np.packbits(m, axis=2, bitorder='little')
+    return np.ascontiguousarray(by).view('<u4').reshape(B, H, Wp)
+
+
+def highlight_mask(ctx, frames, masks, channel, table, in_pad=0):
+    """ frames (B, H, W[, 3]) u8, masks (B, H, W) nonzero = set """
+    be = ctx.be
+    B, H, W = frames.shape[:3]
+    ch = 1 if frames.ndim == 3 else frames.shape[3]
+    src = Img(be, B, H, W * ch, np.uint8, W * ch + in_pad, frames.reshape(B, H, W * ch))
+    bits = Img(be, B, H, mask_words(W), np.uint32, mask_words(W) + 1, pack_bits_np(masks))
+    dst = Img(be, B, H, W * ch, np.uint8, W * ch + in_pad)
+    tab = np.ascontiguousarray(table, np.uint8)
+    ctx.check(ctx.lib.va_highlight_mask_u8(ctx.h, be.stream, src.ptr, src.pitch, src.fstride, bits.ptr, bits.pitch, bits.fstride,
+                                           dst.ptr, dst.pitch, dst.fstride, W, H, ch, B, channel, tab.ctypes.data))
+    out = dst.get()
+    return out if frames.ndim == 3 else out.reshape(B, H, W, ch)
+
+
 def mask_words(W):
     return (W + 31) // 32
 

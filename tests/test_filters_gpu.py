@@ -89,8 +89,11 @@ def test_crop_resize_applymask_and_random_access(frames):
     assert np.array_equal(np.stack(list(frac)), np.stack([ops.resize(f, 0.3) for f in exp]))
     lin = F.FilterResize(crop, (201, 57), interpolation='linear')         # colour, enlarging x, shrinking y
     assert np.array_equal(np.stack(list(lin)), np.stack([ops.resize(ops.crop(f, rect), (201, 57), 'linear') for f in frames[:9]]))
+    big = np.stack(list(F.FilterResize(cm, 2.0)))                          # 'auto' enlarges with INTER_CUBIC
+    ref_big = np.stack([ops.resize(f, 2.0) for f in exp])
+    assert np.abs(big.astype(np.int16) - ref_big).max() <= 1              # cv2's default is Intel IPP here: 1 LSB
     with pytest.raises(NotImplementedError):
-        next(iter(F.FilterResize(cm, 2.0)))                               # 'auto' enlarges with INTER_CUBIC
+        next(iter(F.FilterResize(cm, 1.5, interpolation='lanczos')))
     m = np.zeros((120, 160), bool)
     m[20:90, 30:140] = True
     masked = F.FilterApplyMask(cm, m)
@@ -357,3 +360,35 @@ def test_remaining_filter_classes_and_temporal_statistics(frames):
     assert np.array_equal(m.view(np.uint64), mr.view(np.uint64)) and np.array_equal(s.view(np.uint64), sr.view(np.uint64))
     acc = vstat.reduce_video(mv, lambda f, r: np.maximum(f, r))
     assert np.array_equal(acc, mono.max(0))
+
+
+def test_raw_stream_ingest_and_annotated_egress(frames, ref):
+    """ a raw-video byte stream read into the page-locked ring feeds the chain, and the
+    annotated frames (mask highlighted on the device) leave through a raw-stream writer """
+    import io
+    F, VideoMemory = mods()
+    from video_analysis_b200.chain import SegmentChain
+    from video_analysis_b200.io.pipe import VideoRawStream, RawStreamWriter
+    raw = frames.tobytes()
+    # the filter classes over a stream source: same labels as from memory
+    v = VideoRawStream(io.BytesIO(raw), (320, 240), len(frames), ring_frames=40)
+    full = F.FilterLabel(F.FilterMorphology(
+        F.FilterBackgroundMask(F.FilterBlur(F.FilterMonochrome(v, batch=8), 2)), 'open', 'rect', 3))
+    assert np.array_equal(np.stack(list(full)), ref['labels'])
+    v.close()
+    # the pipelined chain straight from the ring (blocks shorter than the chain's batch)
+    v = VideoRawStream(io.BytesIO(raw), (320, 240), len(frames) + 1, ring_frames=40)      # length over-estimated
+    labels, counts = SegmentChain((320, 240), batch=16).process(v)
+    assert np.array_equal(labels, ref['labels']) and list(counts) == list(ref['counts'])
+    v.close()
+    # annotated egress
+    sink = io.BytesIO()
+    v = VideoRawStream(io.BytesIO(raw), (320, 240), len(frames), ring_frames=40)
+    with RawStreamWriter(sink, (320, 240)) as wr:
+        SegmentChain((320, 240), batch=8).annotate(v, wr, channel='red', strength=100)
+        assert wr.frames_written == len(frames)
+    got = np.frombuffer(sink.getvalue(), np.uint8).reshape(frames.shape)
+    exp = np.stack([ops.highlight_mask(f, m, 'red', 100) for f, m in zip(frames, ref['morph'])])
+    assert np.array_equal(got, exp)
+    marked = SegmentChain((320, 240), batch=16).annotate(frames[:10])
+    assert np.array_equal(marked, np.stack([ops.highlight_mask(f, m) for f, m in zip(frames[:10], ref['morph'][:10])]))

@@ -224,6 +224,43 @@ def test_resize_area_any_factor_and_linear(be, ctx):
         hz.resize_to(ctx, rng_frames(1, (1, 10, 10)), 12, 5, 'area_any')        # INTER_AREA enlarging = linear in cv2
 
 
+def test_resize_cubic(be, ctx):
+    import cv2
+    ipp = cv2.ipp.useIPP()
+    try:
+        for (H, W) in sizes(be, [(24, 60), (37, 53)], [(1080, 1920), (271, 1003)]):
+            g = rng_frames(H + 2, (2, H, W))
+            c = rng_frames(W + 2, (2, H, W, 3))
+            for dw, dh in ((W * 2, H * 2), (W + 7, H + 3), (W * 3 // 10, H * 3 // 10), (W + W // 2 + 1, H // 2), (7, 5), (1, 1)):
+                for fr in (g, c):
+                    out = hz.resize_to(ctx, fr, dw, dh, 'cubic')
+                    for use_ipp, tol in ((False, 0), (True, 1)):     # OpenCV's own arithmetic: exact; Intel IPP's: 1 LSB
+                        cv2.ipp.setUseIPP(use_ipp)
+                        ref = np.stack([ops.resize(f, (dw, dh), 'cubic') for f in fr]).reshape((2, dh, dw) + fr.shape[3:])
+                        assert np.abs(out.astype(np.int16) - ref).max() <= tol, (H, W, dw, dh, fr.ndim, use_ipp)
+    finally:
+        cv2.ipp.setUseIPP(ipp)
+
+
+def test_highlight_mask(be, ctx):
+    for (H, W) in sizes(be, [(13, 37), (24, 64)], [(1080, 1920), (271, 1003)]):
+        g = rng_frames(H + 3, (2, H, W))
+        c = rng_frames(W + 3, (2, H, W, 3))
+        m = rmask(H * W, (2, H, W), 0.3)
+        assert np.array_equal(hz.pack_bits_np(m), hz.pack_bits(ctx, m))
+        for strength in (128, 0, 255, 77):
+            table = np.empty(256, np.uint8)
+            table[:] = strength + (255 - strength) / 255 * np.arange(256, dtype=np.uint8)
+            for fr, channels in ((g, ('all',)), (c, ('all', 'red', 1, 'b'))):
+                for ch in channels:
+                    ref = np.stack([ops.highlight_mask(f, mm, ch, strength) for f, mm in zip(fr, m)])
+                    ci = -1 if ch == 'all' else {'red': 0, 1: 1, 'b': 2}[ch]
+                    for pad in (0, 3):
+                        assert np.array_equal(hz.highlight_mask(ctx, fr, m, ci, table, pad), ref), (H, W, strength, ch, pad)
+    with pytest.raises(ValueError):
+        hz.highlight_mask(ctx, rng_frames(1, (1, 8, 8)), rmask(1, (1, 8, 8), .5), 2, np.zeros(256, np.uint8))
+
+
 # ---- K3 -----------------------------------------------------------------------------------------
 def noisy_video(seed, shape):
     rng = np.random.default_rng(seed)

@@ -323,17 +323,30 @@ class SegmentChain(object):
             return s['labels_host'].numpy()[:m, :, :self.w], s['counts_host'].numpy()[:m]
         return s['stats_host'].numpy()[:m], s['counts_host'].numpy()[:m], s['largest_host'].numpy()[:m]
 
-    def process(self, frames):
-        """ frames: ndarray (n, h, w, 3) uint8 or a video object -> (labels (n, h, w) int32,
-        counts (n,) int32), continuing the background model from earlier calls """
+    def _blocks_of(self, frames):
+        """ (frame count, generator of (m, h, w, 3) blocks of at most `batch` frames) for an ndarray or a video
+        object with `frame_block` (VideoMemory, VideoRawStream: blocks may come shorter than asked for, and a
+        stream's `frame_count` may be an estimate) """
         if hasattr(frames, 'frame_block'):
             video = frames
             n = video.frame_count
-            blocks = (video.frame_block(a, min(a + self.batch, n)) for a in range(0, n, self.batch))
-        else:
-            frames = np.asarray(frames)
-            n = len(frames)
-            blocks = (frames[a:a + self.batch] for a in range(0, n, self.batch))
+
+            def gen():
+                a = 0
+                while a < n:
+                    block = video.frame_block(a, min(a + self.batch, n))
+                    if len(block) == 0:
+                        return
+                    yield block
+                    a += len(block)
+            return n, gen()
+        frames = np.asarray(frames)
+        return len(frames), (frames[a:a + self.batch] for a in range(0, len(frames), self.batch))
+
+    def process(self, frames):
+        """ frames: ndarray (n, h, w, 3) uint8 or a video object -> (labels (n, h, w) int32,
+        counts (n,) int32), continuing the background model from earlier calls """
+        n, blocks = self._blocks_of(frames)
         t = torch()
         labels_t = t.empty((n, self.h, self.w), dtype=t.int32)       # filled by torch's multi-threaded host copy
         labels = labels_t.numpy()
@@ -345,17 +358,40 @@ class SegmentChain(object):
             k += len(lab)
         return labels[:k], counts[:k]
 
+    def annotate(self, frames, writer=None, channel='all', strength=128):
+        """ annotated output (the reference's VideoComposer.highlight_mask, io/composer.py:131-154, fed from the
+        device): runs monochrome -> blur -> background mask -> morphology on every block and highlights the
+        resulting mask in the colour frames on the GPU; the mask never visits the host.  The annotated frames are
+        written to `writer` (anything with `write_block`, e.g. io.pipe.RawStreamWriter on an encoder's stdin) or,
+        without a writer, returned as one (n, h, w, 3) array. """
+        rt, t = self.rt, torch()
+        _, blocks = self._blocks_of(frames)
+        out = []
+        with t.cuda.device(rt.device):
+            for block in blocks:
+                rgb = rt.upload(block)
+                blur = self.blur_device(rgb)
+                mask = rt.ema_diff_thresh(blur, self._bg, self.alpha, self.threshold, not self._started)
+                self._started = True
+                if self.morph_op:
+                    mask = rt.morph(mask, self.morph_op, self.morph_shape, (self.kx, self.ky))
+                marked = rt.highlight_mask(rgb, mask, channel, strength)
+                host = rt.download(marked)
+                t.cuda.current_stream(rt.device).synchronize()
+                view = rt.host_view(marked, host)
+                if writer is not None:
+                    writer.write_block(view)
+                else:
+                    out.append(np.array(view))
+        if writer is not None:
+            return writer
+        return np.concatenate(out) if out else np.empty((0, self.h, self.w, 3), np.uint8)
+
     def process_regions(self, frames, max_regions=256):
         """ like `process`, but returns for every frame the list of its regions (`label`, `area`,
         `bbox`, `moments`: see analysis.regions.stats_to_regions) instead of a label image """
         from .analysis.regions import stats_to_regions
-        if hasattr(frames, 'frame_block'):
-            video = frames
-            n = video.frame_count
-            blocks = (video.frame_block(a, min(a + self.batch, n)) for a in range(0, n, self.batch))
-        else:
-            frames = np.asarray(frames)
-            blocks = (frames[a:a + self.batch] for a in range(0, len(frames), self.batch))
+        _, blocks = self._blocks_of(frames)
         out = []
         for stats, counts, _ in self.process_blocks(blocks, max_regions=max_regions):
             for st, c in zip(stats, counts):

@@ -436,3 +436,156 @@ extern "C" int va_resize_linear_u8(va_ctx *ctx, va_stream stream,
               sx, sy);
     return VA_OK;
 }
+
+// ---------------------------------------------------------------------------------
+// INTER_CUBIC (what 'auto' picks when enlarging, filters.py:282-284).  OpenCV's own 8-bit path
+// (HResizeCubic + VResizeCubic, a = -0.75): coefficients from float32 polynomials scaled to 11 bits,
+//     H(row) = sum_j S[clamp(sx - 1 + j)] a_j      (int32)
+// and the column pass in float32 -- t = H3 b3; t = H2 b2 + t; t = H1 b1 + t; t = H0 b0 + t with
+// b_k = float(beta_k) * 2^-22, every operation rounded on its own, round half to even -- for the first
+// 8 floor(row bytes / 8) bytes of a row (its 8-lane vector body) and (sum + 2^21) >> 22 for the tail.
+// NB: the cv2 wheel routes INTER_CUBIC through Intel IPP when IPP is enabled (its default); IPP's
+// arithmetic is not published and differs from OpenCV's own by at most 1 LSB on a few per cent of the
+// pixels.  This kernel is bit-exact against cv2 with cv2.ipp.setUseIPP(False).
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void cubic_coef(int d, double scale, int &s, int (&a)[4]) {
+    float f = (float)__dadd_rn(__dmul_rn((double)d + 0.5, scale), -0.5);
+    s = (int)floorf(f);
+    f = __fadd_rn(f, -(float)s);
+    const float A = -0.75f;
+    const float x1 = __fadd_rn(f, 1.f), xm = __fadd_rn(1.f, -f);
+    float c[4];
+    c[0] = __fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(A, x1), -5.f * A), x1), 8.f * A), x1), -4.f * A);
+    c[1] = __fadd_rn(__fmul_rn(__fmul_rn(__fadd_rn(__fmul_rn(A + 2.f, f), -(A + 3.f)), f), f), 1.f);
+    c[2] = __fadd_rn(__fmul_rn(__fmul_rn(__fadd_rn(__fmul_rn(A + 2.f, xm), -(A + 3.f)), xm), xm), 1.f);
+    c[3] = __fadd_rn(__fadd_rn(__fadd_rn(1.f, -c[0]), -c[1]), -c[2]);
+#pragma unroll
+    for (int k = 0; k < 4; k++) a[k] = __float2int_rn(__fmul_rn(c[k], 2048.f));
+}
+
+__global__ void __launch_bounds__(256)
+resize_cubic_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstride,
+                    uint8_t *__restrict__ out, size_t out_pitch, size_t out_fstride,
+                    int w, int h, int ow, int oh, int cs, int batch, double scale_x, double scale_y) {
+    const unsigned rowb = (unsigned)(ow * cs);
+    const unsigned vec_end = rowb & ~7u;
+    const unsigned long long total = (unsigned long long)rowb * oh * batch;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned xb = (unsigned)(i % rowb);
+        const unsigned long long rest = i / rowb;
+        const unsigned y = (unsigned)(rest % oh), b = (unsigned)(rest / oh);
+        const unsigned x = xb / cs, c = xb - x * cs;
+        int sx, sy, a[4], bt[4];
+        cubic_coef((int)x, scale_x, sx, a);
+        cubic_coef((int)y, scale_y, sy, bt);
+        const uint8_t *f = in + (size_t)b * in_fstride + c;
+        int hs[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint8_t *row = f + (size_t)min(max(sy - 1 + k, 0), h - 1) * in_pitch;
+            int v = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) v += row[(size_t)min(max(sx - 1 + j, 0), w - 1) * cs] * a[j];
+            hs[k] = v;
+        }
+        int v;
+        if (xb < vec_end) {
+            const float sc = 1.f / (2048.f * 2048.f);
+            float t = __fmul_rn((float)hs[3], __fmul_rn((float)bt[3], sc));
+            t = __fadd_rn(__fmul_rn((float)hs[2], __fmul_rn((float)bt[2], sc)), t);
+            t = __fadd_rn(__fmul_rn((float)hs[1], __fmul_rn((float)bt[1], sc)), t);
+            t = __fadd_rn(__fmul_rn((float)hs[0], __fmul_rn((float)bt[0], sc)), t);
+            v = __float2int_rn(t);
+        } else {
+            v = (hs[0] * bt[0] + hs[1] * bt[1] + hs[2] * bt[2] + hs[3] * bt[3] + (1 << 21)) >> 22;
+        }
+        out[(size_t)b * out_fstride + (size_t)y * out_pitch + xb] = (uint8_t)min(max(v, 0), 255);
+    }
+}
+
+extern "C" int va_resize_cubic_u8(va_ctx *ctx, va_stream stream,
+                                  const uint8_t *in, size_t in_pitch, size_t in_fstride,
+                                  uint8_t *out, size_t out_pitch, size_t out_fstride,
+                                  int w, int h, int dw, int dh, int channels, int batch) {
+    VA_CHECK_CTX(ctx);
+    VA_REQUIRE(ctx, in && out && in != out, "va_resize_cubic_u8: null or aliased pointers");
+    VA_REQUIRE(ctx, w > 0 && h > 0 && dw > 0 && dh > 0 && batch > 0 && (channels == 1 || channels == 3), "va_resize_cubic_u8: bad size");
+    VA_REQUIRE(ctx, in_pitch >= (size_t)w * channels && out_pitch >= (size_t)dw * channels, "va_resize_cubic_u8: pitch smaller than a row");
+    const double sx = 1.0 / ((double)dw / (double)w), sy = 1.0 / ((double)dh / (double)h);
+    const long long items = (long long)dw * channels * dh * batch;
+    const int grid = va_grid(ctx, (items + 255) / 256, 16);
+    auto kfn = resize_cubic_kernel;
+    VA_LAUNCH(ctx, kfn, grid, 256, 0, stream, in, in_pitch, in_fstride, out, out_pitch, out_fstride, w, h, dw, dh, channels, batch,
+              sx, sy);
+    return VA_OK;
+}
+
+// =================================================================================
+// VideoComposer.highlight_mask (video/io/composer.py:131-154): in the pixels of a mask
+//     frame[mask, channel] = strength + (255 - strength) / 255 * frame[mask, channel]      (float64, cast to uint8)
+// i.e. a 256-entry table applied where the mask bit is set (the table is the reference's expression
+// evaluated on 0..255 by the host).  channel = -1 touches every channel, 0..2 one channel of an
+// interleaved frame.  The mask comes as the packed bits K3 / K4 leave on the device, so an annotated
+// output video needs no mask round trip through the host.  One thread per 4 output bytes.
+// =================================================================================
+__global__ void __launch_bounds__(256)
+highlight_mask_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstride,
+                      const uint32_t *__restrict__ mask, size_t mask_pitch_w, size_t mask_fstride_w,
+                      uint8_t *__restrict__ out, size_t out_pitch, size_t out_fstride,
+                      int w, int h, int cs, int batch, int channel, int vec, const __grid_constant__ Lut256 lut) {
+    __shared__ unsigned char s[256];
+    s[threadIdx.x] = lut.v[threadIdx.x];
+    __syncthreads();
+    const unsigned rowb = (unsigned)(w * cs);
+    const unsigned quads = (rowb + 3) >> 2;
+    const unsigned long long total = (unsigned long long)quads * h * batch;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned q = (unsigned)(i % quads);
+        const unsigned long long rest = i / quads;
+        const unsigned y = (unsigned)(rest % h), b = (unsigned)(rest / h);
+        const uint8_t *src = in + (size_t)b * in_fstride + (size_t)y * in_pitch + 4 * q;
+        uint8_t *dst = out + (size_t)b * out_fstride + (size_t)y * out_pitch + 4 * q;
+        const uint32_t *mrow = mask + (size_t)b * mask_fstride_w + (size_t)y * mask_pitch_w;
+        const unsigned nb = min(4u, rowb - 4 * q);
+        unsigned word = 0;
+        if (vec) word = *reinterpret_cast<const unsigned *>(src);
+        else for (unsigned k = 0; k < nb; k++) word |= (unsigned)src[k] << (8 * k);
+        unsigned res = 0;
+#pragma unroll
+        for (unsigned k = 0; k < 4; k++) {
+            const unsigned xb = 4 * q + k;
+            const unsigned px = cs == 3 ? xb / 3 : xb, c = xb - px * cs;
+            unsigned v = (word >> (8 * k)) & 0xff;
+            if (k < nb && (channel < 0 || (int)c == channel) && ((mrow[px >> 5] >> (px & 31)) & 1)) v = s[v];
+            res |= v << (8 * k);
+        }
+        if (vec) *reinterpret_cast<unsigned *>(dst) = res;
+        else for (unsigned k = 0; k < nb; k++) dst[k] = (uint8_t)(res >> (8 * k));
+    }
+}
+
+extern "C" int va_highlight_mask_u8(va_ctx *ctx, va_stream stream,
+                                    const uint8_t *in, size_t in_pitch, size_t in_fstride,
+                                    const uint32_t *mask, size_t mask_pitch_w, size_t mask_fstride_w,
+                                    uint8_t *out, size_t out_pitch, size_t out_fstride,
+                                    int w, int h, int channels, int batch, int channel, const uint8_t *lut256) {
+    VA_CHECK_CTX(ctx);
+    VA_REQUIRE(ctx, in && out && mask && lut256, "va_highlight_mask_u8: null pointer");
+    VA_REQUIRE(ctx, w > 0 && h > 0 && batch > 0 && (channels == 1 || channels == 3), "va_highlight_mask_u8: bad size");
+    VA_REQUIRE(ctx, channel >= -1 && channel < channels && (channels == 3 || channel <= 0),
+               "va_highlight_mask_u8: highlighting a specific channel is only supported for color videos");
+    VA_REQUIRE(ctx, in_pitch >= (size_t)w * channels && out_pitch >= (size_t)w * channels && mask_pitch_w >= (size_t)(w + 31) / 32,
+               "va_highlight_mask_u8: pitch smaller than a row");
+    Lut256 lut;
+    memcpy(lut.v, lut256, 256);
+    const int vec = (w * channels) % 4 == 0 && va_aligned(in, 4) && va_aligned(out, 4) && in_pitch % 4 == 0 && out_pitch % 4 == 0 &&
+                    in_fstride % 4 == 0 && out_fstride % 4 == 0;
+    const long long items = (long long)((w * channels + 3) / 4) * h * batch;
+    const int grid = va_grid(ctx, (items + 255) / 256, 8);
+    auto kfn = highlight_mask_kernel;
+    VA_LAUNCH(ctx, kfn, grid, 256, 0, stream, in, in_pitch, in_fstride, mask, mask_pitch_w, mask_fstride_w, out, out_pitch, out_fstride,
+              w, h, channels, batch, channels == 1 ? -1 : channel, vec, lut);
+    return VA_OK;
+}

@@ -251,6 +251,15 @@ class DeviceRuntime(object):
                                                  src.channels, src.n))
         return out
 
+    def resize_cubic(self, src, dw, dh):
+        """ cv2.resize(INTER_CUBIC) to (dw, dh): OpenCV's own arithmetic (cv2 without IPP) """
+        self.ensure(max(src.w, dw), max(src.h, dh), src.n)
+        out = self.empty_u8(src.n, dh, dw, src.channels)
+        self._check(self.lib.va_resize_cubic_u8(self._h, self.stream, src.ptr, src.pitch, src.fstride,
+                                                out.ptr, out.pitch, out.fstride, src.w, src.h, int(dw), int(dh),
+                                                src.channels, src.n))
+        return out
+
     def apply_mask(self, src, mask_dev):
         """ mask_dev: uint8 device tensor (h, w) """
         self.ensure(src.w, src.h, src.n)
@@ -344,6 +353,30 @@ class DeviceRuntime(object):
         self._check(self.lib.va_lut_u8(self._h, self.stream, src.ptr, src.pitch, src.fstride,
                                        out.ptr, out.pitch, out.fstride, src.w * src.channels, src.h, src.n,
                                        tab.ctypes.data))
+        return out
+
+    def highlight_mask(self, src, bits, channel='all', strength=128):
+        """ VideoComposer.highlight_mask (io/composer.py:131-154) on the device: `src` u8 frames, `bits` the
+        packed mask of the same batch; returns the annotated frames """
+        if channel is None or channel == 'all':
+            ch = -1
+        elif src.channels == 3:
+            try:
+                ch = {0: 0, 'r': 0, 'red': 0, 1: 1, 'g': 1, 'green': 1, 2: 2, 'b': 2, 'blue': 2}[channel]
+            except (KeyError, TypeError):
+                raise ValueError('Unknown value `%s` for channel.' % (channel,))
+        else:
+            raise ValueError('Highlighting a specific channel is only supported for color videos.')
+        if (bits.n, bits.h, bits.w) != (src.n, src.h, src.w):
+            raise ValueError('mask and frames differ in shape')
+        factor = (255 - strength) / 255                                  # the reference's expression on 0..255
+        table = np.empty(256, np.uint8)
+        table[:] = strength + factor * np.arange(256, dtype=np.uint8)
+        self.ensure(src.w, src.h, src.n)
+        out = self.empty_u8(src.n, src.h, src.w, src.channels)
+        self._check(self.lib.va_highlight_mask_u8(self._h, self.stream, src.ptr, src.pitch, src.fstride,
+                                                  bits.ptr, bits.pitch, bits.fstride, out.ptr, out.pitch, out.fstride,
+                                                  src.w, src.h, src.channels, src.n, ch, table.ctypes.data))
         return out
 
     def rot90(self, src, k):

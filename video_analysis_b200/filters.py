@@ -444,8 +444,9 @@ class FilterResize(DeviceFilterBase):
     """ resizes the video (filters.py:252-315).  The device path implements INTER_AREA for any shrink
     factors ('auto' picks INTER_AREA when shrinking; integer factors take OpenCV's exact integer /
     single-rounding form, the others its float32 area tables), INTER_LINEAR (OpenCV's 11-bit fixed point)
-    and INTER_NEAREST for any size; cubic / Lanczos raise NotImplementedError rather than silently
-    running on the CPU. """
+    and INTER_NEAREST for any size, and INTER_CUBIC ('auto' when enlarging) with OpenCV's own arithmetic --
+    bit-exact against cv2 with IPP switched off, within 1 LSB of the IPP routine the cv2 wheel uses by
+    default.  Lanczos raises NotImplementedError rather than silently running on the CPU. """
 
     def __init__(self, source, size=None, interpolation='auto', even_dimensions=False, **kwargs):
         if hasattr(size, '__iter__'):
@@ -486,8 +487,10 @@ class FilterResize(DeviceFilterBase):
         # rule; the device path does not restate that one)
         if self.interpolation == 'nearest':
             return rt.resize_nearest(batch, w, h)
-        raise NotImplementedError('FilterResize on the device supports INTER_AREA (shrinking), INTER_LINEAR and '
-                                  'INTER_NEAREST (%dx%d -> %dx%d with %s requested)'
+        if self.interpolation == 'cubic':
+            return rt.resize_cubic(batch, w, h)
+        raise NotImplementedError('FilterResize on the device supports INTER_AREA (shrinking), INTER_LINEAR, INTER_CUBIC '
+                                  'and INTER_NEAREST (%dx%d -> %dx%d with %s requested)'
                                   % (batch.w, batch.h, w, h, self.interpolation))
 
 

@@ -20,6 +20,7 @@ a short read elsewhere repeats the last good frame with a warning, and a short r
 first frame raises `RawStreamError`.
 """
 
+import collections
 import logging
 import subprocess
 import threading
@@ -54,23 +55,28 @@ class VideoRawStream(VideoBase):
                   the video reopenable and therefore seekable backwards (backend_ffmpeg.py:171-243)
     `size`        (width, height); `is_color` selects 3 bytes or 1 byte per pixel
     `frame_count` announced length (may be an estimate, see module docstring)
-    `ring_frames` frames held in the page-locked ring (at least 3 blocks of what the consumer pulls)
+    `ring_frames` frames held in the page-locked ring: `hold` + 2 blocks of what the consumer pulls
+    `hold`        a block handed out stays untouched until this many further blocks have been requested
+                  (3 covers the three-deep upload pipeline of SegmentChain.process_blocks, whose
+                  asynchronous copy of a block may still run while the next two are being pulled)
     `seek_max_frames`  forward seeks up to this distance skip frames instead of reopening
                   (backend_ffmpeg.py:255-268)
     """
 
     seekable = False
 
-    def __init__(self, source, size, frame_count, fps=25, is_color=True, ring_frames=192, pinned=True,
-                 seek_max_frames=100):
+    def __init__(self, source, size, frame_count, fps=25, is_color=True, ring_frames=320, pinned=True,
+                 seek_max_frames=100, hold=3):
         super(VideoRawStream, self).__init__(size=size, frame_count=frame_count, fps=fps, is_color=is_color)
         self.depth = 3 if is_color else 1
         w, h = size
         self.frame_shape = (h, w, 3) if is_color else (h, w)
         self.frame_bytes = self.depth * w * h
-        if self.frame_bytes <= 0 or ring_frames < 3:
-            raise ValueError('VideoRawStream needs a non-empty frame size and a ring of at least 3 frames')
+        self.hold = int(hold)
+        if self.frame_bytes <= 0 or self.hold < 1 or ring_frames < self.hold + 2:
+            raise ValueError('VideoRawStream needs a non-empty frame size and a ring of at least hold + 2 frames')
         self.ring_frames = int(ring_frames)
+        self.max_block = self.ring_frames // (self.hold + 2)
         self.seek_max_frames = seek_max_frames
         self._factory = source if callable(source) else None
         self._ring, self._ring_owner = _alloc_frames(self.ring_frames, self.frame_shape, pinned)
@@ -97,6 +103,7 @@ class VideoRawStream(VideoBase):
         self._base = index            # video index of the first frame this stream delivers
         self._produced = index        # frames [base, produced) have been read into the ring
         self._release = index         # ring slots of frames < release may be overwritten
+        self._held = collections.deque([index], maxlen=self.hold)   # starts of the blocks still promised intact
         self._eof = False
         self._error = None
         self._stop = False
@@ -197,14 +204,16 @@ class VideoRawStream(VideoBase):
     # ---- VideoBase protocol ------------------------------------------------------------------
     def frame_block(self, start, stop):
         """ frames [start, stop) as one contiguous array in the page-locked ring (device filters upload
-        it as it is).  Forward-only: `start` must be the cursor.  The block may be shorter than asked
-        for -- at the end of the stream and where the ring wraps around.  It stays valid until two
+        it as it is) and moves the cursor behind them.  Forward-only: a `start` other than the cursor
+        seeks first.  The block may be shorter than asked for -- at the end of the stream, where the
+        ring wraps around, and it never exceeds ring_frames // (hold + 2).  It stays valid until `hold`
         further blocks have been requested. """
         if start != self._frame_pos:
             self.set_frame_pos(start)
-        stop = min(stop, start + self.ring_frames // 3)
-        self._advance_release(self._held_from if hasattr(self, '_held_from') else start)
-        self._held_from = start                                     # the previous block survives one more call
+        stop = min(stop, start + self.max_block)
+        if len(self._held) == self.hold:
+            self._advance_release(self._held[0])                    # the block handed out `hold` calls ago expires
+        self._held.append(start)
         avail = self._wait_for(stop)
         if avail <= start:
             return self._ring[0:0]
@@ -212,14 +221,14 @@ class VideoRawStream(VideoBase):
         n = min(avail - start, self.ring_frames - a)
         block = self._ring[a:a + n]
         self.lastread = block[-1]
+        self._frame_pos = start + n                                 # the cursor follows the blocks handed out
         return block
 
     def get_next_frame(self):
         block = self.frame_block(self._frame_pos, self._frame_pos + 1)
         if len(block) == 0:
             raise StopIteration
-        self._frame_pos += 1
-        return self._process_frame(block[0])
+        return block[0]
 
     def get_frame(self, index):
         if index < 0:
@@ -240,14 +249,11 @@ class VideoRawStream(VideoBase):
                     raise NotSeekableError('Cannot seek to frame %d, because the stream is already at frame %d'
                                            % (index, self._frame_pos))
             else:
-                self._held_from = index
                 self._open(self._factory(index), index)             # reopen at the position
                 return
         while self._frame_pos < index:                              # skip frames (they are read and dropped)
-            n = len(self.frame_block(self._frame_pos, index))
-            if n == 0:
+            if len(self.frame_block(self._frame_pos, index)) == 0:
                 raise IndexError('Seeking to frame %d was not possible.' % index)
-            self._frame_pos += n
 
     def close(self):
         self._shutdown_reader()
