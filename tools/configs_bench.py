@@ -1,0 +1,119 @@
+#!/usr/bin/env python
+"""
+Device-resident throughput of the BASELINE.json configurations that are parity-test cases rather than
+the bench line (configs[0], [2] per GPU, [3], [4]); CUDA events on the launch stream, inputs alternate
+between resident batches larger than L2, median of `--iters` timed passes after 3 warm-ups.
+One JSON line per configuration (frames/s, ms per batch, algorithmic GB/s of the whole chain).
+
+    python tools/configs_bench.py [--iters 10] [--only vga,4k,streams,stencil]
+"""
+
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def timed(t, fn, iters):
+    for _ in range(3):
+        fn(0)
+    t.cuda.synchronize()
+    ms = []
+    for i in range(iters):
+        a, b = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+        a.record()
+        fn(i + 1)
+        b.record()
+        b.synchronize()
+        ms.append(a.elapsed_time(b))
+    return float(np.median(ms)), float(np.min(ms))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--iters', type=int, default=10)
+    ap.add_argument('--only', default='vga,4k,streams,stencil')
+    args = ap.parse_args()
+    import torch as t
+    from video_analysis_b200 import synth
+    from video_analysis_b200.chain import SegmentChain
+    from video_analysis_b200.device import get_runtime, DeviceBatch
+    rt = get_runtime(0)
+    peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'MEASURED_PEAKS.json')))['hbm_gbs']
+    only = set(args.only.split(','))
+
+    def report(name, frames, med, mn, alg_bytes, note):
+        print(json.dumps({'config': name, 'frames_per_batch': frames, 'ms': round(med, 4), 'ms_min': round(mn, 4),
+                          'fps': round(frames / med * 1e3, 1), 'alg_GBps': round(alg_bytes / med / 1e6, 1),
+                          'frac_of_measured_hbm': round(alg_bytes / med / 1e6 / peak, 3), 'note': note}), flush=True)
+
+    def chain_case(name, w, h, batch, note):
+        # configs[0] / configs[2]: mono -> blur s=2 -> EMA -> |diff| > 25 -> 3x3 open -> label(4), fused luma+blur
+        n_batches = max(2, int(np.ceil(300e6 / (batch * w * h * 3))))          # > 2 x L2 of input
+        vids = [synth.generate(rt, 0, k * batch, batch, w, h, 8) for k in range(n_batches)]
+        ch = SegmentChain((w, h), batch=batch)
+        labels = rt.empty_i32(batch, h, w)
+        counts = t.empty((batch,), dtype=t.int32, device=rt.device)
+        med, mn = timed(t, lambda i: ch.run_device(vids[i % n_batches], labels, counts), args.iters)
+        n = w * h
+        report(name, batch, med, mn, (9.5 * n + 8.0 * n / batch) * batch, note)
+
+    if 'vga' in only:
+        chain_case('configs[0] 640x480 chain', 640, 480, 256, 'batch 256, 236 MB of RGB per batch')
+    if '4k' in only:
+        chain_case('configs[2] 3840x2160 chain (one GPU of the 8)', 3840, 2160, 16, 'batch 16, 398 MB of RGB per batch')
+
+    if 'streams' in only:
+        # configs[3]: 64 camera streams 1280x720 per launch: crop (one rectangle size, per-stream position is a
+        # pointer offset) + luma + apply-mask (static mask) + threshold + label
+        w, h, n_streams = 1280, 720, 64
+        cw, ch_ = 1024, 576
+        vids = [synth.generate(rt, 3, k * n_streams, n_streams, w, h, 6) for k in range(2)]
+        m = np.zeros((ch_, cw), np.uint8)
+        m[20:-30, 40:-10] = 1
+        mask_dev = t.from_numpy(m).to(rt.device)
+
+        def run(i):
+            rgb = vids[i % 2]
+            g = rt.luma(rgb, rect=(128, 72, cw, ch_))
+            g = rt.apply_mask(g, mask_dev)
+            bits = rt.threshold(g, 110)
+            rt.label(bits, 4)
+        med, mn = timed(t, run, args.iters)
+        n = cw * ch_
+        report('configs[3] 64 x 1280x720 streams: crop+mono, apply-mask, threshold, label', n_streams, med, mn,
+               (4 * n + 3 * n + (n + n / 8) + (n / 8 + 4 * n)) * n_streams,
+               'crop 1024x576; bytes = luma 4N + mask 3N + threshold 1.125N + label 4.125N per cropped frame; '
+               'includes the allocation of the intermediates by the caching allocator')
+
+    if 'stencil' in only:
+        # configs[4]: blur s=15 (91 taps) -> resize 0.5 -> threshold -> 7x7 close, open -> label
+        w, h, batch = 1920, 1080, 32
+        vids = [synth.generate(rt, 2, k * batch, batch, w, h, 12) for k in range(2)]
+
+        def run(i):
+            b = rt.luma_gauss(vids[i % 2], 15.0)
+            hlf = rt.resize_half(b)
+            bits = rt.threshold(hlf, 95)
+            bits = rt.morph(bits, 'close', 'rect', 7)
+            bits = rt.morph(bits, 'open', 'rect', 7)
+            rt.label(bits, 4)
+        med, mn = timed(t, run, args.iters)
+        n = w * h
+        q = n / 4
+        report('configs[4] 1080p stencil-heavy: blur s=15, resize 1/2, threshold, 7x7 close+open, label', batch, med, mn,
+               (4 * n + 1.25 * n + 1.125 * q + 2 * q / 4 + 4.125 * q) * batch,
+               'bound by the 91-tap blur (ALU), not HBM')
+
+        def blur_only(i):
+            rt.luma_gauss(vids[i % 2], 15.0)
+        med, mn = timed(t, blur_only, args.iters)
+        report('configs[4] blur s=15 alone (fused luma)', batch, med, mn, 4 * n * batch, '91 taps: 2 x 91 MACs per pixel')
+
+
+if __name__ == '__main__':
+    main()
