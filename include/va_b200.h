@@ -123,7 +123,8 @@ int va_resize_nearest_u8(va_ctx *ctx, va_stream stream,
 /* the same call site with cv2.INTER_AREA shrinking by any (non-integer) factors to (dw, dh): OpenCV's
  * computeResizeAreaTab / resizeArea_<uchar, float> -- cell tables in doubles, weights and sums in float32
  * with every operation rounded on its own, round half to even.  Integer factors dispatch to the calls above.
- * Enlarging in either direction returns VA_ERR_UNSUPPORTED (OpenCV then interpolates linearly). */
+ * Where either direction enlarges, OpenCV's INTER_AREA is its fixed-point linear interpolation with the area
+ * coefficient rule (s = floor(d scale), f = (d + 1) - (s + 1) / scale, f = f <= 0 ? 0 : f - floor(f)): same here. */
 int va_resize_area_any_u8(va_ctx *ctx, va_stream stream,
                           const uint8_t *in, size_t in_pitch, size_t in_fstride,
                           uint8_t *out, size_t out_pitch, size_t out_fstride,
@@ -145,6 +146,14 @@ int va_resize_cubic_u8(va_ctx *ctx, va_stream stream,
                        const uint8_t *in, size_t in_pitch, size_t in_fstride,
                        uint8_t *out, size_t out_pitch, size_t out_fstride,
                        int w, int h, int dw, int dh, int channels, int batch);
+
+/* the same call site with cv2.INTER_LANCZOS4, any output size: OpenCV's 8-bit fixed-point path (8 taps per
+ * direction, 11-bit coefficients from interpolateLanczos4, out = saturate((sum + 2^21) >> 22)).  The coefficient
+ * tables are computed on the host by this call and copied in a stream-ordered allocation.  Bit-exact against cv2. */
+int va_resize_lanczos4_u8(va_ctx *ctx, va_stream stream,
+                          const uint8_t *in, size_t in_pitch, size_t in_fstride,
+                          uint8_t *out, size_t out_pitch, size_t out_fstride,
+                          int w, int h, int dw, int dh, int channels, int batch);
 
 /* K3 running-average background + |difference| > thr -> packed mask bits.
  * Not in the reference; fold shape follows

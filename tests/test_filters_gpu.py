@@ -92,8 +92,8 @@ def test_crop_resize_applymask_and_random_access(frames):
     big = np.stack(list(F.FilterResize(cm, 2.0)))                          # 'auto' enlarges with INTER_CUBIC
     ref_big = np.stack([ops.resize(f, 2.0) for f in exp])
     assert np.abs(big.astype(np.int16) - ref_big).max() <= 1              # cv2's default is Intel IPP here: 1 LSB
-    with pytest.raises(NotImplementedError):
-        next(iter(F.FilterResize(cm, 1.5, interpolation='lanczos')))
+    lz = F.FilterResize(cm, 1.5, interpolation='lanczos')
+    assert np.array_equal(np.stack(list(lz)), np.stack([ops.resize(f, 1.5, 'lanczos') for f in exp]))
     m = np.zeros((120, 160), bool)
     m[20:90, 30:140] = True
     masked = F.FilterApplyMask(cm, m)

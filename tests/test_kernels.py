@@ -220,8 +220,10 @@ def test_resize_area_any_factor_and_linear(be, ctx):
             for fr in (g, c):
                 ref = np.stack([ops.resize(f, (dw, dh), 'linear') for f in fr]).reshape((2, dh, dw) + fr.shape[3:])
                 assert np.array_equal(hz.resize_to(ctx, fr, dw, dh, 'linear'), ref), (H, W, dw, dh, fr.ndim)
-    with pytest.raises(NotImplementedError):
-        hz.resize_to(ctx, rng_frames(1, (1, 10, 10)), 12, 5, 'area_any')        # INTER_AREA enlarging = linear in cv2
+        for dw, dh in ((W + 5, H // 2), (W // 2, H + 3), (2 * W, 2 * H), (W + 1, H + 1), (3 * W + 2, H)):   # INTER_AREA that enlarges
+            for fr in (g, c):
+                ref = np.stack([ops.resize(f, (dw, dh), 'area') for f in fr]).reshape((2, dh, dw) + fr.shape[3:])
+                assert np.array_equal(hz.resize_to(ctx, fr, dw, dh, 'area_any'), ref), (H, W, dw, dh, fr.ndim)
 
 
 def test_resize_cubic(be, ctx):
@@ -240,6 +242,16 @@ def test_resize_cubic(be, ctx):
                         assert np.abs(out.astype(np.int16) - ref).max() <= tol, (H, W, dw, dh, fr.ndim, use_ipp)
     finally:
         cv2.ipp.setUseIPP(ipp)
+
+
+def test_resize_lanczos4(be, ctx):
+    for (H, W) in sizes(be, [(24, 60), (37, 53)], [(1080, 1920), (271, 1003)]):
+        g = rng_frames(H + 4, (2, H, W))
+        c = rng_frames(W + 4, (2, H, W, 3))
+        for dw, dh in ((W * 2, H * 2), (W + 7, H + 3), (W * 3 // 10, H * 3 // 10), (W + W // 2 + 1, H // 2), (7, 5), (1, 1), (W, H * 3)):
+            for fr in (g, c):
+                ref = np.stack([ops.resize(f, (dw, dh), 'lanczos') for f in fr]).reshape((2, dh, dw) + fr.shape[3:])
+                assert np.array_equal(hz.resize_to(ctx, fr, dw, dh, 'lanczos4'), ref), (H, W, dw, dh, fr.ndim)
 
 
 def test_highlight_mask(be, ctx):

@@ -3,6 +3,10 @@
 // kernels; none of them is on the benchmarked chain.
 #include "va_device.cuh"
 
+#include <cfloat>
+#include <cmath>
+#include <vector>
+
 // =================================================================================
 // FilterNormalize._process_frame (video/filters.py:101-135) for uint8 -> uint8: the clip /
 // scale / cast is a 256-entry table that the host computes with the reference's expression
@@ -336,6 +340,11 @@ resize_area_any_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t i
     }
 }
 
+__global__ void resize_linear_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstride,
+                                     uint8_t *__restrict__ out, size_t out_pitch, size_t out_fstride,
+                                     int w, int h, int ow, int oh, int cs, int batch, double scale_x, double scale_y,
+                                     int area_mode, double inv_scale_x, double inv_scale_y);
+
 // cv::resize's test for the integer-factor INTER_AREA path (both |scale - round(scale)| < DBL_EPSILON)
 static bool resize_area_is_fast(int w, int h, int dw, int dh, double *sx, double *sy, int *kx, int *ky) {
     *sx = 1.0 / ((double)dw / (double)w);
@@ -352,10 +361,20 @@ extern "C" int va_resize_area_any_u8(va_ctx *ctx, va_stream stream,
     VA_CHECK_CTX(ctx);
     VA_REQUIRE(ctx, in && out && in != out, "va_resize_area_any_u8: null or aliased pointers");
     VA_REQUIRE(ctx, w > 0 && h > 0 && dw > 0 && dh > 0 && batch > 0 && (channels == 1 || channels == 3), "va_resize_area_any_u8: bad size");
-    if (dw > w || dh > h)
-        VA_FAIL(ctx, VA_ERR_UNSUPPORTED, "va_resize_area_any_u8: %dx%d -> %dx%d enlarges (INTER_AREA then interpolates linearly)", w, h, dw, dh);
     double sx, sy;
     int kx, ky;
+    if (dw > w || dh > h) {        // cv::resize: INTER_AREA needs both factors >= 1, otherwise it interpolates linearly (area rule)
+        VA_REQUIRE(ctx, in_pitch >= (size_t)w * channels && out_pitch >= (size_t)dw * channels, "va_resize_area_any_u8: pitch smaller than a row");
+        const double isx = (double)dw / (double)w, isy = (double)dh / (double)h;
+        sx = 1.0 / isx;
+        sy = 1.0 / isy;
+        const long long items = (long long)dw * channels * dh * batch;
+        const int grid = va_grid(ctx, (items + 255) / 256, 16);
+        auto kfn = resize_linear_kernel;
+        VA_LAUNCH(ctx, kfn, grid, 256, 0, stream, in, in_pitch, in_fstride, out, out_pitch, out_fstride, w, h, dw, dh, channels, batch,
+                  sx, sy, 1, isx, isy);
+        return VA_OK;
+    }
     if (resize_area_is_fast(w, h, dw, dh, &sx, &sy, &kx, &ky)) {
         if (kx == 1 && ky == 1)
             return va_copy2d_u8(ctx, stream, in, in_pitch, in_fstride, out, out_pitch, out_fstride, w * channels, h, batch);
@@ -385,11 +404,19 @@ __device__ __forceinline__ void linear_coef(int d, double scale, float &f, int &
     s = (int)floorf(f);
     f = __fadd_rn(f, -(float)s);
 }
+// cv::resize with INTER_AREA when either direction enlarges: the linear path with its own coefficient rule,
+//     s = floor(d scale);  f = float((d + 1) - (s + 1) inv_scale);  f = f <= 0 ? 0 : f - floor(f)
+__device__ __forceinline__ void linear_coef_area(int d, double scale, double inv_scale, float &f, int &s) {
+    s = (int)floor(__dmul_rn((double)d, scale));
+    f = (float)__dadd_rn((double)(d + 1), -__dmul_rn((double)(s + 1), inv_scale));
+    f = f <= 0.f ? 0.f : __fadd_rn(f, -floorf(f));
+}
 
 __global__ void __launch_bounds__(256)
 resize_linear_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstride,
                      uint8_t *__restrict__ out, size_t out_pitch, size_t out_fstride,
-                     int w, int h, int ow, int oh, int cs, int batch, double scale_x, double scale_y) {
+                     int w, int h, int ow, int oh, int cs, int batch, double scale_x, double scale_y,
+                     int area_mode, double inv_scale_x, double inv_scale_y) {
     const unsigned rowb = (unsigned)(ow * cs);
     const unsigned long long total = (unsigned long long)rowb * oh * batch;
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
@@ -400,8 +427,13 @@ resize_linear_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_
         const unsigned x = xb / cs, c = xb - x * cs;
         float fx, fy;
         int sx, sy;
-        linear_coef((int)x, scale_x, fx, sx);
-        linear_coef((int)y, scale_y, fy, sy);
+        if (area_mode) {
+            linear_coef_area((int)x, scale_x, inv_scale_x, fx, sx);
+            linear_coef_area((int)y, scale_y, inv_scale_y, fy, sy);
+        } else {
+            linear_coef((int)x, scale_x, fx, sx);
+            linear_coef((int)y, scale_y, fy, sy);
+        }
         if (sx < 0) { sx = 0; fx = 0.f; }
         if (sx >= w - 1) { sx = w - 1; fx = 0.f; }
         const int a0 = __float2int_rn(__fmul_rn(__fadd_rn(1.f, -fx), 2048.f)), a1 = __float2int_rn(__fmul_rn(fx, 2048.f));
@@ -433,7 +465,7 @@ extern "C" int va_resize_linear_u8(va_ctx *ctx, va_stream stream,
     const int grid = va_grid(ctx, (items + 255) / 256, 16);
     auto kfn = resize_linear_kernel;
     VA_LAUNCH(ctx, kfn, grid, 256, 0, stream, in, in_pitch, in_fstride, out, out_pitch, out_fstride, w, h, dw, dh, channels, batch,
-              sx, sy);
+              sx, sy, 0, 0.0, 0.0);
     return VA_OK;
 }
 
@@ -587,5 +619,116 @@ extern "C" int va_highlight_mask_u8(va_ctx *ctx, va_stream stream,
     auto kfn = highlight_mask_kernel;
     VA_LAUNCH(ctx, kfn, grid, 256, 0, stream, in, in_pitch, in_fstride, mask, mask_pitch_w, mask_fstride_w, out, out_pitch, out_fstride,
               w, h, channels, batch, channels == 1 ? -1 : channel, vec, lut);
+    return VA_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// INTER_LANCZOS4 (OpenCV's 8-bit fixed-point path, HResizeLanczos4 + VResizeLanczos4, no vector body):
+//     fx = float((dx + .5) scale - .5), sx = floor(fx), fx -= sx;  8 coefficients from interpolateLanczos4 (sines and
+//     cosines in doubles, normalised in float32), scaled to 11 bits;  H(row) = sum_j S[clamp(sx - 3 + j)] a_j  (int32);
+//     out = saturate((sum_k b_k H(clamp(sy - 3 + k)) + 2^21) >> 22)
+// The coefficient tables are computed on the host with the same libm calls OpenCV makes (so they agree to the last
+// bit) and travel to the device in a stream-ordered allocation.  Bit-exact against cv2 (IPP does not take Lanczos).
+// ---------------------------------------------------------------------------------
+static void lanczos4_table(int dsize, int ssize, std::vector<int> &ofs, std::vector<short> &coef) {
+    static const double s45 = 0.70710678118654752440084436210485;
+    static const double cs[][2] = {{1, 0}, {-s45, -s45}, {0, 1}, {s45, -s45}, {-1, 0}, {s45, s45}, {0, -1}, {-s45, s45}};
+    const double scale = 1.0 / ((double)dsize / (double)ssize);
+    ofs.resize(dsize);
+    coef.resize((size_t)dsize * 8);
+    for (int d = 0; d < dsize; d++) {
+        volatile float fx = (float)((d + 0.5) * scale - 0.5);
+        const int s = (int)std::floor(fx);
+        fx = fx - (float)s;
+        const float x = fx;
+        float c[8];
+        {
+            // interpolateLanczos4 of OpenCV 4.x: float sums, double sines; a tap that falls on the sample itself gets
+            // the weight 1e30 and takes everything after the normalisation
+            volatile float sum = 0.f;
+            volatile float x3 = x + 3;
+            const double y0 = -x3 * 3.1415926535897932384626433832795 * 0.25, s0 = std::sin(y0), c0 = std::cos(y0);
+            for (int i = 0; i < 8; i++) {
+                volatile float yi = x3 - i;
+                if (std::fabs(yi) >= 1e-6f) {
+                    const double y = -yi * 3.1415926535897932384626433832795 * 0.25;
+                    c[i] = (float)((cs[i][0] * s0 + cs[i][1] * c0) / (y * y));
+                } else {
+                    c[i] = 1e30f;
+                }
+                sum = sum + c[i];
+            }
+            volatile float inv = 1.f / sum;
+            for (int i = 0; i < 8; i++) { volatile float t = c[i] * inv; c[i] = t; }
+        }
+        ofs[d] = s;
+        for (int i = 0; i < 8; i++) {
+            volatile float t = c[i] * 2048.f;
+            const long v = std::lrintf(t);                         // saturate_cast<short>(float) = cvRound, saturated
+            coef[(size_t)d * 8 + i] = (short)(v < -32768 ? -32768 : v > 32767 ? 32767 : v);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+resize_lanczos4_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstride,
+                       uint8_t *__restrict__ out, size_t out_pitch, size_t out_fstride,
+                       int w, int h, int ow, int oh, int cs, int batch,
+                       const int *__restrict__ xofs, const short *__restrict__ alpha,
+                       const int *__restrict__ yofs, const short *__restrict__ beta) {
+    const unsigned rowb = (unsigned)(ow * cs);
+    const unsigned long long total = (unsigned long long)rowb * oh * batch;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned xb = (unsigned)(i % rowb);
+        const unsigned long long rest = i / rowb;
+        const unsigned y = (unsigned)(rest % oh), b = (unsigned)(rest / oh);
+        const unsigned x = xb / cs, c = xb - x * cs;
+        const int sx = xofs[x], sy = yofs[y];
+        const short *a = alpha + 8 * (size_t)x, *bt = beta + 8 * (size_t)y;
+        const uint8_t *f = in + (size_t)b * in_fstride + c;
+        int acc = 1 << 21;
+        for (int k = 0; k < 8; k++) {
+            const uint8_t *row = f + (size_t)min(max(sy - 3 + k, 0), h - 1) * in_pitch;
+            int v = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) v += row[(size_t)min(max(sx - 3 + j, 0), w - 1) * cs] * a[j];
+            acc += v * bt[k];
+        }
+        out[(size_t)b * out_fstride + (size_t)y * out_pitch + xb] = (uint8_t)min(max(acc >> 22, 0), 255);
+    }
+}
+
+extern "C" int va_resize_lanczos4_u8(va_ctx *ctx, va_stream stream,
+                                     const uint8_t *in, size_t in_pitch, size_t in_fstride,
+                                     uint8_t *out, size_t out_pitch, size_t out_fstride,
+                                     int w, int h, int dw, int dh, int channels, int batch) {
+    VA_CHECK_CTX(ctx);
+    VA_REQUIRE(ctx, in && out && in != out, "va_resize_lanczos4_u8: null or aliased pointers");
+    VA_REQUIRE(ctx, w > 0 && h > 0 && dw > 0 && dh > 0 && batch > 0 && (channels == 1 || channels == 3), "va_resize_lanczos4_u8: bad size");
+    VA_REQUIRE(ctx, in_pitch >= (size_t)w * channels && out_pitch >= (size_t)dw * channels, "va_resize_lanczos4_u8: pitch smaller than a row");
+    std::vector<int> xo, yo;
+    std::vector<short> xa, ya;
+    lanczos4_table(dw, w, xo, xa);
+    lanczos4_table(dh, h, yo, ya);
+    // one stream-ordered allocation: [xofs | yofs | alpha | beta]
+    const size_t n_ofs = (size_t)dw + dh, n_coef = 8 * n_ofs;
+    const size_t bytes = n_ofs * sizeof(int) + n_coef * sizeof(short);
+    std::vector<unsigned char> host(bytes);
+    memcpy(host.data(), xo.data(), dw * sizeof(int));
+    memcpy(host.data() + dw * sizeof(int), yo.data(), dh * sizeof(int));
+    memcpy(host.data() + n_ofs * sizeof(int), xa.data(), 8 * (size_t)dw * sizeof(short));
+    memcpy(host.data() + n_ofs * sizeof(int) + 8 * (size_t)dw * sizeof(short), ya.data(), 8 * (size_t)dh * sizeof(short));
+    unsigned char *dev = nullptr;
+    VA_CUDA(ctx, cudaMallocAsync((void **)&dev, bytes, (cudaStream_t)stream));
+    VA_CUDA(ctx, cudaMemcpyAsync(dev, host.data(), bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));   // pageable source: staged before the call returns
+    const int *d_xofs = reinterpret_cast<const int *>(dev), *d_yofs = d_xofs + dw;
+    const short *d_alpha = reinterpret_cast<const short *>(dev + n_ofs * sizeof(int)), *d_beta = d_alpha + 8 * (size_t)dw;
+    const long long items = (long long)dw * channels * dh * batch;
+    const int grid = va_grid(ctx, (items + 255) / 256, 16);
+    auto kfn = resize_lanczos4_kernel;
+    VA_LAUNCH(ctx, kfn, grid, 256, 0, stream, in, in_pitch, in_fstride, out, out_pitch, out_fstride, w, h, dw, dh, channels, batch,
+              d_xofs, d_alpha, d_yofs, d_beta);
+    VA_CUDA(ctx, cudaFreeAsync(dev, (cudaStream_t)stream));
     return VA_OK;
 }

@@ -234,8 +234,9 @@ class DeviceRuntime(object):
         return out
 
     def resize_area_any(self, src, dw, dh):
-        """ cv2.resize(INTER_AREA) shrinking to (dw, dh), any factors """
-        self.ensure(src.w, src.h, src.n)
+        """ cv2.resize(INTER_AREA) to (dw, dh), any factors (where a direction enlarges, cv2's INTER_AREA is
+        its linear interpolation with the area coefficient rule) """
+        self.ensure(max(src.w, dw), max(src.h, dh), src.n)
         out = self.empty_u8(src.n, dh, dw, src.channels)
         self._check(self.lib.va_resize_area_any_u8(self._h, self.stream, src.ptr, src.pitch, src.fstride,
                                                    out.ptr, out.pitch, out.fstride, src.w, src.h, int(dw), int(dh),
@@ -258,6 +259,15 @@ class DeviceRuntime(object):
         self._check(self.lib.va_resize_cubic_u8(self._h, self.stream, src.ptr, src.pitch, src.fstride,
                                                 out.ptr, out.pitch, out.fstride, src.w, src.h, int(dw), int(dh),
                                                 src.channels, src.n))
+        return out
+
+    def resize_lanczos4(self, src, dw, dh):
+        """ cv2.resize(INTER_LANCZOS4) to (dw, dh) """
+        self.ensure(max(src.w, dw), max(src.h, dh), src.n)
+        out = self.empty_u8(src.n, dh, dw, src.channels)
+        self._check(self.lib.va_resize_lanczos4_u8(self._h, self.stream, src.ptr, src.pitch, src.fstride,
+                                                   out.ptr, out.pitch, out.fstride, src.w, src.h, int(dw), int(dh),
+                                                   src.channels, src.n))
         return out
 
     def apply_mask(self, src, mask_dev):

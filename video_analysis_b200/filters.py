@@ -441,12 +441,13 @@ class FilterBlur(DeviceFilterBase):
 
 
 class FilterResize(DeviceFilterBase):
-    """ resizes the video (filters.py:252-315).  The device path implements INTER_AREA for any shrink
-    factors ('auto' picks INTER_AREA when shrinking; integer factors take OpenCV's exact integer /
-    single-rounding form, the others its float32 area tables), INTER_LINEAR (OpenCV's 11-bit fixed point)
+    """ resizes the video (filters.py:252-315).  The device path implements INTER_AREA ('auto' picks it when
+    the pixel count shrinks; integer factors take OpenCV's exact integer / single-rounding form, other shrink
+    factors its float32 area tables, and where a direction enlarges its linear interpolation with the area
+    coefficient rule, as cv2 does), INTER_LINEAR (OpenCV's 11-bit fixed point)
     and INTER_NEAREST for any size, and INTER_CUBIC ('auto' when enlarging) with OpenCV's own arithmetic --
     bit-exact against cv2 with IPP switched off, within 1 LSB of the IPP routine the cv2 wheel uses by
-    default.  Lanczos raises NotImplementedError rather than silently running on the CPU. """
+    default -- and INTER_LANCZOS4 (OpenCV's 8-tap fixed point, bit-exact). """
 
     def __init__(self, source, size=None, interpolation='auto', even_dimensions=False, **kwargs):
         if hasattr(size, '__iter__'):
@@ -479,19 +480,15 @@ class FilterResize(DeviceFilterBase):
         w, h = self.size
         if self.interpolation == 'area' and batch.w % w == 0 and batch.h % h == 0:
             return rt.resize_area(batch, batch.w // w, batch.h // h)
-        if self.interpolation == 'area' and w <= batch.w and h <= batch.h:
+        if self.interpolation == 'area':
             return rt.resize_area_any(batch, w, h)
         if self.interpolation == 'linear':
             return rt.resize_linear(batch, w, h)
-        # (INTER_AREA that enlarges in either direction interpolates linearly in cv2, with its own coefficient
-        # rule; the device path does not restate that one)
         if self.interpolation == 'nearest':
             return rt.resize_nearest(batch, w, h)
         if self.interpolation == 'cubic':
             return rt.resize_cubic(batch, w, h)
-        raise NotImplementedError('FilterResize on the device supports INTER_AREA (shrinking), INTER_LINEAR, INTER_CUBIC '
-                                  'and INTER_NEAREST (%dx%d -> %dx%d with %s requested)'
-                                  % (batch.w, batch.h, w, h, self.interpolation))
+        return rt.resize_lanczos4(batch, w, h)
 
 
 class FilterNormalize(DeviceFilterBase):
