@@ -195,6 +195,18 @@ int va_morph_bits(va_ctx *ctx, va_stream stream,
                   uint32_t *out, size_t out_pitch_w, size_t out_fstride_w,
                   int w, int h, int batch, int op, int shape, int kx, int ky);
 
+/* va_label_bits in two halves that share scratch set `slot` (0 or 1) of the ctx: the union-find forest of a batch
+ * (counts[] complete after it) and the write of its label image.  Each is enqueued on the stream it is given; the
+ * caller orders write(k) after forest(k) and, per slot, the next forest after the write that used the slot.
+ * Lets the store-bound write of one batch overlap the latency-bound forest kernels of the next. */
+int va_label_forest(va_ctx *ctx, va_stream stream,
+                    const uint32_t *mask, size_t mask_pitch_w, size_t mask_fstride_w,
+                    int32_t *counts, int w, int h, int batch, int connectivity, int slot);
+int va_label_write(va_ctx *ctx, va_stream stream,
+                   const uint32_t *mask, size_t mask_pitch_w, size_t mask_fstride_w,
+                   int32_t *labels, size_t labels_pitch_e, size_t labels_fstride_e,
+                   int w, int h, int batch, int slot);
+
 /* VideoComposer.highlight_mask, video/io/composer.py:131-154: where the mask is set,
  * frame[mask, channel] = uint8(strength + (255 - strength) / 255 * frame[mask, channel]).  lut256 (HOST pointer,
  * copied into the launch) is that expression on 0..255; channel -1 = all channels, 0..2 = one channel of an

@@ -366,6 +366,26 @@ def label(ctx, words, W, connectivity=4, lab_pad=0):
     return lab.get(), cnt.get()[0, 0]
 
 
+def label_two_batches_split(ctx, words_a, words_b, W, connectivity=4):
+    """ forest(a, slot 0), forest(b, slot 1), write(b, slot 1), write(a, slot 0): the two scratch sets are independent """
+    be = ctx.be
+    out = []
+    imgs = []
+    for slot, words in ((0, words_a), (1, words_b)):
+        B, H, Wp = words.shape
+        src = Img(be, B, H, Wp, np.uint32, data=words)
+        lab = Img(be, B, H, W, np.int32, W + 4)
+        cnt = Img(be, 1, 1, B, np.int32)
+        ctx.check(ctx.lib.va_label_forest(ctx.h, be.stream, src.ptr, src.pitch, src.fstride, cnt.ptr, W, H, B, connectivity, slot))
+        imgs.append((slot, src, lab, cnt, B, H))
+    for slot, src, lab, cnt, B, H in reversed(imgs):
+        ctx.check(ctx.lib.va_label_write(ctx.h, be.stream, src.ptr, src.pitch, src.fstride, lab.ptr, lab.pitch, lab.fstride,
+                                         W, H, B, slot))
+    for slot, src, lab, cnt, B, H in imgs:
+        out.append((lab.get(), cnt.get()[0, 0]))
+    return out
+
+
 def region_areas(ctx, labels, max_labels):
     be = ctx.be
     B, H, W = labels.shape

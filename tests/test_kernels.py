@@ -471,6 +471,19 @@ def test_label_golden_and_pitch(be, ctx):
     assert np.array_equal(lab, GOLD['r_labels']) and np.array_equal(cnt, GOLD['r_counts'])
 
 
+def test_label_forest_and_write_halves_with_two_scratch_slots(be, ctx):
+    for (H, W) in sizes(be, [(40, 70)], [(1080, 1920)]):
+        ma, mb = rmask(5, (2, H, W), 0.55), rmask(6, (2, H, W), 0.35)
+        for conn in (4, 8):
+            (la, ca), (lb, cb) = hz.label_two_batches_split(ctx, hz.pack_bits_np(ma), hz.pack_bits_np(mb), W, conn)
+            for lab, cnt, m in ((la, ca, ma), (lb, cb, mb)):
+                for t in range(2):
+                    ref, n = ops.label(m[t], conn)
+                    assert cnt[t] == n and np.array_equal(lab[t], ref), (H, W, conn, t)
+    with pytest.raises(ValueError):
+        hz.label_two_batches_split(ctx, hz.pack_bits_np(rmask(1, (1, 8, 8), .5)), hz.pack_bits_np(rmask(1, (1, 8, 8), .5)), 8, 5)
+
+
 def test_label_capacity_error(be, ctx):
     m = np.zeros((17, 4, 40), np.uint8)
     with pytest.raises(MemoryError):

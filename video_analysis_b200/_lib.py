@@ -81,6 +81,8 @@ SIGNATURES = {
     'va_resize_cubic_u8': (c_int, [c_void_p, c_void_p] + _IMG + _IMG + [c_int, c_int, c_int, c_int, c_int, c_int]),
     'va_highlight_mask_u8': (c_int, [c_void_p, c_void_p] + _IMG + _IMG + _IMG + [c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'va_resize_lanczos4_u8': (c_int, [c_void_p, c_void_p] + _IMG + _IMG + [c_int, c_int, c_int, c_int, c_int, c_int]),
+    'va_label_forest': (c_int, [c_void_p, c_void_p] + _IMG + [c_void_p, c_int, c_int, c_int, c_int, c_int]),
+    'va_label_write': (c_int, [c_void_p, c_void_p] + _IMG + _IMG + [c_int, c_int, c_int, c_int]),
     'va_lut_u8': (c_int, [c_void_p, c_void_p] + _IMG + _IMG + [c_int, c_int, c_int, c_void_p]),
     'va_time_diff_i16': (c_int, [c_void_p, c_void_p] + _IMG + _IMG + [c_int, c_int, c_int]),
     'va_rot90_u8': (c_int, [c_void_p, c_void_p] + _IMG + _IMG + [c_int, c_int, c_int, c_int, c_int]),

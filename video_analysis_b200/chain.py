@@ -172,21 +172,25 @@ class SegmentChain(object):
 
     # ---- two-stream software pipeline over consecutive device batches -----------------------------------
     def run_device_pipelined(self, rgb, labels, counts, blur=None):
-        """ Same result as `run_device`, but the chain is split over two internal streams:
+        """ Same result as `run_device`, but the chain is split over three internal streams:
         front = RGB -> luma -> blur -> background/threshold (the sequential state lives here),
-        back  = morphology -> labelling.  The issue-bound front kernels of batch k+1 then share
-        the SMs with the latency-bound union-find kernels of batch k.  Call `pipeline_sync()`
-        (or synchronise the device) before reading `labels` / `counts`.  `blur`: the already blurred
-        batch (DeviceBatch 'u8'), when the caller has it. """
+        back  = morphology -> union-find forest of the labelling (counts are complete after it),
+        write = the label image.  The issue-bound front kernels of batch k+2, the latency-bound forest
+        kernels of batch k+1 and the store-bound label write of batch k then share the SMs (the forest
+        scratch is double-buffered in the ctx: `va_label_forest` / `va_label_write` with slot k & 1).
+        Call `pipeline_sync()` (or synchronise the device) before reading `labels` / `counts`.
+        `blur`: the already blurred batch (DeviceBatch 'u8'), when the caller has it. """
         rt, t = self.rt, torch()
         n = rgb.n
         if getattr(self, '_pipe', None) is None:
             self._pipe = {
-                'front': t.cuda.Stream(device=rt.device), 'back': t.cuda.Stream(device=rt.device), 'k': 0,
+                'front': t.cuda.Stream(device=rt.device), 'back': t.cuda.Stream(device=rt.device),
+                'write': t.cuda.Stream(device=rt.device), 'k': 0,
                 'blur': rt.empty_u8(self.batch, self.h, self.w),
                 'mask': [rt.empty_bits(self.batch, self.h, self.w) for _ in range(2)],
-                'morph': rt.empty_bits(self.batch, self.h, self.w),
+                'morph': [rt.empty_bits(self.batch, self.h, self.w) for _ in range(2)],
                 'ev_front': [t.cuda.Event(), t.cuda.Event()], 'ev_back': [t.cuda.Event(), t.cuda.Event()],
+                'ev_write': [t.cuda.Event(), t.cuda.Event()],
             }
         p = self._pipe
         k = p['k']
@@ -199,29 +203,36 @@ class SegmentChain(object):
         lib, h = rt.lib, rt._h
         sub = lambda b: DeviceBatch(b.kind, b.t[:n], n, b.h, b.w, b.channels)
         have_blur = blur is not None
-        blur, mask, morph = (blur if have_blur else sub(p['blur'])), sub(p['mask'][slot]), sub(p['morph'])
+        blur, mask, morph = (blur if have_blur else sub(p['blur'])), sub(p['mask'][slot]), sub(p['morph'][slot])
         with t.cuda.stream(p['front']):
             p['front'].wait_event(ev)
             p['front'].wait_event(p['ev_back'][slot])        # the back half has finished reading this mask slot
-            if not have_blur:
+            p['front'].wait_event(p['ev_write'][slot])       # ... and so has the label write (it reads the mask when
+            if not have_blur:                                #     there is no morphology in between)
                 self.blur_device(rgb, blur)
             rt._check(lib.va_ema_diff_thresh(h, rt.stream, *blur.img(), self._bg.data_ptr(), self._bg.stride(0),
                                              *mask.img(), self.w, self.h, n, self.alpha, self.threshold,
                                              0 if self._started else 1))
             self._started = True
             p['ev_front'][slot].record(p['front'])
+        seg = mask
         with t.cuda.stream(p['back']):
             p['back'].wait_event(ev)
             p['back'].wait_event(p['ev_front'][slot])
-            seg = mask
+            p['back'].wait_event(p['ev_write'][slot])        # the write of batch k - 2 used this morph buffer / scratch slot
             if self.morph_op:
                 rt._check(lib.va_morph_bits(h, rt.stream, *mask.img(), *morph.img(), self.w, self.h, n,
                                             _lib.MORPH_OPS[self.morph_op], _lib.SE_SHAPES[self.morph_shape],
                                             int(self.kx), int(self.ky)))
                 seg = morph
-            rt._check(lib.va_label_bits(h, rt.stream, *seg.img(), *labels.img(), counts.data_ptr(),
-                                        self.w, self.h, n, self.connectivity))
+            rt._check(lib.va_label_forest(h, rt.stream, *seg.img(), counts.data_ptr(), self.w, self.h, n,
+                                          self.connectivity, slot))
             p['ev_back'][slot].record(p['back'])
+        with t.cuda.stream(p['write']):
+            p['write'].wait_event(ev)
+            p['write'].wait_event(p['ev_back'][slot])
+            rt._check(lib.va_label_write(h, rt.stream, *seg.img(), *labels.img(), self.w, self.h, n, slot))
+            p['ev_write'][slot].record(p['write'])
         return labels, counts
 
     def pipeline_sync(self):
@@ -231,6 +242,7 @@ class SegmentChain(object):
             cur = torch().cuda.current_stream(self.rt.device)
             cur.wait_stream(p['front'])
             cur.wait_stream(p['back'])
+            cur.wait_stream(p['write'])
 
     # ---- host frames in, host labels out: pipelined -------------------------------------------------------
     def _make_slots(self):

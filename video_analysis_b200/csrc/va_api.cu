@@ -53,6 +53,8 @@ extern "C" int va_destroy(va_ctx *ctx) {
     if (!ctx) return VA_OK;
     cudaFree(ctx->lab_parent);
     cudaFree(ctx->lab_rowcnt);
+    cudaFree(ctx->lab_parent1);
+    cudaFree(ctx->lab_rowcnt1);
     cudaFree(ctx->ch_mono);
     cudaFree(ctx->ch_blur);
     cudaFree(ctx->ch_mask);

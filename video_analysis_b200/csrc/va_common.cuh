@@ -28,6 +28,7 @@ struct va_ctx {
     int32_t *lab_parent;     // [max_batch * max_h * lab_pitch]  union-find forest, sparse (run starts only)
     size_t lab_pitch;        // elements per row: power of two >= max_w
     int32_t *lab_rowcnt;     // [2][max_batch * max_h]  roots per row -> exclusive prefix; rows' foreground flags
+    int32_t *lab_parent1, *lab_rowcnt1;   // second scratch set (slot 1 of va_label_forest / va_label_write), allocated on first use
     // morphology scratch (intermediate of open / close is kept in shared memory; none needed)
     // chain intermediates (allocated on first use by va_chain_run)
     uint8_t *ch_mono, *ch_blur;

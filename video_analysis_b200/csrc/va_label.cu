@@ -495,9 +495,29 @@ label_write_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
 
 // phases A-D: afterwards every root holds -(rank in its row), rowcnt holds the exclusive prefix of
 // the per-row root counts and counts[b] the number of components
+// scratch set `slot` (0: allocated by va_create, 1: on first use) -- two sets let the label write of one batch
+// run beside the forest kernels of the next
+static int label_scratch(va_ctx *ctx, const char *name, int slot, int **parent, int **rowcnt) {
+    VA_REQUIRE(ctx, slot == 0 || slot == 1, "%s: scratch slot must be 0 or 1", name);
+    if (slot == 1 && !ctx->lab_parent1) {
+        const size_t n_parent = ctx->lab_pitch * (size_t)ctx->max_h * (size_t)ctx->max_batch;
+        if (cudaMalloc((void **)&ctx->lab_parent1, n_parent * sizeof(int32_t)) != cudaSuccess ||
+            cudaMalloc((void **)&ctx->lab_rowcnt1, (size_t)2 * ctx->max_h * ctx->max_batch * sizeof(int32_t)) != cudaSuccess) {
+            cudaGetLastError();
+            cudaFree(ctx->lab_parent1);
+            ctx->lab_parent1 = nullptr;
+            VA_FAIL(ctx, VA_ERR_NOMEM, "%s: cannot allocate the second labelling scratch", name);
+        }
+    }
+    *parent = slot ? ctx->lab_parent1 : ctx->lab_parent;
+    *rowcnt = slot ? ctx->lab_rowcnt1 : ctx->lab_rowcnt;
+    return VA_OK;
+}
+
 static int label_forest(va_ctx *ctx, va_stream stream, const char *name,
                         const uint32_t *mask, size_t mask_pitch_w, size_t mask_fstride_w,
-                        int32_t *counts, int w, int h, int batch, int connectivity, int *LOG_out, size_t *pf_out) {
+                        int32_t *counts, int w, int h, int batch, int connectivity, int *LOG_out, size_t *pf_out,
+                        int slot = 0) {
     VA_REQUIRE(ctx, w > 0 && h > 0 && batch > 0, "%s: bad size", name);
     VA_REQUIRE(ctx, connectivity == 4 || connectivity == 8, "%s: connectivity must be 4 or 8", name);
     VA_REQUIRE(ctx, mask_pitch_w >= (size_t)((w + 31) / 32), "%s: pitch smaller than a row", name);
@@ -507,9 +527,9 @@ static int label_forest(va_ctx *ctx, va_stream stream, const char *name,
     int LOG = 5;
     while (((size_t)1 << LOG) < ctx->lab_pitch) LOG++;
     const size_t pf = ctx->lab_pitch * (size_t)ctx->max_h;
-    int *parent = ctx->lab_parent;
-    int *rowcnt = ctx->lab_rowcnt;
-    int *rowflag = ctx->lab_rowcnt + (size_t)ctx->max_h * ctx->max_batch;      // does the row have foreground?
+    int *parent, *rowcnt;
+    { const int rc = label_scratch(ctx, name, slot, &parent, &rowcnt); if (rc != VA_OK) return rc; }
+    int *rowflag = rowcnt + (size_t)ctx->max_h * ctx->max_batch;               // does the row have foreground?
     const int vec = va_aligned(mask, 16) && mask_pitch_w % 4 == 0 && mask_fstride_w % 4 == 0;
     const int grid_a = va_div_up((long long)((h + 7) / 8) * batch, LAB_WARPS);          // four-lanes-per-row kernels
     { auto k = label_init_kernel;
@@ -528,6 +548,21 @@ static int label_forest(va_ctx *ctx, va_stream stream, const char *name,
     return VA_OK;
 }
 
+static int label_write(va_ctx *ctx, va_stream stream, const char *name,
+                       const uint32_t *mask, size_t mask_pitch_w, size_t mask_fstride_w,
+                       int32_t *labels, size_t labels_pitch_e, size_t labels_fstride_e,
+                       int w, int h, int batch, int LOG, size_t pf, int slot) {
+    int *parent, *rowcnt;
+    { const int rc = label_scratch(ctx, name, slot, &parent, &rowcnt); if (rc != VA_OK) return rc; }
+    auto k = label_write_kernel;
+    const int vec_out = va_aligned(labels, 16) && labels_pitch_e % 4 == 0 && labels_fstride_e % 4 == 0;
+    const dim3 grid(va_div_up(h, LAB_WARPS), batch);
+    VA_LAUNCH(ctx, k, grid, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, (const int *)parent, LOG, pf,
+              (const int *)rowcnt, (const int *)(rowcnt + (size_t)ctx->max_h * ctx->max_batch),
+              labels, labels_pitch_e, labels_fstride_e, w, h, batch, vec_out);
+    return VA_OK;
+}
+
 extern "C" int va_label_bits(va_ctx *ctx, va_stream stream,
                              const uint32_t *mask, size_t mask_pitch_w, size_t mask_fstride_w,
                              int32_t *labels, size_t labels_pitch_e, size_t labels_fstride_e,
@@ -540,13 +575,40 @@ extern "C" int va_label_bits(va_ctx *ctx, va_stream stream,
     const int rc = label_forest(ctx, stream, "va_label_bits", mask, mask_pitch_w, mask_fstride_w, counts, w, h, batch,
                                 connectivity, &LOG, &pf);
     if (rc != VA_OK) return rc;
-    { auto k = label_write_kernel;
-      const int vec_out = va_aligned(labels, 16) && labels_pitch_e % 4 == 0 && labels_fstride_e % 4 == 0;
-      const dim3 grid(va_div_up(h, LAB_WARPS), batch);
-      VA_LAUNCH(ctx, k, grid, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, (const int *)ctx->lab_parent, LOG, pf,
-                (const int *)ctx->lab_rowcnt, (const int *)(ctx->lab_rowcnt + (size_t)ctx->max_h * ctx->max_batch),
-                labels, labels_pitch_e, labels_fstride_e, w, h, batch, vec_out); }
-    return VA_OK;
+    return label_write(ctx, stream, "va_label_bits", mask, mask_pitch_w, mask_fstride_w, labels, labels_pitch_e,
+                       labels_fstride_e, w, h, batch, LOG, pf, 0);
+}
+
+// va_label_bits in two halves, each on the stream it is given, sharing scratch set `slot` (0 or 1): the union-find
+// forest of a batch (counts[] is complete after it) and the write of its label image.  With two scratch sets the
+// write of batch k (pure stores, HBM-bound) can run on one stream while the forest of batch k + 1 (dependent loads,
+// latency-bound) runs on another; the caller orders write(k) after forest(k) and forest(k + 2) after write(k).
+extern "C" int va_label_forest(va_ctx *ctx, va_stream stream,
+                               const uint32_t *mask, size_t mask_pitch_w, size_t mask_fstride_w,
+                               int32_t *counts, int w, int h, int batch, int connectivity, int slot) {
+    VA_CHECK_CTX(ctx);
+    VA_REQUIRE(ctx, mask && counts, "va_label_forest: null pointer");
+    int LOG;
+    size_t pf;
+    return label_forest(ctx, stream, "va_label_forest", mask, mask_pitch_w, mask_fstride_w, counts, w, h, batch,
+                        connectivity, &LOG, &pf, slot);
+}
+
+extern "C" int va_label_write(va_ctx *ctx, va_stream stream,
+                              const uint32_t *mask, size_t mask_pitch_w, size_t mask_fstride_w,
+                              int32_t *labels, size_t labels_pitch_e, size_t labels_fstride_e,
+                              int w, int h, int batch, int slot) {
+    VA_CHECK_CTX(ctx);
+    VA_REQUIRE(ctx, mask && labels, "va_label_write: null pointer");
+    VA_REQUIRE(ctx, w > 0 && h > 0 && batch > 0 && batch <= 65535, "va_label_write: bad size");
+    VA_REQUIRE(ctx, labels_pitch_e >= (size_t)w && mask_pitch_w >= (size_t)((w + 31) / 32), "va_label_write: pitch smaller than a row");
+    if (w > ctx->max_w || h > ctx->max_h || batch > ctx->max_batch)
+        VA_FAIL(ctx, VA_ERR_CAPACITY, "va_label_write: %dx%dx%d exceeds the ctx capacity %dx%dx%d", w, h, batch,
+                ctx->max_w, ctx->max_h, ctx->max_batch);
+    int LOG = 5;
+    while (((size_t)1 << LOG) < ctx->lab_pitch) LOG++;
+    return label_write(ctx, stream, "va_label_write", mask, mask_pitch_w, mask_fstride_w, labels, labels_pitch_e,
+                       labels_fstride_e, w, h, batch, LOG, ctx->lab_pitch * (size_t)ctx->max_h, slot);
 }
 
 // =====================================================================================
