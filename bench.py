@@ -231,7 +231,7 @@ def gpu_arm(args):
             for i in range(n):
                 if args.no_overlap:
                     chain.run_device(batch_of(first + i), labels[i & 1], counts)
-                else:       # front half of batch k+1 overlaps the labelling of batch k (two streams)
+                else:       # blur + EMA of batch k+2, forest of k+1 and label write of k overlap (three streams)
                     chain.run_device_pipelined(batch_of(first + i), labels[i & 1], counts)
             if not args.no_overlap:
                 chain.pipeline_sync()
@@ -324,7 +324,8 @@ def gpu_arm(args):
                        'parallelism': 'frame-range shards x%d, EMA carry via NCCL all-gather' % world if world > 1 else 'single GPU',
                        'l2': 'every step reads a different %d MB batch of the resident video (>> 126 MB L2)' % (B * N * 3 >> 20),
                        'fused_luma_blur': not args.no_fuse,
-                       'two_stream_overlap': (not args.no_overlap) or world > 1},
+                       'two_stream_overlap': (not args.no_overlap) or world > 1,
+                       'pipeline_streams': 1 if (args.no_overlap and world == 1) else 3},
             'clocks': clocks,
             'e2e': {'value': round(e2e_fps, 1), 'unit': 'frames/s', 'h2d_bytes_per_step': Be * N * 3,
                     'd2h_bytes_per_step': Be * N * 4 + Be * 4, 'steps': Ke, 'frames_per_step': Be,

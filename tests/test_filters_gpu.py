@@ -371,19 +371,19 @@ def test_raw_stream_ingest_and_annotated_egress(frames, ref):
     from video_analysis_b200.io.pipe import VideoRawStream, RawStreamWriter
     raw = frames.tobytes()
     # the filter classes over a stream source: same labels as from memory
-    v = VideoRawStream(io.BytesIO(raw), (320, 240), len(frames), ring_frames=40)
+    v = VideoRawStream(io.BytesIO(raw), (320, 240), len(frames), ring_frames=96)
     full = F.FilterLabel(F.FilterMorphology(
         F.FilterBackgroundMask(F.FilterBlur(F.FilterMonochrome(v, batch=8), 2)), 'open', 'rect', 3))
     assert np.array_equal(np.stack(list(full)), ref['labels'])
     v.close()
     # the pipelined chain straight from the ring (blocks shorter than the chain's batch)
-    v = VideoRawStream(io.BytesIO(raw), (320, 240), len(frames) + 1, ring_frames=40)      # length over-estimated
+    v = VideoRawStream(io.BytesIO(raw), (320, 240), len(frames) + 1, ring_frames=96)      # length over-estimated
     labels, counts = SegmentChain((320, 240), batch=16).process(v)
     assert np.array_equal(labels, ref['labels']) and list(counts) == list(ref['counts'])
     v.close()
     # annotated egress
     sink = io.BytesIO()
-    v = VideoRawStream(io.BytesIO(raw), (320, 240), len(frames), ring_frames=40)
+    v = VideoRawStream(io.BytesIO(raw), (320, 240), len(frames), ring_frames=96)
     with RawStreamWriter(sink, (320, 240)) as wr:
         SegmentChain((320, 240), batch=8).annotate(v, wr, channel='red', strength=100)
         assert wr.frames_written == len(frames)

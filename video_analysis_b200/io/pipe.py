@@ -57,16 +57,17 @@ class VideoRawStream(VideoBase):
     `frame_count` announced length (may be an estimate, see module docstring)
     `ring_frames` frames held in the page-locked ring: `hold` + 2 blocks of what the consumer pulls
     `hold`        a block handed out stays untouched until this many further blocks have been requested
-                  (3 covers the three-deep upload pipeline of SegmentChain.process_blocks, whose
-                  asynchronous copy of a block may still run while the next two are being pulled)
+                  (4 covers the three-deep pipeline of SegmentChain.process_blocks: it pulls block k + 3
+                  before it waits for the results of block k, so the asynchronous upload of block k is
+                  only known to be complete when block k + 4 is requested)
     `seek_max_frames`  forward seeks up to this distance skip frames instead of reopening
                   (backend_ffmpeg.py:255-268)
     """
 
     seekable = False
 
-    def __init__(self, source, size, frame_count, fps=25, is_color=True, ring_frames=320, pinned=True,
-                 seek_max_frames=100, hold=3):
+    def __init__(self, source, size, frame_count, fps=25, is_color=True, ring_frames=384, pinned=True,
+                 seek_max_frames=100, hold=4):
         super(VideoRawStream, self).__init__(size=size, frame_count=frame_count, fps=fps, is_color=is_color)
         self.depth = 3 if is_color else 1
         w, h = size
@@ -103,7 +104,7 @@ class VideoRawStream(VideoBase):
         self._base = index            # video index of the first frame this stream delivers
         self._produced = index        # frames [base, produced) have been read into the ring
         self._release = index         # ring slots of frames < release may be overwritten
-        self._held = collections.deque([index], maxlen=self.hold)   # starts of the blocks still promised intact
+        self._held = collections.deque()                            # starts of the blocks still promised intact
         self._eof = False
         self._error = None
         self._stop = False
@@ -211,9 +212,10 @@ class VideoRawStream(VideoBase):
         if start != self._frame_pos:
             self.set_frame_pos(start)
         stop = min(stop, start + self.max_block)
-        if len(self._held) == self.hold:
-            self._advance_release(self._held[0])                    # the block handed out `hold` calls ago expires
         self._held.append(start)
+        if len(self._held) > self.hold:                             # the block handed out `hold` calls ago expires
+            self._held.popleft()
+            self._advance_release(self._held[0])
         avail = self._wait_for(stop)
         if avail <= start:
             return self._ring[0:0]
