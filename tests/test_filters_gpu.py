@@ -392,3 +392,17 @@ def test_raw_stream_ingest_and_annotated_egress(frames, ref):
     assert np.array_equal(got, exp)
     marked = SegmentChain((320, 240), batch=16).annotate(frames[:10])
     assert np.array_equal(marked, np.stack([ops.highlight_mask(f, m) for f, m in zip(frames[:10], ref['morph'][:10])]))
+
+
+def test_config2_full_size_properties_10k_frames():
+    """ BASELINE.json configs[1] at its full size (1080p, 10 000 frames resident in HBM): tests/fullsize_check.py """
+    mods()
+    import json
+    import os
+    import subprocess
+    import sys
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'fullsize_check.py')
+    p = subprocess.run([sys.executable, script], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout + p.stderr
+    out = json.loads(p.stdout.strip().splitlines()[-1])
+    assert out['frames'] == 9984 and all(v for v in out.values() if isinstance(v, bool)), out
