@@ -96,6 +96,11 @@ class VideoRawStream(VideoBase):
         if isinstance(source, (list, tuple)):
             self._proc = subprocess.Popen(list(source), stdout=subprocess.PIPE, bufsize=0)
             self._stream, self._owns_stream = self._proc.stdout, True
+            try:                                        # 1 MiB pipe instead of 64 KiB: 16 times fewer read calls per frame
+                import fcntl
+                fcntl.fcntl(self._stream.fileno(), getattr(fcntl, 'F_SETPIPE_SZ', 1031), 1 << 20)
+            except (ImportError, OSError):
+                pass
         elif isinstance(source, (str, bytes)):
             self._stream, self._owns_stream = open(source, 'rb', buffering=0), True
         else:
