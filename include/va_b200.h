@@ -207,6 +207,25 @@ int va_label_write(va_ctx *ctx, va_stream stream,
                    int32_t *labels, size_t labels_pitch_e, size_t labels_fstride_e,
                    int w, int h, int batch, int slot);
 
+/* BASELINE.json configs[3] -- concurrent streams batched on the leading axis of one launch: FilterCrop
+ * (video/filters.py:158-248) with one rectangle SIZE (w, h) but a position per stream, then FilterMonochrome
+ * (video/filters.py:359-374).  xy: DEVICE table {left_0, top_0, left_1, top_1, ...}; the caller guarantees
+ * left_s + w <= in_w and top_s + h <= in_h (the host layer applies the reference's _check_coordinate rules). */
+int va_luma_crop_multi_u8(va_ctx *ctx, va_stream stream,
+                          const uint8_t *in, size_t in_pitch, size_t in_fstride, int in_w, int in_h,
+                          uint8_t *out, size_t out_pitch, size_t out_fstride,
+                          int w, int h, int batch, int mode, const int32_t *xy);
+
+/* the front of BASELINE.json configs[3] fused into one pass: crop position per stream + monochrome + static mask
+ * (u8, nonzero = keep; smask = NULL: none; smask_fstride = 0: one mask for all streams) + threshold (value > thr)
+ * -> packed mask bits.  Needs w % 32 == 0, word-aligned frames and 16-byte aligned mask rows, otherwise
+ * VA_ERR_UNSUPPORTED (the three separate calls cover every case). */
+int va_streams_threshold_bits(va_ctx *ctx, va_stream stream,
+                              const uint8_t *in, size_t in_pitch, size_t in_fstride, int in_w, int in_h,
+                              const uint8_t *smask, size_t smask_pitch, size_t smask_fstride,
+                              uint32_t *bits, size_t bits_pitch_w, size_t bits_fstride_w,
+                              int w, int h, int batch, int mode, int thr, const int32_t *xy);
+
 /* VideoComposer.highlight_mask, video/io/composer.py:131-154: where the mask is set,
  * frame[mask, channel] = uint8(strength + (255 - strength) / 255 * frame[mask, channel]).  lut256 (HOST pointer,
  * copied into the launch) is that expression on 0..255; channel -1 = all channels, 0..2 = one channel of an

@@ -291,6 +291,36 @@ def highlight_mask(ctx, frames, masks, channel, table, in_pad=0):
     return out if frames.ndim == 3 else out.reshape(B, H, W, ch)
 
 
+def luma_crop_multi(ctx, frames, xy, w, h, mode=-1, in_pad=0, out_pad=3):
+    """ frames (S, H, W, 3); xy (S, 2) left, top """
+    be = ctx.be
+    S, H, W, _ = frames.shape
+    src = Img(be, S, H, 3 * W, np.uint8, 3 * W + in_pad, frames.reshape(S, H, 3 * W))
+    tab = Img(be, 1, 1, 2 * S, np.int32, data=np.asarray(xy, np.int32).reshape(1, 1, 2 * S))
+    dst = Img(be, S, h, w, np.uint8, w + out_pad)
+    ctx.check(ctx.lib.va_luma_crop_multi_u8(ctx.h, be.stream, src.ptr, src.pitch, src.fstride, W, H,
+                                            dst.ptr, dst.pitch, dst.fstride, w, h, S, mode, tab.ptr))
+    assert (dst.raw()[:, :, w:] == 0xCD).all()
+    return dst.get()
+
+
+def streams_threshold(ctx, frames, xy, w, h, masks, thr, mode=-1, in_pad=0):
+    """ frames (S, H, W, 3); xy (S, 2); masks None, (h, w) or (S, h, w) u8 -> packed words (S, h, ceil(w / 32)) """
+    be = ctx.be
+    S, H, W, _ = frames.shape
+    src = Img(be, S, H, 3 * W, np.uint8, 3 * W + in_pad, frames.reshape(S, H, 3 * W))
+    tab = Img(be, 1, 1, 2 * S, np.int32, data=np.asarray(xy, np.int32).reshape(1, 1, 2 * S))
+    margs = (None, 0, 0)
+    if masks is not None:
+        m3 = masks if masks.ndim == 3 else masks[None]
+        mk = Img(be, m3.shape[0], h, w, np.uint8, w + 16, m3)
+        margs = (mk.ptr, mk.pitch, mk.fstride if masks.ndim == 3 else 0)
+    dst = Img(be, S, h, mask_words(w), np.uint32, mask_words(w) + 1)
+    ctx.check(ctx.lib.va_streams_threshold_bits(ctx.h, be.stream, src.ptr, src.pitch, src.fstride, W, H, *margs,
+                                                dst.ptr, dst.pitch, dst.fstride, w, h, S, mode, thr, tab.ptr))
+    return dst.get()
+
+
 def mask_words(W):
     return (W + 31) // 32
 

@@ -406,3 +406,50 @@ def test_config2_full_size_properties_10k_frames():
     assert p.returncode == 0, p.stdout + p.stderr
     out = json.loads(p.stdout.strip().splitlines()[-1])
     assert out['frames'] == 9984 and all(v for v in out.values() if isinstance(v, bool)), out
+
+
+def test_config4_streams_batched_per_launch():
+    """ BASELINE.json configs[3]: the streams advance in lock step, one launch set per time step over all of them
+    (per-stream crop position and mask) -- equal to the per-stream filter stacks of the oracle """
+    F, VideoMemory = mods()
+    from video_analysis_b200.streams import MultiStreamSegmenter
+    W, H, T, S = 1280, 720, 4, 5
+    rng = np.random.default_rng(11)
+    vids = [synth.make_frames(20 + s, 0, T, W, H, 5) for s in range(S)]
+    rects = [(int(rng.integers(0, 600)), int(rng.integers(0, 300)), 642, 363) for _ in range(S)]
+    rects[1] = (-642, -363, 642, 363)                                     # negative: counted from the far edge
+    masks = np.zeros((S, 363, 642), np.uint8)
+    for s in range(S):
+        masks[s, 10 + 5 * s:-20, 30:-10 - 7 * s] = 1
+    seg = MultiStreamSegmenter([VideoMemory(v, copy_data=False) for v in vids], rects, masks, threshold=110)
+    n_steps = 0
+    for t, (labels, counts) in enumerate(seg):
+        n_steps += 1
+        for s in range(S):
+            g = ops.apply_mask(ops.mono(ops.crop(vids[s][t], ops.crop_rect((W, H), rects[s]))), masks[s])
+            lab, n = ops.label(g > 110)
+            assert counts[s] == n and np.array_equal(labels[s], lab), (t, s)
+    assert n_steps == T
+    one = MultiStreamSegmenter([VideoMemory(v, copy_data=False) for v in vids], rects, masks[0], threshold=90, mono_mode='green',
+                               connectivity=8)
+    labels, counts = next(iter(one))
+    for s in range(S):
+        g = ops.apply_mask(ops.mono(ops.crop(vids[s][0], ops.crop_rect((W, H), rects[s])), 'green'), masks[0])
+        lab, n = ops.label(g > 90, 8)
+        assert counts[s] == n and np.array_equal(labels[s], lab)
+    # crop width a multiple of 32: the front of the chain is one fused pass; same results as the separate kernels
+    rects32 = [(r[0] % 600, r[1] % 300, 640, 352) for r in rects]
+    outs = []
+    for fused in (True, False):
+        sg = MultiStreamSegmenter([VideoMemory(v, copy_data=False) for v in vids], rects32, masks[:, :352, :640], threshold=110,
+                                  fused=fused)
+        assert sg._fused == fused
+        outs.append([(lab.copy(), cnt.copy()) for lab, cnt in sg])
+    for (la, ca), (lb, cb) in zip(*outs):
+        assert np.array_equal(la, lb) and np.array_equal(ca, cb)
+    for s in range(S):
+        g = ops.apply_mask(ops.mono(ops.crop(vids[s][2], ops.crop_rect((W, H), rects32[s]))), masks[s, :352, :640])
+        lab, n = ops.label(g > 110)
+        assert outs[0][2][1][s] == n and np.array_equal(outs[0][2][0][s], lab)
+    with pytest.raises(ValueError):
+        MultiStreamSegmenter([VideoMemory(v, copy_data=False) for v in vids], rects[:-1] + [(0, 0, 100, 100)])

@@ -254,6 +254,43 @@ def test_resize_lanczos4(be, ctx):
                 assert np.array_equal(hz.resize_to(ctx, fr, dw, dh, 'lanczos4'), ref), (H, W, dw, dh, fr.ndim)
 
 
+def test_luma_crop_per_stream_positions(be, ctx):
+    for (H, W, w, h) in sizes(be, [(30, 41, 17, 11), (24, 64, 32, 8)], [(720, 1280, 642, 363), (1080, 1920, 1024, 576)]):
+        S = 4
+        fr = rng_frames(H * W + 1, (S, H, W, 3))
+        rng = np.random.default_rng(w)
+        xy = np.stack([rng.integers(0, W - w + 1, S), rng.integers(0, H - h + 1, S)], axis=1)
+        xy[0] = (0, 0)
+        xy[1] = (W - w, H - h)
+        for mode, name in ((-1, 'mean'), (0, 'blue'), (2, 'red')):
+            ref = np.stack([ops.mono(ops.crop(fr[s], (int(xy[s, 0]), int(xy[s, 1]), w, h)), name) for s in range(S)])
+            for pad, out_pad in ((0, 3), (1, 3), (0, 0), (4, 16)):        # the last two take the 16-pixel path when w % 16 == 0
+                got = hz.luma_crop_multi(ctx, fr, xy, w, h, mode, pad, out_pad)
+                assert np.array_equal(got, ref), (H, W, w, h, mode, pad, out_pad)
+    with pytest.raises(ValueError):
+        hz.luma_crop_multi(ctx, rng_frames(1, (1, 8, 8, 3)), [(0, 0)], 9, 4)
+
+
+def test_streams_fused_front(be, ctx):
+    for (H, W, w, h) in sizes(be, [(30, 80, 32, 11), (24, 100, 64, 8)], [(720, 1280, 640, 352), (1080, 1920, 1024, 576)]):
+        S = 3
+        fr = rng_frames(H * W + 2, (S, H, W, 3))
+        rng = np.random.default_rng(h)
+        xy = np.stack([rng.integers(0, W - w + 1, S), rng.integers(0, H - h + 1, S)], axis=1)
+        xy[0] = (W - w, H - h)
+        masks = rmask(w * h, (S, h, w), 0.7)
+        for mode, name in ((-1, 'mean'), (1, 'green')):
+            mono = np.stack([ops.mono(ops.crop(fr[s], (int(xy[s, 0]), int(xy[s, 1]), w, h)), name) for s in range(S)])
+            for mk in (None, masks[0], masks):
+                for thr in (110, 0, 255, -1):
+                    g = mono if mk is None else np.where((mk if mk.ndim == 3 else mk[None]) != 0, mono, 0)
+                    ref = hz.pack_bits_np(((g.astype(np.int32) > thr) * 255).astype(np.uint8))
+                    got = hz.streams_threshold(ctx, fr, xy, w, h, mk, thr, mode, in_pad=0 if thr else 4)
+                    assert np.array_equal(got, ref), (H, W, w, h, mode, None if mk is None else mk.ndim, thr)
+    with pytest.raises(NotImplementedError):
+        hz.streams_threshold(ctx, rng_frames(1, (1, 20, 40, 3)), [(0, 0)], 17, 4, None, 10)
+
+
 def test_highlight_mask(be, ctx):
     for (H, W) in sizes(be, [(13, 37), (24, 64)], [(1080, 1920), (271, 1003)]):
         g = rng_frames(H + 3, (2, H, W))

@@ -68,27 +68,27 @@ def main():
         chain_case('configs[2] 3840x2160 chain (one GPU of the 8)', 3840, 2160, 16, 'batch 16, 398 MB of RGB per batch')
 
     if 'streams' in only:
-        # configs[3]: 64 camera streams 1280x720 per launch: crop (one rectangle size, per-stream position is a
-        # pointer offset) + luma + apply-mask (static mask) + threshold + label
+        # configs[3]: 64 camera streams 1280x720, ONE launch set per time step over the 64 current frames
+        # (video_analysis_b200/streams.py): crop (per-stream rectangle position) + luma + apply-mask (per-stream
+        # static mask) + threshold + label
+        from video_analysis_b200.streams import MultiStreamSegmenter
+        from video_analysis_b200.io.base import VideoBase
         w, h, n_streams = 1280, 720, 64
         cw, ch_ = 1024, 576
+        rng = np.random.default_rng(4)
+        rects = [(int(rng.integers(0, w - cw)), int(rng.integers(0, h - ch_)), cw, ch_) for _ in range(n_streams)]
+        m = np.zeros((n_streams, ch_, cw), np.uint8)
+        for s_ in range(n_streams):
+            m[s_, 20 + s_ % 7:-30, 40:-10 - s_ % 5] = 1
+        seg = MultiStreamSegmenter([VideoBase(size=(w, h), frame_count=1, is_color=True) for _ in range(n_streams)], rects, m,
+                                   threshold=110)
         vids = [synth.generate(rt, 3, k * n_streams, n_streams, w, h, 6) for k in range(2)]
-        m = np.zeros((ch_, cw), np.uint8)
-        m[20:-30, 40:-10] = 1
-        mask_dev = t.from_numpy(m).to(rt.device)
-
-        def run(i):
-            rgb = vids[i % 2]
-            g = rt.luma(rgb, rect=(128, 72, cw, ch_))
-            g = rt.apply_mask(g, mask_dev)
-            bits = rt.threshold(g, 110)
-            rt.label(bits, 4)
-        med, mn = timed(t, run, args.iters)
+        med, mn = timed(t, lambda i: seg.step_device(vids[i % 2]), args.iters)
         n = cw * ch_
-        report('configs[3] 64 x 1280x720 streams: crop+mono, apply-mask, threshold, label', n_streams, med, mn,
-               (4 * n + 3 * n + (n + n / 8) + (n / 8 + 4 * n)) * n_streams,
-               'crop 1024x576; bytes = luma 4N + mask 3N + threshold 1.125N + label 4.125N per cropped frame; '
-               'includes the allocation of the intermediates by the caching allocator')
+        report('configs[3] 64 x 1280x720 streams per launch: crop+mono, apply-mask, threshold, label', n_streams, med, mn,
+               ((3 * n + n + n / 8) + (n / 8 + 4 * n)) * n_streams,
+               'crop 1024x576 at a position per stream, mask per stream; bytes = fused front (3N RGB + N mask in, N/8 bits '
+               'out) + label 4.125N per cropped frame')
 
     if 'stencil' in only:
         # configs[4]: blur s=15 (91 taps) -> resize 0.5 -> threshold -> 7x7 close, open -> label

@@ -732,3 +732,175 @@ extern "C" int va_resize_lanczos4_u8(va_ctx *ctx, va_stream stream,
     VA_CUDA(ctx, cudaFreeAsync(dev, (cudaStream_t)stream));
     return VA_OK;
 }
+
+// =================================================================================
+// BASELINE.json configs[3]: concurrent camera streams batched on the leading axis of one launch, every
+// stream with its own crop rectangle position (FilterCrop, video/filters.py:158-248, one rectangle size for
+// the batch) followed by FilterMonochrome (video/filters.py:359-374):
+//     out[s] = mono(in[s][top_s : top_s + h, left_s : left_s + w])          xy = {left_0, top_0, left_1, top_1, ...}
+// A crop is addressing only, but per-stream offsets cannot be folded into one base pointer + frame stride, so
+// they come as a device table.  One thread per 4 output pixels (12 source bytes, word loads when the
+// stream's offset leaves them aligned); the arithmetic is K1's (va_luma_x4).
+// =================================================================================
+__global__ void __launch_bounds__(256)
+luma_crop_multi_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstride,
+                       uint8_t *__restrict__ out, size_t out_pitch, size_t out_fstride,
+                       int w, int h, int batch, int mode, const int *__restrict__ xy) {
+    const unsigned quads = (unsigned)((w + 3) >> 2);
+    const unsigned long long total = (unsigned long long)quads * h * batch;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned q = (unsigned)(i % quads);
+        const unsigned long long rest = i / quads;
+        const unsigned y = (unsigned)(rest % h), s = (unsigned)(rest / h);
+        const int left = xy[2 * s], top = xy[2 * s + 1];
+        const uint8_t *p = in + (size_t)s * in_fstride + (size_t)(top + (int)y) * in_pitch + (size_t)(left + 4 * (int)q) * 3;
+        uint8_t *o = out + (size_t)s * out_fstride + (size_t)y * out_pitch + 4 * q;
+        const int np = min(4, w - 4 * (int)q);
+        unsigned wd[3] = {0, 0, 0};
+        if (np == 4 && (reinterpret_cast<size_t>(p) & 3) == 0) {
+            const unsigned *pw = reinterpret_cast<const unsigned *>(p);
+            wd[0] = __ldg(pw); wd[1] = __ldg(pw + 1); wd[2] = __ldg(pw + 2);
+        } else {
+            for (int k = 0; k < 3 * np; k++) wd[k >> 2] |= (unsigned)__ldg(p + k) << (8 * (k & 3));
+        }
+        const unsigned r = va_luma_x4(wd[0], wd[1], wd[2], mode);
+        if (np == 4 && (reinterpret_cast<size_t>(o) & 3) == 0) *reinterpret_cast<unsigned *>(o) = r;
+        else for (int k = 0; k < np; k++) o[k] = (uint8_t)(r >> (8 * k));
+    }
+}
+
+// w % 16 == 0, word-aligned source rows, 16-byte aligned destination rows: one thread per 16 output pixels.  The 48
+// source bytes start at any byte offset (3 * left_s): 13 aligned words, realigned by funnel shifts.
+__global__ void __launch_bounds__(256)
+luma_crop_multi16_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstride,
+                         uint8_t *__restrict__ out, size_t out_pitch, size_t out_fstride,
+                         int w, int h, int batch, int mode, const int *__restrict__ xy) {
+    const unsigned groups = (unsigned)(w >> 4);
+    const unsigned long long total = (unsigned long long)groups * h * batch;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned g = (unsigned)(i % groups);
+        const unsigned long long rest = i / groups;
+        const unsigned y = (unsigned)(rest % h), s = (unsigned)(rest / h);
+        const int left = xy[2 * s], top = xy[2 * s + 1];
+        const uint8_t *p = in + (size_t)s * in_fstride + (size_t)(top + (int)y) * in_pitch + (size_t)(left + 16 * (int)g) * 3;
+        const unsigned mis = (unsigned)(reinterpret_cast<size_t>(p) & 3);
+        const unsigned *pw = reinterpret_cast<const unsigned *>(p - mis);
+        unsigned a[13];
+#pragma unroll
+        for (int k = 0; k < 12; k++) a[k] = __ldg(pw + k);
+        a[12] = mis ? __ldg(pw + 12) : 0u;
+        const unsigned sh = 8 * mis;
+        unsigned r[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const unsigned w0 = __funnelshift_r(a[3 * k], a[3 * k + 1], sh);
+            const unsigned w1 = __funnelshift_r(a[3 * k + 1], a[3 * k + 2], sh);
+            const unsigned w2 = __funnelshift_r(a[3 * k + 2], a[3 * k + 3], sh);
+            r[k] = va_luma_x4(w0, w1, w2, mode);
+        }
+        *reinterpret_cast<uint4 *>(out + (size_t)s * out_fstride + (size_t)y * out_pitch + 16 * g) = make_uint4(r[0], r[1], r[2], r[3]);
+    }
+}
+
+// The whole front of configs[3] in one pass: crop position per stream + monochrome + static mask (one per stream, or
+// one for all with mask_fstride = 0, or none) + threshold -> packed bits.  w % 32 == 0; a lane pair assembles one
+// 32-bit mask word.  3N bytes of RGB and N bytes of mask in, N/8 out -- instead of three kernels moving 8.1N.
+__global__ void __launch_bounds__(256)
+streams_threshold_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstride,
+                         const uint8_t *__restrict__ smask, size_t smask_pitch, size_t smask_fstride,
+                         uint32_t *__restrict__ bits, size_t bits_pitch_w, size_t bits_fstride_w,
+                         int w, int h, int batch, int mode, int thr, const int *__restrict__ xy) {
+    const unsigned groups = (unsigned)(w >> 4);
+    const unsigned long long total = (unsigned long long)groups * h * batch;
+    const unsigned lane = threadIdx.x & 31;
+    for (unsigned long long base = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) - lane; base < total;
+         base += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long i = base + lane;
+        unsigned m16 = 0;
+        unsigned g = 0, y = 0, s = 0;
+        if (i < total) {
+            g = (unsigned)(i % groups);
+            const unsigned long long rest = i / groups;
+            y = (unsigned)(rest % h);
+            s = (unsigned)(rest / h);
+            const int left = xy[2 * s], top = xy[2 * s + 1];
+            const uint8_t *p = in + (size_t)s * in_fstride + (size_t)(top + (int)y) * in_pitch + (size_t)(left + 16 * (int)g) * 3;
+            const unsigned mis = (unsigned)(reinterpret_cast<size_t>(p) & 3);
+            const unsigned *pw = reinterpret_cast<const unsigned *>(p - mis);
+            unsigned a[13];
+#pragma unroll
+            for (int k = 0; k < 12; k++) a[k] = __ldg(pw + k);
+            a[12] = mis ? __ldg(pw + 12) : 0u;
+            const unsigned sh = 8 * mis;
+            uint4 mk = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+            if (smask) mk = __ldg(reinterpret_cast<const uint4 *>(smask + (size_t)s * smask_fstride + (size_t)y * smask_pitch + 16 * g));
+            const unsigned mw[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const unsigned w0 = __funnelshift_r(a[3 * k], a[3 * k + 1], sh);
+                const unsigned w1 = __funnelshift_r(a[3 * k + 1], a[3 * k + 2], sh);
+                const unsigned w2 = __funnelshift_r(a[3 * k + 2], a[3 * k + 3], sh);
+                const unsigned r = va_luma_x4(w0, w1, w2, mode);
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const int v = ((mw[k] >> (8 * b)) & 0xffu) ? (int)((r >> (8 * b)) & 0xffu) : 0;     // apply-mask
+                    m16 |= (v > thr ? 1u : 0u) << (4 * k + b);
+                }
+            }
+        }
+        const unsigned other = __shfl_down_sync(0xffffffffu, m16, 1);
+        if (i < total && !(g & 1))
+            bits[(size_t)s * bits_fstride_w + (size_t)y * bits_pitch_w + (g >> 1)] = m16 | (other << 16);
+    }
+}
+
+extern "C" int va_streams_threshold_bits(va_ctx *ctx, va_stream stream,
+                                         const uint8_t *in, size_t in_pitch, size_t in_fstride, int in_w, int in_h,
+                                         const uint8_t *smask, size_t smask_pitch, size_t smask_fstride,
+                                         uint32_t *bits, size_t bits_pitch_w, size_t bits_fstride_w,
+                                         int w, int h, int batch, int mode, int thr, const int32_t *xy) {
+    VA_CHECK_CTX(ctx);
+    VA_REQUIRE(ctx, in && bits && xy, "va_streams_threshold_bits: null pointer");
+    VA_REQUIRE(ctx, w > 0 && h > 0 && batch > 0 && w <= in_w && h <= in_h, "va_streams_threshold_bits: bad size");
+    VA_REQUIRE(ctx, mode >= -1 && mode <= 2, "va_streams_threshold_bits: unsupported conversion method to monochrome: %d", mode);
+    VA_REQUIRE(ctx, in_pitch >= (size_t)3 * in_w && bits_pitch_w >= (size_t)(w + 31) / 32 && (!smask || smask_pitch >= (size_t)w),
+               "va_streams_threshold_bits: pitch smaller than a row");
+    if (!(w % 32 == 0 && va_aligned(in, 4) && in_pitch % 4 == 0 && in_fstride % 4 == 0 &&
+          (!smask || (va_aligned(smask, 16) && smask_pitch % 16 == 0 && smask_fstride % 16 == 0))))
+        VA_FAIL(ctx, VA_ERR_UNSUPPORTED, "va_streams_threshold_bits: needs w %% 32 == 0, word-aligned frames and 16-byte aligned "
+                                         "mask rows (use va_luma_crop_multi_u8 + va_apply_mask_u8 + va_threshold_bits)");
+    const long long items = (long long)(w / 16) * h * batch;
+    const int grid = va_grid(ctx, (items + 255) / 256, 16);
+    auto kfn = streams_threshold_kernel;
+    VA_LAUNCH(ctx, kfn, grid, 256, 0, stream, in, in_pitch, in_fstride, smask, smask_pitch, smask_fstride, bits, bits_pitch_w,
+              bits_fstride_w, w, h, batch, mode, thr, (const int *)xy);
+    return VA_OK;
+}
+
+extern "C" int va_luma_crop_multi_u8(va_ctx *ctx, va_stream stream,
+                                     const uint8_t *in, size_t in_pitch, size_t in_fstride, int in_w, int in_h,
+                                     uint8_t *out, size_t out_pitch, size_t out_fstride,
+                                     int w, int h, int batch, int mode, const int32_t *xy) {
+    VA_CHECK_CTX(ctx);
+    VA_REQUIRE(ctx, in && out && xy, "va_luma_crop_multi_u8: null pointer");
+    VA_REQUIRE(ctx, w > 0 && h > 0 && batch > 0 && w <= in_w && h <= in_h, "va_luma_crop_multi_u8: bad size");
+    VA_REQUIRE(ctx, mode >= -1 && mode <= 2, "va_luma_crop_multi_u8: unsupported conversion method to monochrome: %d", mode);
+    VA_REQUIRE(ctx, in_pitch >= (size_t)3 * in_w && out_pitch >= (size_t)w, "va_luma_crop_multi_u8: pitch smaller than a row");
+    if (w % 16 == 0 && va_aligned(in, 4) && in_pitch % 4 == 0 && in_fstride % 4 == 0 && va_aligned(out, 16) &&
+        out_pitch % 16 == 0 && out_fstride % 16 == 0) {
+        const long long items16 = (long long)(w / 16) * h * batch;
+        const int grid16 = va_grid(ctx, (items16 + 255) / 256, 16);
+        auto k16 = luma_crop_multi16_kernel;
+        VA_LAUNCH(ctx, k16, grid16, 256, 0, stream, in, in_pitch, in_fstride, out, out_pitch, out_fstride, w, h, batch, mode,
+                  (const int *)xy);
+        return VA_OK;
+    }
+    const long long items = (long long)((w + 3) / 4) * h * batch;
+    const int grid = va_grid(ctx, (items + 255) / 256, 16);
+    auto kfn = luma_crop_multi_kernel;
+    VA_LAUNCH(ctx, kfn, grid, 256, 0, stream, in, in_pitch, in_fstride, out, out_pitch, out_fstride, w, h, batch, mode,
+              (const int *)xy);
+    return VA_OK;
+}

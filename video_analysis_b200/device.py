@@ -271,12 +271,25 @@ class DeviceRuntime(object):
         return out
 
     def apply_mask(self, src, mask_dev):
-        """ mask_dev: uint8 device tensor (h, w) """
+        """ mask_dev: uint8 device tensor (h, w) -- one static mask for the whole batch -- or (n, h, w): one per frame
+        of the batch (the streams of a multi-stream batch) """
         self.ensure(src.w, src.h, src.n)
         out = self.empty_u8(src.n, src.h, src.w, src.channels)
+        per_frame = mask_dev.dim() == 3
+        if per_frame and mask_dev.shape[0] != src.n:
+            raise ValueError('%d masks for a batch of %d frames' % (mask_dev.shape[0], src.n))
         self._check(self.lib.va_apply_mask_u8(self._h, self.stream, src.ptr, src.pitch, src.fstride,
-                                              mask_dev.data_ptr(), mask_dev.stride(0), 0,
+                                              mask_dev.data_ptr(), mask_dev.stride(-2), mask_dev.stride(0) if per_frame else 0,
                                               out.ptr, out.pitch, out.fstride, src.w, src.h, src.channels, src.n))
+        return out
+
+    def luma_crop_multi(self, src, xy_dev, w, h, mode=_lib.MONO_MEAN):
+        """ per-frame crop position (device int32 tensor (n, 2) of left, top), common size (w, h), then monochrome """
+        self.ensure(src.w, src.h, src.n)
+        out = self.empty_u8(src.n, h, w)
+        self._check(self.lib.va_luma_crop_multi_u8(self._h, self.stream, src.ptr, src.pitch, src.fstride, src.w, src.h,
+                                                   out.ptr, out.pitch, out.fstride, int(w), int(h), src.n, mode,
+                                                   xy_dev.data_ptr()))
         return out
 
     def ema_diff_thresh(self, src, bg, alpha, thr, first_frame_inits):
