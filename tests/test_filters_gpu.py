@@ -453,3 +453,18 @@ def test_config4_streams_batched_per_launch():
         assert outs[0][2][1][s] == n and np.array_equal(outs[0][2][0][s], lab)
     with pytest.raises(ValueError):
         MultiStreamSegmenter([VideoMemory(v, copy_data=False) for v in vids], rects[:-1] + [(0, 0, 100, 100)])
+
+
+def test_randomised_differential_parity():
+    """ tests/fuzz_parity.py for 20 seconds: random sizes / parameters / input statistics, every stage of the chain, the
+    resize modes, labelling and the multi-stream front against the oracle, bit for bit """
+    mods()
+    import json
+    import os
+    import subprocess
+    import sys
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'fuzz_parity.py')
+    p = subprocess.run([sys.executable, script, '--cases', '100000', '--seconds', '20', '--seed', '7'],
+                       capture_output=True, text=True, timeout=600)
+    out = json.loads(p.stdout.strip().splitlines()[-1])
+    assert p.returncode == 0 and not out['failures'] and sum(out['cases_run'].values()) > 200, out
