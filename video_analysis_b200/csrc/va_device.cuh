@@ -90,9 +90,11 @@ __device__ __forceinline__ unsigned va_div3_h2(unsigned p) {
 
 // (c0 + c1 + c2) / 3 for four interleaved RGB pixels held in three words
 __device__ __forceinline__ unsigned va_mean3_x4(unsigned w0, unsigned w1, unsigned w2) {
+    // pixels 1 and 2 straddle two words: one PRMT (alu pipe) gathers their bytes, so that every pixel costs one
+    // dp4a on the fmaheavy pipe (the pipe the blur's own dot products saturate) instead of two
     const unsigned s0 = __dp4a(w0, 0x00010101u, 0x6400u);
-    const unsigned s1 = __dp4a(w0, 0x01000000u, __dp4a(w1, 0x00000101u, 0x6400u));
-    const unsigned s2 = __dp4a(w1, 0x01010000u, __dp4a(w2, 0x00000001u, 0x6400u));
+    const unsigned s1 = __dp4a(__byte_perm(w0, w1, 0x0543), 0x00010101u, 0x6400u);
+    const unsigned s2 = __dp4a(__byte_perm(w1, w2, 0x0432), 0x00010101u, 0x6400u);
     const unsigned s3 = __dp4a(w2, 0x01010100u, 0x6400u);
     const unsigned q01 = va_div3_h2(__byte_perm(s0, s1, 0x5410));
     const unsigned q23 = va_div3_h2(__byte_perm(s2, s3, 0x5410));
