@@ -170,7 +170,7 @@ class SegmentChain(object):
                                       largest.data_ptr(), self.w, self.h, n, self.connectivity))
         return stats, counts, largest
 
-    # ---- two-stream software pipeline over consecutive device batches -----------------------------------
+    # ---- three-stream software pipeline over consecutive device batches -----------------------------------
     def run_device_pipelined(self, rgb, labels, counts, blur=None):
         """ Same result as `run_device`, but the chain is split over three internal streams:
         front = RGB -> luma -> blur -> background/threshold (the sequential state lives here),

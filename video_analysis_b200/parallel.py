@@ -137,7 +137,7 @@ class ShardedSegmentChain(object):
         S = self._partial_state(blurs, covers_shard=(m == nb))
         n_total = sum(b.n for b in rgb_batches)
         carry = exchange_carry(S, n_total, ch.alpha, lambda c, s, sc: rt.ema_fold(c, s, sc, ch.w, ch.h), self.group)
-        # pass 2: the ordinary two-stream chain from the exact incoming state
+        # pass 2: the ordinary pipelined chain (three streams) from the exact incoming state
         if carry is None:
             ch.reset()
         else:
