@@ -89,3 +89,42 @@ def test_carry_exchange_gloo(world):
         p.join(120)
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
     assert sorted(q.get(timeout=5) for _ in range(world)) == list(range(world))
+
+
+def _stats_worker(rank, world, port, total, out):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from video_analysis_b200.parallel import merge_mean_m2
+    rng = np.random.default_rng(3)
+    video = rng.integers(0, 256, (total, 5, 7)).astype(np.uint8)
+    a, b = shard_range(total, rank, world)
+    mean, m2 = np.zeros(video.shape[1:]), np.zeros(video.shape[1:])
+    for n, frame in enumerate(video[a:b]):                     # the reference's recurrence on this rank's frames
+        delta = frame - mean
+        mean = mean + delta / (n + 1)
+        m2 = m2 + delta * (frame - mean)
+    tm, tm2, tn = merge_mean_m2(torch.from_numpy(mean), torch.from_numpy(m2), b - a)
+    ref_mean, ref_std = ops.measure_mean_std(video)
+    assert tn == total
+    assert np.allclose(tm.numpy(), ref_mean, rtol=1e-12, atol=1e-10)
+    assert np.allclose(np.sqrt(tm2.numpy() / (tn - 1)), ref_std, rtol=1e-10, atol=1e-9)
+    only_mean, none, _ = merge_mean_m2(torch.from_numpy(mean), None, b - a)
+    assert none is None and np.allclose(only_mean.numpy(), ref_mean, rtol=1e-12, atol=1e-10)
+    dist.barrier()
+    dist.destroy_process_group()
+    out.put(rank)
+
+
+@pytest.mark.parametrize('world,total', [(2, 41), (4, 3)])
+def test_temporal_statistics_merge_gloo(world, total):
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_stats_worker, args=(r, world, port, total, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    assert sorted(q.get(timeout=5) for _ in range(world)) == list(range(world))

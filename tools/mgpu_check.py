@@ -56,6 +56,18 @@ def main():
     print('rank %d frames [%d,%d): labels identical=%s (pixel agreement %.6f), counts agreement %.4f, bg max rel err %.2e'
           % (rank, a, b, exact, same_labels, same_counts, bg_err), flush=True)
     ok = bg_err < 1e-5 and same_labels > 0.9999 and same_counts > 0.99 and (rank > 0 or (exact and same_counts == 1.0))
+    # temporal statistics of a frame-sharded video (merge of per-rank mean / M2) against the sequential recurrence
+    import numpy as np
+    from video_analysis_b200.analysis.video import measure_mean_std
+    from video_analysis_b200.io.memory import VideoMemory
+    from video_analysis_b200.parallel import measure_mean_std_sharded
+    vid = VideoMemory(np.random.default_rng(5).integers(0, 256, (37, 48, 64, 3), dtype=np.uint8), copy_data=False)
+    m_par, s_par = measure_mean_std_sharded(vid, batch=8, device=local)
+    m_seq, s_seq = measure_mean_std(vid, batch=8, device=local)
+    stats_err = max(float(np.abs(m_par - m_seq).max()), float(np.abs(s_par - s_seq).max()))
+    print('rank %d temporal mean / std of a sharded video: max abs deviation from the sequential recurrence %.2e' % (rank, stats_err),
+          flush=True)
+    ok = ok and stats_err < 1e-9
     flag = torch.tensor([1 if ok else 0], device=rt.device)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()

@@ -63,6 +63,67 @@ def exchange_carry(S_local, n_local, alpha, fold, group=None):
     return carry
 
 
+def merge_mean_m2(mean, m2, n_local, group=None):
+    """ temporal statistics of a frame-sharded video (video/analysis/video.py:26-55): every
+    rank holds the running mean and the sum of squared deviations M2 of ITS frame range (float64 torch tensors,
+    `m2` may be None for the mean alone) and the number of frames; one all-gather of those per-rank frames
+    and the pairwise combination of Chan et al. in rank order,
+
+        n = nA + nB,  d = meanB - meanA,  mean = meanA + d nB / n,  M2 = M2A + M2B + d^2 nA nB / n,
+
+    give every rank the statistics of the whole video (the same exchange pattern as the background carry:
+    one frame-sized message per rank, nothing else crosses GPUs).  Agrees with the sequential recurrence to
+    float64 rounding, not bit for bit.  Returns (mean, m2, n). """
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    means = [torch.empty_like(mean) for _ in range(world)]
+    dist.all_gather(means, mean.contiguous(), group=group)
+    m2s = None
+    if m2 is not None:
+        m2s = [torch.empty_like(m2) for _ in range(world)]
+        dist.all_gather(m2s, m2.contiguous(), group=group)
+    n_t = torch.tensor([n_local], dtype=torch.int64, device=mean.device)
+    counts = [torch.empty_like(n_t) for _ in range(world)]
+    dist.all_gather(counts, n_t, group=group)
+    counts = [int(c.item()) for c in counts]
+    tot_mean, tot_m2, tot_n = None, None, 0
+    for j in range(world):
+        nb = counts[j]
+        if nb == 0:
+            continue
+        if tot_n == 0:
+            tot_mean, tot_m2, tot_n = means[j].clone(), (m2s[j].clone() if m2s else None), nb
+            continue
+        n = tot_n + nb
+        d = means[j] - tot_mean
+        if tot_m2 is not None:
+            tot_m2 += m2s[j] + d * d * (tot_n * nb / n)
+        tot_mean += d * (nb / n)
+        tot_n = n
+    return tot_mean, tot_m2, tot_n
+
+
+def measure_mean_std_sharded(video, batch=32, device=None, group=None):
+    """ `analysis.video.measure_mean_std` over a video whose frames are sharded by rank (`shard_range`): each
+    rank folds its own frames on its GPU, `merge_mean_m2` combines.  Returns what the reference returns:
+    (mean, sqrt(M2 / index of the last frame)). """
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from .analysis.video import _fold
+    from .io.base import VideoSlice
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    a, b = shard_range(video.frame_count, rank, world)
+    part = VideoSlice(video, a, b)
+    mean, m2, n, last = _fold(part, True, batch, device)
+    dev = torch.device('cuda', torch.cuda.current_device()) if dist.get_backend(group) == 'nccl' else torch.device('cpu')
+    tm, tm2, tn = merge_mean_m2(torch.from_numpy(mean).to(dev), torch.from_numpy(m2).to(dev), n, group)
+    if tn - 1 < 2:
+        return last, 0
+    return tm.cpu().numpy(), np.sqrt(tm2.cpu().numpy() / (tn - 1))
+
+
 class ShardedSegmentChain(object):
     """ runs a SegmentChain over this rank's frame range of a video sharded over the
     ranks of a torch.distributed group (NCCL) """
