@@ -193,7 +193,19 @@ def gpu_arm(args):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        # stdout carries exactly one JSON line: NCCL prints its version banner (NCCL_DEBUG=VERSION in this image) with a
+        # plain printf when the communicator is created, so file descriptor 1 points at stderr until that has happened
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     rt = get_runtime(local)
     B, K, Wm = args.batch, args.steps, args.warmup
     N = W * H
