@@ -327,6 +327,22 @@ def gpu_arm(args):
         reg_s = float(tmax.item())
     reg_fps = world * Ke * Be / reg_s
 
+    # ---- e2e with int16 labels (ndimage.label(..., output=np.int16)): the same label image in half the bytes
+    i16_chain = SegmentChain((W, H), batch=Be, fuse=not args.no_fuse, label_dtype=np.int16, **CHAIN)
+    for lab, cnt in i16_chain.process_blocks(blocks(max(3, min(Wm, 5)))):
+        sink += int(cnt[0])
+    barrier()
+    t0 = time.perf_counter()
+    for lab, cnt in i16_chain.process_blocks(blocks(Ke)):
+        sink += int(cnt[-1]) + int(lab[0, H // 2, W // 2])
+    torch.cuda.synchronize()
+    i16_s = time.perf_counter() - t0
+    if world > 1:
+        tmax = torch.tensor([i16_s], device=rt.device)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        i16_s = float(tmax.item())
+    i16_fps = world * Ke * Be / i16_s
+
     if rank == 0:
         line = {
             'metric': 'frames/sec full filter+segment chain', 'value': round(fps, 1), 'unit': 'frames/s',
@@ -346,6 +362,10 @@ def gpu_arm(args):
                                  'd2h_bytes_per_step': Be * (MAXR * 80 + 8), 'steps': Ke, 'frames_per_step': Be,
                                  'api': 'SegmentChain.process_blocks(max_regions=%d): pinned host frames in, per-region '
                                         'moments + bounding boxes + counts out (no label image crosses PCIe)' % MAXR},
+            'e2e_labels_int16': {'value': round(i16_fps, 1), 'unit': 'frames/s', 'h2d_bytes_per_step': Be * N * 3,
+                                 'd2h_bytes_per_step': Be * N * 2 + Be * 4, 'steps': Ke, 'frames_per_step': Be,
+                                 'api': 'SegmentChain(label_dtype=np.int16).process_blocks: pinned host frames in, int16 labels '
+                                        '(ndimage.label(..., output=np.int16)) + counts out'},
             'gpu_launches': int(launches),
             'roofline': roof,
         }

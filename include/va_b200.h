@@ -226,6 +226,14 @@ int va_streams_threshold_bits(va_ctx *ctx, va_stream stream,
                               uint32_t *bits, size_t bits_pitch_w, size_t bits_fstride_w,
                               int w, int h, int batch, int mode, int thr, const int32_t *xy);
 
+/* va_label_write with int16 labels -- ndimage.label(mask, output=np.int16) at the same call site: half the bytes to
+ * write and to copy to the host.  The caller checks counts[] <= 32767 first (scipy raises "insufficient bit-depth in
+ * requested output type"; larger labels would wrap). */
+int va_label_write_i16(va_ctx *ctx, va_stream stream,
+                       const uint32_t *mask, size_t mask_pitch_w, size_t mask_fstride_w,
+                       int16_t *labels, size_t labels_pitch_e, size_t labels_fstride_e,
+                       int w, int h, int batch, int slot);
+
 /* VideoComposer.highlight_mask, video/io/composer.py:131-154: where the mask is set,
  * frame[mask, channel] = uint8(strength + (255 - strength) / 255 * frame[mask, channel]).  lut256 (HOST pointer,
  * copied into the launch) is that expression on 0..255; channel -1 = all channels, 0..2 = one channel of an

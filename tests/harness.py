@@ -416,6 +416,19 @@ def label_two_batches_split(ctx, words_a, words_b, W, connectivity=4):
     return out
 
 
+def label_i16(ctx, words, W, connectivity=4, lab_pad=0):
+    """ forest + int16 label write -> (labels int16 [B, H, W], counts int32 [B]) """
+    be = ctx.be
+    B, H, Wp = words.shape
+    src = Img(be, B, H, Wp, np.uint32, data=words)
+    lab = Img(be, B, H, W, np.int16, W + lab_pad)
+    cnt = Img(be, 1, 1, B, np.int32)
+    ctx.check(ctx.lib.va_label_forest(ctx.h, be.stream, src.ptr, src.pitch, src.fstride, cnt.ptr, W, H, B, connectivity, 0))
+    ctx.check(ctx.lib.va_label_write_i16(ctx.h, be.stream, src.ptr, src.pitch, src.fstride, lab.ptr, lab.pitch, lab.fstride,
+                                         W, H, B, 0))
+    return lab.get(), cnt.get()[0, 0]
+
+
 def region_areas(ctx, labels, max_labels):
     be = ctx.be
     B, H, W = labels.shape

@@ -468,3 +468,34 @@ def test_randomised_differential_parity():
                        capture_output=True, text=True, timeout=600)
     out = json.loads(p.stdout.strip().splitlines()[-1])
     assert p.returncode == 0 and not out['failures'] and sum(out['cases_run'].values()) > 200, out
+
+
+def test_segment_chain_int16_labels(frames, ref):
+    """ label_dtype=np.int16 (ndimage.label(..., output=np.int16)): same labels in half the bytes, through the host pipeline,
+    the device call and the pipelined device call """
+    mods()
+    import torch
+    from video_analysis_b200.chain import SegmentChain
+    from video_analysis_b200.device import get_runtime
+    seg = SegmentChain((320, 240), batch=16, label_dtype=np.int16)
+    labels, counts = seg.process(frames)
+    assert labels.dtype == np.int16 and np.array_equal(labels, ref['labels']) and list(counts) == list(ref['counts'])
+    assert np.array_equal(seg.background.view(np.uint32), ref['bg'].view(np.uint32))
+    rt = get_runtime()
+    for piped in (False, True):
+        ch = SegmentChain((320, 240), batch=8, label_dtype=np.int16)
+        outs = []
+        for a in range(0, len(frames), 8):
+            rgb = rt.upload(frames[a:a + 8])
+            lab = rt.empty_i16(rgb.n, 240, 320)
+            cnt = torch.empty((rgb.n,), dtype=torch.int32, device=rt.device)
+            if piped:
+                ch.run_device_pipelined(rgb, lab, cnt)
+                ch.pipeline_sync()
+            else:
+                ch.run_device(rgb, lab, cnt)
+            torch.cuda.synchronize()
+            outs.append(lab.t[:, :, :320].cpu().numpy())
+        assert np.array_equal(np.concatenate(outs), ref['labels']), piped
+    with pytest.raises(ValueError):
+        SegmentChain((320, 240), label_dtype=np.int8)

@@ -9,6 +9,7 @@ thread-emulation shim, small sizes only -- a logic check that runs without a GPU
 import os
 
 import numpy as np
+from scipy import ndimage
 import pytest
 
 from oracle import ops, synth
@@ -519,6 +520,23 @@ def test_label_forest_and_write_halves_with_two_scratch_slots(be, ctx):
                     assert cnt[t] == n and np.array_equal(lab[t], ref), (H, W, conn, t)
     with pytest.raises(ValueError):
         hz.label_two_batches_split(ctx, hz.pack_bits_np(rmask(1, (1, 8, 8), .5)), hz.pack_bits_np(rmask(1, (1, 8, 8), .5)), 8, 5)
+
+
+def test_label_int16_output(be, ctx):
+    """ ndimage.label(mask, output=np.int16): same numbering, half the bytes """
+    for (H, W) in sizes(be, [(40, 70), (9, 131)], [(1080, 1920), (271, 1003)]):
+        for p in (0.03, 0.55):
+            m = rmask(H + int(100 * p), (2, H, W), p)
+            if H * W > 100000:            # keep the component count of the large frames below 32767: 8 x 8 blocks of a coarse mask
+                coarse = rmask(H + int(100 * p), (2, (H + 7) // 8, (W + 7) // 8), p)
+                m = np.kron(coarse, np.ones((1, 8, 8), np.uint8))[:, :H, :W]
+            for pad in (0, 3, 4):
+                lab, cnt = hz.label_i16(ctx, hz.pack_bits_np(m), W, 4, pad)
+                assert lab.dtype == np.int16
+                for t in range(2):
+                    ref = np.zeros((H, W), np.int16)
+                    n = ndimage.label(m[t], output=ref)
+                    assert cnt[t] == n and np.array_equal(lab[t], ref), (H, W, p, pad, t)
 
 
 def test_label_capacity_error(be, ctx):

@@ -85,6 +85,7 @@ SIGNATURES = {
     'va_label_write': (c_int, [c_void_p, c_void_p] + _IMG + _IMG + [c_int, c_int, c_int, c_int]),
     'va_luma_crop_multi_u8': (c_int, [c_void_p, c_void_p] + _IMG + [c_int, c_int] + _IMG + [c_int, c_int, c_int, c_int, c_void_p]),
     'va_streams_threshold_bits': (c_int, [c_void_p, c_void_p] + _IMG + [c_int, c_int] + _IMG + _IMG + [c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    'va_label_write_i16': (c_int, [c_void_p, c_void_p] + _IMG + _IMG + [c_int, c_int, c_int, c_int]),
     'va_lut_u8': (c_int, [c_void_p, c_void_p] + _IMG + _IMG + [c_int, c_int, c_int, c_void_p]),
     'va_time_diff_i16': (c_int, [c_void_p, c_void_p] + _IMG + _IMG + [c_int, c_int, c_int]),
     'va_rot90_u8': (c_int, [c_void_p, c_void_p] + _IMG + _IMG + [c_int, c_int, c_int, c_int, c_int]),

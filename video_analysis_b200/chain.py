@@ -24,7 +24,8 @@ from .filters import COLOR_CHANNELS
 
 class SegmentChain(object):
     def __init__(self, size, sigma=2.0, alpha=0.05, threshold=25.0, morph_op='open', morph_shape='rect',
-                 morph_ksize=3, connectivity=4, mono_mode='mean', batch=64, device=None, fuse=True, depth=3):
+                 morph_ksize=3, connectivity=4, mono_mode='mean', batch=64, device=None, fuse=True, depth=3,
+                 label_dtype=np.int32):
         self.w, self.h = int(size[0]), int(size[1])
         self.sigma, self.alpha, self.threshold = float(sigma), float(alpha), float(threshold)
         if morph_op is not None and morph_op not in _lib.MORPH_OPS:
@@ -41,6 +42,11 @@ class SegmentChain(object):
         self.kx, self.ky = (morph_ksize, morph_ksize) if np.isscalar(morph_ksize) else morph_ksize
         self.connectivity = connectivity
         self.batch, self.fuse, self.depth = int(batch), bool(fuse), int(depth)
+        # label_dtype: np.int32 (what ndimage.label returns by default) or np.int16 (ndimage.label(..., output=np.int16)):
+        # half the bytes for the device to write and for PCIe to carry; frames with more than 32767 regions raise
+        self.label_dtype = np.dtype(label_dtype)
+        if self.label_dtype not in (np.dtype(np.int32), np.dtype(np.int16)):
+            raise ValueError('label_dtype must be int32 or int16')
         self.rt = get_runtime(device)
         self.rt.ensure(self.w, self.h, self.batch)
         self._bg = self.rt.empty_f32(self.h, self.w)
@@ -75,9 +81,27 @@ class SegmentChain(object):
         if (rgb.w, rgb.h, rgb.channels) != (self.w, self.h, 3):
             raise ValueError('chain built for %dx%d colour frames, got %dx%dx%d' % (self.w, self.h, rgb.w, rgb.h, rgb.channels))
         if labels is None and self.connectivity:
-            labels = rt.empty_i32(n, self.h, self.w)
+            labels = self._empty_labels(n)
         if counts is None and self.connectivity:
             counts = t.empty((n,), dtype=t.int32, device=rt.device)
+        if labels is not None and labels.kind == 'i16':
+            # int16 labels: the chain as separate calls (va_chain_run writes int32 labels), forest + int16 write
+            b = self.blur_device(rgb, blur)
+            m = mask if mask is not None else rt.empty_bits(n, self.h, self.w)
+            rt._check(rt.lib.va_ema_diff_thresh(rt._h, rt.stream, *b.img(), self._bg.data_ptr(), self._bg.stride(0),
+                                                *m.img(), self.w, self.h, n, self.alpha, self.threshold,
+                                                0 if self._started else 1))
+            self._started = True
+            seg = m
+            if self.morph_op:
+                seg = morph if morph is not None else rt.empty_bits(n, self.h, self.w)
+                rt._check(rt.lib.va_morph_bits(rt._h, rt.stream, *m.img(), *seg.img(), self.w, self.h, n,
+                                               _lib.MORPH_OPS[self.morph_op], _lib.SE_SHAPES[self.morph_shape],
+                                               int(self.kx), int(self.ky)))
+            rt._check(rt.lib.va_label_forest(rt._h, rt.stream, *seg.img(), counts.data_ptr(), self.w, self.h, n,
+                                             self.connectivity, 0))
+            rt._check(rt.lib.va_label_write_i16(rt._h, rt.stream, *seg.img(), *labels.img(), self.w, self.h, n, 0))
+            return labels, counts
         d = _lib.ChainDesc(w=self.w, h=self.h, batch=n, mono_mode=self.mono_mode, sigma=self.sigma,
                            alpha=self.alpha, thr=self.threshold, first_frame_inits=0 if self._started else 1,
                            morph_op=_lib.MORPH_OPS[self.morph_op] if self.morph_op else -1,
@@ -99,6 +123,9 @@ class SegmentChain(object):
         rt.chain_run(d, io, self.w, self.h, n)
         self._started = True
         return labels, counts
+
+    def _empty_labels(self, n):
+        return self.rt.empty_i16(n, self.h, self.w) if self.label_dtype == np.int16 else self.rt.empty_i32(n, self.h, self.w)
 
     # ---- the two halves, used when the background state arrives between them (parallel.py) ------
     def blur_device(self, rgb, out=None):
@@ -231,7 +258,8 @@ class SegmentChain(object):
         with t.cuda.stream(p['write']):
             p['write'].wait_event(ev)
             p['write'].wait_event(p['ev_back'][slot])
-            rt._check(lib.va_label_write(h, rt.stream, *seg.img(), *labels.img(), self.w, self.h, n, slot))
+            write = lib.va_label_write_i16 if labels.kind == 'i16' else lib.va_label_write
+            rt._check(write(h, rt.stream, *seg.img(), *labels.img(), self.w, self.h, n, slot))
             p['ev_write'][slot].record(p['write'])
         return labels, counts
 
@@ -267,8 +295,8 @@ class SegmentChain(object):
         t, rt = torch(), self.rt
         if max_regions is None:
             if 'labels' not in s:
-                s['labels'] = rt.empty_i32(self.batch, self.h, self.w)
-                s['labels_host'] = t.empty(tuple(s['labels'].t.shape), dtype=t.int32, pin_memory=True)
+                s['labels'] = self._empty_labels(self.batch)
+                s['labels_host'] = t.empty(tuple(s['labels'].t.shape), dtype=s['labels'].t.dtype, pin_memory=True)
         elif s.get('stats') is None or s['stats'].shape[1] != max_regions:
             s['stats'] = t.empty((self.batch, max_regions, 10), dtype=t.int64, device=rt.device)
             s['largest'] = t.empty((self.batch,), dtype=t.int32, device=rt.device)
@@ -310,7 +338,7 @@ class SegmentChain(object):
                     self._s_run.wait_event(s['ev_out'])    # previous download of this slot's labels is done
                     rgb = DeviceBatch('u8', s['in'][:m], m, self.h, self.w, 3)
                     if max_regions is None:
-                        lab = DeviceBatch('i32', s['labels'].t[:m], m, self.h, self.w)
+                        lab = DeviceBatch(s['labels'].kind, s['labels'].t[:m], m, self.h, self.w)
                         self.run_device(rgb, lab, s['counts'][:m])
                     else:
                         self.regions_device(rgb, s['stats'][:m], s['counts'][:m], s['largest'][:m])
@@ -332,6 +360,8 @@ class SegmentChain(object):
         s, m, max_regions = item
         s['ev_out'].synchronize()
         if max_regions is None:
+            if self.label_dtype == np.int16 and m and int(s['counts_host'].numpy()[:m].max()) > 32767:
+                raise RuntimeError('insufficient bit-depth in requested output type')      # what ndimage.label raises
             return s['labels_host'].numpy()[:m, :, :self.w], s['counts_host'].numpy()[:m]
         return s['stats_host'].numpy()[:m], s['counts_host'].numpy()[:m], s['largest_host'].numpy()[:m]
 
@@ -360,7 +390,7 @@ class SegmentChain(object):
         counts (n,) int32), continuing the background model from earlier calls """
         n, blocks = self._blocks_of(frames)
         t = torch()
-        labels_t = t.empty((n, self.h, self.w), dtype=t.int32)       # filled by torch's multi-threaded host copy
+        labels_t = t.empty((n, self.h, self.w), dtype=t.int16 if self.label_dtype == np.int16 else t.int32)   # filled by torch's multi-threaded host copy
         labels = labels_t.numpy()
         counts = np.empty((n,), np.int32)
         k = 0

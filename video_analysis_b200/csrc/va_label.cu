@@ -393,11 +393,36 @@ label_scan_kernel(int *__restrict__ rowcnt, int *__restrict__ counts, int h) {
 //          the slab; one 16-byte store per lane, 512 contiguous bytes per warp instruction
 // The slab index is skewed by one word per 32 pixels so that both steps are conflict-free.
 #define LAB_SKEW(p) ((p) + ((p) >> 5))
+// four consecutive labels of a row starting at pixel x (x % 4 == 0): one 16-byte store for int32 labels, one 8-byte
+// store for int16 labels (scipy.ndimage.label(..., output=np.int16): half the bytes to write and to copy to the host)
+__device__ __forceinline__ void lab_store4(int32_t *lr, int x, int w, int4 v, bool vec) {
+    if (vec && x + 4 <= w) {
+        *reinterpret_cast<int4 *>(lr + x) = v;
+    } else {
+        if (x < w) lr[x] = v.x;
+        if (x + 1 < w) lr[x + 1] = v.y;
+        if (x + 2 < w) lr[x + 2] = v.z;
+        if (x + 3 < w) lr[x + 3] = v.w;
+    }
+}
+__device__ __forceinline__ void lab_store4(int16_t *lr, int x, int w, int4 v, bool vec) {
+    if (vec && x + 4 <= w) {
+        *reinterpret_cast<uint2 *>(lr + x) = make_uint2(((unsigned)v.x & 0xffffu) | ((unsigned)v.y << 16),
+                                                        ((unsigned)v.z & 0xffffu) | ((unsigned)v.w << 16));
+    } else {
+        if (x < w) lr[x] = (int16_t)v.x;
+        if (x + 1 < w) lr[x + 1] = (int16_t)v.y;
+        if (x + 2 < w) lr[x + 2] = (int16_t)v.z;
+        if (x + 3 < w) lr[x + 3] = (int16_t)v.w;
+    }
+}
+
+template <typename T>
 __global__ void __launch_bounds__(LAB_THREADS)
 label_write_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
                    const int *__restrict__ parent, int LOG, size_t pf, const int *__restrict__ rowoff,
                    const int *__restrict__ rowflag,
-                   int32_t *__restrict__ labels, size_t lpe, size_t lfe, int w, int h, int batch, int vec_out) {
+                   T *__restrict__ labels, size_t lpe, size_t lfe, int w, int h, int batch, int vec_out) {
     // grid = (groups of 8 rows, frames): one row per warp
     __shared__ int slab_all[LAB_WARPS][1024 + 32];
     const int lane = threadIdx.x & 31;
@@ -407,18 +432,11 @@ label_write_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
     {
         const int b = blockIdx.y, y = blockIdx.x * LAB_WARPS + (threadIdx.x >> 5);
         if (y >= h) return;
-        int32_t *lr = labels + (size_t)b * lfe + (size_t)y * lpe;
+        T *lr = labels + (size_t)b * lfe + (size_t)y * lpe;
         if (rowflag[(size_t)b * h + y] == 0) {
             // background row (flag of kernel A): zeros straight to memory, the mask is not even read
             const int4 z = make_int4(0, 0, 0, 0);
-            for (int x = 4 * lane; x < w; x += 128) {
-                if (vec_out && x + 4 <= w) {
-                    *reinterpret_cast<int4 *>(lr + x) = z;
-                } else {
-                    for (int k = 0; k < 4; k++)
-                        if (x + k < w) lr[x + k] = 0;
-                }
-            }
+            for (int x = 4 * lane; x < w; x += 128) lab_store4(lr, x, w, z, vec_out != 0);
             return;
         }
         const uint32_t *mr = mask + (size_t)b * mfw + (size_t)y * mpw;
@@ -433,15 +451,7 @@ label_write_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
             if (!__any_sync(FULL, wd != 0u)) {
                 // background only: zeros straight to memory
                 const int4 z = make_int4(0, 0, 0, 0);
-                for (int it = 0; 4 * it < nwords; it++) {
-                    const int x = 32 * base + 128 * it + 4 * lane;
-                    if (vec_out && x + 4 <= w) {
-                        *reinterpret_cast<int4 *>(lr + x) = z;
-                    } else {
-                        for (int k = 0; k < 4; k++)
-                            if (x + k < w) lr[x + k] = 0;
-                    }
-                }
+                for (int it = 0; 4 * it < nwords; it++) lab_store4(lr, 32 * base + 128 * it + 4 * lane, w, z, vec_out != 0);
                 carry = 32 * (base + 32);
                 continue;
             }
@@ -478,14 +488,7 @@ label_write_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
                     if (nib & 4u) v.z = slab[LAB_SKEW(px + 2)];
                     if (nib & 8u) v.w = slab[LAB_SKEW(px + 3)];
                 }
-                if (vec_out && x + 4 <= w) {
-                    *reinterpret_cast<int4 *>(lr + x) = v;
-                } else {
-                    if (x < w) lr[x] = v.x;
-                    if (x + 1 < w) lr[x + 1] = v.y;
-                    if (x + 2 < w) lr[x + 2] = v.z;
-                    if (x + 3 < w) lr[x + 3] = v.w;
-                }
+                lab_store4(lr, x, w, v, vec_out != 0);
             }
             __syncwarp();
             carry = __shfl_sync(FULL, top, 31);
@@ -548,14 +551,15 @@ static int label_forest(va_ctx *ctx, va_stream stream, const char *name,
     return VA_OK;
 }
 
+template <typename T>
 static int label_write(va_ctx *ctx, va_stream stream, const char *name,
                        const uint32_t *mask, size_t mask_pitch_w, size_t mask_fstride_w,
-                       int32_t *labels, size_t labels_pitch_e, size_t labels_fstride_e,
+                       T *labels, size_t labels_pitch_e, size_t labels_fstride_e,
                        int w, int h, int batch, int LOG, size_t pf, int slot) {
     int *parent, *rowcnt;
     { const int rc = label_scratch(ctx, name, slot, &parent, &rowcnt); if (rc != VA_OK) return rc; }
-    auto k = label_write_kernel;
-    const int vec_out = va_aligned(labels, 16) && labels_pitch_e % 4 == 0 && labels_fstride_e % 4 == 0;
+    auto k = label_write_kernel<T>;
+    const int vec_out = va_aligned(labels, 4 * sizeof(T)) && labels_pitch_e % 4 == 0 && labels_fstride_e % 4 == 0;
     const dim3 grid(va_div_up(h, LAB_WARPS), batch);
     VA_LAUNCH(ctx, k, grid, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, (const int *)parent, LOG, pf,
               (const int *)rowcnt, (const int *)(rowcnt + (size_t)ctx->max_h * ctx->max_batch),
@@ -592,6 +596,25 @@ extern "C" int va_label_forest(va_ctx *ctx, va_stream stream,
     size_t pf;
     return label_forest(ctx, stream, "va_label_forest", mask, mask_pitch_w, mask_fstride_w, counts, w, h, batch,
                         connectivity, &LOG, &pf, slot);
+}
+
+// the same write with int16 labels (scipy.ndimage.label(..., output=np.int16)); the caller checks counts[] <= 32767
+// (scipy raises "insufficient bit-depth in requested output type" otherwise; labels above 32767 would wrap here)
+extern "C" int va_label_write_i16(va_ctx *ctx, va_stream stream,
+                                  const uint32_t *mask, size_t mask_pitch_w, size_t mask_fstride_w,
+                                  int16_t *labels, size_t labels_pitch_e, size_t labels_fstride_e,
+                                  int w, int h, int batch, int slot) {
+    VA_CHECK_CTX(ctx);
+    VA_REQUIRE(ctx, mask && labels, "va_label_write_i16: null pointer");
+    VA_REQUIRE(ctx, w > 0 && h > 0 && batch > 0 && batch <= 65535, "va_label_write_i16: bad size");
+    VA_REQUIRE(ctx, labels_pitch_e >= (size_t)w && mask_pitch_w >= (size_t)((w + 31) / 32), "va_label_write_i16: pitch smaller than a row");
+    if (w > ctx->max_w || h > ctx->max_h || batch > ctx->max_batch)
+        VA_FAIL(ctx, VA_ERR_CAPACITY, "va_label_write_i16: %dx%dx%d exceeds the ctx capacity %dx%dx%d", w, h, batch,
+                ctx->max_w, ctx->max_h, ctx->max_batch);
+    int LOG = 5;
+    while (((size_t)1 << LOG) < ctx->lab_pitch) LOG++;
+    return label_write(ctx, stream, "va_label_write_i16", mask, mask_pitch_w, mask_fstride_w, labels, labels_pitch_e,
+                       labels_fstride_e, w, h, batch, LOG, ctx->lab_pitch * (size_t)ctx->max_h, slot);
 }
 
 extern "C" int va_label_write(va_ctx *ctx, va_stream stream,

@@ -129,6 +129,11 @@ class DeviceRuntime(object):
         t = torch().empty((n, h, pitch), dtype=torch().int32, device=self.device)
         return DeviceBatch('i32', t, n, h, w)
 
+    def empty_i16(self, n, h, w):
+        pitch = _round_up(w, 8)
+        t = torch().empty((n, h, pitch), dtype=torch().int16, device=self.device)
+        return DeviceBatch('i16', t, n, h, w)
+
     def empty_f32(self, h, w):
         return torch().empty((h, _round_up(w, 4)), dtype=torch().float32, device=self.device)
 
@@ -166,7 +171,7 @@ class DeviceRuntime(object):
                     np.lib.stride_tricks.as_strided(a, (batch.n, batch.h, batch.w, 3),
                                                     (a.strides[0], a.strides[1], 3, 1))
             return a
-        if batch.kind == 'i32':
+        if batch.kind in ('i32', 'i16'):
             return a[:, :, :batch.w]
         raise ValueError('packed masks are unpacked on the device before download')
 
