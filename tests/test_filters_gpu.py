@@ -499,3 +499,8 @@ def test_segment_chain_int16_labels(frames, ref):
         assert np.array_equal(np.concatenate(outs), ref['labels']), piped
     with pytest.raises(ValueError):
         SegmentChain((320, 240), label_dtype=np.int8)
+    F, VideoMemory = mods()
+    full = F.FilterLabel(F.FilterMorphology(F.FilterBackgroundMask(
+        F.FilterBlur(F.FilterMonochrome(VideoMemory(frames, copy_data=False), batch=16), 2)), 'open', 'rect', 3), dtype=np.int16)
+    got = np.stack(list(full))
+    assert got.dtype == np.int16 and np.array_equal(got, ref['labels']) and full.num_features == list(ref['counts'])

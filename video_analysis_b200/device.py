@@ -340,11 +340,18 @@ class DeviceRuntime(object):
                                            op_id, shape_id, int(kx), int(ky)))
         return out
 
-    def label(self, src, connectivity=4):
-        """ -> (labels DeviceBatch 'i32', counts int32 device tensor (n,)) """
+    def label(self, src, connectivity=4, dtype=np.int32):
+        """ -> (labels DeviceBatch 'i32' -- or 'i16' for dtype=np.int16 --, counts int32 device tensor (n,)) """
         self.ensure(src.w, src.h, src.n)
-        out = self.empty_i32(src.n, src.h, src.w)
         counts = torch().empty((src.n,), dtype=torch().int32, device=self.device)
+        if np.dtype(dtype) == np.int16:
+            out = self.empty_i16(src.n, src.h, src.w)
+            self._check(self.lib.va_label_forest(self._h, self.stream, src.ptr, src.pitch, src.fstride, counts.data_ptr(),
+                                                 src.w, src.h, src.n, int(connectivity), 0))
+            self._check(self.lib.va_label_write_i16(self._h, self.stream, src.ptr, src.pitch, src.fstride,
+                                                    out.ptr, out.pitch, out.fstride, src.w, src.h, src.n, 0))
+            return out, counts
+        out = self.empty_i32(src.n, src.h, src.w)
         self._check(self.lib.va_label_bits(self._h, self.stream, src.ptr, src.pitch, src.fstride,
                                            out.ptr, out.pitch, out.fstride, counts.data_ptr(),
                                            src.w, src.h, src.n, int(connectivity)))

@@ -779,10 +779,15 @@ class FilterLabel(DeviceFilterBase):
     consumes = 'bits'
     produces_dtype = np.int32
 
-    def __init__(self, source, connectivity=4, **kwargs):
+    def __init__(self, source, connectivity=4, dtype=np.int32, **kwargs):
         if connectivity not in (4, 8):
             raise ValueError('connectivity must be 4 or 8')
         self.connectivity = connectivity
+        # dtype=np.int16 is ndimage.label(mask, output=np.int16): the same numbering in half the bytes (frames with more
+        # than 32767 regions raise RuntimeError, as scipy does)
+        self.produces_dtype = np.dtype(dtype).type
+        if self.produces_dtype not in (np.int32, np.int16):
+            raise ValueError('labels are int32 or int16')
         self.num_features = []
         self._counts_dev = None
         super(FilterLabel, self).__init__(source, **kwargs)
@@ -791,7 +796,7 @@ class FilterLabel(DeviceFilterBase):
         self.num_features = []
 
     def _device_process(self, rt, batch):
-        labels, counts = rt.label(batch, self.connectivity)
+        labels, counts = rt.label(batch, self.connectivity, self.produces_dtype)
         self._counts_dev = counts
         return labels
 
@@ -805,4 +810,7 @@ class FilterLabel(DeviceFilterBase):
 
     def _on_batch(self, job):
         if job.extras is not None:
-            self.num_features.extend(int(v) for v in job.extras.numpy())
+            counts = [int(v) for v in job.extras.numpy()[:job.n]]
+            if self.produces_dtype is np.int16 and counts and max(counts) > 32767:
+                raise RuntimeError('insufficient bit-depth in requested output type')
+            self.num_features.extend(counts)
