@@ -275,6 +275,25 @@ def gpu_arm(args):
         ms = float(tmax.item())
     fps = world * K * B / (ms * 1e-3)
 
+    # ---- the same device-resident steps with int16 label images (ndimage.label(..., output=np.int16)): extra key only
+    fps_i16 = None
+    if world == 1 and not args.no_overlap:
+        ch16 = SegmentChain((W, H), batch=B, fuse=not args.no_fuse, label_dtype=np.int16, **CHAIN)
+        labels16 = [rt.empty_i16(B, H, W) for _ in range(2)]
+        for i in range(Wm):
+            ch16.run_device_pipelined(batch_of(i), labels16[i & 1], counts)
+        ch16.pipeline_sync()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            ch16.run_device_pipelined(batch_of(Wm + i), labels16[i & 1], counts)
+        ch16.pipeline_sync()
+        e1.record()
+        torch.cuda.synchronize()
+        fps_i16 = K * B / (e0.elapsed_time(e1) * 1e-3)
+        del ch16, labels16
+
     # ---- roofline of the dominant kernel: instrumented pass, events around each launch group ------
     roof = None
     if rank == 0:
@@ -366,6 +385,7 @@ def gpu_arm(args):
                                  'd2h_bytes_per_step': Be * N * 2 + Be * 4, 'steps': Ke, 'frames_per_step': Be,
                                  'api': 'SegmentChain(label_dtype=np.int16).process_blocks: pinned host frames in, int16 labels '
                                         '(ndimage.label(..., output=np.int16)) + counts out'},
+            'value_labels_int16': None if fps_i16 is None else round(fps_i16, 1),
             'gpu_launches': int(launches),
             'roofline': roof,
         }
