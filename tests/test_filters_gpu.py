@@ -504,3 +504,90 @@ def test_segment_chain_int16_labels(frames, ref):
         F.FilterBlur(F.FilterMonochrome(VideoMemory(frames, copy_data=False), batch=16), 2)), 'open', 'rect', 3), dtype=np.int16)
     got = np.stack(list(full))
     assert got.dtype == np.int16 and np.array_equal(got, ref['labels']) and full.num_features == list(ref['counts'])
+
+
+@pytest.mark.parametrize('batch,ring', [(128, 384), (50, 384), (32, 100)])
+def test_filter_chain_over_a_stream_with_short_blocks(batch, ring):
+    """ a raw stream hands out blocks shorter than the filter's batch (capped at ring // (hold + 2), cut at
+    the ring's wrap): every frame must still come out (round-1 advisor finding: the chain stopped at the
+    first short block) """
+    import io
+    F, VideoMemory = mods()
+    from video_analysis_b200.io.pipe import VideoRawStream
+    fr = synth.make_frames(2, 0, 500, 64, 48, 3)
+    v = VideoRawStream(io.BytesIO(fr.tobytes()), (64, 48), len(fr), ring_frames=ring)
+    got = np.stack([f.copy() for f in F.FilterBlur(F.FilterMonochrome(v, batch=batch), 2)])
+    assert got.shape[0] == 500
+    assert np.array_equal(got, np.stack([ops.blur(ops.mono(f), 2) for f in fr]))
+    v.close()
+    # single-frame collectors over a stream: FilterTimeDifference
+    v = VideoRawStream(io.BytesIO(fr[:120].tobytes()), (64, 48), 120, ring_frames=12)
+    td = F.FilterTimeDifference(F.FilterFunction(v, lambda f: f[:, :, 1]), batch=40)
+    mono = fr[:120, :, :, 1]
+    assert np.array_equal(np.stack(list(td)), mono[1:].astype(np.int16) - mono[:-1])
+    v.close()
+
+
+def test_fused_crop_monochrome_checks_the_rectangle(frames):
+    """ `_check_coordinate` validates each value alone: left + width may leave the frame, and size_alignment may
+    enlarge it.  Fused (crop -> monochrome by pointer offset) and unfused paths raise the same IndexError """
+    F, VideoMemory = mods()
+    v = VideoMemory(frames[:4], copy_data=False)
+    for kw in (dict(rect=(300, 10, 100, 50)), dict(rect=(10, 200, 50, 100)),
+               dict(rect=(250, 10, 67, 50), size_alignment=8)):
+        with pytest.raises(IndexError):
+            list(F.FilterMonochrome(F.FilterCrop(v, batch=2, **kw)))
+        with pytest.raises(IndexError):
+            list(F.FilterCrop(v, batch=2, **kw))
+    rt = F.get_runtime()
+    dev = rt.upload(frames[:2])
+    with pytest.raises(IndexError):
+        rt.luma(dev, rect=(300, 0, 100, 10))
+    with pytest.raises(IndexError):
+        rt.crop(dev, (0, 230, 10, 20))
+
+
+def test_interleaved_label_chains_share_the_runtime_safely(frames, ref):
+    """ two label chains iterated in lock step (zip) run on different streams over ONE ctx: the library orders
+    the uses of its union-find scratch with an event, so neither corrupts the other; the analysis helpers
+    may be called in between """
+    F, VideoMemory = mods()
+    from video_analysis_b200.analysis import regions
+    v1 = VideoMemory(frames, copy_data=False)
+    v2 = VideoMemory(frames[::-1].copy(), copy_data=False)
+    ref2 = ops.chain(frames[::-1])
+
+    def chain(v, batch):
+        return F.FilterLabel(F.FilterMorphology(F.FilterBackgroundMask(
+            F.FilterBlur(F.FilterMonochrome(v, batch=batch), 2)), 'open', 'rect', 3))
+    for rep in range(3):
+        a, b = chain(v1, 5), chain(v2, 7)
+        for t, (la, lb) in enumerate(zip(a, b)):
+            assert np.array_equal(la, ref['labels'][t]), (rep, t)
+            assert np.array_equal(lb, ref2['labels'][t]), (rep, t)
+            if t % 9 == 0:
+                lab, n = regions.label(ref['morph'][t])
+                assert n == ref['counts'][t] and np.array_equal(lab, ref['labels'][t])
+
+
+def test_region_helpers_beyond_the_table_size_and_value_weighting():
+    """ more regions than the default table (4096 rows) and cv2.moments' weighting by the pixel value """
+    mods()
+    import cv2
+    from video_analysis_b200.analysis import image, regions
+    m = np.zeros((200, 300), np.uint8)
+    m[::2, ::2] = 1                                                 # 15 000 single-pixel regions
+    regs = regions.region_stats(m)
+    assert len(regs) == 15000 and all(r['area'] == 1 for r in regs)
+    assert regions.find_bounding_box(np.pad(np.ones((5, 9), np.uint8), 3)) == (3, 3, 9, 5)
+    blob = np.zeros((60, 80), np.uint8)
+    blob[10:30, 20:50] = 255
+    blob[40:45, 5:70] = 255
+    for mask in (blob, blob // 255, blob.astype(bool)):
+        want = cv2.moments(mask.astype(np.uint8))
+        p = image.regionprops(mask)
+        assert p.area == want['m00']
+        for k in ('m10', 'm01', 'm20', 'm11', 'm02'):
+            assert p.moments[k] == want[k]
+        for k in ('mu20', 'mu11', 'mu02'):
+            assert abs(p.moments[k] - want[k]) <= 1e-9 * abs(want[k])

@@ -153,3 +153,45 @@ def test_writer_round_trip():
     back = VideoRawStream(io.BytesIO(sink.getvalue()), (W, H), 7, ring_frames=6)
     got = np.stack([f.copy() for f in back])
     assert np.array_equal(got[:6], fr[:6]) and np.array_equal(got[6], np.repeat(fr[6, :, :, :1], 3, axis=2))
+
+
+def test_single_frames_are_copies_and_survive_the_ring():
+    """ get_next_frame / get_frame hand out fresh arrays like the reference's reader: collecting more
+    frames than the ring holds before looking at them must not see overwritten data """
+    fr = frames_of(200)
+    v = VideoRawStream(io.BytesIO(fr.tobytes()), (W, H), 200, ring_frames=12)
+    held = [v.get_next_frame() for _ in range(150)]                 # no copy by the caller
+    time.sleep(0.05)
+    assert np.array_equal(np.stack(held), fr[:150])
+    assert all(f.base is None or not np.shares_memory(f, v._ring) for f in held)
+    last = v.get_frame(149)                                         # lastread path
+    assert np.array_equal(last, fr[149]) and not np.shares_memory(last, v._ring)
+    v.close()
+    # the collectors that stack single frames: FilterTimeDifference-style and analysis.video._blocks
+    from video_analysis_b200.analysis.video import _blocks
+    v = VideoRawStream(io.BytesIO(fr.tobytes()), (W, H), 200, ring_frames=12)
+    got = np.concatenate([np.asarray(b) for b in _blocks(v, 32)])
+    assert np.array_equal(got, fr)
+    v.close()
+
+
+@pytest.mark.parametrize('batch,ring', [(128, 384), (50, 384), (32, 100), (7, 12)])
+def test_device_filter_pull_loop_sees_every_frame_of_a_stream(batch, ring):
+    """ the loop DeviceFilterBase._launch runs (pull blocks until an EMPTY one comes back) over a raw
+    stream whose blocks are capped at ring // (hold + 2) and cut where the ring wraps """
+    from video_analysis_b200.filters import DeviceFilterBase
+    fr = frames_of(1000, color=False, seed=5)
+    v = VideoRawStream(io.BytesIO(fr.tobytes()), (W, H), 1000, is_color=False, ring_frames=ring, pinned=False)
+    if batch == 32:
+        v.set_frame_pos(5)                                          # a forward seek shifts the wrap position
+    start = v.get_frame_pos()
+    out, short = [], 0
+    while True:
+        block = DeviceFilterBase._pull_block(v, batch)
+        if len(block) == 0:
+            break
+        short += len(block) < batch
+        out.append(np.array(block))
+    assert np.array_equal(np.concatenate(out), fr[start:])
+    assert short > 1                                                # short blocks occurred and did not end the video
+    v.close()

@@ -51,7 +51,15 @@ class regionprops(object):
         elif mask is not None:
             from .regions import RAW_KEYS, moments_from_raw, region_stats
             parts = region_stats(mask, connectivity=8, device=device)
-            raw = [sum(int(p['moments'][k]) for p in parts) for k in RAW_KEYS]
+            # cv2.moments(mask.astype(np.uint8)) (image.py:350) weights every pixel by its value: a mask of
+            # 0 / 255 has 255 times the moments of the same mask of 0 / 1
+            values = np.unique(np.asarray(mask).astype(np.uint8))
+            values = values[values != 0]
+            if len(values) > 1:
+                raise ValueError('regionprops(mask=...) on the device takes a two-valued mask; '
+                                 'grey-value weighted moments are outside the filter -> segment path')
+            weight = int(values[0]) if len(values) else 1
+            raw = [weight * sum(int(p['moments'][k]) for p in parts) for k in RAW_KEYS]
             self.moments = moments_from_raw(raw)
         elif contour is not None:
             raise NotImplementedError('contour moments are outside the filter -> segment path')

@@ -59,6 +59,10 @@ extern "C" int va_destroy(va_ctx *ctx) {
     cudaFree(ctx->ch_blur);
     cudaFree(ctx->ch_mask);
     cudaFree(ctx->ch_morph);
+#ifndef VA_EMU
+    for (int i = 0; i < 3; i++)
+        if (ctx->lab_event[i]) cudaEventDestroy((cudaEvent_t)ctx->lab_event[i]);
+#endif
     free(ctx);
     return VA_OK;
 }
@@ -90,6 +94,7 @@ extern "C" int va_chain_run(va_ctx *ctx, va_stream stream, const va_chain_desc *
                 ctx->max_w, ctx->max_h, ctx->max_batch);
     int rc = chain_scratch(ctx);
     if (rc != VA_OK) return rc;
+    VA_REQUIRE(ctx, va_scratch_acquire(ctx, stream, 2) == 0, "va_chain_run: cannot order the chain scratch");
     const size_t sp = ctx->ch_pitch, sf = ctx->ch_pitch * (size_t)ctx->max_h;
     const size_t wp = ctx->ch_pitch_w, wf = ctx->ch_pitch_w * (size_t)ctx->max_h;
 
@@ -147,5 +152,6 @@ extern "C" int va_chain_run(va_ctx *ctx, va_stream stream, const va_chain_desc *
                            io->counts, w, h, batch, d->connectivity);
         if (rc != VA_OK) return rc;
     }
+    VA_REQUIRE(ctx, va_scratch_release(ctx, stream, 2) == 0, "va_chain_run: cannot order the chain scratch");
     return VA_OK;
 }

@@ -29,12 +29,34 @@ struct va_ctx {
     size_t lab_pitch;        // elements per row: power of two >= max_w
     int32_t *lab_rowcnt;     // [2][max_batch * max_h]  roots per row -> exclusive prefix; rows' foreground flags
     int32_t *lab_parent1, *lab_rowcnt1;   // second scratch set (slot 1 of va_label_forest / va_label_write), allocated on first use
+    // last use of each scratch set: every entry point that touches a set first makes its stream wait for
+    // this event and re-records it when it has enqueued its kernels, so callers on different streams
+    // (two filter chains, a chain next to region_stats, ...) never run forest kernels on one set at once
+    void *lab_event[3];      // [2]: the chain intermediates of va_chain_run
     // morphology scratch (intermediate of open / close is kept in shared memory; none needed)
     // chain intermediates (allocated on first use by va_chain_run)
     uint8_t *ch_mono, *ch_blur;
     uint32_t *ch_mask, *ch_morph;
     size_t ch_pitch, ch_pitch_w;
 };
+
+#ifdef VA_EMU
+static inline int va_scratch_acquire(va_ctx *, va_stream, int) { return 0; }
+static inline int va_scratch_release(va_ctx *, va_stream, int) { return 0; }
+#else
+static inline int va_scratch_acquire(va_ctx *ctx, va_stream stream, int slot) {
+    if (!ctx->lab_event[slot]) return 0;
+    return cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)ctx->lab_event[slot], 0) == cudaSuccess ? 0 : -1;
+}
+static inline int va_scratch_release(va_ctx *ctx, va_stream stream, int slot) {
+    if (!ctx->lab_event[slot]) {
+        cudaEvent_t ev;
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return -1;
+        ctx->lab_event[slot] = (void *)ev;
+    }
+    return cudaEventRecord((cudaEvent_t)ctx->lab_event[slot], (cudaStream_t)stream) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 #define VA_SET_ERR(ctx, ...)                                              \
     do {                                                                  \

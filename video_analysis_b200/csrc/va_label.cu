@@ -533,6 +533,7 @@ static int label_forest(va_ctx *ctx, va_stream stream, const char *name,
     int *parent, *rowcnt;
     { const int rc = label_scratch(ctx, name, slot, &parent, &rowcnt); if (rc != VA_OK) return rc; }
     int *rowflag = rowcnt + (size_t)ctx->max_h * ctx->max_batch;               // does the row have foreground?
+    VA_REQUIRE(ctx, va_scratch_acquire(ctx, stream, slot) == 0, "%s: cannot order the scratch set", name);
     const int vec = va_aligned(mask, 16) && mask_pitch_w % 4 == 0 && mask_fstride_w % 4 == 0;
     const int grid_a = va_div_up((long long)((h + 7) / 8) * batch, LAB_WARPS);          // four-lanes-per-row kernels
     { auto k = label_init_kernel;
@@ -546,6 +547,7 @@ static int label_forest(va_ctx *ctx, va_stream stream, const char *name,
       VA_LAUNCH(ctx, k, grid_a, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, parent, LOG, pf, rowcnt, w, h, batch, vec); }
     { auto k = label_scan_kernel;
       VA_LAUNCH(ctx, k, batch, LAB_THREADS, 0, stream, rowcnt, counts, h); }
+    VA_REQUIRE(ctx, va_scratch_release(ctx, stream, slot) == 0, "%s: cannot order the scratch set", name);
     *LOG_out = LOG;
     *pf_out = pf;
     return VA_OK;
@@ -558,12 +560,14 @@ static int label_write(va_ctx *ctx, va_stream stream, const char *name,
                        int w, int h, int batch, int LOG, size_t pf, int slot) {
     int *parent, *rowcnt;
     { const int rc = label_scratch(ctx, name, slot, &parent, &rowcnt); if (rc != VA_OK) return rc; }
+    VA_REQUIRE(ctx, va_scratch_acquire(ctx, stream, slot) == 0, "%s: cannot order the scratch set", name);
     auto k = label_write_kernel<T>;
     const int vec_out = va_aligned(labels, 4 * sizeof(T)) && labels_pitch_e % 4 == 0 && labels_fstride_e % 4 == 0;
     const dim3 grid(va_div_up(h, LAB_WARPS), batch);
     VA_LAUNCH(ctx, k, grid, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, (const int *)parent, LOG, pf,
               (const int *)rowcnt, (const int *)(rowcnt + (size_t)ctx->max_h * ctx->max_batch),
               labels, labels_pitch_e, labels_fstride_e, w, h, batch, vec_out);
+    VA_REQUIRE(ctx, va_scratch_release(ctx, stream, slot) == 0, "%s: cannot order the scratch set", name);
     return VA_OK;
 }
 
@@ -764,6 +768,7 @@ extern "C" int va_region_stats(va_ctx *ctx, va_stream stream,
         auto k = region_largest64_kernel;
         VA_LAUNCH(ctx, k, batch, LAB_THREADS, 0, stream, (const long long *)stats, max_regions, (const int *)counts, largest);
     }
+    VA_REQUIRE(ctx, va_scratch_release(ctx, stream, 0) == 0, "va_region_stats: cannot order the scratch set");
     return VA_OK;
 }
 

@@ -179,6 +179,7 @@ class DeviceRuntime(object):
     def luma(self, src, mode=_lib.MONO_MEAN, rect=None):
         """ K1 (+ crop by pointer offset): (n,h,w,3) -> (n,h',w') """
         left, top, w, h = rect if rect is not None else (0, 0, src.w, src.h)
+        self._check_rect(src, left, top, w, h)
         self.ensure(w, h, src.n)
         out = self.empty_u8(src.n, h, w)
         ptr = src.ptr + top * src.pitch + left * 3
@@ -186,8 +187,15 @@ class DeviceRuntime(object):
                                         out.ptr, out.pitch, out.fstride, w, h, src.n, mode))
         return out
 
+    @staticmethod
+    def _check_rect(src, left, top, w, h):
+        """ a rectangle is turned into a pointer offset: it must lie inside the frame """
+        if left < 0 or top < 0 or w <= 0 or h <= 0 or left + w > src.w or top + h > src.h:
+            raise IndexError('rectangle %s exceeds the %dx%d frame' % ((left, top, w, h), src.w, src.h))
+
     def crop(self, src, rect):
         left, top, w, h = rect
+        self._check_rect(src, left, top, w, h)
         self.ensure(w, h, src.n)
         out = self.empty_u8(src.n, h, w, src.channels)
         ptr = src.ptr + top * src.pitch + left * src.channels

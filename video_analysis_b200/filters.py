@@ -187,6 +187,7 @@ class DeviceFilterBase(VideoFilterBase):
             # peephole fusions: crop -> mono is pointer arithmetic; mono -> blur never writes the luma frame
             if isinstance(st, FilterCrop) and isinstance(nxt, FilterMonochrome) and not st._listeners \
                     and st.color_channel is None and dev.channels == 3:
+                st._check_rect(dev)                        # same IndexError as the unfused crop
                 dev = nxt._device_process(rt, dev, rect=st.rect)
                 st, i = nxt, i + 1
             elif isinstance(st, FilterMonochrome) and isinstance(nxt, FilterBlur) and not st._listeners \
@@ -213,10 +214,11 @@ class DeviceFilterBase(VideoFilterBase):
         root, stages = self._stages()
         block = self._pull_block(root, self.batch)
         if len(block) == 0:
+            # only an empty block ends the video: sources with `frame_block` may legitimately hand out
+            # short blocks (VideoRawStream caps them at ring_frames // (hold + 2) and cuts them where its
+            # ring wraps around), exactly as SegmentChain._blocks_of treats them
             self._exhausted = True
             return None
-        if len(block) < self.batch:
-            self._exhausted = True
         t = torch()
         rt = self.runtime
         if self._streams is None:
@@ -386,10 +388,16 @@ class FilterCrop(DeviceFilterBase):
         super(FilterCrop, self).__init__(source, size=self.rect[2:], is_color=is_color, **kwargs)
         logger.debug('Created filter for cropping to rectangle %s', self.rect)
 
-    def _device_process(self, rt, batch):
+    def _check_rect(self, batch):
+        """ `_check_coordinate` validates every value on its own, so left + width (or a width enlarged by
+        `size_alignment`) can still leave the frame; the reference's NumPy slicing would silently clip and
+        hand out frames smaller than `size` says -- the device path raises instead of reading past a row """
         left, top, w, h = self.rect
-        if left + w > batch.w or top + h > batch.h:
+        if left < 0 or top < 0 or w <= 0 or h <= 0 or left + w > batch.w or top + h > batch.h:
             raise IndexError('Crop rectangle %s exceeds the %dx%d frame' % (self.rect, batch.w, batch.h))
+
+    def _device_process(self, rt, batch):
+        self._check_rect(batch)
         if self.color_channel is None:
             return rt.crop(batch, self.rect)
         if batch.channels != 3:

@@ -232,16 +232,20 @@ class VideoRawStream(VideoBase):
         return block
 
     def get_next_frame(self):
+        """ one frame, as a fresh array like the reference's reader (backend_ffmpeg.py:318-319): callers collect
+        frames one by one before they stack them (filters._pull_block, FilterTimeDifference, analysis.video),
+        and a view into the ring would be overwritten by the reader thread `hold` requests later.  Only
+        `frame_block` hands out views (documented there). """
         block = self.frame_block(self._frame_pos, self._frame_pos + 1)
         if len(block) == 0:
             raise StopIteration
-        return block[0]
+        return block[0].copy()
 
     def get_frame(self, index):
         if index < 0:
             index += self.frame_count
         if index == self._frame_pos - 1 and self.lastread is not None:
-            return self.lastread                                    # backend_ffmpeg.py:336-337
+            return self.lastread.copy()                             # backend_ffmpeg.py:336-337
         self.set_frame_pos(index)
         return self.get_next_frame()
 
