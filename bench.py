@@ -456,6 +456,7 @@ def instrumented_pass(rt, chain, batch_of, labels, counts, Wm, K, B, N, hbm_peak
 
 
 def main():
+    global W, H, WORKLOAD
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=200)
@@ -468,8 +469,13 @@ def main():
     ap.add_argument('--no-fuse', action='store_true')
     ap.add_argument('--no-overlap', action='store_true', help='one stream, one va_chain_run call per step')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--width', type=int, default=W, help='frame width (default: configs[1], 1920; configs[2] is 3840)')
+    ap.add_argument('--height', type=int, default=H, help='frame height (default 1080; configs[2] is 2160)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if (args.width, args.height) != (W, H):
+        WORKLOAD = WORKLOAD.replace('%dx%d' % (W, H), '%dx%d' % (args.width, args.height))
+        W, H = args.width, args.height
     if args.impl == 'reference':
         reference_arm(args)
     else:

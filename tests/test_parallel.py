@@ -2,7 +2,8 @@
 Frame-range sharding: partition arithmetic and the EMA carry exchange.  The collective
 plumbing runs here on CPU with the gloo backend (world_size 2 and 3); the fold callable
 is NumPy so that no kernel is needed.  The GPU version of the same path is exercised by
-`bench.py --gpus N` and tests/test_filters_gpu.py::test_sharded_equals_sequential.
+`bench.py --gpus N`, tools/mgpu_check.py (real ranks) and, with R ranks emulated on one GPU,
+tests/test_filters_gpu.py::test_sharded_equals_sequential.
 """
 
 import os
@@ -61,7 +62,8 @@ def _worker(rank, world, port, total, alpha, out):
 
     def fold(carry, s, scale):
         carry.mul_(np.float32(scale)).add_(s)
-    carry = exchange_carry(S, b - a, alpha, fold)
+    counts = [shard_range(total, j, world)[1] - shard_range(total, j, world)[0] for j in range(world)]
+    carry = exchange_carry(S, counts, alpha, fold)           # counts are host knowledge: nothing but S is exchanged
     # the state before this rank's first frame, from the sequential float32 model
     if rank == 0:
         assert carry is None

@@ -209,17 +209,7 @@ class SegmentChain(object):
         `blur`: the already blurred batch (DeviceBatch 'u8'), when the caller has it. """
         rt, t = self.rt, torch()
         n = rgb.n
-        if getattr(self, '_pipe', None) is None:
-            self._pipe = {
-                'front': t.cuda.Stream(device=rt.device), 'back': t.cuda.Stream(device=rt.device),
-                'write': t.cuda.Stream(device=rt.device), 'k': 0,
-                'blur': rt.empty_u8(self.batch, self.h, self.w),
-                'mask': [rt.empty_bits(self.batch, self.h, self.w) for _ in range(2)],
-                'morph': [rt.empty_bits(self.batch, self.h, self.w) for _ in range(2)],
-                'ev_front': [t.cuda.Event(), t.cuda.Event()], 'ev_back': [t.cuda.Event(), t.cuda.Event()],
-                'ev_write': [t.cuda.Event(), t.cuda.Event()],
-            }
-        p = self._pipe
+        p = self.pipeline_streams()
         k = p['k']
         p['k'] = k + 1
         slot = k & 1
@@ -262,6 +252,21 @@ class SegmentChain(object):
             rt._check(write(h, rt.stream, *seg.img(), *labels.img(), self.w, self.h, n, slot))
             p['ev_write'][slot].record(p['write'])
         return labels, counts
+
+    def pipeline_streams(self):
+        """ streams, events and intermediate buffers of `run_device_pipelined` (made on first use) """
+        if getattr(self, '_pipe', None) is None:
+            rt, t = self.rt, torch()
+            self._pipe = {
+                'front': t.cuda.Stream(device=rt.device), 'back': t.cuda.Stream(device=rt.device),
+                'write': t.cuda.Stream(device=rt.device), 'k': 0,
+                'blur': rt.empty_u8(self.batch, self.h, self.w),
+                'mask': [rt.empty_bits(self.batch, self.h, self.w) for _ in range(2)],
+                'morph': [rt.empty_bits(self.batch, self.h, self.w) for _ in range(2)],
+                'ev_front': [t.cuda.Event(), t.cuda.Event()], 'ev_back': [t.cuda.Event(), t.cuda.Event()],
+                'ev_write': [t.cuda.Event(), t.cuda.Event()],
+            }
+        return self._pipe
 
     def pipeline_sync(self):
         """ make the caller's current stream wait for everything `run_device_pipelined` enqueued """

@@ -37,30 +37,50 @@ def ema_tail(alpha, bits=30):
     return int(math.ceil(-bits * math.log(2.0) / math.log(1.0 - alpha)))
 
 
-def exchange_carry(S_local, n_local, alpha, fold, group=None):
+def fold_carry(gathered, counts, rank, alpha, fold):
+    """ the background state before rank `rank`'s first frame from the partial states of the ranks before it:
+
+        carry = S_0;  carry = a^(n_j) * carry + S_j   for j = 1 .. rank-1          (a = 1 - alpha)
+
+    gathered : sequence / tensor indexed by rank of the (H, pitch) float32 partials
+    counts   : frames owned by every rank (host integers -- every rank knows every `shard_range`)
+    fold     : callable(carry, S, scale) doing carry = scale * carry + S in place
+    The fold runs in place in gathered[0] (the gather buffer belongs to this rank).  None on rank 0. """
+    if rank == 0:
+        return None
+    a = 1.0 - alpha
+    carry = gathered[0]
+    for j in range(1, rank):
+        fold(carry, gathered[j], a ** int(counts[j]))
+    return carry
+
+
+def exchange_carry(S_local, counts, alpha, fold, group=None, out=None):
     """ all-gather the per-rank partial states and fold the ones of the ranks before us.
 
     S_local : torch tensor (H, pitch) float32 -- this rank's partial (rank 0: its true state)
-    n_local : number of frames this rank owns
+    counts  : frames owned by every rank, host integers (an int means "the same on every rank");
+              nothing about the counts crosses the network and nothing is read back from the device
     fold    : callable(carry, S, scale) doing carry = scale * carry + S in place
+    out     : optional preallocated (world, H, pitch) gather buffer
+    One `all_gather_into_tensor` of one frame per rank is the only communication.
     returns the background state before this rank's first frame, or None on rank 0 """
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    gathered = [torch.empty_like(S_local) for _ in range(world)]
-    dist.all_gather(gathered, S_local.contiguous(), group=group)
-    n_t = torch.tensor([n_local], dtype=torch.int64, device=S_local.device)
-    counts = [torch.empty_like(n_t) for _ in range(world)]
-    dist.all_gather(counts, n_t, group=group)
-    counts = [int(c.item()) for c in counts]
-    if rank == 0:
-        return None
-    a = 1.0 - alpha
-    carry = gathered[0].clone()
-    for j in range(1, rank):
-        fold(carry, gathered[j], a ** counts[j])
-    return carry
+    if isinstance(counts, int):
+        counts = [counts] * world
+    if len(counts) != world:
+        raise ValueError('%d frame counts for %d ranks' % (len(counts), world))
+    S_local = S_local.contiguous()
+    if out is None:
+        out = torch.empty((world,) + tuple(S_local.shape), dtype=S_local.dtype, device=S_local.device)
+    if dist.get_backend(group) == 'nccl':
+        dist.all_gather_into_tensor(out, S_local, group=group)
+    else:                                               # gloo (CPU tests): gather into the rows of the same buffer
+        dist.all_gather(list(out.unbind(0)), S_local, group=group)
+    return fold_carry(out, counts, rank, alpha, fold)
 
 
 def merge_mean_m2(mean, m2, n_local, group=None):
@@ -125,38 +145,60 @@ def measure_mean_std_sharded(video, batch=32, device=None, group=None):
 
 
 class ShardedSegmentChain(object):
-    """ runs a SegmentChain over this rank's frame range of a video sharded over the
-    ranks of a torch.distributed group (NCCL) """
+    """ runs a SegmentChain over this rank's frame range of a video sharded over the ranks of a
+    torch.distributed group (NCCL).
 
-    def __init__(self, chain, group=None, tail=None):
+    The work of one range is three phases, all enqueued without a host synchronisation:
+
+      pass1     on the chain's front stream: blur the last `tail` frames of the range and fold them into the
+                partial state S (the blurred batches are kept for pass 2)
+      exchange  one asynchronous `all_gather_into_tensor` of S (a frame per rank); while it is in flight the
+                front stream already blurs the first batches of the range (only the EMA needs the carry)
+      pass2     fold the carry from the gathered partials (<= world-2 AXPYs), then the ordinary three-stream
+                pipelined chain from that state
+
+    `run_device_range` strings them together.  They are separate methods so that a test can emulate R ranks
+    on ONE GPU: pass1 for every rank, stack the partials in place of the all-gather, pass2 for every rank. """
+
+    PREBLUR = 2               # head batches blurred while the all-gather is in flight
+
+    def __init__(self, chain, group=None, tail=None, rank=None, world=None):
         self.chain = chain
         self.group = group
         self.tail = tail if tail is not None else ema_tail(chain.alpha)
+        if rank is None or world is None:
+            import torch.distributed as dist
+            rank, world = dist.get_rank(group), dist.get_world_size(group)
+        self.rank, self.world = int(rank), int(world)
         self._blurs = []
+        self._head = []
         self._S = None
-        self._scratch_mask = None
+        self._G = None
 
     def tail_batches(self, n_batches):
         """ how many of the last batches of a shard carry weight into the next shard """
         return min(n_batches, -(-self.tail // self.chain.batch) + 1)
 
     def reserve(self, n_batches):
-        """ allocate the blurred-frame storage of pass 1 up front (keeps cudaMalloc out of the hot loop) """
+        """ allocate the storage of pass 1 / the exchange up front (keeps cudaMalloc out of the hot loop) """
         ch, rt = self.chain, self.chain.rt
-        while len(self._blurs) < self.tail_batches(n_batches):
+        m = self.tail_batches(n_batches)
+        while len(self._blurs) < m:
             self._blurs.append(rt.empty_u8(ch.batch, ch.h, ch.w))
+        while len(self._head) < min(self.PREBLUR, n_batches - m):
+            self._head.append(rt.empty_u8(ch.batch, ch.h, ch.w))
         if self._S is None:
             self._S = rt.empty_f32(ch.h, ch.w)
+        if self._G is None:
+            t = torch_mod()
+            self._G = t.empty((self.world,) + tuple(self._S.shape), dtype=t.float32, device=rt.device)
+        ch.pipeline_streams()
 
     def _partial_state(self, blurs, covers_shard):
         """ S of this rank from (the last of) its blurred batches (device) """
-        import torch.distributed as dist
         ch, rt = self.chain, self.chain.rt
-        if self._S is None:
-            self._S = rt.empty_f32(ch.h, ch.w)
         self._S.zero_()
         n = sum(b.n for b in blurs)
-        rank = dist.get_rank(self.group)
         # only the last `tail` frames matter
         skip = max(0, n - self.tail)
         first = True
@@ -167,10 +209,8 @@ class ShardedSegmentChain(object):
             if lo >= b.n:
                 continue
             part = b if lo == 0 else _slice_batch(b, lo, b.n)
-            if first and rank == 0 and skip == 0 and covers_shard:
+            if first and self.rank == 0 and skip == 0 and covers_shard:
                 # the sequential model starts from its first frame: S = float(x_0)
-                if self._scratch_mask is None:
-                    self._scratch_mask = rt.empty_bits(1, ch.h, ch.w)
                 rt.ema_diff_thresh(_slice_batch(part, 0, 1), self._S, ch.alpha, ch.threshold, True)
                 if part.n > 1:
                     rt.ema_partial(_slice_batch(part, 1, part.n), self._S, ch.alpha, True)
@@ -179,34 +219,89 @@ class ShardedSegmentChain(object):
             first = False
         return self._S
 
-    def run_device_range(self, rgb_batches, labels_ring, counts):
+    # ---- the three phases ---------------------------------------------------------------------------
+    def pass1(self, rgb_batches):
+        """ blur the last batches of the shard -- the only frames whose weight a^k reaches the next rank -- and
+        fold them into the partial state S (returned; valid on the chain's front stream) """
+        ch, rt, t = self.chain, self.chain.rt, torch_mod()
+        nb = len(rgb_batches)
+        m = self.tail_batches(nb)
+        self.reserve(nb)
+        front = ch.pipeline_streams()['front']
+        ready = t.cuda.Event()
+        ready.record(t.cuda.current_stream(rt.device))
+        blurs = []
+        with t.cuda.stream(front):
+            front.wait_event(ready)
+            for i in range(nb - m, nb):
+                rgb = rgb_batches[i]
+                buf = self._blurs[i - (nb - m)]
+                blurs.append(ch.blur_device(rgb, buf if rgb.n == ch.batch else _slice_batch(buf, 0, rgb.n)))
+            S = self._partial_state(blurs, covers_shard=(m == nb))
+        self._p1 = (nb, m, blurs)
+        return S
+
+    def exchange(self, S):
+        """ start the all-gather of the partial states (asynchronous); -> (gather buffer, work handle) """
+        import torch.distributed as dist
+        t = torch_mod()
+        front = self.chain.pipeline_streams()['front']
+        with t.cuda.stream(front):                       # NCCL's stream waits for what `front` holds now: S is complete
+            work = dist.all_gather_into_tensor(self._G, S, group=self.group, async_op=True)
+        return self._G, work
+
+    def preblur(self, rgb_batches):
+        """ blur the first batches of the range on the front stream (they do not need the carry) """
+        ch, t = self.chain, torch_mod()
+        nb, m, _ = self._p1
+        front = ch.pipeline_streams()['front']
+        head = []
+        with t.cuda.stream(front):
+            for i in range(min(len(self._head), nb - m)):
+                rgb = rgb_batches[i]
+                buf = self._head[i]
+                head.append(ch.blur_device(rgb, buf if rgb.n == ch.batch else _slice_batch(buf, 0, rgb.n)))
+        return head
+
+    def pass2(self, rgb_batches, labels_ring, counts, gathered, shard_counts, work=None, head=()):
+        """ fold the carry out of `gathered` ((world, H, pitch) partial states) and run the pipelined chain over
+        the range.  `shard_counts`: frames owned by every rank (host integers).  Ends with `pipeline_sync()`. """
+        ch, rt, t = self.chain, self.chain.rt, torch_mod()
+        nb, m, blurs = self._p1
+        front = ch.pipeline_streams()['front']
+        with t.cuda.stream(front):
+            if work is not None:
+                work.wait()                               # stream-side wait: `front` continues after the gather
+            carry = fold_carry(gathered, shard_counts, self.rank, ch.alpha,
+                               lambda c, s, sc: rt.ema_fold(c, s, sc, ch.w, ch.h))
+            if carry is None:
+                ch.reset()
+            else:
+                ch.set_background(carry)
+        for i, rgb in enumerate(rgb_batches):
+            blur = blurs[i - (nb - m)] if i >= nb - m else (head[i] if i < len(head) else None)
+            ch.run_device_pipelined(rgb, labels_ring[i % len(labels_ring)], counts[i] if counts.dim() == 2 else counts,
+                                    blur=blur)
+        ch.pipeline_sync()
+
+    def run_device_range(self, rgb_batches, labels_ring, counts, shard_counts=None):
         """ rgb_batches: this rank's frames as a list of DeviceBatch (n, h, w, 3), in order.
         labels_ring: list of label DeviceBatches reused round-robin; counts: int32 tensor (batch,)
         shared by all batches, or (len(rgb_batches), batch) with one row per batch.
+        shard_counts: frames owned by every rank (default: every rank owns as many as this one).
         Results are complete once the caller's stream has passed `chain.pipeline_sync()` (done here). """
-        ch, rt = self.chain, self.chain.rt
-        nb = len(rgb_batches)
-        # pass 1: blur the last batches of the shard -- the only frames whose weight a^k reaches the
-        # next rank -- and fold them into the partial state; the blurred frames are kept for pass 2
-        m = self.tail_batches(nb)
-        self.reserve(nb)
-        blurs = []
-        for i in range(nb - m, nb):
-            rgb = rgb_batches[i]
-            buf = self._blurs[i - (nb - m)]
-            blurs.append(ch.blur_device(rgb, buf if rgb.n == ch.batch else _slice_batch(buf, 0, rgb.n)))
-        S = self._partial_state(blurs, covers_shard=(m == nb))
         n_total = sum(b.n for b in rgb_batches)
-        carry = exchange_carry(S, n_total, ch.alpha, lambda c, s, sc: rt.ema_fold(c, s, sc, ch.w, ch.h), self.group)
-        # pass 2: the ordinary pipelined chain (three streams) from the exact incoming state
-        if carry is None:
-            ch.reset()
-        else:
-            ch.set_background(carry)
-        for i, rgb in enumerate(rgb_batches):
-            ch.run_device_pipelined(rgb, labels_ring[i % len(labels_ring)], counts[i] if counts.dim() == 2 else counts,
-                                    blur=blurs[i - (nb - m)] if i >= nb - m else None)
-        ch.pipeline_sync()
+        if shard_counts is None:
+            shard_counts = [n_total] * self.world
+        S = self.pass1(rgb_batches)
+        gathered, work = self.exchange(S)
+        head = self.preblur(rgb_batches)
+        self.pass2(rgb_batches, labels_ring, counts, gathered, shard_counts, work, head)
+
+
+def torch_mod():
+    from .device import torch
+    return torch()
 
 
 def _slice_batch(b, lo, hi):
