@@ -531,20 +531,31 @@ def test_filter_chain_over_a_stream_with_short_blocks(batch, ring):
 
 def test_fused_crop_monochrome_checks_the_rectangle(frames):
     """ `_check_coordinate` validates each value alone: left + width may leave the frame, and size_alignment may
-    enlarge it.  Fused (crop -> monochrome by pointer offset) and unfused paths raise the same IndexError """
+    enlarge it.  The constructor rejects such rectangles (IndexError, like a bad coordinate); the pointer-offset
+    paths of the runtime -- fused crop -> monochrome included -- refuse them too (ValueError: VideoIterator would
+    turn an IndexError into the end of the video) """
     F, VideoMemory = mods()
     v = VideoMemory(frames[:4], copy_data=False)
     for kw in (dict(rect=(300, 10, 100, 50)), dict(rect=(10, 200, 50, 100)),
-               dict(rect=(250, 10, 67, 50), size_alignment=8)):
+               dict(rect=(250, 10, 69, 50), size_alignment=8)):          # 69 -> 72: 250 + 72 > 320
         with pytest.raises(IndexError):
-            list(F.FilterMonochrome(F.FilterCrop(v, batch=2, **kw)))
-        with pytest.raises(IndexError):
-            list(F.FilterCrop(v, batch=2, **kw))
+            F.FilterCrop(v, batch=2, **kw)
+    with pytest.raises(IndexError):
+        F.FilterCrop(F.FilterCrop(v, rect=(200, 100, 100, 100)), rect=(50, 50, 60, 60))     # nested: 200 + 50 + 60 > 320
+    ok = F.FilterCrop(v, rect=(250, 10, 67, 50), size_alignment=8, batch=2)                   # 67 -> 64: fits
+    assert ok.rect == (250, 10, 64, 48) and np.stack(list(F.FilterMonochrome(ok))).shape == (4, 48, 64)
+    # a source whose frames are smaller than its metadata: the runtime check fires on both paths
+    liar = VideoMemory(frames[:4, :100, :100].copy(), copy_data=False)
+    liar.size = (320, 240)
+    for chain in (F.FilterMonochrome(F.FilterCrop(liar, rect=(90, 10, 50, 50), batch=2)),
+                  F.FilterCrop(liar, rect=(90, 10, 50, 50), batch=2)):
+        with pytest.raises(ValueError):
+            list(chain)
     rt = F.get_runtime()
     dev = rt.upload(frames[:2])
-    with pytest.raises(IndexError):
+    with pytest.raises(ValueError):
         rt.luma(dev, rect=(300, 0, 100, 10))
-    with pytest.raises(IndexError):
+    with pytest.raises(ValueError):
         rt.crop(dev, (0, 230, 10, 20))
 
 

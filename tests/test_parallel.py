@@ -29,9 +29,10 @@ def test_shard_ranges_partition_the_video():
 
 
 def test_tail_length():
-    assert ema_tail(0.05) == 406
-    assert (1 - 0.05) ** ema_tail(0.05) < 2 ** -30 <= (1 - 0.05) ** (ema_tail(0.05) - 1)
-    assert ema_tail(0.5) == 30
+    assert ema_tail(0.05) == 352
+    assert (1 - 0.05) ** ema_tail(0.05) < 2 ** -26 <= (1 - 0.05) ** (ema_tail(0.05) - 1)
+    assert ema_tail(0.05, bits=30) == 406
+    assert ema_tail(0.5) == 26
 
 
 def _free_port():

@@ -50,6 +50,7 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         out = fn()
+        ch.pipeline_sync()                     # the phases run on the chain's own streams
         e1.record()
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], device=rt.device)
@@ -66,8 +67,11 @@ def main():
         report('sharded range, %d GPUs, rep %d' % (world, rep), ms)
     ms1, S = timed(lambda: sh.pass1(batches))
     report('  pass 1 (%d tail blurs + partial state)' % sh.tail_batches(K), ms1)
-    msx, (G, work) = timed(lambda: sh.exchange(S))
-    work.wait()
+    def exch():
+        G, work = sh.exchange(S)
+        work.wait()                            # stream-side: the current stream continues after the gather
+        return G
+    msx, G = timed(exch)
     report('  exchange (all-gather of one frame per rank)', msx)
     msh, head = timed(lambda: sh.preblur(batches))
     report('  pre-blur of %d head batches' % len(head), msh)

@@ -191,7 +191,7 @@ class DeviceRuntime(object):
     def _check_rect(src, left, top, w, h):
         """ a rectangle is turned into a pointer offset: it must lie inside the frame """
         if left < 0 or top < 0 or w <= 0 or h <= 0 or left + w > src.w or top + h > src.h:
-            raise IndexError('rectangle %s exceeds the %dx%d frame' % ((left, top, w, h), src.w, src.h))
+            raise ValueError('rectangle %s exceeds the %dx%d frame' % ((left, top, w, h), src.w, src.h))
 
     def crop(self, src, rect):
         left, top, w, h = rect

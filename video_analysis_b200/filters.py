@@ -384,17 +384,24 @@ class FilterCrop(DeviceFilterBase):
             width = int(round(width / size_alignment) * size_alignment)
             height = int(round(height / size_alignment) * size_alignment)
         self.rect = (left, top, width, height)
+        # `_check_coordinate` validates every value on its own, so left + width (or a width enlarged by
+        # `size_alignment`) can still leave the frame.  The reference's NumPy slicing would then silently clip and
+        # hand out frames smaller than `size` says; the device path turns the rectangle into a pointer offset and
+        # must not read past a row, so the rectangle is rejected here, with the error type of a bad coordinate
+        # (collapsed nested crops are checked against the frame of the outermost source)
+        if left + width > source.size[0] or top + height > source.size[1] or width <= 0 or height <= 0:
+            raise IndexError('Crop rectangle %s exceeds the %dx%d frame' % (self.rect, source.size[0], source.size[1]))
         self.slices = rect_to_slices(self.rect)
         super(FilterCrop, self).__init__(source, size=self.rect[2:], is_color=is_color, **kwargs)
         logger.debug('Created filter for cropping to rectangle %s', self.rect)
 
     def _check_rect(self, batch):
-        """ `_check_coordinate` validates every value on its own, so left + width (or a width enlarged by
-        `size_alignment`) can still leave the frame; the reference's NumPy slicing would silently clip and
-        hand out frames smaller than `size` says -- the device path raises instead of reading past a row """
+        """ the constructor checked the rectangle against the source's `size`; this guards the pointer arithmetic
+        against a source whose frames are smaller than its metadata says """
         left, top, w, h = self.rect
         if left < 0 or top < 0 or w <= 0 or h <= 0 or left + w > batch.w or top + h > batch.h:
-            raise IndexError('Crop rectangle %s exceeds the %dx%d frame' % (self.rect, batch.w, batch.h))
+            # not an IndexError: VideoIterator turns those into the end of the video (io/base.py:279-283)
+            raise ValueError('Crop rectangle %s exceeds the %dx%d frames the source delivers' % (self.rect, batch.w, batch.h))
 
     def _device_process(self, rt, batch):
         self._check_rect(batch)

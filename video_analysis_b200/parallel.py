@@ -30,8 +30,10 @@ def shard_range(total, rank, world):
     return rank * total // world, (rank + 1) * total // world
 
 
-def ema_tail(alpha, bits=30):
-    """ number of trailing frames whose weight a^k is still above 2^-bits """
+def ema_tail(alpha, bits=26):
+    """ number of trailing frames whose weight a^k is still above 2^-bits.  float32 carries 24 bits: a term of
+    weight 2^-26 times a value <= 255 changes a background value of the usual size by less than half a unit in
+    the last place """
     if not 0 < alpha < 1:
         return 1
     return int(math.ceil(-bits * math.log(2.0) / math.log(1.0 - alpha)))
@@ -175,14 +177,18 @@ class ShardedSegmentChain(object):
         self._S = None
         self._G = None
 
-    def tail_batches(self, n_batches):
-        """ how many of the last batches of a shard carry weight into the next shard """
-        return min(n_batches, -(-self.tail // self.chain.batch) + 1)
+    def tail_batches(self, n_batches, last_n=None):
+        """ how many of the last batches of a shard carry weight into the next shard: the ones that hold its
+        last `tail` frames (`last_n`: frames in the last batch when it is a ragged one) """
+        B = self.chain.batch
+        last_n = B if last_n is None else last_n
+        need = max(0, self.tail - last_n)
+        return min(n_batches, 1 + -(-need // B))
 
     def reserve(self, n_batches):
         """ allocate the storage of pass 1 / the exchange up front (keeps cudaMalloc out of the hot loop) """
         ch, rt = self.chain, self.chain.rt
-        m = self.tail_batches(n_batches)
+        m = min(n_batches, self.tail_batches(n_batches) + 1)      # + 1: a ragged last batch needs one more
         while len(self._blurs) < m:
             self._blurs.append(rt.empty_u8(ch.batch, ch.h, ch.w))
         while len(self._head) < min(self.PREBLUR, n_batches - m):
@@ -194,52 +200,61 @@ class ShardedSegmentChain(object):
             self._G = t.empty((self.world,) + tuple(self._S.shape), dtype=t.float32, device=rt.device)
         ch.pipeline_streams()
 
-    def _partial_state(self, blurs, covers_shard):
-        """ S of this rank from (the last of) its blurred batches (device) """
+    def _fold_batch(self, b, lo, first, init_from_first_frame):
+        """ fold frames lo.. of the blurred batch `b` into S (current stream) """
         ch, rt = self.chain, self.chain.rt
-        self._S.zero_()
-        n = sum(b.n for b in blurs)
-        # only the last `tail` frames matter
-        skip = max(0, n - self.tail)
-        first = True
-        seen = 0
-        for b in blurs:
-            lo = max(0, skip - seen)
-            seen += b.n
-            if lo >= b.n:
-                continue
-            part = b if lo == 0 else _slice_batch(b, lo, b.n)
-            if first and self.rank == 0 and skip == 0 and covers_shard:
-                # the sequential model starts from its first frame: S = float(x_0)
-                rt.ema_diff_thresh(_slice_batch(part, 0, 1), self._S, ch.alpha, ch.threshold, True)
-                if part.n > 1:
-                    rt.ema_partial(_slice_batch(part, 1, part.n), self._S, ch.alpha, True)
-            else:
-                rt.ema_partial(part, self._S, ch.alpha, not first)
-            first = False
-        return self._S
+        part = b if lo == 0 else _slice_batch(b, lo, b.n)
+        if init_from_first_frame:
+            # the sequential model starts from its first frame: S = float(x_0)
+            rt.ema_diff_thresh(_slice_batch(part, 0, 1), self._S, ch.alpha, ch.threshold, True)
+            if part.n > 1:
+                rt.ema_partial(_slice_batch(part, 1, part.n), self._S, ch.alpha, True)
+        else:
+            rt.ema_partial(part, self._S, ch.alpha, not first)
 
     # ---- the three phases ---------------------------------------------------------------------------
     def pass1(self, rgb_batches):
         """ blur the last batches of the shard -- the only frames whose weight a^k reaches the next rank -- and
-        fold them into the partial state S (returned; valid on the chain's front stream) """
+        fold them into the partial state S (returned; valid on the chain's front stream).  The blurs run on the
+        front stream; the fold of batch i (memory-bound) runs on the back stream beside the blur of batch i + 1
+        (issue-bound). """
         ch, rt, t = self.chain, self.chain.rt, torch_mod()
         nb = len(rgb_batches)
-        m = self.tail_batches(nb)
+        m = self.tail_batches(nb, rgb_batches[-1].n)
         self.reserve(nb)
-        front = ch.pipeline_streams()['front']
+        streams = ch.pipeline_streams()
+        front, back = streams['front'], streams['back']
         ready = t.cuda.Event()
         ready.record(t.cuda.current_stream(rt.device))
-        blurs = []
-        with t.cuda.stream(front):
-            front.wait_event(ready)
-            for i in range(nb - m, nb):
-                rgb = rgb_batches[i]
-                buf = self._blurs[i - (nb - m)]
-                blurs.append(ch.blur_device(rgb, buf if rgb.n == ch.batch else _slice_batch(buf, 0, rgb.n)))
-            S = self._partial_state(blurs, covers_shard=(m == nb))
+        n = sum(rgb_batches[i].n for i in range(nb - m, nb))
+        skip = max(0, n - self.tail)                      # only the last `tail` frames matter
+        covers_shard = (m == nb)
+        blurs, seen, first = [], 0, True
+        front.wait_event(ready)
+        back.wait_event(ready)
+        with t.cuda.stream(back):
+            self._S.zero_()
+        for i in range(nb - m, nb):
+            rgb = rgb_batches[i]
+            buf = self._blurs[i - (nb - m)]
+            with t.cuda.stream(front):
+                b = ch.blur_device(rgb, buf if rgb.n == ch.batch else _slice_batch(buf, 0, rgb.n))
+                done = t.cuda.Event()
+                done.record(front)
+            blurs.append(b)
+            lo = max(0, skip - seen)
+            seen += b.n
+            if lo >= b.n:
+                continue
+            with t.cuda.stream(back):
+                back.wait_event(done)
+                self._fold_batch(b, lo, first, first and self.rank == 0 and skip == 0 and covers_shard)
+            first = False
+        folded = t.cuda.Event()
+        folded.record(back)
+        front.wait_event(folded)                          # S is complete for whatever `front` does next
         self._p1 = (nb, m, blurs)
-        return S
+        return self._S
 
     def exchange(self, S):
         """ start the all-gather of the partial states (asynchronous); -> (gather buffer, work handle) """
