@@ -65,6 +65,11 @@ extern "C" int va_gauss_taps(double sigma, int *taps, int capacity) {
     return va_gauss_build_taps(sigma, taps, capacity);
 }
 
+int va_gauss_mma_launch(va_ctx *ctx, va_stream stream, const char *name, bool fuse,
+                        const uint8_t *in, size_t in_pitch, size_t in_fstride,
+                        uint8_t *out, size_t out_pitch, size_t out_fstride,
+                        int w, int h, int batch, int mode, const int *taps, int ksize);
+
 struct GaussFast {
     int r, o, nw, np;
     unsigned cw[4][GAUSS_NW_MAX];   // row pass: tap bytes for output pixel i, staged word j
@@ -570,6 +575,15 @@ static int gauss_launch(va_ctx *ctx, va_stream stream, const char *name, bool fu
 
     const bool fast = (fuse || channels == 1) && kmax <= 255 && r <= GAUSS_FAST_MAX_R && r >= 1;
     if (fast) {
+        // tensor-core kernel (va_gauss_mma.cu) wherever its shape constraints hold; VA_GAUSS_MMA=0 keeps the dot-product kernels
+        {
+            const char *env = getenv("VA_GAUSS_MMA");
+            if (!env || atoi(env) != 0) {
+                const int rc = va_gauss_mma_launch(ctx, stream, name, fuse, in, in_pitch, in_fstride, out, out_pitch, out_fstride,
+                                                   w, h, batch, mode, taps, ksize);
+                if (rc != VA_ERR_UNSUPPORTED) return rc;
+            }
+        }
         GaussFast g;
         memset(&g, 0, sizeof(g));
         g.r = r;

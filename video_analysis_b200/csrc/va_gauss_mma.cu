@@ -1,0 +1,387 @@
+// va_gauss_mma.cu -- K2 on the integer tensor cores: bit-exact cv2.GaussianBlur on uint8 (video/filters.py:392)
+// as two products with banded Toeplitz matrices, staged by TMA.
+//
+// OpenCV's 8-bit Gaussian is  out = (sum_ky K[ky] * Hrow[y + ky - r][x] + 32768) >> 16,  Hrow = sum_kx K[kx] * src[.][x + kx - r]
+// (taps K are 8-bit, sum 256).  Both passes are products with a banded Toeplitz matrix of the
+// taps, and  mma.sync.m16n8k32.s32.u8.u8.s32  is exact, so the result is bit-identical however the sums are grouped:
+//
+//   row pass     C1[x_out (16)][row (8)]   = T1[x_out][k]  *  src[row][window start + k]          k = 32 KS source columns
+//   column pass  C2[y_out (16)][x (8)]     = T2[y_out][k]  *  byte plane of Hrow[16-row groups][x] k = 16 G input rows,
+//                twice: low and high byte of the 16-bit Hrow,  out = byte 2 of ((C2_hi << 8) + C2_lo + 32768)
+//
+// The constant Toeplitz fragments live in registers (built once per warp from the tap table).  Because the matrix is
+// ours, the k index of a fragment is a free permutation: B fragments are whatever 8 consecutive source bytes a lane
+// reads with one LDS.64 (row pass), and whatever four rows a lane already holds in its row-pass accumulators (column
+// pass), so the 16-bit intermediate goes from accumulator to operand through a per-warp shared-memory ring without any
+// transposition.
+//
+// A warp owns a strip of 128 columns and walks down a segment of rows, 8 rows per half-step; warps share nothing.
+// Staging: one lane issues a TMA box load (cp.async.bulk.tensor) of the next 8 rows of strip + halo, two half-steps
+// ahead, and the warp waits on the stage's mbarrier.  Rows above / below the image are fetched as single-row boxes at
+// their BORDER_REFLECT_101 row; columns outside the image arrive as TMA zero fill and are overwritten with the mirrored
+// luma bytes in shared memory (strips at the image edge only).  The fused variant converts RGB -> luma from the raw
+// stage into the row buffer; the plain variant lets TMA write the row buffer itself.
+//
+// Algorithmic HBM bytes: 2N (4N fused).  Not handled here (gauss_launch falls back to the dot-product kernels):
+// rows that are not 16-byte aligned, widths that are not a multiple of 16, images smaller than the radius, radius > 56.
+#include <cstring>
+
+#include "va_mma.cuh"
+
+#define GM_STRIP 128
+#define GM_TILES 8
+#define GM_OUT_PITCH 144            // bytes per row of the output tile: rows land in different banks
+#define GM_MAX_G 8
+
+struct GaussMma {
+    int r;                  // radius, taps K[0 .. 2r]
+    int HL;                 // staged halo columns on either side of the strip
+    int off;                // row pass: output x = window start + off
+    int SH;                 // rows per segment (multiple of 16)
+    int strips, segs;       // task grid: strips x segments x frames
+    int mode;               // fused: -1 mean, 0..2 channel
+    unsigned char taps[128];
+};
+
+int va_tmap_encode(va_tmap *map, const void *base, size_t row_bytes, size_t rows, size_t frames, size_t pitch, size_t fstride,
+                   unsigned box_w32, unsigned box_rows) {
+#ifdef VA_EMU
+    map->base = reinterpret_cast<const uint8_t *>(base);
+    map->w32 = (unsigned)(row_bytes / 4);
+    map->rows = (unsigned)rows;
+    map->frames = (unsigned)frames;
+    map->pitch = pitch;
+    map->fstride = fstride;
+    map->box_w32 = box_w32;
+    map->box_rows = box_rows;
+    return 0;
+#else
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return -1;
+        encode = (encode_fn)fn;
+    }
+    // a single frame still needs a non-zero, 16-byte-multiple stride for the (unused) third dimension
+    const cuuint64_t dims[3] = {(cuuint64_t)(row_bytes / 4), (cuuint64_t)rows, (cuuint64_t)frames};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)(frames > 1 ? fstride : pitch * rows)};
+    const cuuint32_t box[3] = {box_w32, box_rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult rc = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void *>(base), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return rc == CUDA_SUCCESS ? 0 : -1;
+#endif
+}
+
+__device__ __forceinline__ unsigned gm_tap(const GaussMma &g, int idx) {
+    return (idx >= 0 && idx <= 2 * g.r) ? g.taps[idx] : 0u;
+}
+
+// bytes of the shared memory one warp needs
+__host__ __device__ inline int gm_lw(int HL) { return GM_STRIP + 2 * HL; }
+__host__ __device__ inline size_t gm_warp_smem(bool fuse, int G, int HL) {
+    const size_t LW = (size_t)gm_lw(HL);
+    const size_t SP = ((fuse ? 3 * LW : LW) + 127) & ~(size_t)127;   // stage row pitch of a half-step fetched row by row
+    size_t b = 0;
+    b += 2 * 8 * SP;                                // TMA stages
+    b += fuse ? 8 * LW : 0;                         // luma rows of the current half-step
+    b += (size_t)G * GM_TILES * 32 * 16;            // ring of row-pass results (16 rows x 128 columns x 16 bit per group)
+    b += 16 * GM_OUT_PITCH;                         // output tile
+    return (b + 127) & ~(size_t)127;
+}
+
+template <bool FUSE, int G>
+__global__ void __launch_bounds__(128)
+gauss_mma_kernel(const __grid_constant__ va_tmap map8, const __grid_constant__ va_tmap map1,
+                 uint8_t *__restrict__ out, size_t out_pitch, size_t out_fstride,
+                 int w, int h, int batch, const __grid_constant__ GaussMma gp) {
+    constexpr int KS = (G + 1) / 2;                 // row pass: 16 + 2r <= 32 KS  <=>  column pass: 16 + 2r <= 16 G
+    constexpr int KF = G / 2;                       // column pass: full k32 steps (two groups each), then one k16 step if G is odd
+    constexpr int C = FUSE ? 3 : 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int r = gp.r, HL = gp.HL, off = gp.off, SH = gp.SH;
+    const int LW = GM_STRIP + 2 * HL;               // staged luma bytes per row
+    const int BOXB = C * LW;                        // bytes per staged row
+    const int SP = (BOXB + 127) & ~127;             // pitch of the rows of a half-step that is fetched row by row (TMA
+                                                    // destinations are 128-byte aligned); a box of 8 rows lands densely
+
+    // ---- which strip / segment / frame ----------------------------------------------------------------
+    const long long task = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    const long long n_tasks = (long long)gp.strips * gp.segs * batch;
+    if (task >= n_tasks) return;                    // warps are independent: no block-wide barrier below
+    const int strip = (int)(task % gp.strips);
+    const int seg = (int)((task / gp.strips) % gp.segs);
+    const int frame = (int)(task / ((long long)gp.strips * gp.segs));
+    const int x0 = strip * GM_STRIP, y0 = seg * SH;
+    const int rows = min(SH, h - y0);
+    const int nblocks = (rows + 15) >> 4;
+
+    // ---- shared memory of this warp ---------------------------------------------------------------------
+    VA_DYN_SMEM(unsigned char, smem_raw);
+#ifdef VA_EMU
+    unsigned char *sm0 = smem_raw;
+#else
+    unsigned char *sm0 = smem_raw + ((128u - ((unsigned)__cvta_generic_to_shared(smem_raw) & 127u)) & 127u);
+#endif
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm0) + 2 * warp;                   // [warps][2]
+    unsigned char *wsm = sm0 + 128 + (size_t)warp * gm_warp_smem(FUSE, G, HL);      // 8 warps x 16 bytes of barriers fit in 128
+    unsigned char *stage0 = wsm;
+    unsigned char *lbuf = wsm + 2 * 8 * SP;                                          // FUSE only
+    uint4 *ring = reinterpret_cast<uint4 *>(wsm + 2 * 8 * SP + (FUSE ? 8 * LW : 0));
+    unsigned char *otile = reinterpret_cast<unsigned char *>(ring + G * GM_TILES * 32);
+
+    // ---- constant Toeplitz fragments ------------------------------------------------------------------
+    unsigned A1[KS][4];
+#pragma unroll
+    for (int ks = 0; ks < KS; ks++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int m = g + ((q & 1) ? 8 : 0);
+            unsigned wd = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int c = 32 * ks + 8 * t + ((q & 2) ? 4 : 0) + j;            // source column relative to the window start
+                wd |= gm_tap(gp, c - off - m + r) << (8 * j);
+            }
+            A1[ks][q] = wd;
+        }
+    // column pass: physical k = 4t + j of a 16-row group is its local row rho(t, j) (what the row-pass fragments hold)
+    unsigned A2[KF > 0 ? KF : 1][4], A2t[2] = {0, 0};
+#pragma unroll
+    for (int grp = 0; grp < G; grp++)
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const int m = g + (q ? 8 : 0);
+            unsigned wd = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int rho = j < 2 ? 2 * t + j : 8 + 2 * t + (j - 2);
+                wd |= gm_tap(gp, 16 * grp + rho - m) << (8 * j);                  // input row 16 grp + rho, output row r + m
+            }
+            if (grp < 2 * KF) A2[grp >> 1][q + ((grp & 1) ? 2 : 0)] = wd;
+            else A2t[q] = wd;
+        }
+
+    // ---- TMA producer (lane 0) ----------------------------------------------------------------------------
+    if (lane == 0) {
+        va_mbar_init(&bars[0], 1);
+        va_mbar_init(&bars[1], 1);
+        va_mbar_fence_init();
+    }
+    __syncwarp();
+    const int n_half = 2 * (nblocks + G - 1);
+    const int x32 = ((x0 - HL) * C) >> 2;          // (x0 - HL) * C is a multiple of 16 (may be negative: arithmetic shift is exact)
+    auto issue = [&](int hs) {                     // rows 8 hs .. 8 hs + 7 of the segment's padded row space
+        if (lane != 0 || hs >= n_half) return;
+        uint64_t *bar = &bars[hs & 1];
+        unsigned char *dst = stage0 + (size_t)(hs & 1) * 8 * SP;
+        const int ya = y0 - r + 8 * hs;
+        va_mbar_expect_tx(bar, 8u * (unsigned)BOXB);
+        if (ya >= 0 && ya + 7 < h) {
+            va_tma_load_3d(dst, &map8, bar, x32, ya, frame);
+        } else {                                   // rows above / below the image: one box per row at its reflected position
+            for (int i = 0; i < 8; i++) va_tma_load_3d(dst + (size_t)i * SP, &map1, bar, x32, va_reflect101(ya + i, h), frame);
+        }
+    };
+    issue(0);
+    issue(1);
+
+    const bool fix_l = x0 - HL < 0, fix_r = x0 + GM_STRIP + HL > w;
+    const bool mean = gp.mode < 0;
+    const unsigned sel_a = gp.mode == 0 ? 0x0630u : gp.mode == 1 ? 0x0741u : 0x0052u;
+    const unsigned sel_b = gp.mode == 0 ? 0x5210u : gp.mode == 1 ? 0x6210u : 0x7410u;
+    uint8_t *fout = out + (size_t)frame * out_fstride;
+    unsigned hold[GM_TILES][2];
+
+    for (int S = 0; S < nblocks + G - 1; S++) {
+        const int slot = S % G;
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            const int hs = 2 * S + half;
+            va_mbar_wait(&bars[half], (unsigned)(S & 1));
+            unsigned char *stg = stage0 + (size_t)half * 8 * SP;
+            const int ya = y0 - r + 8 * hs;
+            const int sp = (ya >= 0 && ya + 7 < h) ? BOXB : SP;      // row pitch of this stage (see issue())
+            unsigned char *lrow = FUSE ? lbuf : stg;                // 8 rows of luma
+            const int lp = FUSE ? LW : sp;
+            if (FUSE) {
+                // RGB -> luma, items of 16 pixels (three 16-byte loads, one 16-byte store)
+                const int ipr = LW >> 4;
+                for (int it = lane; it < 8 * ipr; it += 32) {
+                    const int row = it / ipr, ci = it - row * ipr;
+                    const uint4 *q = reinterpret_cast<const uint4 *>(stg + (size_t)row * sp + 48 * ci);
+                    const uint4 a = q[0], b = q[1], c = q[2];
+                    uint4 v;
+                    if (mean) {
+                        v = make_uint4(va_mean3_x4(a.x, a.y, a.z), va_mean3_x4(a.w, b.x, b.y), va_mean3_x4(b.z, b.w, c.x), va_mean3_x4(c.y, c.z, c.w));
+                    } else {
+                        v = make_uint4(__byte_perm(__byte_perm(a.x, a.y, sel_a), a.z, sel_b), __byte_perm(__byte_perm(a.w, b.x, sel_a), b.y, sel_b),
+                                       __byte_perm(__byte_perm(b.z, b.w, sel_a), c.x, sel_b), __byte_perm(__byte_perm(c.y, c.z, sel_a), c.w, sel_b));
+                    }
+                    *reinterpret_cast<uint4 *>(lbuf + (size_t)row * LW + 16 * ci) = v;
+                }
+                __syncwarp();
+                issue(hs + 2);                                      // the raw stage is free again
+            }
+            if (fix_l || fix_r) {
+                // BORDER_REFLECT_101 in x: columns -k <- k and w - 1 + k <- w - 1 - k, k = 1 .. r (luma bytes, in place)
+                for (int it = lane; it < 8 * r; it += 32) {
+                    const int row = it / r, k = it - row * r + 1;
+                    unsigned char *p = lrow + (size_t)row * lp + HL;
+                    if (fix_l) p[-x0 - k] = p[-x0 + k];
+                    if (fix_r) {
+                        const int d = w - 1 - x0 + k;
+                        if (d < GM_STRIP + HL) p[d] = p[w - 1 - x0 - k];
+                    }
+                }
+                __syncwarp();
+            }
+            // ---- row pass: 8 rows x 128 columns
+#pragma unroll
+            for (int j = 0; j < GM_TILES; j++) {
+                int c[4] = {0, 0, 0, 0};
+                const unsigned char *bp = lrow + (size_t)g * lp + (HL - off) + 16 * j + 8 * t;
+#pragma unroll
+                for (int ks = 0; ks < KS; ks++) {
+                    const uint2 b = *reinterpret_cast<const uint2 *>(bp + 32 * ks);
+                    va_imma_16832(c, A1[ks], b.x, b.y);
+                }
+                // (row 2t, row 2t + 1) of column g and of column g + 8: low bytes, then high bytes
+                const unsigned pg = __byte_perm((unsigned)c[0], (unsigned)c[1], 0x5140);
+                const unsigned pg8 = __byte_perm((unsigned)c[2], (unsigned)c[3], 0x5140);
+                if (half == 0) {
+                    hold[j][0] = pg;
+                    hold[j][1] = pg8;
+                } else {
+                    // rows {2t, 2t+1, 8+2t, 9+2t} of this 16-row group: one operand word per byte plane
+                    const uint4 v = make_uint4(__byte_perm(hold[j][0], pg, 0x5410), __byte_perm(hold[j][0], pg, 0x7632),
+                                               __byte_perm(hold[j][1], pg8, 0x5410), __byte_perm(hold[j][1], pg8, 0x7632));
+                    ring[(slot * GM_TILES + j) * 32 + lane] = v;
+                }
+            }
+            if (!FUSE) {
+                __syncwarp();
+                issue(hs + 2);                                      // TMA wrote the luma rows itself: the stage is free now
+            }
+        }
+        __syncwarp();
+        if (S < G - 1) continue;
+        // ---- column pass: output rows y0 + 16 b .. + 15 from groups b .. b + G - 1
+        const int b = S - (G - 1);
+#pragma unroll
+        for (int j = 0; j < GM_TILES; j++) {
+            uint4 v[G];
+#pragma unroll
+            for (int i = 0; i < G; i++) {
+                int sl = b + i;
+                sl -= (sl / G) * G;
+                v[i] = ring[(sl * GM_TILES + j) * 32 + lane];
+            }
+#pragma unroll
+            for (int nh = 0; nh < 2; nh++) {
+                int lo[4] = {32768, 32768, 32768, 32768}, hi[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int ks = 0; ks < KF; ks++) {
+                    va_imma_16832(lo, A2[ks], nh ? v[2 * ks].z : v[2 * ks].x, nh ? v[2 * ks + 1].z : v[2 * ks + 1].x);
+                    va_imma_16832(hi, A2[ks], nh ? v[2 * ks].w : v[2 * ks].y, nh ? v[2 * ks + 1].w : v[2 * ks + 1].y);
+                }
+                if (G & 1) {
+                    va_imma_16816(lo, A2t[0], A2t[1], nh ? v[G - 1].z : v[G - 1].x);
+                    va_imma_16816(hi, A2t[0], A2t[1], nh ? v[G - 1].w : v[G - 1].y);
+                }
+                // byte 2 of (hi << 8) + lo (< 2^24) is the rounded result; two neighbouring columns per store
+                const unsigned v0 = ((unsigned)hi[0] << 8) + (unsigned)lo[0], v1 = ((unsigned)hi[1] << 8) + (unsigned)lo[1];
+                const unsigned v2 = ((unsigned)hi[2] << 8) + (unsigned)lo[2], v3 = ((unsigned)hi[3] << 8) + (unsigned)lo[3];
+                unsigned char *op = otile + g * GM_OUT_PITCH + 16 * j + 8 * nh + 2 * t;
+                *reinterpret_cast<unsigned short *>(op) = (unsigned short)__byte_perm(v0, v1, 0x0062);
+                *reinterpret_cast<unsigned short *>(op + 8 * GM_OUT_PITCH) = (unsigned short)__byte_perm(v2, v3, 0x0062);
+            }
+        }
+        __syncwarp();
+        // ---- 16 rows x 128 bytes -> global, 16 bytes per lane and round
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int idx = lane + 32 * i, row = idx >> 3, c16 = idx & 7;
+            const int yl = 16 * b + row, x = x0 + 16 * c16;
+            if (yl < rows && x < w) {
+                const uint4 val = *reinterpret_cast<const uint4 *>(otile + row * GM_OUT_PITCH + 16 * c16);
+                va_st_stream16(fout + (size_t)(y0 + yl) * out_pitch + x, val);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// launch; returns VA_ERR_UNSUPPORTED when the shape is outside this kernel's range (the caller falls back)
+// ---------------------------------------------------------------------------------------------------------
+int va_gauss_mma_launch(va_ctx *ctx, va_stream stream, const char *name, bool fuse,
+                        const uint8_t *in, size_t in_pitch, size_t in_fstride,
+                        uint8_t *out, size_t out_pitch, size_t out_fstride,
+                        int w, int h, int batch, int mode, const int *taps, int ksize) {
+    const int r = ksize / 2;
+    if (r < 1 || r > 56 || w % 16 != 0 || w < r + 2 || h < r + 1) return VA_ERR_UNSUPPORTED;
+    if (!va_aligned(in, 16) || in_pitch % 16 || in_fstride % 16 || !va_aligned(out, 16) || out_pitch % 16 || out_fstride % 16)
+        return VA_ERR_UNSUPPORTED;
+    for (int i = 0; i < ksize; i++)
+        if (taps[i] > 255) return VA_ERR_UNSUPPORTED;
+    const int C = fuse ? 3 : 1;
+    if ((unsigned long long)h * in_pitch >= (1ull << 40)) return VA_ERR_UNSUPPORTED;
+    const int G = (16 + 2 * r + 15) / 16;
+    const int KS = (G + 1) / 2;
+    GaussMma gp;
+    memset(&gp, 0, sizeof(gp));
+    gp.r = r;
+    gp.off = 16 * KS - 8;
+    gp.HL = KS == 1 ? 16 : KS <= 3 ? 48 : 80;       // >= off, and 128 + 2 HL = 32 (mod 64): conflict-free LDS.64 of the B fragments
+    gp.mode = mode;
+    for (int i = 0; i < ksize; i++) gp.taps[i] = (unsigned char)taps[i];
+    const int LW = gm_lw(gp.HL);
+    if ((unsigned)(C * LW / 4) > 256u) return VA_ERR_UNSUPPORTED;
+    gp.strips = va_div_up(w, GM_STRIP);
+    // segments: enough warp tasks to fill the machine a few times over, but every segment re-stages 16 (G - 1) rows
+    const size_t wsm = gm_warp_smem(fuse, G, gp.HL);
+    int wpc = 4;
+    while (wpc > 1 && 256 + (size_t)wpc * wsm > 200 * 1024) wpc >>= 1;
+    if (256 + (size_t)wpc * wsm > 220 * 1024) return VA_ERR_UNSUPPORTED;
+    const size_t smem = 256 + (size_t)wpc * wsm;
+    int ctas_per_sm = (int)((size_t)(220 * 1024) / smem);
+    if (ctas_per_sm > 8) ctas_per_sm = 8;
+    const long long slots = (long long)ctx->sm_count * ctas_per_sm * wpc;
+    int segs = (int)va_div_up(4 * slots, (long long)gp.strips * batch);
+    const int max_segs = h / (64 * (G - 1)) > 0 ? h / (64 * (G - 1)) : 1;            // re-staged rows <= 25 %
+    if (segs > max_segs) segs = max_segs;
+    if (getenv("VA_GM_SEGS")) segs = atoi(getenv("VA_GM_SEGS"));
+    if (segs < 1) segs = 1;
+    gp.SH = 16 * va_div_up(h, 16 * segs);
+    gp.segs = va_div_up(h, gp.SH);
+    va_tmap map8, map1;
+    if (va_tmap_encode(&map8, in, (size_t)w * C, h, batch, in_pitch, in_fstride, (unsigned)(C * LW / 4), 8) != 0 ||
+        va_tmap_encode(&map1, in, (size_t)w * C, h, batch, in_pitch, in_fstride, (unsigned)(C * LW / 4), 1) != 0)
+        return VA_ERR_UNSUPPORTED;
+    const long long tasks = (long long)gp.strips * gp.segs * batch;
+    const long long grid = va_div_up(tasks, wpc);
+    if (grid > 0x7fffffffll) return VA_ERR_UNSUPPORTED;
+#define GM_GO(FUSE, GG)                                                                                          \
+    do {                                                                                                         \
+        auto kfn = gauss_mma_kernel<FUSE, GG>;                                                                   \
+        if (smem > 48 * 1024)                                                                                    \
+            VA_CUDA(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+        VA_LAUNCH(ctx, kfn, (unsigned)grid, 32 * wpc, smem, stream, map8, map1, out, out_pitch, out_fstride, w, h, batch, gp); \
+    } while (0)
+#define GM_CASE(GG) case GG: if (fuse) GM_GO(true, GG); else GM_GO(false, GG); break;
+    switch (G) {
+        GM_CASE(2) GM_CASE(3) GM_CASE(4) GM_CASE(5) GM_CASE(6) GM_CASE(7) GM_CASE(8)
+        default: return VA_ERR_UNSUPPORTED;
+    }
+#undef GM_CASE
+#undef GM_GO
+    (void)name;
+    return VA_OK;
+}
