@@ -541,7 +541,7 @@ def test_fused_crop_monochrome_checks_the_rectangle(frames):
         with pytest.raises(IndexError):
             F.FilterCrop(v, batch=2, **kw)
     with pytest.raises(IndexError):
-        F.FilterCrop(F.FilterCrop(v, rect=(200, 100, 100, 100)), rect=(50, 50, 60, 60))     # nested: 200 + 50 + 60 > 320
+        F.FilterCrop(F.FilterCrop(v, rect=(200, 100, 100, 100)), rect=(70, 50, 60, 40))     # nested: 200 + 70 + 60 > 320
     ok = F.FilterCrop(v, rect=(250, 10, 67, 50), size_alignment=8, batch=2)                   # 67 -> 64: fits
     assert ok.rect == (250, 10, 64, 48) and np.stack(list(F.FilterMonochrome(ok))).shape == (4, 48, 64)
     # a source whose frames are smaller than its metadata: the runtime check fires on both paths

@@ -99,6 +99,7 @@ def test_gauss_streaming_kernel(be, ctx, monkeypatch):
     # 16-byte aligned frames with W % 16 == 0 take the register-window kernel (radius <= 9): every radius,
     # strips cut by the right image edge, several row segments, images barely taller than the window,
     # fused and unfused, mean and single-channel luma
+    monkeypatch.setenv('VA_GAUSS_MMA', '0')              # the dot-product kernels (fallback of the tensor-core kernel)
     cases = sizes(be, [(33, 160), (12, 16), (40, 640), (21, 336)], [(480, 640), (271, 1008), (67, 2064)])
     for (H, W) in cases:
         fr = rng_frames(H * W, (2, H, W, 3))
@@ -118,6 +119,42 @@ def test_gauss_streaming_kernel(be, ctx, monkeypatch):
                                           np.stack([ops.blur(ops.mono(f), s) for f in fr])), (H, W, s, segs, nt)
     monkeypatch.setenv('VA_GAUSS_STREAM', '0')           # and the tile kernel on the same inputs
     assert np.array_equal(hz.gauss(ctx, g, 2), np.stack([ops.blur(f, 2) for f in g]))
+
+
+def test_gauss_tensor_core_kernel(be, ctx, monkeypatch):
+    # va_gauss_mma.cu (16-byte aligned frames, W % 16 == 0): every group count G = 2 .. 8 of the column pass (radius 1 .. 56),
+    # both strip widths, 2 .. 4 TMA stages, one and several row segments, strips cut by the right image edge, images
+    # barely larger than the radius, fused (mean and channel pick) and plain; identical to the dot-product kernels
+    cases = sizes(be, [(40, 160), (70, 272), (21, 336), (130, 144)], [(480, 640), (1080, 1920), (271, 1008), (67, 2064)])
+    sig = [0.5, 1, 2, 2.6, 3, 3.5, 5, 6, 8, 9, 12, 15, 18]
+    for n, (H, W) in enumerate(cases):
+        fr = rng_frames(H * W, (2, H, W, 3))
+        g = fr[..., 2].copy()
+        for s in sig:
+            want = np.stack([ops.blur(f, s) for f in g])
+            full = n == 0 and (be.name == 'cuda' or s in (2, 5, 15))
+            variants = [dict(), dict(VA_GM_SEGS=1), dict(VA_GM_SEGS=3, VA_GM_TILES=8), dict(VA_GM_STAGES=2),
+                        dict(VA_GM_STAGES=3, VA_GM_MINB=3)] if full else [dict()]
+            for var in variants:
+                for key in ('VA_GM_SEGS', 'VA_GM_TILES', 'VA_GM_STAGES', 'VA_GM_MINB'):
+                    monkeypatch.delenv(key, raising=False)
+                for key, val in var.items():
+                    monkeypatch.setenv(key, str(val))
+                monkeypatch.setenv('VA_GAUSS_MMA', '2')       # 2: also for radius 9, where the streaming kernel is the default
+                assert np.array_equal(hz.gauss(ctx, g, s), want), (H, W, s, var)
+                assert np.array_equal(hz.luma_gauss(ctx, fr, s, mode=2), want), (H, W, s, var)
+                if s in (1, 2, 15):
+                    assert np.array_equal(hz.luma_gauss(ctx, fr, s), np.stack([ops.blur(ops.mono(f), s) for f in fr])), (H, W, s, var)
+    for key in ('VA_GM_SEGS', 'VA_GM_TILES', 'VA_GM_STAGES', 'VA_GM_MINB'):
+        monkeypatch.delenv(key, raising=False)
+    monkeypatch.setenv('VA_GAUSS_MMA', '0')
+    assert np.array_equal(hz.gauss(ctx, g, 5), np.stack([ops.blur(f, 5) for f in g]))
+    # unaligned rows and ragged widths fall back to the dot-product kernels (same bytes)
+    monkeypatch.delenv('VA_GAUSS_MMA', raising=False)
+    odd = rng_frames(9, (1, 40, 150))
+    assert np.array_equal(hz.gauss(ctx, odd, 2), np.stack([ops.blur(f, 2) for f in odd]))
+    al = rng_frames(10, (1, 40, 160))
+    assert np.array_equal(hz.gauss(ctx, al, 2, in_pad=3, out_pad=5), np.stack([ops.blur(f, 2) for f in al]))
 
 
 def test_gauss_large_sigma_identity_and_generic_paths(be, ctx):

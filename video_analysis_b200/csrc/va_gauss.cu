@@ -578,10 +578,28 @@ static int gauss_launch(va_ctx *ctx, va_stream stream, const char *name, bool fu
         // tensor-core kernel (va_gauss_mma.cu) wherever its shape constraints hold; VA_GAUSS_MMA=0 keeps the dot-product kernels
         {
             const char *env = getenv("VA_GAUSS_MMA");
-            if (!env || atoi(env) != 0) {
-                const int rc = va_gauss_mma_launch(ctx, stream, name, fuse, in, in_pitch, in_fstride, out, out_pitch, out_fstride,
-                                                   w, h, batch, mode, taps, ksize);
+            // radius 9 (16 + 2r = 34: a third 16-row group for two rows) is the one case where the streaming dot-product
+            // kernel is still ahead (0.159 against 0.183 ms per 64 frames of 1080p)
+            if ((!env || atoi(env) != 0) && !(r == 9 && (!env || atoi(env) != 2))) {
+                int rc = va_gauss_mma_launch(ctx, stream, name, fuse, in, in_pitch, in_fstride, out, out_pitch, out_fstride,
+                                             w, h, batch, mode, taps, ksize);
                 if (rc != VA_ERR_UNSUPPORTED) return rc;
+                if (fuse && r > 8 && w % 16 == 0) {
+                    // the fused tensor-core kernel covers radius <= 8; beyond that the monochrome frames go through a
+                    // stream-ordered temporary (N bytes per frame more traffic on a kernel that is far from HBM-bound)
+                    uint8_t *tmp = nullptr;
+                    const size_t tp = (size_t)w, tf = tp * (size_t)h;
+                    if (cudaMallocAsync((void **)&tmp, tf * (size_t)batch, (cudaStream_t)stream) == cudaSuccess) {
+                        rc = va_luma_u8(ctx, stream, in, in_pitch, in_fstride, tmp, tp, tf, w, h, batch, mode);
+                        if (rc == VA_OK)
+                            rc = va_gauss_mma_launch(ctx, stream, name, false, tmp, tp, tf, out, out_pitch, out_fstride,
+                                                     w, h, batch, mode, taps, ksize);
+                        cudaFreeAsync(tmp, (cudaStream_t)stream);
+                        if (rc != VA_ERR_UNSUPPORTED) return rc;
+                    } else {
+                        cudaGetLastError();
+                    }
+                }
             }
         }
         GaussFast g;

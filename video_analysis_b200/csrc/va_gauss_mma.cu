@@ -28,17 +28,15 @@
 
 #include "va_mma.cuh"
 
-#define GM_STRIP 128
-#define GM_TILES 8
-#define GM_OUT_PITCH 144            // bytes per row of the output tile: rows land in different banks
+#define GM_OUT_PITCH(TILES) (16 * (TILES) + 16)   // bytes per row of the output tile: rows land in different banks
 #define GM_MAX_G 8
+#define GM_MAX_STAGES 4
 
 struct GaussMma {
     int r;                  // radius, taps K[0 .. 2r]
-    int HL;                 // staged halo columns on either side of the strip
-    int off;                // row pass: output x = window start + off
     int SH;                 // rows per segment (multiple of 16)
     int strips, segs;       // task grid: strips x segments x frames
+    int stages;             // TMA stages of 8 rows in flight per warp (<= GM_MAX_STAGES)
     int mode;               // fused: -1 mean, 0..2 channel
     unsigned char taps[128];
 };
@@ -83,33 +81,53 @@ __device__ __forceinline__ unsigned gm_tap(const GaussMma &g, int idx) {
 }
 
 // bytes of the shared memory one warp needs
-__host__ __device__ inline int gm_lw(int HL) { return GM_STRIP + 2 * HL; }
-__host__ __device__ inline size_t gm_warp_smem(bool fuse, int G, int HL) {
-    const size_t LW = (size_t)gm_lw(HL);
+__host__ __device__ inline int gm_hl(int G) { const int KS = (G + 1) / 2; return KS == 1 ? 16 : KS <= 3 ? 48 : 80; }
+__host__ __device__ inline size_t gm_warp_smem(bool fuse, int G, int tiles, int stages) {
+    const size_t LW = (size_t)(16 * tiles + 2 * gm_hl(G));
     const size_t SP = ((fuse ? 3 * LW : LW) + 127) & ~(size_t)127;   // stage row pitch of a half-step fetched row by row
     size_t b = 0;
-    b += 2 * 8 * SP;                                // TMA stages
-    b += fuse ? 8 * LW : 0;                         // luma rows of the current half-step
-    b += (size_t)G * GM_TILES * 32 * 16;            // ring of row-pass results (16 rows x 128 columns x 16 bit per group)
-    b += 16 * GM_OUT_PITCH;                         // output tile
+    b += (size_t)stages * 8 * SP;                   // TMA stages
+    size_t ot = 16 * (size_t)GM_OUT_PITCH(tiles);   // output tile; the fused variant keeps its 8 luma rows in the same place
+    if (fuse && 8 * LW > ot) ot = 8 * LW;
+    b += (ot + 15) & ~(size_t)15;
+    if (G > 2) b += (size_t)G * tiles * 32 * 16;    // ring of row-pass results (16 rows x strip x 16 bit per group)
     return (b + 127) & ~(size_t)127;
 }
 
-template <bool FUSE, int G>
-__global__ void __launch_bounds__(128)
+// geometry that follows from the number of 16-row groups G of a column-pass block (16 + 2r <= 16 G)
+template <int G, int TILES> struct GmGeom {
+    static constexpr int KS = (G + 1) / 2;                        // row pass: 16 + 2r <= 32 KS
+    static constexpr int OFF = 16 * KS - 8;                       // row pass: output x = window start + OFF (>= r, multiple of 8)
+    static constexpr int HL = KS == 1 ? 16 : KS <= 3 ? 48 : 80;   // staged halo: >= OFF, and 128 + 2 HL = 32 (mod 64) so that the
+                                                                  // LDS.64 of the B fragments are bank-conflict free
+    static constexpr int STRIP = 16 * TILES;                      // columns a warp owns
+    static constexpr int LW = STRIP + 2 * HL;                     // staged luma bytes per row
+};
+
+// fetch 8 rows row by row at their BORDER_REFLECT_101 position (top / bottom of the image only; kept out of line)
+static __device__ __noinline__ void gm_issue_rows(unsigned char *dst, const va_tmap *map1, uint64_t *bar, int x32, int ya, int h,
+                                                  int frame, int sp) {
+#pragma unroll 1
+    for (int i = 0; i < 8; i++) va_tma_load_3d(dst + (size_t)i * sp, map1, bar, x32, va_reflect101(ya + i, h), frame);
+}
+
+template <bool FUSE, int G, int TILES, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 gauss_mma_kernel(const __grid_constant__ va_tmap map8, const __grid_constant__ va_tmap map1,
                  uint8_t *__restrict__ out, size_t out_pitch, size_t out_fstride,
                  int w, int h, int batch, const __grid_constant__ GaussMma gp) {
-    constexpr int KS = (G + 1) / 2;                 // row pass: 16 + 2r <= 32 KS  <=>  column pass: 16 + 2r <= 16 G
+    constexpr int KS = GmGeom<G, TILES>::KS, HL = GmGeom<G, TILES>::HL, off = GmGeom<G, TILES>::OFF, LW = GmGeom<G, TILES>::LW;
+    constexpr int GM_STRIP = 16 * TILES, GM_TILES = TILES, OPITCH = GM_OUT_PITCH(TILES);
     constexpr int KF = G / 2;                       // column pass: full k32 steps (two groups each), then one k16 step if G is odd
     constexpr int C = FUSE ? 3 : 1;
+    constexpr int BOXB = C * LW;                    // bytes per staged row
+    constexpr int SP = (BOXB + 127) & ~127;         // pitch of the rows of a half-step that is fetched row by row (TMA
+                                                    // destinations are 128-byte aligned); a box of 8 rows lands densely
+    const int NS = gp.stages;                       // TMA stages of 8 rows in flight per warp
+    constexpr bool REG_RING = (G == 2);             // two groups: the previous group stays in registers, no ring
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int r = gp.r, HL = gp.HL, off = gp.off, SH = gp.SH;
-    const int LW = GM_STRIP + 2 * HL;               // staged luma bytes per row
-    const int BOXB = C * LW;                        // bytes per staged row
-    const int SP = (BOXB + 127) & ~127;             // pitch of the rows of a half-step that is fetched row by row (TMA
-                                                    // destinations are 128-byte aligned); a box of 8 rows lands densely
+    const int r = gp.r, SH = gp.SH;
 
     // ---- which strip / segment / frame ----------------------------------------------------------------
     const long long task = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
@@ -129,25 +147,28 @@ gauss_mma_kernel(const __grid_constant__ va_tmap map8, const __grid_constant__ v
 #else
     unsigned char *sm0 = smem_raw + ((128u - ((unsigned)__cvta_generic_to_shared(smem_raw) & 127u)) & 127u);
 #endif
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sm0) + 2 * warp;                   // [warps][2]
-    unsigned char *wsm = sm0 + 128 + (size_t)warp * gm_warp_smem(FUSE, G, HL);      // 8 warps x 16 bytes of barriers fit in 128
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm0) + NS * warp;                  // [warps][NS]
+    unsigned char *wsm = sm0 + 256 + (size_t)warp * gm_warp_smem(FUSE, G, TILES, NS);   // 4 warps x NS x 8 bytes of barriers fit in 256
     unsigned char *stage0 = wsm;
-    unsigned char *lbuf = wsm + 2 * 8 * SP;                                          // FUSE only
-    uint4 *ring = reinterpret_cast<uint4 *>(wsm + 2 * 8 * SP + (FUSE ? 8 * LW : 0));
-    unsigned char *otile = reinterpret_cast<unsigned char *>(ring + G * GM_TILES * 32);
+    unsigned char *lbuf = wsm + NS * 8 * SP;                                         // FUSE: luma rows; shares its place with the output tile
+    unsigned char *otile = lbuf;
+    uint4 *ring = reinterpret_cast<uint4 *>(lbuf + (((FUSE && 8 * LW > 16 * OPITCH) ? 8 * LW : 16 * OPITCH) + 15 & ~15));   // G > 2 only
 
     // ---- constant Toeplitz fragments ------------------------------------------------------------------
+    // row pass: fragment row m is output column pi(m) of the tile, pi(2u) = 4u, pi(2u+1) = 4u+1, pi(8+2u) = 4u+2, pi(9+2u) = 4u+3,
+    // so that a lane's column-pass results are four neighbouring columns
     unsigned A1[KS][4];
 #pragma unroll
     for (int ks = 0; ks < KS; ks++)
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const int m = g + ((q & 1) ? 8 : 0);
+            const int xo = 4 * ((m & 7) >> 1) + (m & 1) + ((m & 8) ? 2 : 0);
             unsigned wd = 0;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const int c = 32 * ks + 8 * t + ((q & 2) ? 4 : 0) + j;            // source column relative to the window start
-                wd |= gm_tap(gp, c - off - m + r) << (8 * j);
+                wd |= gm_tap(gp, c - off - xo + r) << (8 * j);
             }
             A1[ks][q] = wd;
         }
@@ -170,27 +191,22 @@ gauss_mma_kernel(const __grid_constant__ va_tmap map8, const __grid_constant__ v
 
     // ---- TMA producer (lane 0) ----------------------------------------------------------------------------
     if (lane == 0) {
-        va_mbar_init(&bars[0], 1);
-        va_mbar_init(&bars[1], 1);
+        for (int i = 0; i < NS; i++) va_mbar_init(&bars[i], 1);
         va_mbar_fence_init();
     }
     __syncwarp();
     const int n_half = 2 * (nblocks + G - 1);
     const int x32 = ((x0 - HL) * C) >> 2;          // (x0 - HL) * C is a multiple of 16 (may be negative: arithmetic shift is exact)
-    auto issue = [&](int hs) {                     // rows 8 hs .. 8 hs + 7 of the segment's padded row space
+    auto issue = [&](int hs, int st) {             // rows 8 hs .. 8 hs + 7 of the segment's padded row space into stage st
         if (lane != 0 || hs >= n_half) return;
-        uint64_t *bar = &bars[hs & 1];
-        unsigned char *dst = stage0 + (size_t)(hs & 1) * 8 * SP;
+        uint64_t *bar = &bars[st];
+        unsigned char *dst = stage0 + (size_t)st * 8 * SP;
         const int ya = y0 - r + 8 * hs;
         va_mbar_expect_tx(bar, 8u * (unsigned)BOXB);
-        if (ya >= 0 && ya + 7 < h) {
-            va_tma_load_3d(dst, &map8, bar, x32, ya, frame);
-        } else {                                   // rows above / below the image: one box per row at its reflected position
-            for (int i = 0; i < 8; i++) va_tma_load_3d(dst + (size_t)i * SP, &map1, bar, x32, va_reflect101(ya + i, h), frame);
-        }
+        if (ya >= 0 && ya + 7 < h) va_tma_load_3d(dst, &map8, bar, x32, ya, frame);
+        else gm_issue_rows(dst, &map1, bar, x32, ya, h, frame, SP);
     };
-    issue(0);
-    issue(1);
+    for (int i = 0; i < NS; i++) issue(i, i);
 
     const bool fix_l = x0 - HL < 0, fix_r = x0 + GM_STRIP + HL > w;
     const bool mean = gp.mode < 0;
@@ -198,21 +214,25 @@ gauss_mma_kernel(const __grid_constant__ va_tmap map8, const __grid_constant__ v
     const unsigned sel_b = gp.mode == 0 ? 0x5210u : gp.mode == 1 ? 0x6210u : 0x7410u;
     uint8_t *fout = out + (size_t)frame * out_fstride;
     unsigned hold[GM_TILES][2];
+    uint4 prev[REG_RING ? GM_TILES : 1], cur[REG_RING ? GM_TILES : 1];
+    int st = 0;                                    // stage of the next half-step
+    unsigned phases = 0;                           // bit i: parity the next wait on stage i expects
 
     for (int S = 0; S < nblocks + G - 1; S++) {
         const int slot = S % G;
 #pragma unroll
         for (int half = 0; half < 2; half++) {
             const int hs = 2 * S + half;
-            va_mbar_wait(&bars[half], (unsigned)(S & 1));
-            unsigned char *stg = stage0 + (size_t)half * 8 * SP;
+            va_mbar_wait(&bars[st], (phases >> st) & 1u);
+            phases ^= 1u << st;
+            unsigned char *stg = stage0 + (size_t)st * 8 * SP;
             const int ya = y0 - r + 8 * hs;
             const int sp = (ya >= 0 && ya + 7 < h) ? BOXB : SP;      // row pitch of this stage (see issue())
             unsigned char *lrow = FUSE ? lbuf : stg;                // 8 rows of luma
             const int lp = FUSE ? LW : sp;
             if (FUSE) {
                 // RGB -> luma, items of 16 pixels (three 16-byte loads, one 16-byte store)
-                const int ipr = LW >> 4;
+                constexpr int ipr = LW >> 4;
                 for (int it = lane; it < 8 * ipr; it += 32) {
                     const int row = it / ipr, ci = it - row * ipr;
                     const uint4 *q = reinterpret_cast<const uint4 *>(stg + (size_t)row * sp + 48 * ci);
@@ -227,14 +247,14 @@ gauss_mma_kernel(const __grid_constant__ va_tmap map8, const __grid_constant__ v
                     *reinterpret_cast<uint4 *>(lbuf + (size_t)row * LW + 16 * ci) = v;
                 }
                 __syncwarp();
-                issue(hs + 2);                                      // the raw stage is free again
+                issue(hs + NS, st);                                 // the raw stage is free again
             }
             if (fix_l || fix_r) {
                 // BORDER_REFLECT_101 in x: columns -k <- k and w - 1 + k <- w - 1 - k, k = 1 .. r (luma bytes, in place)
                 for (int it = lane; it < 8 * r; it += 32) {
                     const int row = it / r, k = it - row * r + 1;
                     unsigned char *p = lrow + (size_t)row * lp + HL;
-                    if (fix_l) p[-x0 - k] = p[-x0 + k];
+                    if (fix_l && x0 + k <= HL) p[-x0 - k] = p[-x0 + k];
                     if (fix_r) {
                         const int d = w - 1 - x0 + k;
                         if (d < GM_STRIP + HL) p[d] = p[w - 1 - x0 - k];
@@ -252,7 +272,7 @@ gauss_mma_kernel(const __grid_constant__ va_tmap map8, const __grid_constant__ v
                     const uint2 b = *reinterpret_cast<const uint2 *>(bp + 32 * ks);
                     va_imma_16832(c, A1[ks], b.x, b.y);
                 }
-                // (row 2t, row 2t + 1) of column g and of column g + 8: low bytes, then high bytes
+                // (row 2t, row 2t + 1) of fragment row g and of fragment row g + 8: low bytes, then high bytes
                 const unsigned pg = __byte_perm((unsigned)c[0], (unsigned)c[1], 0x5140);
                 const unsigned pg8 = __byte_perm((unsigned)c[2], (unsigned)c[3], 0x5140);
                 if (half == 0) {
@@ -262,59 +282,75 @@ gauss_mma_kernel(const __grid_constant__ va_tmap map8, const __grid_constant__ v
                     // rows {2t, 2t+1, 8+2t, 9+2t} of this 16-row group: one operand word per byte plane
                     const uint4 v = make_uint4(__byte_perm(hold[j][0], pg, 0x5410), __byte_perm(hold[j][0], pg, 0x7632),
                                                __byte_perm(hold[j][1], pg8, 0x5410), __byte_perm(hold[j][1], pg8, 0x7632));
-                    ring[(slot * GM_TILES + j) * 32 + lane] = v;
+                    if constexpr (REG_RING) cur[j] = v;
+                    else ring[(slot * GM_TILES + j) * 32 + lane] = v;
                 }
             }
             if (!FUSE) {
                 __syncwarp();
-                issue(hs + 2);                                      // TMA wrote the luma rows itself: the stage is free now
+                issue(hs + NS, st);                                 // TMA wrote the luma rows itself: the stage is free now
             }
+            st = st + 1 == NS ? 0 : st + 1;
         }
-        __syncwarp();
-        if (S < G - 1) continue;
-        // ---- column pass: output rows y0 + 16 b .. + 15 from groups b .. b + G - 1
-        const int b = S - (G - 1);
+        if (S >= G - 1) {
+            // ---- column pass: output rows y0 + 16 b .. + 15 from groups b .. b + G - 1
+            const int b = S - (G - 1);
+            __syncwarp();                                           // FUSE: every lane is done with the luma rows the tile overwrites
 #pragma unroll
-        for (int j = 0; j < GM_TILES; j++) {
-            uint4 v[G];
+            for (int j = 0; j < GM_TILES; j++) {
+                uint4 v[G];
+                if constexpr (REG_RING) {
+                    v[0] = prev[j];
+                    v[G - 1] = cur[j];
+                } else {
 #pragma unroll
-            for (int i = 0; i < G; i++) {
-                int sl = b + i;
-                sl -= (sl / G) * G;
-                v[i] = ring[(sl * GM_TILES + j) * 32 + lane];
-            }
-#pragma unroll
-            for (int nh = 0; nh < 2; nh++) {
-                int lo[4] = {32768, 32768, 32768, 32768}, hi[4] = {0, 0, 0, 0};
-#pragma unroll
-                for (int ks = 0; ks < KF; ks++) {
-                    va_imma_16832(lo, A2[ks], nh ? v[2 * ks].z : v[2 * ks].x, nh ? v[2 * ks + 1].z : v[2 * ks + 1].x);
-                    va_imma_16832(hi, A2[ks], nh ? v[2 * ks].w : v[2 * ks].y, nh ? v[2 * ks + 1].w : v[2 * ks + 1].y);
+                    for (int i = 0; i < G; i++) {
+                        int sl = b + i;
+                        sl -= (sl / G) * G;
+                        v[i] = ring[(sl * GM_TILES + j) * 32 + lane];
+                    }
                 }
-                if (G & 1) {
-                    va_imma_16816(lo, A2t[0], A2t[1], nh ? v[G - 1].z : v[G - 1].x);
-                    va_imma_16816(hi, A2t[0], A2t[1], nh ? v[G - 1].w : v[G - 1].y);
-                }
-                // byte 2 of (hi << 8) + lo (< 2^24) is the rounded result; two neighbouring columns per store
-                const unsigned v0 = ((unsigned)hi[0] << 8) + (unsigned)lo[0], v1 = ((unsigned)hi[1] << 8) + (unsigned)lo[1];
-                const unsigned v2 = ((unsigned)hi[2] << 8) + (unsigned)lo[2], v3 = ((unsigned)hi[3] << 8) + (unsigned)lo[3];
-                unsigned char *op = otile + g * GM_OUT_PITCH + 16 * j + 8 * nh + 2 * t;
-                *reinterpret_cast<unsigned short *>(op) = (unsigned short)__byte_perm(v0, v1, 0x0062);
-                *reinterpret_cast<unsigned short *>(op + 8 * GM_OUT_PITCH) = (unsigned short)__byte_perm(v2, v3, 0x0062);
-            }
-        }
-        __syncwarp();
-        // ---- 16 rows x 128 bytes -> global, 16 bytes per lane and round
+                unsigned res[2][2];                                 // [fragment row g / g + 8][nh]: two neighbouring columns each
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int idx = lane + 32 * i, row = idx >> 3, c16 = idx & 7;
-            const int yl = 16 * b + row, x = x0 + 16 * c16;
-            if (yl < rows && x < w) {
-                const uint4 val = *reinterpret_cast<const uint4 *>(otile + row * GM_OUT_PITCH + 16 * c16);
-                va_st_stream16(fout + (size_t)(y0 + yl) * out_pitch + x, val);
+                for (int nh = 0; nh < 2; nh++) {
+                    int lo[4] = {32768, 32768, 32768, 32768}, hi[4] = {0, 0, 0, 0};
+#pragma unroll
+                    for (int ks = 0; ks < KF; ks++) {
+                        va_imma_16832(lo, A2[ks], nh ? v[2 * ks].z : v[2 * ks].x, nh ? v[2 * ks + 1].z : v[2 * ks + 1].x);
+                        va_imma_16832(hi, A2[ks], nh ? v[2 * ks].w : v[2 * ks].y, nh ? v[2 * ks + 1].w : v[2 * ks + 1].y);
+                    }
+                    if (G & 1) {
+                        va_imma_16816(lo, A2t[0], A2t[1], nh ? v[G - 1].z : v[G - 1].x);
+                        va_imma_16816(hi, A2t[0], A2t[1], nh ? v[G - 1].w : v[G - 1].y);
+                    }
+                    // byte 2 of (hi << 8) + lo (< 2^24) is the rounded result
+                    const unsigned v0 = ((unsigned)hi[0] << 8) + (unsigned)lo[0], v1 = ((unsigned)hi[1] << 8) + (unsigned)lo[1];
+                    const unsigned v2 = ((unsigned)hi[2] << 8) + (unsigned)lo[2], v3 = ((unsigned)hi[3] << 8) + (unsigned)lo[3];
+                    res[0][nh] = __byte_perm(v0, v1, 0x0062);
+                    res[1][nh] = __byte_perm(v2, v3, 0x0062);
+                }
+                // fragment columns 2t, 2t + 1 are tile columns 4t, 4t + 1 (nh = 0) and 4t + 2, 4t + 3 (nh = 1): one word per row
+                unsigned char *op = otile + g * OPITCH + 16 * j + 4 * t;
+                *reinterpret_cast<unsigned *>(op) = __byte_perm(res[0][0], res[0][1], 0x5410);
+                *reinterpret_cast<unsigned *>(op + 8 * OPITCH) = __byte_perm(res[1][0], res[1][1], 0x5410);
             }
+            __syncwarp();
+            // ---- 16 rows x 128 bytes -> global, 16 bytes per lane and round
+#pragma unroll
+            for (int i = 0; i < (16 * TILES) / 32; i++) {
+                const int idx = lane + 32 * i, row = idx / TILES, c16 = idx % TILES;
+                const int yl = 16 * b + row, x = x0 + 16 * c16;
+                if (yl < rows && x < w) {
+                    const uint4 val = *reinterpret_cast<const uint4 *>(otile + row * OPITCH + 16 * c16);
+                    va_st_stream16(fout + (size_t)(y0 + yl) * out_pitch + x, val);
+                }
+            }
+            __syncwarp();
         }
-        __syncwarp();
+        if constexpr (REG_RING) {
+#pragma unroll
+            for (int j = 0; j < GM_TILES; j++) prev[j] = cur[j];
+        }
     }
 }
 
@@ -334,25 +370,33 @@ int va_gauss_mma_launch(va_ctx *ctx, va_stream stream, const char *name, bool fu
     const int C = fuse ? 3 : 1;
     if ((unsigned long long)h * in_pitch >= (1ull << 40)) return VA_ERR_UNSUPPORTED;
     const int G = (16 + 2 * r + 15) / 16;
-    const int KS = (G + 1) / 2;
+    // strip width: 128 columns; 64 where the ring of row-pass results (16 G rows x strip x 16 bit per warp) would leave too few
+    // warps per SM.  The fused variant exists for G == 2 (the chain's sigma); larger radii convert first (gauss_launch).
+    if (fuse && G > 2) return VA_ERR_UNSUPPORTED;
+    int tiles = G <= 2 ? 8 : 4;
+    if (getenv("VA_GM_TILES")) tiles = atoi(getenv("VA_GM_TILES")) == 8 ? 8 : 4;
+    if (G == 2) tiles = 8;
     GaussMma gp;
     memset(&gp, 0, sizeof(gp));
     gp.r = r;
-    gp.off = 16 * KS - 8;
-    gp.HL = KS == 1 ? 16 : KS <= 3 ? 48 : 80;       // >= off, and 128 + 2 HL = 32 (mod 64): conflict-free LDS.64 of the B fragments
     gp.mode = mode;
+    gp.stages = fuse ? 2 : 4;
+    if (getenv("VA_GM_STAGES")) gp.stages = atoi(getenv("VA_GM_STAGES"));
+    if (gp.stages < 2) gp.stages = 2;
+    if (gp.stages > GM_MAX_STAGES) gp.stages = GM_MAX_STAGES;
     for (int i = 0; i < ksize; i++) gp.taps[i] = (unsigned char)taps[i];
-    const int LW = gm_lw(gp.HL);
+    const int LW = 16 * tiles + 2 * gm_hl(G);
     if ((unsigned)(C * LW / 4) > 256u) return VA_ERR_UNSUPPORTED;
-    gp.strips = va_div_up(w, GM_STRIP);
+    gp.strips = va_div_up(w, 16 * tiles);
     // segments: enough warp tasks to fill the machine a few times over, but every segment re-stages 16 (G - 1) rows
-    const size_t wsm = gm_warp_smem(fuse, G, gp.HL);
+    const size_t wsm = gm_warp_smem(fuse, G, tiles, gp.stages);
     int wpc = 4;
-    while (wpc > 1 && 256 + (size_t)wpc * wsm > 200 * 1024) wpc >>= 1;
-    if (256 + (size_t)wpc * wsm > 220 * 1024) return VA_ERR_UNSUPPORTED;
-    const size_t smem = 256 + (size_t)wpc * wsm;
-    int ctas_per_sm = (int)((size_t)(220 * 1024) / smem);
+    while (wpc > 1 && 512 + (size_t)wpc * wsm > 110 * 1024) wpc >>= 1;      // at least two CTAs per SM
+    if (512 + (size_t)wpc * wsm > 220 * 1024) return VA_ERR_UNSUPPORTED;
+    const size_t smem = 512 + (size_t)wpc * wsm;
+    int ctas_per_sm = (int)((size_t)(224 * 1024) / (smem + 1024));
     if (ctas_per_sm > 8) ctas_per_sm = 8;
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
     const long long slots = (long long)ctx->sm_count * ctas_per_sm * wpc;
     int segs = (int)va_div_up(4 * slots, (long long)gp.strips * batch);
     const int max_segs = h / (64 * (G - 1)) > 0 ? h / (64 * (G - 1)) : 1;            // re-staged rows <= 25 %
@@ -368,16 +412,21 @@ int va_gauss_mma_launch(va_ctx *ctx, va_stream stream, const char *name, bool fu
     const long long tasks = (long long)gp.strips * gp.segs * batch;
     const long long grid = va_div_up(tasks, wpc);
     if (grid > 0x7fffffffll) return VA_ERR_UNSUPPORTED;
-#define GM_GO(FUSE, GG)                                                                                          \
+#define GM_GO(FUSE, GG, TT, MB)                                                                                  \
     do {                                                                                                         \
-        auto kfn = gauss_mma_kernel<FUSE, GG>;                                                                   \
+        auto kfn = gauss_mma_kernel<FUSE, GG, TT, MB>;                                                             \
         if (smem > 48 * 1024)                                                                                    \
             VA_CUDA(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
         VA_LAUNCH(ctx, kfn, (unsigned)grid, 32 * wpc, smem, stream, map8, map1, out, out_pitch, out_fstride, w, h, batch, gp); \
     } while (0)
-#define GM_CASE(GG) case GG: if (fuse) GM_GO(true, GG); else GM_GO(false, GG); break;
+#define GM_CASE(GG) case GG: if (tiles == 8) GM_GO(false, GG, 8, 1); else GM_GO(false, GG, 4, 1); break;
+    const int minb = getenv("VA_GM_MINB") ? atoi(getenv("VA_GM_MINB")) : 4;
     switch (G) {
-        GM_CASE(2) GM_CASE(3) GM_CASE(4) GM_CASE(5) GM_CASE(6) GM_CASE(7) GM_CASE(8)
+        case 2:
+            if (fuse) { if (minb == 4) GM_GO(true, 2, 8, 4); else GM_GO(true, 2, 8, 3); }
+            else { if (minb == 4) GM_GO(false, 2, 8, 4); else GM_GO(false, 2, 8, 3); }
+            break;
+        GM_CASE(3) GM_CASE(4) GM_CASE(5) GM_CASE(6) GM_CASE(7) GM_CASE(8)
         default: return VA_ERR_UNSUPPORTED;
     }
 #undef GM_CASE

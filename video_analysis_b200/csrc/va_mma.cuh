@@ -115,7 +115,8 @@ __device__ __forceinline__ void va_mbar_expect_tx(uint64_t *bar, unsigned bytes)
 }
 __device__ __forceinline__ void va_mbar_wait(uint64_t *bar, unsigned parity) {
 #ifdef VA_EMU
-    (void)bar; (void)parity;             // emulated TMA loads complete inside va_tma_load_3d
+    (void)bar; (void)parity;             // emulated TMA loads complete inside va_tma_load_3d, which the issuing lane
+    __syncwarp();                        // has left by the time it arrives here (every lane of the warp waits)
 #else
     asm volatile(
         "{\n"
