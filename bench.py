@@ -50,6 +50,27 @@ def peaks():
         return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
+def pcie_roofline(h2d_bytes, d2h_bytes, fps_per_gpu, frames_per_step):
+    """ the end-to-end legs are bound by the host link: bytes per step in the busier direction against the pinned-copy
+    bandwidth measured on this pool with both directions running (tools/pcie_bench.py -> profiles/pcie_r2.txt) """
+    peak = None
+    try:
+        for line in open(os.path.join(ROOT, 'profiles', 'pcie_r2.txt')):
+            d = json.loads(line)
+            if d.get('n_gpus') == 1:
+                peak = (d['h2d_alone_GBps_per_gpu'], d['d2h_alone_GBps_per_gpu'], d['both_GBps_per_gpu'])
+    except Exception:
+        pass
+    if peak is None:
+        return None
+    both = d2h_bytes > 0.25 * h2d_bytes                 # a thin return stream leaves the upload at its stand-alone rate
+    link = peak[2] if both else peak[0]
+    busy = max(h2d_bytes, d2h_bytes)
+    achieved = busy * fps_per_gpu / frames_per_step / 1e9
+    return {'bound': 'pcie', 'achieved': round(achieved, 2), 'peak': link, 'unit': 'GB/s', 'frac': round(achieved / link, 3),
+            'peak_source': 'profiles/pcie_r2.txt (N=1: %s GB/s in the busier direction)' % ('both directions busy' if both else 'upload alone')}
+
+
 # ------------------------------------------------------------------------------------------
 # clocks: sample nvidia-smi during the timed region
 # ------------------------------------------------------------------------------------------
@@ -318,16 +339,35 @@ def gpu_arm(args):
     for lab, cnt in e2e_chain.process_blocks(blocks(max(3, min(Wm, 5)))):
         sink += int(cnt[0])
     barrier()
+    e2e_chain.egress_bytes = 0
     t0 = time.perf_counter()
     for lab, cnt in e2e_chain.process_blocks(blocks(Ke)):
         sink += int(cnt[-1]) + int(lab[0, H // 2, W // 2])       # touch the results on the host
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    e2e_d2h = e2e_chain.egress_bytes // Ke                       # what the device stored into host memory per step
     if world > 1:
         tmax = torch.tensor([e2e_s], device=rt.device)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         e2e_s = float(tmax.item())
     e2e_fps = world * Ke * Be / e2e_s
+
+    # ---- the same with a dense device -> host copy of the label images (round 1's e2e), for comparison
+    dense_chain = SegmentChain((W, H), batch=Be, fuse=not args.no_fuse, sparse_egress=False, **CHAIN)
+    for lab, cnt in dense_chain.process_blocks(blocks(max(3, min(Wm, 5)))):
+        sink += int(cnt[0])
+    barrier()
+    t0 = time.perf_counter()
+    for lab, cnt in dense_chain.process_blocks(blocks(Ke)):
+        sink += int(cnt[-1]) + int(lab[0, H // 2, W // 2])
+    torch.cuda.synchronize()
+    dense_s = time.perf_counter() - t0
+    if world > 1:
+        tmax = torch.tensor([dense_s], device=rt.device)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dense_s = float(tmax.item())
+    dense_fps = world * Ke * Be / dense_s
+    del dense_chain
 
     # ---- e2e with the region table as the result: same chain, same host input, but
     # per-region moments / boxes come back instead of the 4-bytes-per-pixel label image
@@ -375,8 +415,14 @@ def gpu_arm(args):
                        'pipeline_streams': 1 if (args.no_overlap and world == 1) else 3},
             'clocks': clocks,
             'e2e': {'value': round(e2e_fps, 1), 'unit': 'frames/s', 'h2d_bytes_per_step': Be * N * 3,
-                    'd2h_bytes_per_step': Be * N * 4 + Be * 4, 'steps': Ke, 'frames_per_step': Be,
-                    'api': 'SegmentChain.process_blocks (pinned host frames in, int32 labels + counts out)'},
+                    'd2h_bytes_per_step': int(e2e_d2h), 'steps': Ke, 'frames_per_step': Be,
+                    'api': 'SegmentChain.process_blocks (pinned host frames in; dense int32 label images + counts out, '
+                           'brought over PCIe as their non-empty 64-label chunks and rebuilt on the host)',
+                    'roofline': pcie_roofline(Be * N * 3, int(e2e_d2h), e2e_fps / world, Be)},
+            'e2e_dense_copy': {'value': round(dense_fps, 1), 'unit': 'frames/s', 'h2d_bytes_per_step': Be * N * 3,
+                               'd2h_bytes_per_step': Be * N * 4 + Be * 4, 'steps': Ke, 'frames_per_step': Be,
+                               'api': 'SegmentChain(sparse_egress=False).process_blocks: the label images copied densely',
+                               'roofline': pcie_roofline(Be * N * 3, Be * N * 4 + Be * 4, dense_fps / world, Be)},
             'e2e_region_table': {'value': round(reg_fps, 1), 'unit': 'frames/s', 'h2d_bytes_per_step': Be * N * 3,
                                  'd2h_bytes_per_step': Be * (MAXR * 80 + 8), 'steps': Ke, 'frames_per_step': Be,
                                  'api': 'SegmentChain.process_blocks(max_regions=%d): pinned host frames in, per-region '

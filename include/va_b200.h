@@ -364,6 +364,26 @@ typedef struct va_chain_io {
 
 int va_chain_run(va_ctx *ctx, va_stream stream, const va_chain_desc *desc, const va_chain_io *io);
 
+/* Sparse egress of a label image (the label image of analysis/regions.py:162 is mostly background): the non-empty
+ * chunks -- VA_CHUNK_E = 64 consecutive labels of a row, numbered y * ceil(w / 64) + c -- of every frame in raster
+ * order.  ids [batch][cap], data [batch][cap][64] and n_chunks [batch] are written by the device; they may be
+ * PAGE-LOCKED HOST memory (the kernels then store over PCIe and no copy has to be sized or issued), n_chunks_dev
+ * (optional) is a device copy of the counts.  A frame with more than cap non-empty chunks reports its true count and
+ * exports the first cap.  mask is the packed image the labels were made from (va_label_bits). */
+int va_label_export_chunks(va_ctx *ctx, va_stream stream,
+                           const uint32_t *mask, size_t mask_pitch_w, size_t mask_fstride_w,
+                           const int32_t *labels, size_t labels_pitch_e, size_t labels_fstride_e,
+                           int w, int h, int batch,
+                           int32_t *ids, int32_t *data, int32_t *n_chunks, int32_t *n_chunks_dev, int cap);
+
+/* HOST function (no CUDA call, no ctx): rebuilds dense (batch, h, pitch_e) int32 label images from exported chunks.
+ * dirty_ids [batch][cap] / n_dirty [batch] name the chunks of `dense` that are non-zero from its previous use: they
+ * are cleared first and replaced by the chunk list written now, so a ring of result buffers never has to be zeroed
+ * as a whole.  `threads` host threads share the frames. */
+int va_host_densify_chunks(int32_t *dense, size_t pitch_e, size_t fstride_e, int w, int h, int batch,
+                           const int32_t *ids, const int32_t *data, const int32_t *n_chunks, int cap,
+                           int32_t *dirty_ids, int32_t *n_dirty, int threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, 'video_analysis_b200', 'csrc')
 INCLUDE = os.path.join(ROOT, 'include')
 LIB = os.path.join(HERE, 'libva_b200_emu.so')
-SOURCES = ['va_api.cu', 'va_pointwise.cu', 'va_gauss.cu', 'va_gauss_mma.cu', 'va_ema.cu', 'va_morph.cu', 'va_label.cu', 'va_extra.cu']
+SOURCES = ['va_api.cu', 'va_pointwise.cu', 'va_gauss.cu', 'va_gauss_mma.cu', 'va_ema.cu', 'va_morph.cu', 'va_label.cu', 'va_extra.cu', 'va_export.cu']
 
 
 def build(force=False):

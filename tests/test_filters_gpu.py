@@ -680,3 +680,30 @@ def test_sharded_equals_sequential(world):
         else:
             rel = ((ch._bg[:, :Wd] - want[:, :Wd]).abs() / want[:, :Wd].abs().clamp(min=1)).max()
             assert float(rel) < 1e-5, float(rel)
+
+
+def test_sparse_egress_gives_the_dense_label_images(frames, ref):
+    """ SegmentChain.process_blocks brings the label images to the host as their non-empty chunks (default) or as a
+    dense copy: same arrays, same counts, across buffer reuse (more blocks than ring slots), short last blocks and a
+    frame full of foreground """
+    mods()
+    from video_analysis_b200.chain import SegmentChain
+    for batch in (16, 7):
+        a = SegmentChain((320, 240), batch=batch)
+        b = SegmentChain((320, 240), batch=batch, sparse_egress=False)
+        assert a._sparse() and not b._sparse()
+        la, ca = a.process(frames)
+        lb, cb = b.process(frames)
+        assert np.array_equal(la, ref['labels']) and np.array_equal(lb, ref['labels'])
+        assert list(ca) == list(ref['counts']) and list(cb) == list(ref['counts'])
+        assert a.egress_bytes < la.nbytes // 4
+    # noisy input: nearly every chunk is non-empty, then quiet again in the same buffers
+    rng = np.random.default_rng(3)
+    noisy = rng.integers(0, 256, (20, 240, 320, 3), dtype=np.uint8)
+    calm = frames[:20]
+    c = SegmentChain((320, 240), batch=8, sigma=0.5, threshold=10.0, morph_op=None)
+    for video in (noisy, calm, noisy):
+        want = ops.chain(video, sigma=0.5, alpha=0.05, thr=10.0, morph_op=None)
+        c.reset()
+        got, cnt = c.process(video)
+        assert np.array_equal(got, want['labels']) and list(cnt) == list(want['counts'])

@@ -183,6 +183,31 @@ def test_luma_gauss_fused_equals_two_step(be, ctx):
     assert np.array_equal(hz.luma_gauss(ctx, fr, 2, mode=1), np.stack([ops.blur(f[..., 1], 2) for f in fr]))
 
 
+# ---- sparse egress of label images ----------------------------------------------------------------
+def test_label_export_chunks_and_host_densify(be, ctx):
+    # the non-empty 64-label chunks written by the device (straight into page-locked host memory on the GPU) and the
+    # host-side rebuild give the dense label image bit for bit; the result buffer is reused without being zeroed
+    for (H, W) in sizes(be, [(20, 64), (23, 200), (9, 130)], [(1080, 1920), (480, 640), (271, 1003)]):
+        rng = np.random.default_rng(H * W)
+        state = None
+        for rep, density in enumerate((0.02, 0.5, 0.0, 0.001, 1.0)):
+            m = (rng.random((2, H, W)) < density)
+            if density == 0.02:
+                m[0, H // 3: H // 2, W // 4: W // 2] = True
+            words = ops.pack_bits(m)
+            dense, n, state, direct = hz.label_export_dense(ctx, words, W, reuse=state, lab_pad=(H + W) % 3)
+            assert np.array_equal(dense, direct), (H, W, density)
+            want = np.stack([ops.label(f)[0] for f in m])
+            assert np.array_equal(dense, want), (H, W, density)
+            cpr = (W + 63) // 64
+            nz = [(np.add.reduceat(f != 0, np.arange(0, W, 64), axis=1) > 0).sum() for f in m]
+            assert list(n) == nz and max(nz) <= cpr * H
+    # capacity smaller than the number of chunks: the true count is reported (the caller falls back to a dense copy)
+    m = np.ones((1, 8, 128), bool)
+    _, n, _, _ = hz.label_export_dense(ctx, ops.pack_bits(m), 128, cap=5)
+    assert n[0] == 16
+
+
 # ---- K2b ----------------------------------------------------------------------------------------
 def test_resize_half(be, ctx):
     for (H, W) in sizes(be, [(12, 40), (20, 64)], [(1080, 1920)]):

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
 LIB = os.path.join(CSRC, 'libva_b200.so')
-SOURCES = ['va_api.cu', 'va_pointwise.cu', 'va_gauss.cu', 'va_gauss_mma.cu', 'va_ema.cu', 'va_morph.cu', 'va_label.cu', 'va_extra.cu']
+SOURCES = ['va_api.cu', 'va_pointwise.cu', 'va_gauss.cu', 'va_gauss_mma.cu', 'va_ema.cu', 'va_morph.cu', 'va_label.cu', 'va_extra.cu', 'va_export.cu']
 HEADERS = ['va_common.cuh', 'va_device.cuh', 'va_mma.cuh', os.path.join(INCLUDE, 'va_b200.h')]
 
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',

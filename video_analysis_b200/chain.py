@@ -25,7 +25,7 @@ from .filters import COLOR_CHANNELS
 class SegmentChain(object):
     def __init__(self, size, sigma=2.0, alpha=0.05, threshold=25.0, morph_op='open', morph_shape='rect',
                  morph_ksize=3, connectivity=4, mono_mode='mean', batch=64, device=None, fuse=True, depth=3,
-                 label_dtype=np.int32):
+                 label_dtype=np.int32, sparse_egress=True):
         self.w, self.h = int(size[0]), int(size[1])
         self.sigma, self.alpha, self.threshold = float(sigma), float(alpha), float(threshold)
         if morph_op is not None and morph_op not in _lib.MORPH_OPS:
@@ -47,6 +47,12 @@ class SegmentChain(object):
         self.label_dtype = np.dtype(label_dtype)
         if self.label_dtype not in (np.dtype(np.int32), np.dtype(np.int16)):
             raise ValueError('label_dtype must be int32 or int16')
+        # sparse_egress: `process_blocks` brings int32 label images to the host as their non-empty 64-label chunks
+        # (written by the device straight into page-locked memory) and rebuilds the dense arrays there -- the same
+        # arrays, a fraction of the PCIe traffic; False copies the dense images
+        self.sparse_egress = bool(sparse_egress)
+        self.host_threads = 4
+        self.egress_bytes = 0
         self.rt = get_runtime(device)
         self.rt.ensure(self.w, self.h, self.batch)
         self._bg = self.rt.empty_f32(self.h, self.w)
@@ -301,12 +307,29 @@ class SegmentChain(object):
         if max_regions is None:
             if 'labels' not in s:
                 s['labels'] = self._empty_labels(self.batch)
-                s['labels_host'] = t.empty(tuple(s['labels'].t.shape), dtype=s['labels'].t.dtype, pin_memory=True)
+                if self._sparse():
+                    # export buffers for the worst case (every chunk non-empty), written by the device over PCIe; the
+                    # dense result lives in ordinary host memory and is only ever touched where chunks are / were
+                    cap = -(-self.w // 64) * self.h
+                    s['cap'] = cap
+                    s['exp_ids'] = t.empty((self.batch, cap), dtype=t.int32, pin_memory=True)
+                    s['exp_data'] = t.empty((self.batch, cap, 64), dtype=t.int32, pin_memory=True)
+                    s['exp_n'] = t.zeros((self.batch,), dtype=t.int32, pin_memory=True)
+                    s['dense'] = t.zeros(tuple(s['labels'].t.shape), dtype=t.int32)
+                    s['dirty_ids'] = t.zeros((self.batch, cap), dtype=t.int32)
+                    s['n_dirty'] = t.zeros((self.batch,), dtype=t.int32)
+                    s['seg_mask'] = rt.empty_bits(self.batch, self.h, self.w)
+                    s['seg_morph'] = rt.empty_bits(self.batch, self.h, self.w)
+                else:
+                    s['labels_host'] = t.empty(tuple(s['labels'].t.shape), dtype=s['labels'].t.dtype, pin_memory=True)
         elif s.get('stats') is None or s['stats'].shape[1] != max_regions:
             s['stats'] = t.empty((self.batch, max_regions, 10), dtype=t.int64, device=rt.device)
             s['largest'] = t.empty((self.batch,), dtype=t.int32, device=rt.device)
             s['stats_host'] = t.empty((self.batch, max_regions, 10), dtype=t.int64, pin_memory=True)
             s['largest_host'] = t.empty((self.batch,), dtype=t.int32, pin_memory=True)
+
+    def _sparse(self):
+        return self.sparse_egress and self.label_dtype == np.int32 and bool(self.connectivity)
 
     def process_blocks(self, blocks, max_regions=None):
         """ blocks: iterable of host arrays (m, h, w, 3) uint8 with m <= batch (page-locked memory
@@ -344,14 +367,24 @@ class SegmentChain(object):
                     rgb = DeviceBatch('u8', s['in'][:m], m, self.h, self.w, 3)
                     if max_regions is None:
                         lab = DeviceBatch(s['labels'].kind, s['labels'].t[:m], m, self.h, self.w)
-                        self.run_device(rgb, lab, s['counts'][:m])
+                        if self._sparse():
+                            sub = lambda b: DeviceBatch(b.kind, b.t[:m], m, b.h, b.w, b.channels)
+                            mask, morph = sub(s['seg_mask']), sub(s['seg_morph'])
+                            self.run_device(rgb, lab, s['counts'][:m], mask=mask, morph=morph if self.morph_op else None)
+                            seg = morph if self.morph_op else mask
+                            rt._check(rt.lib.va_label_export_chunks(rt._h, rt.stream, *seg.img(), *lab.img(), self.w, self.h, m,
+                                                                    s['exp_ids'].data_ptr(), s['exp_data'].data_ptr(),
+                                                                    s['exp_n'].data_ptr(), None, s['cap']))
+                        else:
+                            self.run_device(rgb, lab, s['counts'][:m])
                     else:
                         self.regions_device(rgb, s['stats'][:m], s['counts'][:m], s['largest'][:m])
                     s['ev_run'].record(self._s_run)
                 with t.cuda.stream(self._s_out):
                     self._s_out.wait_event(s['ev_run'])
                     if max_regions is None:
-                        s['labels_host'][:m].copy_(s['labels'].t[:m], non_blocking=True)
+                        if not self._sparse():
+                            s['labels_host'][:m].copy_(s['labels'].t[:m], non_blocking=True)
                     else:
                         s['stats_host'][:m].copy_(s['stats'][:m], non_blocking=True)
                         s['largest_host'][:m].copy_(s['largest'][:m], non_blocking=True)
@@ -367,6 +400,16 @@ class SegmentChain(object):
         if max_regions is None:
             if self.label_dtype == np.int16 and m and int(s['counts_host'].numpy()[:m].max()) > 32767:
                 raise RuntimeError('insufficient bit-depth in requested output type')      # what ndimage.label raises
+            if self._sparse():
+                d = s['dense']
+                rc = self.rt.lib.va_host_densify_chunks(d.data_ptr(), d.stride(1), d.stride(0), self.w, self.h, m,
+                                                        s['exp_ids'].data_ptr(), s['exp_data'].data_ptr(), s['exp_n'].data_ptr(),
+                                                        s['cap'], s['dirty_ids'].data_ptr(), s['n_dirty'].data_ptr(),
+                                                        self.host_threads)
+                _lib.check(self.rt.lib, None, rc)
+                # bytes the device stored over PCIe for this block: chunk data + chunk ids + the two count vectors
+                self.egress_bytes += int(s['exp_n'].numpy()[:m].sum()) * (64 * 4 + 4) + 8 * m
+                return d.numpy()[:m, :, :self.w], s['counts_host'].numpy()[:m]
             return s['labels_host'].numpy()[:m, :, :self.w], s['counts_host'].numpy()[:m]
         return s['stats_host'].numpy()[:m], s['counts_host'].numpy()[:m], s['largest_host'].numpy()[:m]
 

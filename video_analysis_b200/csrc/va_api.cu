@@ -35,6 +35,17 @@ extern "C" int va_create(va_ctx **out, int device, int max_w, int max_h, int max
         return VA_ERR_CUDA;
     }
     ctx->sm_count = sms;
+#ifndef VA_EMU
+    {   // stream-ordered temporaries (cudaMallocAsync in the blur / resize entry points) stay in the pool across
+        // synchronisations instead of going back to the driver every time the stream runs dry
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
+#endif
     ctx->lab_pitch = 32;                       // power of two: forest index = (y << log2 pitch) + x
     while (ctx->lab_pitch < (size_t)max_w) ctx->lab_pitch <<= 1;
     if (ctx->lab_pitch * (size_t)max_h >= ((size_t)1 << 31)) { free(ctx); return VA_ERR_CAPACITY; }
@@ -59,8 +70,9 @@ extern "C" int va_destroy(va_ctx *ctx) {
     cudaFree(ctx->ch_blur);
     cudaFree(ctx->ch_mask);
     cudaFree(ctx->ch_morph);
+    cudaFree(ctx->exp_rowoff);
 #ifndef VA_EMU
-    for (int i = 0; i < 3; i++)
+    for (int i = 0; i < 4; i++)
         if (ctx->lab_event[i]) cudaEventDestroy((cudaEvent_t)ctx->lab_event[i]);
 #endif
     free(ctx);

@@ -32,7 +32,8 @@ struct va_ctx {
     // last use of each scratch set: every entry point that touches a set first makes its stream wait for
     // this event and re-records it when it has enqueued its kernels, so callers on different streams
     // (two filter chains, a chain next to region_stats, ...) never run forest kernels on one set at once
-    void *lab_event[3];      // [2]: the chain intermediates of va_chain_run
+    void *lab_event[4];      // [2]: the chain intermediates of va_chain_run, [3]: the row offsets of va_label_export_chunks
+    int *exp_rowoff;         // [max_batch * max_h] chunk counts per row -> exclusive prefix (allocated on first use)
     // morphology scratch (intermediate of open / close is kept in shared memory; none needed)
     // chain intermediates (allocated on first use by va_chain_run)
     uint8_t *ch_mono, *ch_blur;
