@@ -369,7 +369,8 @@ int va_chain_run(va_ctx *ctx, va_stream stream, const va_chain_desc *desc, const
  * order.  ids [batch][cap], data [batch][cap][64] and n_chunks [batch] are written by the device; they may be
  * PAGE-LOCKED HOST memory (the kernels then store over PCIe and no copy has to be sized or issued), n_chunks_dev
  * (optional) is a device copy of the counts.  A frame with more than cap non-empty chunks reports its true count and
- * exports the first cap.  mask is the packed image the labels were made from (va_label_bits). */
+ * exports the first cap.  mask is the packed image the labels were made from (va_label_bits).  With ids = data = NULL
+ * only the counts are produced (how sparse is this batch?). */
 int va_label_export_chunks(va_ctx *ctx, va_stream stream,
                            const uint32_t *mask, size_t mask_pitch_w, size_t mask_fstride_w,
                            const int32_t *labels, size_t labels_pitch_e, size_t labels_fstride_e,

@@ -431,6 +431,14 @@ def test_config4_streams_batched_per_launch():
             lab, n = ops.label(g > 110)
             assert counts[s] == n and np.array_equal(labels[s], lab), (t, s)
     assert n_steps == T
+    # dense copies instead of chunk egress, a shallower ring, one gather thread: same results
+    ref_steps = [(l.copy(), c.copy()) for l, c in MultiStreamSegmenter([VideoMemory(v, copy_data=False) for v in vids], rects, masks,
+                                                                       threshold=110)]
+    alt = MultiStreamSegmenter([VideoMemory(v, copy_data=False) for v in vids], rects, masks, threshold=110, sparse_egress=False,
+                               depth=2, gather_threads=1)
+    for (la, ca), (lb, cb) in zip(ref_steps, [(l.copy(), c.copy()) for l, c in alt]):
+        assert np.array_equal(la, lb) and np.array_equal(ca, cb)
+    assert len(ref_steps) == T
     one = MultiStreamSegmenter([VideoMemory(v, copy_data=False) for v in vids], rects, masks[0], threshold=90, mono_mode='green',
                                connectivity=8)
     labels, counts = next(iter(one))

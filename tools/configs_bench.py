@@ -33,6 +33,20 @@ def timed(t, fn, iters):
     return float(np.median(ms)), float(np.min(ms))
 
 
+def synth_host(seed, stream, n, w, h):
+    """ n frames of one camera in host memory (a few distinct frames, cycled by the source) """
+    rng = np.random.default_rng(seed * 1000 + stream)
+    base = rng.integers(60, 120, (h, w, 3), dtype=np.uint8)
+    out = np.empty((n, h, w, 3), np.uint8)
+    yy, xx = np.mgrid[:h, :w]
+    for k in range(n):
+        f = base.copy()
+        cx, cy = (200 + 97 * stream + 40 * k) % w, (150 + 53 * stream + 25 * k) % h
+        f[(xx - cx) ** 2 + (yy - cy) ** 2 < 60 ** 2] = 200
+        out[k] = f
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--iters', type=int, default=10)
@@ -89,6 +103,38 @@ def main():
                ((3 * n + n + n / 8) + (n / 8 + 4 * n)) * n_streams,
                'crop 1024x576 at a position per stream, mask per stream; bytes = fused front (3N RGB + N mask in, N/8 bits '
                'out) + label 4.125N per cropped frame')
+
+        # end to end: frames of the 64 streams in host memory -> gather threads -> pinned block -> upload -> kernels ->
+        # label images back on the host (chunk egress), three steps in flight
+        import time
+
+        class Camera(VideoBase):
+            def __init__(self, data, steps):
+                super(Camera, self).__init__(size=(w, h), frame_count=steps, is_color=True)
+                self.data = data
+
+            def get_frame(self, index):
+                if index >= self.frame_count:
+                    raise IndexError
+                return self.data[index % len(self.data)]
+        host = [synth_host(3, s_, 4, w, h) for s_ in range(n_streams)]
+        for sparse in (True, False):
+            steps = 40
+            seg2 = MultiStreamSegmenter([Camera(host[s_], 5) for s_ in range(n_streams)], rects, m, threshold=110, sparse_egress=sparse)
+            for _ in seg2:
+                pass                                               # warm-up: buffers, streams, thread pool
+            seg2.videos = [Camera(host[s_], steps) for s_ in range(n_streams)]
+            seg2.egress_bytes = 0
+            t.cuda.synchronize()
+            t0 = time.perf_counter()
+            sink = 0
+            for lab, cnt in seg2:
+                sink += int(cnt[0]) + int(lab[1, 5, 5])
+            dt = time.perf_counter() - t0
+            print(json.dumps({'config': 'configs[3] end to end, 64 x 1280x720 streams from host memory, %s egress' % ('chunk' if sparse else 'dense'),
+                              'steps': steps, 'fps': round(steps * n_streams / dt, 1), 'ms_per_step': round(dt / steps * 1e3, 3),
+                              'h2d_bytes_per_step': n_streams * w * h * 3,
+                              'd2h_bytes_per_step': int(seg2.egress_bytes / steps) if sparse else n_streams * (cw * ch_ * 4 + 4)}), flush=True)
 
     if 'stencil' in only:
         # configs[4]: blur s=15 (91 taps) -> resize 0.5 -> threshold -> 7x7 close, open -> label

@@ -22,6 +22,78 @@ from .device import DeviceBatch, get_runtime, torch
 from .filters import COLOR_CHANNELS
 
 
+class SparseLabelEgress(object):
+    """ label images of one ring slot on their way to the host as non-empty 64-label chunks (csrc/va_export.cu): the
+    device stores chunk data, chunk ids and per-frame chunk counts straight into page-locked host memory, `finish`
+    rebuilds the dense int32 images in ordinary host memory -- clearing only the chunks the slot's previous batch left
+    behind -- and returns them.
+
+    Masks that are mostly noise (a plain threshold on an unblurred frame) have foreground in most chunks; chunks then
+    cost more than a dense copy.  `policy` (shared by the slots of one pipeline) watches the chunk fraction of the
+    finished batches and switches the following ones to dense copies above 35 %, back to chunks below 20 %; in dense
+    mode the device still counts the chunks so that the way back is seen. """
+
+    class Policy(object):
+        def __init__(self):
+            self.dense = False
+
+        def update(self, fraction):
+            if fraction > 0.35:
+                self.dense = True
+            elif fraction < 0.20:
+                self.dense = False
+
+    def __init__(self, rt, batch, h, w, pitch_e, host_threads=4, policy=None):
+        t = torch()
+        self.rt, self.batch, self.h, self.w, self.pitch_e = rt, batch, h, w, pitch_e
+        self.cap = -(-w // 64) * h                       # worst case: every chunk non-empty
+        self.ids = t.empty((batch, self.cap), dtype=t.int32, pin_memory=True)
+        self.data = t.empty((batch, self.cap, 64), dtype=t.int32, pin_memory=True)
+        self.n = t.zeros((batch,), dtype=t.int32, pin_memory=True)
+        self.dense = t.zeros((batch, h, pitch_e), dtype=t.int32)
+        self.dirty_ids = t.zeros((batch, self.cap), dtype=t.int32)
+        self.n_dirty = t.zeros((batch,), dtype=t.int32)
+        self.host_threads = host_threads
+        self.policy = policy if policy is not None else SparseLabelEgress.Policy()
+        self.bytes = 0
+        self._mode_dense = False
+        self._pinned_dense = None
+
+    def enqueue(self, seg, labels, m):
+        """ on the current stream: export the first m frames (`seg`: packed mask the labels were made from) """
+        rt = self.rt
+        self._mode_dense = self.policy.dense
+        if self._mode_dense:
+            if self._pinned_dense is None:
+                self._pinned_dense = torch().empty((self.batch, self.h, self.pitch_e), dtype=torch().int32, pin_memory=True)
+            rt._check(rt.lib.va_label_export_chunks(rt._h, rt.stream, *seg.img(), *labels.img(), self.w, self.h, m,
+                                                    None, None, self.n.data_ptr(), None, self.cap))
+        else:
+            rt._check(rt.lib.va_label_export_chunks(rt._h, rt.stream, *seg.img(), *labels.img(), self.w, self.h, m,
+                                                    self.ids.data_ptr(), self.data.data_ptr(), self.n.data_ptr(), None, self.cap))
+
+    def enqueue_copy(self, labels, m):
+        """ on the egress stream, after the kernels: the dense device -> host copy of a batch that travels densely """
+        if self._mode_dense:
+            self._pinned_dense[:m].copy_(labels.t[:m], non_blocking=True)
+
+    def finish(self, m):
+        """ after the export has completed (event): dense (m, h, w) int32 view, valid until the slot is reused """
+        n_chunks = int(self.n.numpy()[:m].sum())
+        self.policy.update(n_chunks / float(max(1, m * self.cap)))
+        if self._mode_dense:
+            self.bytes = m * self.h * self.pitch_e * 4 + 4 * m
+            return self._pinned_dense.numpy()[:m, :, :self.w]
+        d = self.dense
+        rc = self.rt.lib.va_host_densify_chunks(d.data_ptr(), d.stride(1), d.stride(0), self.w, self.h, m,
+                                                self.ids.data_ptr(), self.data.data_ptr(), self.n.data_ptr(), self.cap,
+                                                self.dirty_ids.data_ptr(), self.n_dirty.data_ptr(), self.host_threads)
+        _lib.check(self.rt.lib, None, rc)
+        # bytes the device stored over PCIe for this block: chunk data + chunk ids + the count vector
+        self.bytes = n_chunks * (64 * 4 + 4) + 4 * m
+        return d.numpy()[:m, :, :self.w]
+
+
 class SegmentChain(object):
     def __init__(self, size, sigma=2.0, alpha=0.05, threshold=25.0, morph_op='open', morph_shape='rect',
                  morph_ksize=3, connectivity=4, mono_mode='mean', batch=64, device=None, fuse=True, depth=3,
@@ -53,6 +125,7 @@ class SegmentChain(object):
         self.sparse_egress = bool(sparse_egress)
         self.host_threads = 4
         self.egress_bytes = 0
+        self._egress_policy = SparseLabelEgress.Policy()
         self.rt = get_runtime(device)
         self.rt.ensure(self.w, self.h, self.batch)
         self._bg = self.rt.empty_f32(self.h, self.w)
@@ -308,16 +381,8 @@ class SegmentChain(object):
             if 'labels' not in s:
                 s['labels'] = self._empty_labels(self.batch)
                 if self._sparse():
-                    # export buffers for the worst case (every chunk non-empty), written by the device over PCIe; the
-                    # dense result lives in ordinary host memory and is only ever touched where chunks are / were
-                    cap = -(-self.w // 64) * self.h
-                    s['cap'] = cap
-                    s['exp_ids'] = t.empty((self.batch, cap), dtype=t.int32, pin_memory=True)
-                    s['exp_data'] = t.empty((self.batch, cap, 64), dtype=t.int32, pin_memory=True)
-                    s['exp_n'] = t.zeros((self.batch,), dtype=t.int32, pin_memory=True)
-                    s['dense'] = t.zeros(tuple(s['labels'].t.shape), dtype=t.int32)
-                    s['dirty_ids'] = t.zeros((self.batch, cap), dtype=t.int32)
-                    s['n_dirty'] = t.zeros((self.batch,), dtype=t.int32)
+                    s['egress'] = SparseLabelEgress(rt, self.batch, self.h, self.w, s['labels'].t.shape[2], self.host_threads,
+                                                    self._egress_policy)
                     s['seg_mask'] = rt.empty_bits(self.batch, self.h, self.w)
                     s['seg_morph'] = rt.empty_bits(self.batch, self.h, self.w)
                 else:
@@ -372,9 +437,7 @@ class SegmentChain(object):
                             mask, morph = sub(s['seg_mask']), sub(s['seg_morph'])
                             self.run_device(rgb, lab, s['counts'][:m], mask=mask, morph=morph if self.morph_op else None)
                             seg = morph if self.morph_op else mask
-                            rt._check(rt.lib.va_label_export_chunks(rt._h, rt.stream, *seg.img(), *lab.img(), self.w, self.h, m,
-                                                                    s['exp_ids'].data_ptr(), s['exp_data'].data_ptr(),
-                                                                    s['exp_n'].data_ptr(), None, s['cap']))
+                            s['egress'].enqueue(seg, lab, m)
                         else:
                             self.run_device(rgb, lab, s['counts'][:m])
                     else:
@@ -383,7 +446,9 @@ class SegmentChain(object):
                 with t.cuda.stream(self._s_out):
                     self._s_out.wait_event(s['ev_run'])
                     if max_regions is None:
-                        if not self._sparse():
+                        if self._sparse():
+                            s['egress'].enqueue_copy(s['labels'], m)
+                        else:
                             s['labels_host'][:m].copy_(s['labels'].t[:m], non_blocking=True)
                     else:
                         s['stats_host'][:m].copy_(s['stats'][:m], non_blocking=True)
@@ -401,15 +466,9 @@ class SegmentChain(object):
             if self.label_dtype == np.int16 and m and int(s['counts_host'].numpy()[:m].max()) > 32767:
                 raise RuntimeError('insufficient bit-depth in requested output type')      # what ndimage.label raises
             if self._sparse():
-                d = s['dense']
-                rc = self.rt.lib.va_host_densify_chunks(d.data_ptr(), d.stride(1), d.stride(0), self.w, self.h, m,
-                                                        s['exp_ids'].data_ptr(), s['exp_data'].data_ptr(), s['exp_n'].data_ptr(),
-                                                        s['cap'], s['dirty_ids'].data_ptr(), s['n_dirty'].data_ptr(),
-                                                        self.host_threads)
-                _lib.check(self.rt.lib, None, rc)
-                # bytes the device stored over PCIe for this block: chunk data + chunk ids + the two count vectors
-                self.egress_bytes += int(s['exp_n'].numpy()[:m].sum()) * (64 * 4 + 4) + 8 * m
-                return d.numpy()[:m, :, :self.w], s['counts_host'].numpy()[:m]
+                dense = s['egress'].finish(m)
+                self.egress_bytes += s['egress'].bytes + 4 * m
+                return dense, s['counts_host'].numpy()[:m]
             return s['labels_host'].numpy()[:m, :, :self.w], s['counts_host'].numpy()[:m]
         return s['stats_host'].numpy()[:m], s['counts_host'].numpy()[:m], s['largest_host'].numpy()[:m]
 

@@ -110,9 +110,9 @@ extern "C" int va_label_export_chunks(va_ctx *ctx, va_stream stream,
                                       int w, int h, int batch,
                                       int32_t *ids, int32_t *data, int32_t *n_chunks, int32_t *n_chunks_dev, int cap) {
     VA_CHECK_CTX(ctx);
-    VA_REQUIRE(ctx, mask && labels && ids && data && n_chunks, "va_label_export_chunks: null pointer");
+    VA_REQUIRE(ctx, mask && n_chunks && ((ids && data && labels) || (!ids && !data)), "va_label_export_chunks: null pointer");
     VA_REQUIRE(ctx, w > 0 && h > 0 && batch > 0 && batch <= 65535 && cap > 0, "va_label_export_chunks: bad size");
-    VA_REQUIRE(ctx, labels_pitch_e >= (size_t)w && labels_pitch_e % 2 == 0 && labels_fstride_e % 2 == 0 && va_aligned(labels, 8),
+    VA_REQUIRE(ctx, !data || (labels_pitch_e >= (size_t)w && labels_pitch_e % 2 == 0 && labels_fstride_e % 2 == 0 && va_aligned(labels, 8)),
                "va_label_export_chunks: label rows must be 8-byte aligned");
     VA_REQUIRE(ctx, mask_pitch_w >= (size_t)((w + 31) / 32), "va_label_export_chunks: pitch smaller than a row");
     if (w > ctx->max_w || h > ctx->max_h || batch > ctx->max_batch)
@@ -131,7 +131,8 @@ extern "C" int va_label_export_chunks(va_ctx *ctx, va_stream stream,
       VA_LAUNCH(ctx, k, grid, EXP_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, ctx->exp_rowoff, w, h, cpr); }
     { auto k = export_scan_kernel;
       VA_LAUNCH(ctx, k, batch, EXP_THREADS, 0, stream, ctx->exp_rowoff, n_chunks_dev, n_chunks, h); }
-    { auto k = export_write_kernel;
+    if (data) {
+      auto k = export_write_kernel;
       VA_LAUNCH(ctx, k, grid, EXP_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, labels, labels_pitch_e, labels_fstride_e,
                 (const int *)ctx->exp_rowoff, ids, data, w, h, cpr, cap); }
     VA_REQUIRE(ctx, va_scratch_release(ctx, stream, 3) == 0, "va_label_export_chunks: cannot order the scratch");
