@@ -115,19 +115,50 @@ class ClockSampler(object):
 # ------------------------------------------------------------------------------------------
 # CPU reference chain (oracle): the only places bench.py touches oracle/
 # ------------------------------------------------------------------------------------------
-def cpu_frames(n_unique):
+_W = {}
+
+
+def cpu_frames(n_unique, w=None, h=None):
     from oracle import synth
-    return synth.make_frames(0, 0, n_unique, W, H, 8)
+    return synth.make_frames(0, 0, n_unique, w or W, h or H, 8)
 
 
-def cpu_chain_run(frames, n_frames, bg=None):
-    """ reference-style loop: one frame per iteration; returns (seconds, bg) """
+def _reference_front():
+    """ the reference's OWN FilterMonochrome / FilterBlur classes (oracle/_ref, converted by oracle/build_ref.py) when that
+    tree travelled with the repository; None otherwise (the oracle restates the same two calls) """
+    try:
+        from oracle import build_ref
+        return build_ref.import_ref()
+    except Exception:
+        return None
+
+
+def cpu_chain_run(frames, n_frames, bg=None, stages=None):
+    """ reference-style loop: one frame per iteration; returns (seconds, bg).  `stages` (dict) accumulates seconds per
+    stage.  Monochrome and blur run through the reference's own filter classes when oracle/_ref is there; the steps
+    the reference does not have (EMA / threshold / open) and the label call are the oracle's. """
     from oracle import ops
     alpha32, thr32 = np.float32(CHAIN['alpha']), np.float32(CHAIN['threshold'])
-    t0 = time.perf_counter()
+    ref = _W.get('ref', False)
+    if ref is False:
+        ref = _W['ref'] = _reference_front()
+    tick = time.perf_counter
+    acc = stages if stages is not None else {}
+    for k in ('mono', 'blur', 'ema_diff_thresh', 'morph_open', 'label'):
+        acc.setdefault(k, 0.0)
+    if ref is not None:
+        class _One(object):                    # a one-frame source for the reference's filter objects
+            size, frame_count, fps, is_color = (frames.shape[2], frames.shape[1]), 1, 25, True
+        mono_f = ref.filters.FilterMonochrome(_One())
+        blur_f = ref.filters.FilterBlur(mono_f, CHAIN['sigma'])
+    t0 = tick()
     for i in range(n_frames):
         f = frames[i % len(frames)]
-        b = ops.blur(ops.mono(f), CHAIN['sigma'])
+        t1 = tick()
+        m = mono_f._process_frame(f) if ref is not None else ops.mono(f)
+        t2 = tick()
+        b = blur_f._process_frame(m) if ref is not None else ops.blur(m, CHAIN['sigma'])
+        t3 = tick()
         x = b.astype(np.float32)
         if bg is None:
             bg = x.copy()
@@ -136,9 +167,17 @@ def cpu_chain_run(frames, n_frames, bg=None):
             d = x - bg
             mask = np.where(np.abs(d) > thr32, 255, 0).astype(np.uint8)
             bg = bg + alpha32 * d
+        t4 = tick()
         mo = ops.morph(mask, CHAIN['morph_op'], CHAIN['morph_shape'], CHAIN['morph_ksize'])
+        t5 = tick()
         ops.label(mo, CHAIN['connectivity'])
-    return time.perf_counter() - t0, bg
+        t6 = tick()
+        acc['mono'] += t2 - t1
+        acc['blur'] += t3 - t2
+        acc['ema_diff_thresh'] += t4 - t3
+        acc['morph_open'] += t5 - t4
+        acc['label'] += t6 - t5
+    return tick() - t0, bg
 
 
 def cpu_baseline_single(budget_s=12.0):
@@ -146,13 +185,23 @@ def cpu_baseline_single(budget_s=12.0):
     frames = cpu_frames(8)
     dt, bg = cpu_chain_run(frames, 8)                 # warm-up + rate estimate
     n = int(max(16, min(400, budget_s / (dt / 8))))
-    dt, _ = cpu_chain_run(frames, n, bg)
-    return {'value': round(n / dt, 2), 'unit': 'frames/s', 'cores': int(cv2.getNumThreads()), 'kind': 'port',
+    stages = {}
+    dt, _ = cpu_chain_run(frames, n, bg, stages)
+    kind = 'reference' if _W.get('ref') is not None else 'port'
+    # configs[0] (the reference's own CPU-runnable case): 640x480, bounded sample
+    vga = cpu_frames(8, 640, 480)
+    dv, bgv = cpu_chain_run(vga, 8)
+    nv = int(max(32, min(1000, 4.0 / (dv / 8))))
+    vstages = {}
+    dv, _ = cpu_chain_run(vga, nv, bgv, vstages)
+    return {'value': round(n / dt, 2), 'unit': 'frames/s', 'cores': int(cv2.getNumThreads()), 'kind': kind,
             'sample': '%d frames 1080p (8 unique synthetic frames cycled), one process, one frame per iteration, '
-                      'cv2 threads=%d' % (n, cv2.getNumThreads())}
-
-
-_W = {}
+                      'cv2 threads=%d; monochrome + blur through %s, EMA / threshold / open / label through the oracle '
+                      '(absent from the reference, SURVEY 8c)'
+                      % (n, cv2.getNumThreads(), "the reference's own filter classes (oracle/_ref)" if kind == 'reference' else 'the oracle'),
+            'per_stage_ms': {k: round(v / n * 1e3, 3) for k, v in stages.items()},
+            'vga_640x480': {'value': round(nv / dv, 2), 'unit': 'frames/s', 'sample': '%d frames' % nv,
+                            'per_stage_ms': {k: round(v / nv * 1e3, 3) for k, v in vstages.items()}}}
 
 
 def _worker_init():
@@ -190,10 +239,12 @@ def reference_arm(args):
         'n_gpus': args.gpus, 'steps': steps, 'warmup': max(args.warmup, 1), 'ms_per_step': round(dt / steps * 1e3, 3),
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'frames_per_step': procs * per},
-        'cpu_baseline': {'value': round(fps, 2), 'unit': 'frames/s', 'cores': procs, 'kind': 'port',
-                         'sample': '%d steps x %d processes x %d frames 1080p, frame-sharded, cv2 threads=1 per process, '
-                                   'oracle restatement of the reference calls (reference is Python 2, not importable)'
-                                   % (steps, procs, per)},
+        'cpu_baseline': {'value': round(fps, 2), 'unit': 'frames/s', 'cores': procs,
+                         'kind': 'reference' if _reference_front() is not None else 'port',
+                         'sample': '%d steps x %d processes x %d frames 1080p, frame-sharded, cv2 threads=1 per process; '
+                                   'monochrome + blur through the reference\'s own filter classes where oracle/_ref is present '
+                                   '(Python-3 conversion of /root/reference, oracle/build_ref.py), the steps the reference lacks '
+                                   'through the oracle' % (steps, procs, per)},
         'e2e': {'value': round(fps, 2), 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line), flush=True)
@@ -490,7 +541,7 @@ def instrumented_pass(rt, chain, batch_of, labels, counts, Wm, K, B, N, hbm_peak
                       'frac': round(alg_bytes[s] * B / (avg[s] * 1e-3) / 1e9 / hbm_peak, 3)} for s in stages}
     traffic = None
     try:        # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed ncu --set full capture
-        for tr in json.load(open(os.path.join(ROOT, 'profiles', 'traffic_r1.json'))).get(dom, []):
+        for tr in json.load(open(os.path.join(ROOT, 'profiles', 'traffic_r2.json'))).get(dom, []):
             if tr.get('batch') == B:
                 traffic = int(tr['dram_bytes_read'] + tr['dram_bytes_write'])
     except Exception:

@@ -32,5 +32,17 @@ mask = rt.ema_diff_thresh(blur, bg, 0.05, 25.0, False)
 mo = rt.morph(mask, 'open', 'rect', 3)
 lab, cnt = rt.label(mo, 4)
 stats, cnt2, big = rt.region_stats(mo, 4, 256)
+# round 2: the tensor-core blur at a large radius (sigma 15: seven 16-row groups, 64-column strips) and the chunk export
+if os.environ.get('PROF_EXTRA', '1') != '0':
+    n15 = min(B, 32)
+    from video_analysis_b200.device import DeviceBatch
+    m15 = DeviceBatch('u8', mono.t[:n15], n15, H, W, 1)
+    blur15 = rt.gauss(m15, 15.0)
+    import torch as _t
+    ids = _t.empty((B, 30 * H), dtype=_t.int32, pin_memory=True)
+    data = _t.empty((B, 30 * H, 64), dtype=_t.int32, pin_memory=True)
+    nn = _t.empty((B,), dtype=_t.int32, pin_memory=True)
+    rt._check(rt.lib.va_label_export_chunks(rt._h, rt.stream, *mo.img(), *lab.img(), W, H, B, ids.data_ptr(), data.data_ptr(),
+                                            nn.data_ptr(), None, 30 * H))
 torch.cuda.synchronize()
 print('ok', cnt[:4].tolist(), rt.launches)

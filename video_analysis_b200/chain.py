@@ -455,11 +455,26 @@ class SegmentChain(object):
                         s['largest_host'][:m].copy_(s['largest'][:m], non_blocking=True)
                     s['counts_host'][:m].copy_(s['counts'][:m], non_blocking=True)
                     s['ev_out'].record(self._s_out)
-                pending.append((s, m, max_regions))
+                pending.append(self._finish_async((s, m, max_regions)))
             while pending:
                 yield self._finish(pending.popleft())
 
+    def _finish_async(self, item):
+        """ hand a block whose work is enqueued to the finisher thread: it waits for the block's event and rebuilds the
+        dense label images (host threads, GIL released) while the caller enqueues the next blocks """
+        if not self._sparse() or item[2] is not None:
+            return item
+        import concurrent.futures
+        if getattr(self, '_finisher', None) is None:
+            self._finisher = concurrent.futures.ThreadPoolExecutor(max_workers=1, thread_name_prefix='va-egress')
+        return self._finisher.submit(self._finish_now, item)
+
     def _finish(self, item):
+        if hasattr(item, 'result'):
+            return item.result()
+        return self._finish_now(item)
+
+    def _finish_now(self, item):
         s, m, max_regions = item
         s['ev_out'].synchronize()
         if max_regions is None:
