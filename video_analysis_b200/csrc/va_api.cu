@@ -71,8 +71,9 @@ extern "C" int va_destroy(va_ctx *ctx) {
     cudaFree(ctx->ch_mask);
     cudaFree(ctx->ch_morph);
     cudaFree(ctx->exp_rowoff);
+    cudaFree(ctx->rs_tab);
 #ifndef VA_EMU
-    for (int i = 0; i < 4; i++)
+    for (int i = 0; i < 5; i++)
         if (ctx->lab_event[i]) cudaEventDestroy((cudaEvent_t)ctx->lab_event[i]);
 #endif
     free(ctx);

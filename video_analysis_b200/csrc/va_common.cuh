@@ -32,8 +32,10 @@ struct va_ctx {
     // last use of each scratch set: every entry point that touches a set first makes its stream wait for
     // this event and re-records it when it has enqueued its kernels, so callers on different streams
     // (two filter chains, a chain next to region_stats, ...) never run forest kernels on one set at once
-    void *lab_event[4];      // [2]: the chain intermediates of va_chain_run, [3]: the row offsets of va_label_export_chunks
+    void *lab_event[5];      // [2]: the chain intermediates of va_chain_run, [3]: the row offsets of va_label_export_chunks
     int *exp_rowoff;         // [max_batch * max_h] chunk counts per row -> exclusive prefix (allocated on first use)
+    void *rs_tab;            // resize coefficient tables of the launch in flight (event [4] orders its users)
+    size_t rs_tab_bytes;
     // morphology scratch (intermediate of open / close is kept in shared memory; none needed)
     // chain intermediates (allocated on first use by va_chain_run)
     uint8_t *ch_mono, *ch_blur;

@@ -314,20 +314,35 @@ __device__ __forceinline__ float area_weight(const AreaCell &c, int i) {
     return c.a_mid;
 }
 
+// tables: one cell per destination column (entries 0 .. ow - 1) and per destination row (entries ow .. ow + oh - 1),
+// computed once per launch by resize_area_tables_kernel with the double operations above (FP64 is slow on this part:
+// doing them per output byte was what bounded the old one-thread-per-byte kernel)
 __global__ void __launch_bounds__(256)
+resize_area_tables_kernel(AreaCell *__restrict__ tab, int w, int h, int ow, int oh, double scale_x, double scale_y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ow) tab[i] = area_cell(i, scale_x, w);
+    else if (i < ow + oh) tab[i] = area_cell(i - ow, scale_y, h);
+}
+
+// one thread per 4 consecutive output bytes of a row (one 32-bit store); grid = (row words, rows, frames)
+__global__ void __launch_bounds__(128)
 resize_area_any_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstride,
                        uint8_t *__restrict__ out, size_t out_pitch, size_t out_fstride,
-                       int w, int h, int ow, int oh, int cs, int batch, double scale_x, double scale_y) {
-    const unsigned rowb = (unsigned)(ow * cs);
-    const unsigned long long total = (unsigned long long)rowb * oh * batch;
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
-         i += (unsigned long long)gridDim.x * blockDim.x) {
-        const unsigned xb = (unsigned)(i % rowb);
-        const unsigned long long rest = i / rowb;
-        const unsigned y = (unsigned)(rest % oh), b = (unsigned)(rest / oh);
-        const unsigned x = xb / cs, c = xb - x * cs;
-        const AreaCell cx = area_cell((int)x, scale_x, w), cy = area_cell((int)y, scale_y, h);
-        const uint8_t *p = in + (size_t)b * in_fstride + (size_t)cy.s0 * in_pitch + (size_t)cx.s0 * cs + c;
+                       int ow, int oh, int cs, const AreaCell *__restrict__ tab, int vec_out) {
+    const int rowb = ow * cs;
+    const int xb0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (xb0 >= rowb) return;
+    const int y = blockIdx.y, b = blockIdx.z;
+    const AreaCell cy = tab[ow + y];
+    const uint8_t *frame = in + (size_t)b * in_fstride + (size_t)cy.s0 * in_pitch;
+    unsigned packed = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int xb = xb0 + q;
+        if (xb >= rowb) break;
+        const int x = cs == 1 ? xb : xb / 3, c = cs == 1 ? 0 : xb - 3 * x;
+        const AreaCell cx = tab[x];
+        const uint8_t *p = frame + (size_t)cx.s0 * cs + c;
         float sum = 0.f;
         for (int j = 0; j < cy.n; j++, p += in_pitch) {
             float buf = 0.f;
@@ -336,14 +351,45 @@ resize_area_any_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t i
             sum = j == 0 ? t : __fadd_rn(sum, t);
         }
         const int v = __float2int_rn(sum);
-        out[(size_t)b * out_fstride + (size_t)y * out_pitch + xb] = (uint8_t)min(max(v, 0), 255);
+        packed |= (unsigned)min(max(v, 0), 255) << (8 * q);
+    }
+    uint8_t *o = out + (size_t)b * out_fstride + (size_t)y * out_pitch + xb0;
+    if (vec_out && xb0 + 4 <= rowb) {
+        *reinterpret_cast<unsigned *>(o) = packed;
+    } else {
+        for (int q = 0; q < 4 && xb0 + q < rowb; q++) o[q] = (uint8_t)(packed >> (8 * q));
     }
 }
 
-__global__ void resize_linear_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstride,
-                                     uint8_t *__restrict__ out, size_t out_pitch, size_t out_fstride,
-                                     int w, int h, int ow, int oh, int cs, int batch, double scale_x, double scale_y,
-                                     int area_mode, double inv_scale_x, double inv_scale_y);
+// scratch for the per-launch coefficient tables (ctx-owned, grown on demand, ordered across streams by event 4)
+static int resize_tables(va_ctx *ctx, const char *name, size_t bytes, void **tab) {
+    if (ctx->rs_tab_bytes < bytes) {
+        if (ctx->rs_tab) {
+            VA_CUDA(ctx, cudaDeviceSynchronize());
+            cudaFree(ctx->rs_tab);
+            ctx->rs_tab = nullptr;
+            ctx->rs_tab_bytes = 0;
+        }
+        const size_t want = bytes < (1u << 20) ? (1u << 20) : bytes;
+        if (cudaMalloc(&ctx->rs_tab, want) != cudaSuccess) {
+            cudaGetLastError();
+            VA_FAIL(ctx, VA_ERR_NOMEM, "%s: cannot allocate the coefficient tables", name);
+        }
+        ctx->rs_tab_bytes = want;
+    }
+    *tab = ctx->rs_tab;
+    return VA_OK;
+}
+
+static int resize_linear_launch(va_ctx *ctx, va_stream stream, const char *name,
+                                const uint8_t *in, size_t in_pitch, size_t in_fstride,
+                                uint8_t *out, size_t out_pitch, size_t out_fstride,
+                                int w, int h, int dw, int dh, int channels, int batch,
+                                double sx, double sy, int area_mode, double isx, double isy);
+template <int MODE>
+static int resize_staged_launch(va_ctx *ctx, va_stream stream, const uint8_t *in, size_t in_pitch, size_t in_fstride,
+                                uint8_t *out, size_t out_pitch, size_t out_fstride,
+                                int w, int h, int dw, int dh, int channels, int batch, double sx, double sy, const void *tab);
 
 // cv::resize's test for the integer-factor INTER_AREA path (both |scale - round(scale)| < DBL_EPSILON)
 static bool resize_area_is_fast(int w, int h, int dw, int dh, double *sx, double *sy, int *kx, int *ky) {
@@ -368,12 +414,8 @@ extern "C" int va_resize_area_any_u8(va_ctx *ctx, va_stream stream,
         const double isx = (double)dw / (double)w, isy = (double)dh / (double)h;
         sx = 1.0 / isx;
         sy = 1.0 / isy;
-        const long long items = (long long)dw * channels * dh * batch;
-        const int grid = va_grid(ctx, (items + 255) / 256, 16);
-        auto kfn = resize_linear_kernel;
-        VA_LAUNCH(ctx, kfn, grid, 256, 0, stream, in, in_pitch, in_fstride, out, out_pitch, out_fstride, w, h, dw, dh, channels, batch,
-                  sx, sy, 1, isx, isy);
-        return VA_OK;
+        return resize_linear_launch(ctx, stream, "va_resize_area_any_u8", in, in_pitch, in_fstride, out, out_pitch, out_fstride,
+                                    w, h, dw, dh, channels, batch, sx, sy, 1, isx, isy);
     }
     if (resize_area_is_fast(w, h, dw, dh, &sx, &sy, &kx, &ky)) {
         if (kx == 1 && ky == 1)
@@ -383,11 +425,23 @@ extern "C" int va_resize_area_any_u8(va_ctx *ctx, va_stream stream,
         return va_resize_area_u8(ctx, stream, in, in_pitch, in_fstride, out, out_pitch, out_fstride, w, h, channels, batch, kx, ky);
     }
     VA_REQUIRE(ctx, in_pitch >= (size_t)w * channels && out_pitch >= (size_t)dw * channels, "va_resize_area_any_u8: pitch smaller than a row");
-    const long long items = (long long)dw * channels * dh * batch;
-    const int grid = va_grid(ctx, (items + 255) / 256, 16);
-    auto kfn = resize_area_any_kernel;
-    VA_LAUNCH(ctx, kfn, grid, 256, 0, stream, in, in_pitch, in_fstride, out, out_pitch, out_fstride, w, h, dw, dh, channels, batch,
-              sx, sy);
+    VA_REQUIRE(ctx, dh <= 65535 && batch <= 65535, "va_resize_area_any_u8: too many rows or frames for one launch");
+    void *tab;
+    { const int rc = resize_tables(ctx, "va_resize_area_any_u8", (size_t)(dw + dh) * sizeof(AreaCell), &tab); if (rc != VA_OK) return rc; }
+    VA_REQUIRE(ctx, va_scratch_acquire(ctx, stream, 4) == 0, "va_resize_area_any_u8: cannot order the table scratch");
+    { auto kfn = resize_area_tables_kernel;
+      VA_LAUNCH(ctx, kfn, va_div_up(dw + dh, 256), 256, 0, stream, (AreaCell *)tab, w, h, dw, dh, sx, sy); }
+    const int rs = resize_staged_launch<0>(ctx, stream, in, in_pitch, in_fstride, out, out_pitch, out_fstride, w, h, dw, dh, channels, batch,
+                                           sx, sy, tab);
+    if (rs != VA_OK && rs != VA_ERR_UNSUPPORTED) return rs;
+    if (rs == VA_ERR_UNSUPPORTED) {
+      auto kfn = resize_area_any_kernel;
+      const int words = va_div_up(dw * channels, 4);
+      const dim3 grid(va_div_up(words, 128), dh, batch);
+      const int vec_out = va_aligned(out, 4) && out_pitch % 4 == 0 && out_fstride % 4 == 0;
+      VA_LAUNCH(ctx, kfn, grid, 128, 0, stream, in, in_pitch, in_fstride, out, out_pitch, out_fstride, dw, dh, channels,
+                (const AreaCell *)tab, vec_out); }
+    VA_REQUIRE(ctx, va_scratch_release(ctx, stream, 4) == 0, "va_resize_area_any_u8: cannot order the table scratch");
     return VA_OK;
 }
 
@@ -412,41 +466,238 @@ __device__ __forceinline__ void linear_coef_area(int d, double scale, double inv
     f = f <= 0.f ? 0.f : __fadd_rn(f, -floorf(f));
 }
 
+struct LinCell { int s0, s1, a0, a1; };      // two source indices (clipped) and their 11-bit weights
+
+// tables: columns 0 .. ow - 1 (s1 = s0 + 1 or s0 at the last pixel, where its weight is not used), rows ow .. ow + oh - 1
 __global__ void __launch_bounds__(256)
+resize_linear_tables_kernel(LinCell *__restrict__ tab, int w, int h, int ow, int oh, double scale_x, double scale_y,
+                            int area_mode, double inv_scale_x, double inv_scale_y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ow + oh) return;
+    const bool col = i < ow;
+    const int d = col ? i : i - ow;
+    float f;
+    int sidx;
+    if (area_mode) linear_coef_area(d, col ? scale_x : scale_y, col ? inv_scale_x : inv_scale_y, f, sidx);
+    else linear_coef(d, col ? scale_x : scale_y, f, sidx);
+    LinCell c;
+    if (col) {
+        if (sidx < 0) { sidx = 0; f = 0.f; }
+        if (sidx >= w - 1) { sidx = w - 1; f = 0.f; }
+        c.s0 = sidx;
+        c.s1 = sidx < w - 1 ? sidx + 1 : -1;             // -1: no second tap (the last pixel alone)
+    } else {
+        c.s0 = min(max(sidx, 0), h - 1);
+        c.s1 = min(max(sidx + 1, 0), h - 1);
+    }
+    c.a0 = __float2int_rn(__fmul_rn(__fadd_rn(1.f, -f), 2048.f));
+    c.a1 = __float2int_rn(__fmul_rn(f, 2048.f));
+    tab[i] = c;
+}
+
+__global__ void __launch_bounds__(128)
 resize_linear_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstride,
                      uint8_t *__restrict__ out, size_t out_pitch, size_t out_fstride,
-                     int w, int h, int ow, int oh, int cs, int batch, double scale_x, double scale_y,
-                     int area_mode, double inv_scale_x, double inv_scale_y) {
-    const unsigned rowb = (unsigned)(ow * cs);
-    const unsigned long long total = (unsigned long long)rowb * oh * batch;
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
-         i += (unsigned long long)gridDim.x * blockDim.x) {
-        const unsigned xb = (unsigned)(i % rowb);
-        const unsigned long long rest = i / rowb;
-        const unsigned y = (unsigned)(rest % oh), b = (unsigned)(rest / oh);
-        const unsigned x = xb / cs, c = xb - x * cs;
-        float fx, fy;
-        int sx, sy;
-        if (area_mode) {
-            linear_coef_area((int)x, scale_x, inv_scale_x, fx, sx);
-            linear_coef_area((int)y, scale_y, inv_scale_y, fy, sy);
-        } else {
-            linear_coef((int)x, scale_x, fx, sx);
-            linear_coef((int)y, scale_y, fy, sy);
-        }
-        if (sx < 0) { sx = 0; fx = 0.f; }
-        if (sx >= w - 1) { sx = w - 1; fx = 0.f; }
-        const int a0 = __float2int_rn(__fmul_rn(__fadd_rn(1.f, -fx), 2048.f)), a1 = __float2int_rn(__fmul_rn(fx, 2048.f));
-        const int b0 = __float2int_rn(__fmul_rn(__fadd_rn(1.f, -fy), 2048.f)), b1 = __float2int_rn(__fmul_rn(fy, 2048.f));
-        const int y0 = min(max(sy, 0), h - 1), y1 = min(max(sy + 1, 0), h - 1);
-        const int x1 = sx < w - 1 ? sx + 1 : sx;                   // its weight is 0 at the last pixel
-        const uint8_t *f0 = in + (size_t)b * in_fstride + (size_t)y0 * in_pitch + c;
-        const uint8_t *f1 = in + (size_t)b * in_fstride + (size_t)y1 * in_pitch + c;
-        const int h0 = f0[(size_t)sx * cs] * a0 + (sx < w - 1 ? f0[(size_t)x1 * cs] * a1 : 0);
-        const int h1 = f1[(size_t)sx * cs] * a0 + (sx < w - 1 ? f1[(size_t)x1 * cs] * a1 : 0);
-        const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
-        out[(size_t)b * out_fstride + (size_t)y * out_pitch + xb] = (uint8_t)v;
+                     int ow, int oh, int cs, const LinCell *__restrict__ tab, int vec_out) {
+    const int rowb = ow * cs;
+    const int xb0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (xb0 >= rowb) return;
+    const int y = blockIdx.y, b = blockIdx.z;
+    const LinCell cy = tab[ow + y];
+    const uint8_t *f0 = in + (size_t)b * in_fstride + (size_t)cy.s0 * in_pitch;
+    const uint8_t *f1 = in + (size_t)b * in_fstride + (size_t)cy.s1 * in_pitch;
+    unsigned packed = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int xb = xb0 + q;
+        if (xb >= rowb) break;
+        const int x = cs == 1 ? xb : xb / 3, c = cs == 1 ? 0 : xb - 3 * x;
+        const LinCell cx = tab[x];
+        const size_t o0 = (size_t)cx.s0 * cs + c, o1 = (size_t)(cx.s1 < 0 ? cx.s0 : cx.s1) * cs + c;
+        const int h0 = f0[o0] * cx.a0 + (cx.s1 >= 0 ? f0[o1] * cx.a1 : 0);
+        const int h1 = f1[o0] * cx.a0 + (cx.s1 >= 0 ? f1[o1] * cx.a1 : 0);
+        const int v = (((cy.a0 * (h0 >> 4)) >> 16) + ((cy.a1 * (h1 >> 4)) >> 16) + 2) >> 2;
+        packed |= (unsigned)(v & 0xff) << (8 * q);
     }
+    uint8_t *o = out + (size_t)b * out_fstride + (size_t)y * out_pitch + xb0;
+    if (vec_out && xb0 + 4 <= rowb) {
+        *reinterpret_cast<unsigned *>(o) = packed;
+    } else {
+        for (int q = 0; q < 4 && xb0 + q < rowb; q++) o[q] = (uint8_t)(packed >> (8 * q));
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Staged, separable evaluation of INTER_AREA (float tables) and INTER_LINEAR for whole output tiles: a CTA owns
+// RS_TH output rows x RS_TWB output bytes.  It stages the source rows / columns the tile's table cells reach into
+// shared memory with 16-byte loads, evaluates the horizontal pass ONCE per source row (H[j][xb], the `buf` / `h`
+// value of the per-byte kernels above, same operations in the same order), then combines the rows of H per
+// output row.  Source bytes are read from global memory once per tile instead of once per output byte and tap,
+// and the horizontal pass is shared by the output rows that use the same source row.
+// ---------------------------------------------------------------------------------
+#define RS_TH 8
+#define RS_TWB 512
+#define RS_THREADS 256
+
+struct RsTile { int rows_max, cols_max; };     // shared-memory extent in source rows / source bytes (host-computed bound)
+
+template <int MODE>     // 0: INTER_AREA (AreaCell, float), 1: INTER_LINEAR (LinCell, int)
+__global__ void __launch_bounds__(RS_THREADS)
+resize_staged_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstride,
+                     uint8_t *__restrict__ out, size_t out_pitch, size_t out_fstride,
+                     int w, int h, int ow, int oh, int cs, const void *__restrict__ tabv, int vec_in, int vec_out, RsTile tile) {
+    VA_DYN_SMEM(unsigned char, smem);
+    const AreaCell *ta = reinterpret_cast<const AreaCell *>(tabv);
+    const LinCell *tl = reinterpret_cast<const LinCell *>(tabv);
+    const int tid = threadIdx.x;
+    const int rowb = ow * cs, srcb = w * cs;
+    const int xb0 = blockIdx.x * RS_TWB, y0 = blockIdx.y * RS_TH, b = blockIdx.z;
+    const int nxb = min(RS_TWB, rowb - xb0), ny = min(RS_TH, oh - y0);
+    // source extent of the tile (cells are monotonic in the destination index)
+    const int xf = xb0 / cs, xl = (xb0 + nxb - 1) / cs;
+    int c_lo, c_hi, r_lo, r_hi;
+    if (MODE == 0) {
+        c_lo = ta[xf].s0 * cs; c_hi = (ta[xl].s0 + ta[xl].n) * cs;
+        r_lo = ta[ow + y0].s0; r_hi = ta[ow + y0 + ny - 1].s0 + ta[ow + y0 + ny - 1].n;
+    } else {
+        c_lo = tl[xf].s0 * cs; c_hi = (max(tl[xl].s0, tl[xl].s1) + 1) * cs;
+        r_lo = min(tl[ow + y0].s0, tl[ow + y0].s1);
+        r_hi = max(tl[ow + y0 + ny - 1].s0, tl[ow + y0 + ny - 1].s1) + 1;
+        // clipped row indices are monotonic too; an enlarging resize may repeat rows
+    }
+    const int c_al = c_lo & ~15;                         // staged columns start 16-byte aligned (relative to the row)
+    const int ncols = c_hi - c_al, nrows = r_hi - r_lo;
+    const int spitch = (tile.cols_max + 31) & ~15;       // bytes per staged row
+    unsigned char *S = smem;                             // [rows_max][spitch]
+    float *Hf = reinterpret_cast<float *>(smem + (((size_t)tile.rows_max * spitch + 15) & ~(size_t)15));   // [rows_max][RS_TWB]
+    int *Hi = reinterpret_cast<int *>(Hf);
+    if (nrows > tile.rows_max || ncols > spitch) return;   // cannot happen for the bound the host computed; never write out of bounds
+    const uint8_t *src = in + (size_t)b * in_fstride + (size_t)r_lo * in_pitch + c_al;
+    // ---- stage
+    const int chunks = (ncols + 15) >> 4;
+    for (int it = tid; it < nrows * chunks; it += RS_THREADS) {
+        const int r = it / chunks, ch = it - r * chunks;
+        const uint8_t *g = src + (size_t)r * in_pitch + 16 * ch;
+        unsigned char *d = S + (size_t)r * spitch + 16 * ch;
+        if (vec_in && c_al + 16 * ch + 16 <= srcb) {
+            *reinterpret_cast<uint4 *>(d) = *reinterpret_cast<const uint4 *>(g);
+        } else {
+            for (int k = 0; k < 16; k++) d[k] = (c_al + 16 * ch + k < srcb) ? g[k] : (unsigned char)0;
+        }
+    }
+    __syncthreads();
+    // ---- horizontal pass: H[j][xb] for every staged source row; a thread keeps the cell of its column and walks the rows
+    for (int q = tid; q < nxb; q += RS_THREADS) {
+        const int xb = xb0 + q;
+        const int x = cs == 1 ? xb : xb / 3, c = cs == 1 ? 0 : xb - 3 * x;
+        if (MODE == 0) {
+            const AreaCell cx = ta[x];
+            const unsigned char *p = S - c_al + c + cx.s0 * cs;
+            const int nk = cx.n;
+            const float w0 = area_weight(cx, 0), wl = area_weight(cx, nk - 1), wm = cx.a_mid;
+            for (int j = 0; j < nrows; j++, p += spitch) {
+                float buf = __fadd_rn(0.f, __fmul_rn((float)p[0], w0));
+                for (int k = 1; k < nk - 1; k++) buf = __fadd_rn(buf, __fmul_rn((float)p[k * cs], wm));
+                if (nk > 1) buf = __fadd_rn(buf, __fmul_rn((float)p[(nk - 1) * cs], wl));
+                Hf[j * RS_TWB + q] = buf;
+            }
+        } else {
+            const LinCell cx = tl[x];
+            const unsigned char *p0 = S - c_al + c + cx.s0 * cs;
+            const unsigned char *p1 = S - c_al + c + (cx.s1 >= 0 ? cx.s1 : cx.s0) * cs;
+            const int a1 = cx.s1 >= 0 ? cx.a1 : 0;
+            for (int j = 0; j < nrows; j++, p0 += spitch, p1 += spitch) Hi[j * RS_TWB + q] = p0[0] * cx.a0 + p1[0] * a1;
+        }
+    }
+    __syncthreads();
+    // ---- vertical pass: 4 output bytes per thread and row
+    // a thread owns a word column (4 bytes) and walks every second row of the tile: no index divisions in the loop
+    constexpr int WPT = RS_TWB / 4;                       // word columns of a full tile
+    const int q0 = 4 * (tid % WPT);
+    for (int yy = tid / WPT; yy < ny && q0 < nxb; yy += RS_THREADS / WPT) {
+        const int y = y0 + yy;
+        unsigned packed = 0;
+        if (MODE == 0) {
+            const AreaCell cy = ta[ow + y];
+            const int j0 = cy.s0 - r_lo;
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                if (q0 + e >= nxb) break;
+                float sum = 0.f;
+                for (int j = 0; j < cy.n; j++) {
+                    const float t = __fmul_rn(area_weight(cy, j), Hf[(j0 + j) * RS_TWB + q0 + e]);
+                    sum = j == 0 ? t : __fadd_rn(sum, t);
+                }
+                const int v = __float2int_rn(sum);
+                packed |= (unsigned)min(max(v, 0), 255) << (8 * e);
+            }
+        } else {
+            const LinCell cy = tl[ow + y];
+            const int ja = cy.s0 - r_lo, jb = cy.s1 - r_lo;
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                if (q0 + e >= nxb) break;
+                const int h0 = Hi[ja * RS_TWB + q0 + e], h1 = Hi[jb * RS_TWB + q0 + e];
+                const int v = (((cy.a0 * (h0 >> 4)) >> 16) + ((cy.a1 * (h1 >> 4)) >> 16) + 2) >> 2;
+                packed |= (unsigned)(v & 0xff) << (8 * e);
+            }
+        }
+        uint8_t *o = out + (size_t)b * out_fstride + (size_t)y * out_pitch + xb0 + q0;
+        if (vec_out && q0 + 4 <= nxb) {
+            *reinterpret_cast<unsigned *>(o) = packed;
+        } else {
+            for (int e = 0; e < 4 && q0 + e < nxb; e++) o[e] = (uint8_t)(packed >> (8 * e));
+        }
+    }
+}
+
+// launches the staged kernel when the tile's source extent fits in shared memory; returns VA_ERR_UNSUPPORTED otherwise
+// (strong shrink factors: the per-byte kernels take over)
+template <int MODE>
+static int resize_staged_launch(va_ctx *ctx, va_stream stream, const uint8_t *in, size_t in_pitch, size_t in_fstride,
+                                uint8_t *out, size_t out_pitch, size_t out_fstride,
+                                int w, int h, int dw, int dh, int channels, int batch, double sx, double sy, const void *tab) {
+    if (getenv("VA_RESIZE_STAGED") && atoi(getenv("VA_RESIZE_STAGED")) == 0) return VA_ERR_UNSUPPORTED;
+    if (dh > 65535 * RS_TH || batch > 65535) return VA_ERR_UNSUPPORTED;
+    RsTile tile;
+    tile.rows_max = (int)ceil(RS_TH * (sy > 1.0 ? sy : 1.0)) + 3;
+    tile.cols_max = ((int)ceil((RS_TWB / channels + 2) * (sx > 1.0 ? sx : 1.0)) + 3) * channels + 16;
+    const size_t spitch = ((size_t)tile.cols_max + 31) & ~(size_t)15;
+    const size_t smem = (((size_t)tile.rows_max * spitch + 15) & ~(size_t)15) + (size_t)tile.rows_max * RS_TWB * 4;
+    if (smem > 100 * 1024) return VA_ERR_UNSUPPORTED;
+    auto kfn = resize_staged_kernel<MODE>;
+    if (smem > 48 * 1024) VA_CUDA(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const dim3 grid(va_div_up(dw * channels, RS_TWB), va_div_up(dh, RS_TH), batch);
+    const int vec_in = va_aligned(in, 16) && in_pitch % 16 == 0 && in_fstride % 16 == 0;
+    const int vec_out = va_aligned(out, 4) && out_pitch % 4 == 0 && out_fstride % 4 == 0;
+    VA_LAUNCH(ctx, kfn, grid, RS_THREADS, smem, stream, in, in_pitch, in_fstride, out, out_pitch, out_fstride, w, h, dw, dh, channels,
+              tab, vec_in, vec_out, tile);
+    return VA_OK;
+}
+
+static int resize_linear_launch(va_ctx *ctx, va_stream stream, const char *name,
+                                const uint8_t *in, size_t in_pitch, size_t in_fstride,
+                                uint8_t *out, size_t out_pitch, size_t out_fstride,
+                                int w, int h, int dw, int dh, int channels, int batch,
+                                double sx, double sy, int area_mode, double isx, double isy) {
+    VA_REQUIRE(ctx, dh <= 65535 && batch <= 65535, "%s: too many rows or frames for one launch", name);
+    void *tab;
+    { const int rc = resize_tables(ctx, name, (size_t)(dw + dh) * sizeof(LinCell), &tab); if (rc != VA_OK) return rc; }
+    VA_REQUIRE(ctx, va_scratch_acquire(ctx, stream, 4) == 0, "%s: cannot order the table scratch", name);
+    { auto kfn = resize_linear_tables_kernel;
+      VA_LAUNCH(ctx, kfn, va_div_up(dw + dh, 256), 256, 0, stream, (LinCell *)tab, w, h, dw, dh, sx, sy, area_mode, isx, isy); }
+    const int rs = resize_staged_launch<1>(ctx, stream, in, in_pitch, in_fstride, out, out_pitch, out_fstride, w, h, dw, dh, channels, batch,
+                                           sx, sy, tab);
+    if (rs != VA_OK && rs != VA_ERR_UNSUPPORTED) return rs;
+    if (rs == VA_ERR_UNSUPPORTED) {
+      auto kfn = resize_linear_kernel;
+      const int words = va_div_up(dw * channels, 4);
+      const dim3 grid(va_div_up(words, 128), dh, batch);
+      const int vec_out = va_aligned(out, 4) && out_pitch % 4 == 0 && out_fstride % 4 == 0;
+      VA_LAUNCH(ctx, kfn, grid, 128, 0, stream, in, in_pitch, in_fstride, out, out_pitch, out_fstride, dw, dh, channels,
+                (const LinCell *)tab, vec_out); }
+    VA_REQUIRE(ctx, va_scratch_release(ctx, stream, 4) == 0, "%s: cannot order the table scratch", name);
+    return VA_OK;
 }
 
 extern "C" int va_resize_linear_u8(va_ctx *ctx, va_stream stream,
@@ -461,12 +712,8 @@ extern "C" int va_resize_linear_u8(va_ctx *ctx, va_stream stream,
     if (resize_area_is_fast(w, h, dw, dh, &sx, &sy, &kx, &ky) && kx == 2 && ky == 2)
         return va_resize_half_u8(ctx, stream, in, in_pitch, in_fstride, out, out_pitch, out_fstride, w, h, channels, batch);
     VA_REQUIRE(ctx, in_pitch >= (size_t)w * channels && out_pitch >= (size_t)dw * channels, "va_resize_linear_u8: pitch smaller than a row");
-    const long long items = (long long)dw * channels * dh * batch;
-    const int grid = va_grid(ctx, (items + 255) / 256, 16);
-    auto kfn = resize_linear_kernel;
-    VA_LAUNCH(ctx, kfn, grid, 256, 0, stream, in, in_pitch, in_fstride, out, out_pitch, out_fstride, w, h, dw, dh, channels, batch,
-              sx, sy, 0, 0.0, 0.0);
-    return VA_OK;
+    return resize_linear_launch(ctx, stream, "va_resize_linear_u8", in, in_pitch, in_fstride, out, out_pitch, out_fstride,
+                                w, h, dw, dh, channels, batch, sx, sy, 0, 0.0, 0.0);
 }
 
 // ---------------------------------------------------------------------------------

@@ -162,7 +162,7 @@ class ShardedSegmentChain(object):
     `run_device_range` strings them together.  They are separate methods so that a test can emulate R ranks
     on ONE GPU: pass1 for every rank, stack the partials in place of the all-gather, pass2 for every rank. """
 
-    PREBLUR = 2               # head batches blurred while the all-gather is in flight
+    PREBLUR = 1               # head batches blurred while the all-gather is in flight (one 128-frame blur outlasts the gather)
 
     def __init__(self, chain, group=None, tail=None, rank=None, world=None):
         self.chain = chain
