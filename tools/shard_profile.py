@@ -77,6 +77,11 @@ def main():
     report('  pre-blur of %d head batches' % len(head), msh)
     ms2, _ = timed(lambda: sh.pass2(batches, labels, counts, G, shard_counts, None, head))
     report('  pass 2 (carry fold + pipelined chain)', ms2)
+    blur0 = ch.blur_device(batches[0])
+    S2 = rt.empty_f32(H, W)
+    for rep in range(3):
+        msf, _ = timed(lambda: rt.ema_partial(blur0, S2, ch.alpha, True))
+    report('  (one va_ema_partial over %d frames, alone)' % B, msf)
     single = SegmentChain((W, H), batch=B)
 
     def plain():

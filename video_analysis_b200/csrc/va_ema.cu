@@ -241,12 +241,19 @@ ema_partial_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fs
         float s[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) s[k] = (accumulate && x + k < w) ? sp[k] : 0.0f;
-        for (int t = 0; t < batch; t++) {
-            unsigned v[1];
-            ema_load<4>(rp + (size_t)t * in_fstride, x, w, vec_in != 0, v);
+        // eight frames of loads in flight per thread (the recurrence itself is sequential in t)
+        for (int t0 = 0; t0 < batch; t0 += 8) {
+            unsigned v[8][1];
 #pragma unroll
-            for (int k = 0; k < 4; k++)
-                s[k] = __fadd_rn(__fmul_rn(a, s[k]), __fmul_rn(alpha, ema_byte_to_float(v[0], k)));
+            for (int u = 0; u < 8; u++)
+                if (t0 + u < batch) ema_load<4>(rp + (size_t)(t0 + u) * in_fstride, x, w, vec_in != 0, v[u]);
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                if (t0 + u >= batch) break;
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    s[k] = __fadd_rn(__fmul_rn(a, s[k]), __fmul_rn(alpha, ema_byte_to_float(v[u][0], k)));
+            }
         }
 #pragma unroll
         for (int k = 0; k < 4; k++)
