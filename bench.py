@@ -75,13 +75,42 @@ def pcie_roofline(h2d_bytes, d2h_bytes, fps_per_gpu, frames_per_step):
 # clocks: sample nvidia-smi during the timed region
 # ------------------------------------------------------------------------------------------
 class ClockSampler(object):
+    """ SM clock and throttle reasons while the timed region runs.  NVML is polled from a thread every millisecond (the
+    timed region of a 20-step run is 12 ms: `nvidia-smi -lms` would not deliver a single sample inside it); samples
+    are stamped, and the ones between `mark_begin` and `mark_end` are reported.  Falls back to `nvidia-smi -lms 20`
+    when NVML cannot be loaded. """
     Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.samples, self.t0, self.t1 = [], None, None
+        self._stop = False
+        self.nvml = None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber the devices: address the GPU by its PCI bus id
+            import torch
+            bus = torch.cuda.get_device_properties(self.index).pci_bus_id if hasattr(torch.cuda.get_device_properties(self.index), 'pci_bus_id') else None
+            handle = None
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if int(pynvml.nvmlDeviceGetPciInfo(h).bus) == int(bus):
+                        handle = h
+                        break
+            if handle is None:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.nvml, self.handle = pynvml, handle
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
                                           '--format=csv,noheader,nounits', '-lms', '20'],
@@ -91,11 +120,47 @@ class ClockSampler(object):
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        get_reasons = getattr(n, 'nvmlDeviceGetCurrentClocksEventReasons', None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop:
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                reasons = int(get_reasons(self.handle))
+                self.samples.append((time.perf_counter(), mhz, reasons))
+            except Exception:
+                pass
+            time.sleep(0.001)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(',')])
 
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
+
     def stop(self):
+        if self.nvml is not None:
+            time.sleep(0.01)
+            self._stop = True
+            self.thread.join(timeout=1)
+            inside = [s for s in self.samples if self.t0 is not None and self.t0 <= s[0] <= (self.t1 or s[0])]
+            where = 'inside the timed region'
+            if not inside and self.samples:                        # a region shorter than one poll: the samples around it
+                mid = 0.5 * ((self.t0 or 0) + (self.t1 or 0))
+                inside = sorted(self.samples, key=lambda s: abs(s[0] - mid))[:3]
+                where = 'nearest to the timed region'
+            n = self.nvml
+            bits = {'hw_slowdown': getattr(n, 'nvmlClocksEventReasonHwSlowdown', 0x8),
+                    'hw_thermal_slowdown': getattr(n, 'nvmlClocksEventReasonHwThermalSlowdown', 0x40),
+                    'sw_thermal_slowdown': getattr(n, 'nvmlClocksEventReasonSwThermalSlowdown', 0x20),
+                    'sw_power_cap': getattr(n, 'nvmlClocksEventReasonSwPowerCap', 0x4)}
+            reasons = [k for k, bit in bits.items() if any(s[2] & bit for s in inside)]
+            return {'sm_mhz': float(np.median([s[1] for s in inside])) if inside else None, 'sm_max_mhz': self.max_mhz,
+                    'reasons': reasons, 'samples': len(inside), 'source': 'NVML polled every ms, samples ' + where}
         if not self.proc:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         time.sleep(0.15)
@@ -109,7 +174,7 @@ class ClockSampler(object):
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith('active') for r in self.rows)]
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': reasons, 'samples': len(sm)}
+                'reasons': reasons, 'samples': len(sm), 'source': 'nvidia-smi -lms 20'}
 
 
 # ------------------------------------------------------------------------------------------
@@ -334,10 +399,14 @@ def gpu_arm(args):
     launches0 = rt.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if rank == 0:
+        sampler.mark_begin()
     ev0.record()
     run_steps(Wm, K)
     ev1.record()
     barrier()
+    if rank == 0:
+        sampler.mark_end()
     ms = ev0.elapsed_time(ev1)
     launches = rt.launches - launches0
     clocks = sampler.stop() if rank == 0 else None
