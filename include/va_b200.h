@@ -56,6 +56,10 @@ const char *va_status_string(int status);
 
 /* scratch is sized for frames up to max_w x max_h and batches up to max_batch */
 int va_create(va_ctx **out, int device, int max_w, int max_h, int max_batch);
+/* grows the capacity of a live ctx (never shrinks it) without invalidating the handle: the device is synchronised, the
+ * scratch reallocated.  Other users of the same ctx keep working; only a va_label_forest / va_label_write pair must
+ * not straddle the call. */
+int va_reserve(va_ctx *ctx, int max_w, int max_h, int max_batch);
 int va_destroy(va_ctx *ctx);
 const char *va_last_error(const va_ctx *ctx);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */

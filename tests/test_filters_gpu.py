@@ -715,3 +715,24 @@ def test_sparse_egress_gives_the_dense_label_images(frames, ref):
         c.reset()
         got, cnt = c.process(video)
         assert np.array_equal(got, want['labels']) and list(cnt) == list(want['counts'])
+
+
+def test_ctx_grows_under_a_live_chain(frames, ref):
+    """ the va_ctx of a GPU is shared by every chain of the process: a larger chain created while a smaller one is in
+    the middle of its video grows the capacity in place (va_reserve) and neither loses its state """
+    mods()
+    from video_analysis_b200.chain import SegmentChain
+    from video_analysis_b200.device import get_runtime
+    small = SegmentChain((320, 240), batch=8)
+    l1, c1 = small.process(frames[:16])
+    rt = get_runtime()
+    cap0 = rt._cap
+    big_frames = synth.make_frames(4, 0, 6, cap0[0] + 64, cap0[1] + 32, 3)
+    big = SegmentChain((cap0[0] + 64, cap0[1] + 32), batch=max(cap0[2], 8) + 3)         # grows every dimension of the ctx
+    assert rt._cap[0] > cap0[0] and rt._cap[1] > cap0[1] and rt._cap[2] > cap0[2]
+    lb, cb = big.process(big_frames)
+    want = ops.chain(big_frames)
+    assert np.array_equal(lb, want['labels']) and list(cb) == list(want['counts'])
+    l2, c2 = small.process(frames[16:])                                               # continues from its own background
+    assert np.array_equal(np.concatenate([l1, l2]), ref['labels'])
+    assert list(np.concatenate([c1, c2])) == list(ref['counts'])

@@ -53,6 +53,7 @@ SIGNATURES = {
     'va_status_string': (c_char_p, [c_int]),
     'va_create': (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int]),
     'va_destroy': (c_int, [c_void_p]),
+    'va_reserve': (c_int, [c_void_p, c_int, c_int, c_int]),
     'va_last_error': (c_char_p, [c_void_p]),
     'va_launch_count': (c_longlong, [c_void_p]),
     'va_luma_u8': (c_int, [c_void_p, c_void_p] + _IMG + _IMG + [c_int, c_int, c_int, c_int]),

@@ -60,6 +60,41 @@ extern "C" int va_create(va_ctx **out, int device, int max_w, int max_h, int max
     return VA_OK;
 }
 
+extern "C" int va_reserve(va_ctx *ctx, int max_w, int max_h, int max_batch) {
+    VA_CHECK_CTX(ctx);
+    VA_REQUIRE(ctx, max_w > 0 && max_h > 0 && max_batch > 0, "va_reserve: bad size");
+    const int w = max_w > ctx->max_w ? max_w : ctx->max_w, h = max_h > ctx->max_h ? max_h : ctx->max_h;
+    const int b = max_batch > ctx->max_batch ? max_batch : ctx->max_batch;
+    if (w == ctx->max_w && h == ctx->max_h && b == ctx->max_batch) return VA_OK;
+    size_t lab_pitch = 32;
+    while (lab_pitch < (size_t)w) lab_pitch <<= 1;
+    if (lab_pitch * (size_t)h >= ((size_t)1 << 31)) VA_FAIL(ctx, VA_ERR_CAPACITY, "va_reserve: %dx%d frames exceed the forest's index range", w, h);
+    VA_CUDA(ctx, cudaSetDevice(ctx->device));
+    VA_CUDA(ctx, cudaDeviceSynchronize());              // nothing in flight uses the old scratch any more
+    int32_t *parent = nullptr, *rowcnt = nullptr;
+    if (cudaMalloc((void **)&parent, lab_pitch * (size_t)h * (size_t)b * sizeof(int32_t)) != cudaSuccess ||
+        cudaMalloc((void **)&rowcnt, (size_t)2 * h * b * sizeof(int32_t)) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(parent);
+        VA_FAIL(ctx, VA_ERR_NOMEM, "va_reserve: cannot allocate the labelling scratch for %dx%dx%d", w, h, b);
+    }
+    cudaFree(ctx->lab_parent);
+    cudaFree(ctx->lab_rowcnt);
+    ctx->lab_parent = parent;
+    ctx->lab_rowcnt = rowcnt;
+    ctx->lab_pitch = lab_pitch;
+    // everything sized by the capacity and allocated on first use starts over
+    cudaFree(ctx->lab_parent1); ctx->lab_parent1 = nullptr;
+    cudaFree(ctx->lab_rowcnt1); ctx->lab_rowcnt1 = nullptr;
+    cudaFree(ctx->ch_mono); ctx->ch_mono = nullptr;
+    cudaFree(ctx->ch_blur); ctx->ch_blur = nullptr;
+    cudaFree(ctx->ch_mask); ctx->ch_mask = nullptr;
+    cudaFree(ctx->ch_morph); ctx->ch_morph = nullptr;
+    cudaFree(ctx->exp_rowoff); ctx->exp_rowoff = nullptr;
+    ctx->max_w = w; ctx->max_h = h; ctx->max_batch = b;
+    return VA_OK;
+}
+
 extern "C" int va_destroy(va_ctx *ctx) {
     if (!ctx) return VA_OK;
     cudaFree(ctx->lab_parent);

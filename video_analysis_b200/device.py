@@ -77,20 +77,23 @@ class DeviceRuntime(object):
 
     # ---- ctx management ------------------------------------------------------------------
     def ensure(self, w, h, n):
+        """ make sure the ctx can take frames of w x h in batches of n.  The ctx of a GPU is shared by every chain of the
+        process: growing it keeps the handle (va_reserve synchronises the device and reallocates the scratch), so other
+        users are not disturbed """
         cw, ch, cn = self._cap
         if w <= cw and h <= ch and n <= cn and self._h:
             return
         cap = (max(w, cw), max(h, ch), max(n, cn))
-        if self._h:
-            torch().cuda.synchronize(self.device)
-            self._retired_launches += self.lib.va_launch_count(self._h)
-            self.lib.va_destroy(self._h)
-            self._h = ctypes.c_void_p()
         with torch().cuda.device(self.device):
-            rc = self.lib.va_create(ctypes.byref(self._h), self.device.index, cap[0], cap[1], cap[2])
-        if rc != _lib.VA_OK:
-            self._cap = (0, 0, 0)
-            _lib.check(self.lib, None, rc)
+            if self._h:
+                rc = self.lib.va_reserve(self._h, cap[0], cap[1], cap[2])
+                if rc != _lib.VA_OK:
+                    _lib.check(self.lib, self._h, rc)
+            else:
+                rc = self.lib.va_create(ctypes.byref(self._h), self.device.index, cap[0], cap[1], cap[2])
+                if rc != _lib.VA_OK:
+                    self._cap = (0, 0, 0)
+                    _lib.check(self.lib, None, rc)
         self._cap = cap
 
     @property
