@@ -8,6 +8,23 @@
 #define ITERS 4096
 #define ILP 8
 
+// packed float32 pairs (sm_100: FADD2 / FFMA2)
+__device__ __forceinline__ void pk_add(float &x, float &y, float g, float h) {
+    unsigned long long a, b;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(a) : "f"(x), "f"(y));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(b) : "f"(g), "f"(h));
+    asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(b));
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(x), "=f"(y) : "l"(a));
+}
+__device__ __forceinline__ void pk_fma(float &x, float &y, float g, float h) {
+    unsigned long long a, b, c;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(a) : "f"(x), "f"(y));
+    asm("mov.b64 %0, {%1,%1};" : "=l"(b) : "f"(g));
+    asm("mov.b64 %0, {%1,%1};" : "=l"(c) : "f"(h));
+    asm("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a) : "l"(b), "l"(c));
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(x), "=f"(y) : "l"(a));
+}
+
 template <int OP>
 __global__ void __launch_bounds__(1024) k(unsigned *out, unsigned seed, long long *clk) {
     unsigned a[ILP], b = seed | 1u, c = seed * 3u + 7u;
@@ -39,6 +56,10 @@ __global__ void __launch_bounds__(1024) k(unsigned *out, unsigned seed, long lon
             if (OP == 16) a[i] = __popc(a[i]) + c;                             // POPC
             if (OP == 17) f[i] = (float)a[i];                                  // I2F
             if (OP == 18) { a[i] = __dp4a(a[i], b, c); a[(i + 1) % ILP] = a[(i + 1) % ILP] * b + c; }   // IDP + IMAD
+            if (OP == 19 && (i & 1) == 0) pk_add(f[i], f[i + 1], g, hh);                                 // FADD2
+            if (OP == 20 && (i & 1) == 0) pk_fma(f[i], f[i + 1], g, hh);                                 // FFMA2
+            if (OP == 21) { if ((i & 1) == 0) pk_add(f[i], f[i + 1], g, hh); a[i] = __funnelshift_r(a[i], b, c); }   // FADD2 per pair + SHF each
+            if (OP == 22) { f[i] = __fadd_rn(f[i], g); a[i] = __funnelshift_r(a[i], b, c); }             // FADD + SHF
         }
     }
     long long t1 = clock64();
@@ -92,6 +113,11 @@ int main() {
     run<11>("IDP.4A + LOP3", 2);
     run<12>("IMAD + FFMA", 2);
     run<18>("IDP.4A + IMAD", 2);
+    printf("packed float32 pairs: rates are PACKED instructions (2 lanes-worth each) per clock\n");
+    run<19>("FADD2 (per pair)", 1);      // ILP/2 packed instructions per ILP slots: printed rate is x2 the instruction rate
+    run<20>("FFMA2 (per pair)", 1);
+    run<22>("FADD + SHF", 2);
+    run<21>("FADD2/2 + SHF", 2);
     cudaError_t e = cudaGetLastError();
     printf("status %s\n", cudaGetErrorString(e));
     return e != cudaSuccess;

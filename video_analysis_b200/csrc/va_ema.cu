@@ -54,6 +54,89 @@ __device__ __forceinline__ unsigned ema_step(const unsigned (&v)[PX / 4], float 
     return m;
 }
 
+// The same step on packed float32 pairs (sm_100's FADD2 / FFMA2: one instruction, two IEEE-754 results, each rounded
+// exactly like its scalar counterpart): byte -> float, the difference and the state update of a pixel pair are one
+// instruction each, 5 instead of 7 issue slots per pixel.  ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2
+// (a single rounding -- not what NumPy does), so the product is written as fma(alpha, d, nz) with nz = -0.0f arriving as a
+// kernel argument: x + (-0) == x for every x including both zeros, and an FFMA2 followed by an FADD2 is left alone.
+typedef unsigned long long ema_f2;
+#ifdef VA_EMU
+// CPU emulation build: the same IEEE-754 operations, one lane at a time (compiled without -ffast-math / FMA contraction)
+__device__ __forceinline__ ema_f2 ema_pack(float a, float b) {
+    return (ema_f2)__float_as_uint(a) | ((ema_f2)__float_as_uint(b) << 32);
+}
+__device__ __forceinline__ void ema_unpack(ema_f2 v, float &a, float &b) {
+    a = __uint_as_float((unsigned)v);
+    b = __uint_as_float((unsigned)(v >> 32));
+}
+__device__ __forceinline__ ema_f2 ema_add2(ema_f2 a, ema_f2 b) {
+    float a0, a1, b0, b1;
+    ema_unpack(a, a0, a1);
+    ema_unpack(b, b0, b1);
+    return ema_pack(__fadd_rn(a0, b0), __fadd_rn(a1, b1));
+}
+__device__ __forceinline__ ema_f2 ema_sub2(ema_f2 a, ema_f2 b) {
+    float a0, a1, b0, b1;
+    ema_unpack(a, a0, a1);
+    ema_unpack(b, b0, b1);
+    return ema_pack(__fadd_rn(a0, -b0), __fadd_rn(a1, -b1));
+}
+__device__ __forceinline__ ema_f2 ema_fma2(ema_f2 a, ema_f2 b, ema_f2 c) {
+    float a0, a1, b0, b1, c0, c1;
+    ema_unpack(a, a0, a1);
+    ema_unpack(b, b0, b1);
+    ema_unpack(c, c0, c1);
+    return ema_pack(fmaf(a0, b0, c0), fmaf(a1, b1, c1));
+}
+#else
+__device__ __forceinline__ ema_f2 ema_pack(float a, float b) {
+    ema_f2 r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void ema_unpack(ema_f2 v, float &a, float &b) {
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ ema_f2 ema_add2(ema_f2 a, ema_f2 b) {
+    ema_f2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ ema_f2 ema_sub2(ema_f2 a, ema_f2 b) {
+    ema_f2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ ema_f2 ema_fma2(ema_f2 a, ema_f2 b, ema_f2 c) {
+    ema_f2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+#endif
+
+template <int PX>
+__device__ __forceinline__ unsigned ema_step_packed(const unsigned (&v)[PX / 4], float (&s)[PX], float alpha, float thr, float nz) {
+    unsigned m = 0;
+    const ema_f2 alpha2 = ema_pack(alpha, alpha), nz2 = ema_pack(nz, nz), two23 = ema_pack(8388608.0f, 8388608.0f);
+#pragma unroll
+    for (int i = PX / 2 - 1; i >= 0; i--) {
+        const unsigned word = v[i >> 1];
+        const int b = 2 * (i & 1);
+        // (2^23 + byte as float bits by PRMT on the alu pipe; the same by IDP.4A with a one-hot byte, i.e. on the
+        // fmaheavy pipe, for all or half of the pixels measured slower: 0.088 / 0.084 against 0.082 ms per 128 frames)
+        const ema_f2 big = ema_pack(__uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540u + b)),
+                                    __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540u + b + 1)));
+        const ema_f2 s2 = ema_pack(s[2 * i], s[2 * i + 1]);
+        const ema_f2 d2 = ema_sub2(ema_sub2(big, two23), s2);
+        float d0, d1;
+        ema_unpack(d2, d0, d1);
+        m = __funnelshift_l(__float_as_uint(__fadd_rn(thr, -fabsf(d1))), m, 1);
+        m = __funnelshift_l(__float_as_uint(__fadd_rn(thr, -fabsf(d0))), m, 1);
+        ema_unpack(ema_add2(s2, ema_fma2(alpha2, d2, nz2)), s[2 * i], s[2 * i + 1]);
+    }
+    return m;
+}
+
 // Frames are streamed through a per-thread ring in shared memory filled by cp.async: RING
 // frames of loads are in flight per thread at no register cost, and nobody waits on a block
 // barrier because a thread only ever reads the slots it filled itself.
@@ -77,12 +160,13 @@ __device__ __forceinline__ void ema_issue(unsigned *slot, const uint8_t *rp, int
 // batch) is long and indivisible, so the block scheduler has to be able to even the warps out over the SMs -- with
 // 8-warp blocks a 1080p launch (4050 warps, 27.4 per SM) left some SMs with 32 warps and others with 24 and ran
 // as long as the fullest one.
-template <int PX, int NT>
+template <int PX, int NT, int MODE>
 __global__ void __launch_bounds__(NT, NT == 32 ? 32 : PX == 16 ? 4 : 5)
 ema_diff_thresh_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstride,
                        float *__restrict__ bg, size_t bg_pitch_e,
                        uint32_t *__restrict__ mask, size_t mask_pitch_w, size_t mask_fstride_w,
-                       int w, int h, int batch, float alpha, float thr, int first_init, int vec_in, int vec_bg, int flat) {
+                       int w, int h, int batch, float alpha, float thr, int first_init, int vec_in, int vec_bg, int flat,
+                       float nz) {
     constexpr int NW = PX / 4;
     constexpr int RING = PX == 16 ? 8 : 16;                            // frames in flight per thread
     __shared__ uint4 ring_raw[RING * NT * NW / 4];                     // uint4: 16-byte aligned slots
@@ -157,7 +241,7 @@ ema_diff_thresh_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t i
                 for (int i = 0; i < PX; i++) s[i] = ema_byte_to_float(v[i >> 2], i & 3);
                 m = 0;
             } else {
-                m = ema_step<PX>(v, s, alpha, thr) & valid;
+                m = (MODE ? ema_step_packed<PX>(v, s, alpha, thr, nz) : ema_step<PX>(v, s, alpha, thr)) & valid;
             }
 #pragma unroll
             for (int sh = PX, d = 1; sh < 32; sh <<= 1, d <<= 1) m |= __shfl_down_sync(0xffffffffu, m, d) << sh;
@@ -194,6 +278,7 @@ extern "C" int va_ema_diff_thresh(va_ctx *ctx, va_stream stream,
     const long long threads16 = (long long)((w + 511) / 512) * 32 * h;
     bool use16 = threads16 >= (long long)ctx->sm_count * 128;
     if (getenv("VA_EMA_PX")) use16 = atoi(getenv("VA_EMA_PX")) == 16;     // tuning only
+    const int packed = getenv("VA_EMA_PACKED") ? atoi(getenv("VA_EMA_PACKED")) : 1;      // 0: the scalar arithmetic of round 1
     if (use16) {
         const int vec_in = va_aligned(in, 16) && in_pitch % 16 == 0 && in_fstride % 16 == 0;
         const int flat = w % 32 == 0 && w % 512 != 0 && !getenv("VA_EMA_NOFLAT");
@@ -202,23 +287,23 @@ extern "C" int va_ema_diff_thresh(va_ctx *ctx, va_stream stream,
         const int nt = getenv("VA_EMA_NT") ? atoi(getenv("VA_EMA_NT")) : 32;                // tuning only
         if (nt == 256) {
             const int grid = va_grid(ctx, (warps + 7) / 8, 8);
-            auto kfn = ema_diff_thresh_kernel<16, 256>;
+            auto kfn = ema_diff_thresh_kernel<16, 256, 0>;
             VA_LAUNCH(ctx, kfn, grid, 256, 0, stream, in, in_pitch, in_fstride, bg, bg_pitch_e, mask, mask_pitch_w,
-                      mask_fstride_w, w, h, batch, alpha, thr, first_frame_inits, vec_in, vec_bg, flat);
+                      mask_fstride_w, w, h, batch, alpha, thr, first_frame_inits, vec_in, vec_bg, flat, -0.0f);
             return VA_OK;
         }
         const int grid = (int)warps;                      // one warp per block, no grid-stride rounds
-        auto kfn = ema_diff_thresh_kernel<16, 32>;
+        auto kfn = packed ? ema_diff_thresh_kernel<16, 32, 1> : ema_diff_thresh_kernel<16, 32, 0>;
         VA_LAUNCH(ctx, kfn, grid, 32, 0, stream, in, in_pitch, in_fstride, bg, bg_pitch_e, mask, mask_pitch_w,
-                  mask_fstride_w, w, h, batch, alpha, thr, first_frame_inits, vec_in, vec_bg, flat);
+                  mask_fstride_w, w, h, batch, alpha, thr, first_frame_inits, vec_in, vec_bg, flat, -0.0f);
     } else {
         const int vec_in = va_aligned(in, 4) && in_pitch % 4 == 0 && in_fstride % 4 == 0;
         const int flat = w % 32 == 0 && w % 128 != 0 && !getenv("VA_EMA_NOFLAT");
         const long long warps = flat ? ((long long)(w / 4) * h + 31) / 32 : (long long)((w + 127) / 128) * h;
         const int grid = va_grid(ctx, (warps + 7) / 8, 8);
-        auto kfn = ema_diff_thresh_kernel<4, EMA_THREADS>;
+        auto kfn = packed ? ema_diff_thresh_kernel<4, EMA_THREADS, 1> : ema_diff_thresh_kernel<4, EMA_THREADS, 0>;
         VA_LAUNCH(ctx, kfn, grid, EMA_THREADS, 0, stream, in, in_pitch, in_fstride, bg, bg_pitch_e, mask, mask_pitch_w,
-                  mask_fstride_w, w, h, batch, alpha, thr, first_frame_inits, vec_in, vec_bg, flat);
+                  mask_fstride_w, w, h, batch, alpha, thr, first_frame_inits, vec_in, vec_bg, flat, -0.0f);
     }
     return VA_OK;
 }

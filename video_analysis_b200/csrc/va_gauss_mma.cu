@@ -81,27 +81,32 @@ __device__ __forceinline__ unsigned gm_tap(const GaussMma &g, int idx) {
 }
 
 // bytes of the shared memory one warp needs
-__host__ __device__ inline int gm_hl(int G) { const int KS = (G + 1) / 2; return KS == 1 ? 16 : KS <= 3 ? 48 : 80; }
+// staged halo per side: a multiple of 16 pixels, so that the box of the fused variant (3 bytes per pixel) starts on a 16-byte
+// boundary of the row -- a box starting 24 bytes before the strip (halo 8) faults with "illegal instruction" on the B200
+__host__ __device__ inline int gm_hl(int G, bool fuse) { (void)fuse; const int KS = (G + 1) / 2; return KS == 1 ? 16 : KS <= 3 ? 48 : 80; }
+// pitch of the luma rows the fused variant writes: >= LW and 32 (mod 64), which keeps the LDS.64 of the B fragments conflict-free
+__host__ __device__ inline int gm_lp(int LW) { return ((LW - 32 + 63) / 64) * 64 + 32; }
 __host__ __device__ inline size_t gm_warp_smem(bool fuse, int G, int tiles, int stages) {
-    const size_t LW = (size_t)(16 * tiles + 2 * gm_hl(G));
+    const size_t LW = (size_t)(16 * tiles + 2 * gm_hl(G, fuse));
     const size_t SP = ((fuse ? 3 * LW : LW) + 127) & ~(size_t)127;   // stage row pitch of a half-step fetched row by row
     size_t b = 0;
     b += (size_t)stages * 8 * SP;                   // TMA stages
     size_t ot = 16 * (size_t)GM_OUT_PITCH(tiles);   // output tile; the fused variant keeps its 8 luma rows in the same place
-    if (fuse && 8 * LW > ot) ot = 8 * LW;
+    if (fuse && 8 * (size_t)gm_lp((int)LW) > ot) ot = 8 * (size_t)gm_lp((int)LW);
     b += (ot + 15) & ~(size_t)15;
     if (G > 2) b += (size_t)G * tiles * 32 * 16;    // ring of row-pass results (16 rows x strip x 16 bit per group)
     return (b + 127) & ~(size_t)127;
 }
 
 // geometry that follows from the number of 16-row groups G of a column-pass block (16 + 2r <= 16 G)
-template <int G, int TILES> struct GmGeom {
+template <bool FUSE, int G, int TILES> struct GmGeom {
     static constexpr int KS = (G + 1) / 2;                        // row pass: 16 + 2r <= 32 KS
     static constexpr int OFF = 16 * KS - 8;                       // row pass: output x = window start + OFF (>= r, multiple of 8)
-    static constexpr int HL = KS == 1 ? 16 : KS <= 3 ? 48 : 80;   // staged halo: >= OFF, and 128 + 2 HL = 32 (mod 64) so that the
-                                                                  // LDS.64 of the B fragments are bank-conflict free
+    static constexpr int HL = KS == 1 ? 16 : KS <= 3 ? 48 : 80;   // staged halo (gm_hl): >= OFF, and 128 + 2 HL = 32 (mod 64) so that
+                                                                  // the LDS.64 of the B fragments are bank-conflict free
     static constexpr int STRIP = 16 * TILES;                      // columns a warp owns
-    static constexpr int LW = STRIP + 2 * HL;                     // staged luma bytes per row
+    static constexpr int LW = STRIP + 2 * HL;                     // staged pixels per row
+    static constexpr int LP = ((LW - 32 + 63) / 64) * 64 + 32;    // fused: pitch of the converted luma rows (gm_lp)
 };
 
 // fetch 8 rows row by row at their BORDER_REFLECT_101 position (top / bottom of the image only; kept out of line)
@@ -116,7 +121,9 @@ __global__ void __launch_bounds__(128, MINB)
 gauss_mma_kernel(const __grid_constant__ va_tmap map8, const __grid_constant__ va_tmap map1,
                  uint8_t *__restrict__ out, size_t out_pitch, size_t out_fstride,
                  int w, int h, int batch, const __grid_constant__ GaussMma gp) {
-    constexpr int KS = GmGeom<G, TILES>::KS, HL = GmGeom<G, TILES>::HL, off = GmGeom<G, TILES>::OFF, LW = GmGeom<G, TILES>::LW;
+    typedef GmGeom<FUSE, G, TILES> Geo;
+    constexpr int KS = Geo::KS, HL = Geo::HL, off = Geo::OFF, LW = Geo::LW, LP = Geo::LP;
+    static_assert(!FUSE || (G == 2 && TILES == 8), "the fused conversion is laid out for 128-column strips, halo 16, window offset 8");
     constexpr int GM_STRIP = 16 * TILES, GM_TILES = TILES, OPITCH = GM_OUT_PITCH(TILES);
     constexpr int KF = G / 2;                       // column pass: full k32 steps (two groups each), then one k16 step if G is odd
     constexpr int C = FUSE ? 3 : 1;
@@ -152,7 +159,7 @@ gauss_mma_kernel(const __grid_constant__ va_tmap map8, const __grid_constant__ v
     unsigned char *stage0 = wsm;
     unsigned char *lbuf = wsm + NS * 8 * SP;                                         // FUSE: luma rows; shares its place with the output tile
     unsigned char *otile = lbuf;
-    uint4 *ring = reinterpret_cast<uint4 *>(lbuf + (((FUSE && 8 * LW > 16 * OPITCH) ? 8 * LW : 16 * OPITCH) + 15 & ~15));   // G > 2 only
+    uint4 *ring = reinterpret_cast<uint4 *>(lbuf + (((FUSE && 8 * LP > 16 * OPITCH) ? 8 * LP : 16 * OPITCH) + 15 & ~15));   // G > 2 only
 
     // ---- constant Toeplitz fragments ------------------------------------------------------------------
     // row pass: fragment row m is output column pi(m) of the tile, pi(2u) = 4u, pi(2u+1) = 4u+1, pi(8+2u) = 4u+2, pi(9+2u) = 4u+3,
@@ -229,22 +236,27 @@ gauss_mma_kernel(const __grid_constant__ va_tmap map8, const __grid_constant__ v
             const int ya = y0 - r + 8 * hs;
             const int sp = (ya >= 0 && ya + 7 < h) ? BOXB : SP;      // row pitch of this stage (see issue())
             unsigned char *lrow = FUSE ? lbuf : stg;                // 8 rows of luma
-            const int lp = FUSE ? LW : sp;
+            const int lp = FUSE ? LP : sp;
             if (FUSE) {
-                // RGB -> luma, items of 16 pixels (three 16-byte loads, one 16-byte store)
-                constexpr int ipr = LW >> 4;
-                for (int it = lane; it < 8 * ipr; it += 32) {
-                    const int row = it / ipr, ci = it - row * ipr;
-                    const uint4 *q = reinterpret_cast<const uint4 *>(stg + (size_t)row * sp + 48 * ci);
+                // RGB -> luma of the 8 x 144 pixels the row pass reads (staged pixels 8 .. 151 of 160).  Two rounds of 16-pixel
+                // items (three 16-byte loads, one 16-byte store; lane -> row lane / 8 (+ 4), item 1 + lane % 8: every address
+                // static, conflict-free), then the two half items at the ends of the 8 rows as 32 pieces of 4 pixels: no lane
+                // idles in any round (the loop over all 80 items of the stage ran 3 rounds of 32 lanes for 2.5 rounds of work)
+                auto conv4 = [&](unsigned w0, unsigned w1, unsigned w2) {
+                    return mean ? va_mean3_x4(w0, w1, w2) : __byte_perm(__byte_perm(w0, w1, sel_a), w2, sel_b);
+                };
+#pragma unroll
+                for (int rd = 0; rd < 2; rd++) {
+                    const int row = (lane >> 3) + 4 * rd, ci = 1 + (lane & 7);
+                    const uint4 *q = reinterpret_cast<const uint4 *>(stg + row * sp + 48 * ci);
                     const uint4 a = q[0], b = q[1], c = q[2];
-                    uint4 v;
-                    if (mean) {
-                        v = make_uint4(va_mean3_x4(a.x, a.y, a.z), va_mean3_x4(a.w, b.x, b.y), va_mean3_x4(b.z, b.w, c.x), va_mean3_x4(c.y, c.z, c.w));
-                    } else {
-                        v = make_uint4(__byte_perm(__byte_perm(a.x, a.y, sel_a), a.z, sel_b), __byte_perm(__byte_perm(a.w, b.x, sel_a), b.y, sel_b),
-                                       __byte_perm(__byte_perm(b.z, b.w, sel_a), c.x, sel_b), __byte_perm(__byte_perm(c.y, c.z, sel_a), c.w, sel_b));
-                    }
-                    *reinterpret_cast<uint4 *>(lbuf + (size_t)row * LW + 16 * ci) = v;
+                    *reinterpret_cast<uint4 *>(lbuf + row * LP + 16 * ci) =
+                        make_uint4(conv4(a.x, a.y, a.z), conv4(a.w, b.x, b.y), conv4(b.z, b.w, c.x), conv4(c.y, c.z, c.w));
+                }
+                {
+                    const int row = lane >> 2, px = ((lane & 2) ? 136 : 8) + 4 * (lane & 3);     // 8, 12, 144, 148
+                    const unsigned *q = reinterpret_cast<const unsigned *>(stg + row * sp + 3 * px);
+                    *reinterpret_cast<unsigned *>(lbuf + row * LP + px) = conv4(q[0], q[1], q[2]);
                 }
                 __syncwarp();
                 issue(hs + NS, st);                                 // the raw stage is free again
@@ -385,7 +397,7 @@ int va_gauss_mma_launch(va_ctx *ctx, va_stream stream, const char *name, bool fu
     if (gp.stages < 2) gp.stages = 2;
     if (gp.stages > GM_MAX_STAGES) gp.stages = GM_MAX_STAGES;
     for (int i = 0; i < ksize; i++) gp.taps[i] = (unsigned char)taps[i];
-    const int LW = 16 * tiles + 2 * gm_hl(G);
+    const int LW = 16 * tiles + 2 * gm_hl(G, fuse);
     if ((unsigned)(C * LW / 4) > 256u) return VA_ERR_UNSUPPORTED;
     gp.strips = va_div_up(w, 16 * tiles);
     // segments: enough warp tasks to fill the machine a few times over, but every segment re-stages 16 (G - 1) rows
