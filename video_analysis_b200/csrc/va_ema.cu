@@ -160,7 +160,11 @@ __device__ __forceinline__ void ema_issue(unsigned *slot, const uint8_t *rp, int
 // batch) is long and indivisible, so the block scheduler has to be able to even the warps out over the SMs -- with
 // 8-warp blocks a 1080p launch (4050 warps, 27.4 per SM) left some SMs with 32 warps and others with 24 and ran
 // as long as the fullest one.
-template <int PX, int NT, int MODE>
+// ALLFAST: every lane of every warp owns PX pixels inside the image, reads them with one aligned cp.async and holds its
+// state in aligned float4s -- the common case (any width that is a multiple of 2 PX with aligned buffers).  The frame loop
+// is then unrolled over one turn of the ring: slot addresses are immediates, the next load is a predicated LDGSTS and
+// the bytewise path does not exist (122 -> 104 instructions per thread and frame).
+template <int PX, int NT, int MODE, bool ALLFAST>
 __global__ void __launch_bounds__(NT, NT == 32 ? 32 : PX == 16 ? 4 : 5)
 ema_diff_thresh_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstride,
                        float *__restrict__ bg, size_t bg_pitch_e,
@@ -195,8 +199,9 @@ ema_diff_thresh_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t i
         }
         const uint8_t *rp = in + (size_t)y * in_pitch;
         float *bgp = bg + (size_t)y * bg_pitch_e + x;
-        const unsigned valid = x >= w ? 0u : (x + PX <= w ? ((1u << PX) - 1u) : ((1u << (w - x)) - 1u));
-        const bool fast = vec_in && x + PX <= w;
+        const unsigned valid = (ALLFAST || x + PX <= w) ? ((1u << PX) - 1u) : x >= w ? 0u : ((1u << (w - x)) - 1u);
+        const bool fast = ALLFAST || (vec_in && x + PX <= w);
+        const bool fast_bg = ALLFAST || (vec_bg && x + PX <= w);
 
         // prologue: RING - 1 frames in flight
         const uint8_t *rnext = rp;                     // row y of the next frame to put in flight
@@ -208,7 +213,7 @@ ema_diff_thresh_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t i
         }
 
         float s[PX];
-        if (vec_bg && x + PX <= w) {
+        if (fast_bg) {
 #pragma unroll
             for (int k = 0; k < NW; k++) {
                 const float4 q = *reinterpret_cast<const float4 *>(bgp + 4 * k);
@@ -221,6 +226,46 @@ ema_diff_thresh_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t i
 
         uint32_t *mrow = mask + (size_t)y * mask_pitch_w + (x >> 5);
         const bool writer = (lane & (32 / PX - 1)) == 0 && x < w;
+        if constexpr (ALLFAST) {
+            // one frame: `uslot` = ring slot of frame t (static), frame t + RING - 1 goes into the slot before it
+            auto frame = [&](int t, int uslot, bool may_init) {
+                if (t + RING - 1 < batch) {
+                    if (PX == 16) va_cp_async16(myslot + ((uslot + RING - 1) % RING) * SLOT_STRIDE, rnext + x);
+                    else va_cp_async4(myslot + ((uslot + RING - 1) % RING) * SLOT_STRIDE, rnext + x);
+                }
+                va_cp_async_commit();
+                rnext += in_fstride;
+                va_cp_async_wait_group<RING - 1>();          // frame t has landed
+                unsigned v[NW];
+                const unsigned *slot = myslot + uslot * SLOT_STRIDE;
+                if (PX == 16) {
+                    const uint4 q = *reinterpret_cast<const uint4 *>(slot);
+                    v[0] = q.x; v[NW > 1 ? 1 : 0] = q.y; v[NW > 2 ? 2 : 0] = q.z; v[NW > 3 ? 3 : 0] = q.w;
+                } else {
+                    v[0] = slot[0];
+                }
+                unsigned m;
+                if (may_init && t == 0 && first_init) {
+#pragma unroll
+                    for (int i = 0; i < PX; i++) s[i] = ema_byte_to_float(v[i >> 2], i & 3);
+                    m = 0;
+                } else {
+                    m = MODE ? ema_step_packed<PX>(v, s, alpha, thr, nz) : ema_step<PX>(v, s, alpha, thr);
+                }
+#pragma unroll
+                for (int sh = PX, d = 1; sh < 32; sh <<= 1, d <<= 1) m |= __shfl_down_sync(0xffffffffu, m, d) << sh;
+                if (writer) *mrow = m;
+                mrow += mask_fstride_w;
+            };
+            int t0 = 0;
+            for (; t0 + RING <= batch; t0 += RING) {
+#pragma unroll
+                for (int u = 0; u < RING; u++) frame(t0 + u, u, u == 0);
+            }
+#pragma unroll
+            for (int u = 0; u < RING - 1; u++)
+                if (t0 + u < batch) frame(t0 + u, u, u == 0);
+        } else
         for (int t = 0; t < batch; t++) {
             const int tn = t + RING - 1;                 // frame to put in flight now
             if (tn < batch) ema_issue<PX>(myslot + (tn % RING) * SLOT_STRIDE, rnext, x, w, fast);
@@ -250,7 +295,7 @@ ema_diff_thresh_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t i
         }
         va_cp_async_wait_group<0>();
 
-        if (vec_bg && x + PX <= w) {
+        if (fast_bg) {
 #pragma unroll
             for (int k = 0; k < NW; k++)
                 *reinterpret_cast<float4 *>(bgp + 4 * k) = make_float4(s[4 * k], s[4 * k + 1], s[4 * k + 2], s[4 * k + 3]);
@@ -287,13 +332,15 @@ extern "C" int va_ema_diff_thresh(va_ctx *ctx, va_stream stream,
         const int nt = getenv("VA_EMA_NT") ? atoi(getenv("VA_EMA_NT")) : 32;                // tuning only
         if (nt == 256) {
             const int grid = va_grid(ctx, (warps + 7) / 8, 8);
-            auto kfn = ema_diff_thresh_kernel<16, 256, 0>;
+            auto kfn = ema_diff_thresh_kernel<16, 256, 0, false>;
             VA_LAUNCH(ctx, kfn, grid, 256, 0, stream, in, in_pitch, in_fstride, bg, bg_pitch_e, mask, mask_pitch_w,
                       mask_fstride_w, w, h, batch, alpha, thr, first_frame_inits, vec_in, vec_bg, flat, -0.0f);
             return VA_OK;
         }
         const int grid = (int)warps;                      // one warp per block, no grid-stride rounds
-        auto kfn = packed ? ema_diff_thresh_kernel<16, 32, 1> : ema_diff_thresh_kernel<16, 32, 0>;
+        const bool allfast = vec_in && vec_bg && (flat ? ((long long)(w / 16) * h) % 32 == 0 : w % 512 == 0) && !getenv("VA_EMA_GENERAL");
+        auto kfn = !packed ? ema_diff_thresh_kernel<16, 32, 0, false>
+                 : allfast ? ema_diff_thresh_kernel<16, 32, 1, true> : ema_diff_thresh_kernel<16, 32, 1, false>;
         VA_LAUNCH(ctx, kfn, grid, 32, 0, stream, in, in_pitch, in_fstride, bg, bg_pitch_e, mask, mask_pitch_w,
                   mask_fstride_w, w, h, batch, alpha, thr, first_frame_inits, vec_in, vec_bg, flat, -0.0f);
     } else {
@@ -301,7 +348,9 @@ extern "C" int va_ema_diff_thresh(va_ctx *ctx, va_stream stream,
         const int flat = w % 32 == 0 && w % 128 != 0 && !getenv("VA_EMA_NOFLAT");
         const long long warps = flat ? ((long long)(w / 4) * h + 31) / 32 : (long long)((w + 127) / 128) * h;
         const int grid = va_grid(ctx, (warps + 7) / 8, 8);
-        auto kfn = packed ? ema_diff_thresh_kernel<4, EMA_THREADS, 1> : ema_diff_thresh_kernel<4, EMA_THREADS, 0>;
+        const bool allfast = vec_in && vec_bg && (flat ? ((long long)(w / 4) * h) % 32 == 0 : w % 128 == 0) && !getenv("VA_EMA_GENERAL");
+        auto kfn = !packed ? ema_diff_thresh_kernel<4, EMA_THREADS, 0, false>
+                 : allfast ? ema_diff_thresh_kernel<4, EMA_THREADS, 1, true> : ema_diff_thresh_kernel<4, EMA_THREADS, 1, false>;
         VA_LAUNCH(ctx, kfn, grid, EMA_THREADS, 0, stream, in, in_pitch, in_fstride, bg, bg_pitch_e, mask, mask_pitch_w,
                   mask_fstride_w, w, h, batch, alpha, thr, first_frame_inits, vec_in, vec_bg, flat, -0.0f);
     }
