@@ -200,17 +200,22 @@ __device__ __forceinline__ void lab_merge_probe(int *pr, unsigned cur, int cur_s
 __global__ void __launch_bounds__(LAB_THREADS, 8)
 label_merge_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
                    int *__restrict__ parent, int LOG, size_t pf, const int *__restrict__ rowflag,
-                   int w, int h, int batch, int conn8) {
-    // grid = (groups of 8 rows, frames): one row per warp
+                   int w, int h, int batch, int conn8, int R) {
+    // grid = (groups of 8 R rows, frames): R consecutive rows per warp (R > 1 for narrow frames, where a row is too
+    // little work for a warp's start-up; see lab_rows_per_warp)
     const int lane = threadIdx.x & 31;
     const int wpw = (w + 31) >> 5;
     const unsigned lastmask = (w & 31) ? ((1u << (w & 31)) - 1u) : FULL;
-    {
-        const int b = blockIdx.y, y = blockIdx.x * LAB_WARPS + (threadIdx.x >> 5);
-        if (y == 0 || y >= h) return;
-        // a row can only be merged with the one above if both have foreground at all (flags of kernel A)
-        const int f = rowflag[(size_t)b * h + y - (lane & 1)];
-        if (!__all_sync(FULL, f != 0)) return;
+    const int yw = (blockIdx.x * LAB_WARPS + (threadIdx.x >> 5)) * R;
+    // flags of rows yw - 1 .. yw + R - 1 (kernel A): lane i holds the flag of row yw - 1 + i
+    const int yf = yw - 1 + lane;
+    const int myflag = (lane <= R && yf >= 0 && yf < h) ? rowflag[(size_t)blockIdx.y * h + yf] : 0;
+    const unsigned flags = __ballot_sync(FULL, myflag != 0);
+    for (int rr = 0; rr < R; rr++) {
+        const int b = blockIdx.y, y = yw + rr;
+        if (y >= h) break;
+        // a row can only be merged with the one above if both have foreground at all
+        if (y == 0 || ((flags >> rr) & 3u) != 3u) continue;
         const uint32_t *mc = mask + (size_t)b * mfw + (size_t)y * mpw;
         const uint32_t *mu = mc - mpw;
         int *pr = parent + (size_t)b * pf;
@@ -422,22 +427,25 @@ __global__ void __launch_bounds__(LAB_THREADS)
 label_write_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
                    const int *__restrict__ parent, int LOG, size_t pf, const int *__restrict__ rowoff,
                    const int *__restrict__ rowflag,
-                   T *__restrict__ labels, size_t lpe, size_t lfe, int w, int h, int batch, int vec_out) {
-    // grid = (groups of 8 rows, frames): one row per warp
+                   T *__restrict__ labels, size_t lpe, size_t lfe, int w, int h, int batch, int vec_out, int R) {
+    // grid = (groups of 8 R rows, frames): R consecutive rows per warp (R > 1 for narrow frames)
     __shared__ int slab_all[LAB_WARPS][1024 + 32];
     const int lane = threadIdx.x & 31;
     int *slab = slab_all[threadIdx.x >> 5];
     const int wpw = (w + 31) >> 5;
     const unsigned lastmask = (w & 31) ? ((1u << (w & 31)) - 1u) : FULL;
-    {
-        const int b = blockIdx.y, y = blockIdx.x * LAB_WARPS + (threadIdx.x >> 5);
-        if (y >= h) return;
+    const int yw = (blockIdx.x * LAB_WARPS + (threadIdx.x >> 5)) * R;
+    const int myflag = (lane < R && yw + lane < h) ? rowflag[(size_t)blockIdx.y * h + yw + lane] : 0;
+    const unsigned flags = __ballot_sync(FULL, myflag != 0);      // bit i: row yw + i has foreground (flag of kernel A)
+    for (int rr = 0; rr < R; rr++) {
+        const int b = blockIdx.y, y = yw + rr;
+        if (y >= h) break;
         T *lr = labels + (size_t)b * lfe + (size_t)y * lpe;
-        if (rowflag[(size_t)b * h + y] == 0) {
-            // background row (flag of kernel A): zeros straight to memory, the mask is not even read
+        if (!((flags >> rr) & 1u)) {
+            // background row: zeros straight to memory, the mask is not even read
             const int4 z = make_int4(0, 0, 0, 0);
             for (int x = 4 * lane; x < w; x += 128) lab_store4(lr, x, w, z, vec_out != 0);
-            return;
+            continue;
         }
         const uint32_t *mr = mask + (size_t)b * mfw + (size_t)y * mpw;
         const int *pf_ = parent + (size_t)b * pf;
@@ -496,6 +504,17 @@ label_write_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
     }
 }
 
+// rows a warp of the row-per-warp kernels takes one after the other.  Measured (blob masks): the merge gains from 2 rows
+// at 1080p (forest 0.110 -> 0.101 ms per 128 frames) and 3 at VGA (0.085 -> 0.077 per 256 frames: a 640-pixel row is 20
+// mask words -- too little per warp start-up); the write gains only on narrow frames (VGA 0.103 -> 0.094) and loses on
+// wide ones (1080p 0.194 -> 0.203 with 2 rows)
+static int lab_rows_per_warp(int w, bool merge) {
+    if (getenv("VA_LABEL_ROWS")) { const int r = atoi(getenv("VA_LABEL_ROWS")); return r < 1 ? 1 : r > 8 ? 8 : r; }   // tuning only
+    if (!merge) return w <= 1024 ? 2 : 1;
+    const int r = 2048 / (w > 0 ? w : 1);
+    return r < 2 ? 2 : r > 8 ? 8 : r;
+}
+
 // phases A-D: afterwards every root holds -(rank in its row), rowcnt holds the exclusive prefix of
 // the per-row root counts and counts[b] the number of components
 // scratch set `slot` (0: allocated by va_create, 1: on first use) -- two sets let the label write of one batch
@@ -540,9 +559,10 @@ static int label_forest(va_ctx *ctx, va_stream stream, const char *name,
       VA_LAUNCH(ctx, k, grid_a, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, parent, LOG, pf, rowflag, w, h, batch, vec); }
     { auto k = label_merge_kernel;
       VA_REQUIRE(ctx, batch <= 65535, "%s: more than 65535 frames in one call", name);
-      const dim3 grid_b(va_div_up(h, LAB_WARPS), batch);
+      const int R = lab_rows_per_warp(w, true);
+      const dim3 grid_b(va_div_up(h, LAB_WARPS * R), batch);
       VA_LAUNCH(ctx, k, grid_b, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, parent, LOG, pf, (const int *)rowflag,
-                w, h, batch, connectivity == 8 ? 1 : 0); }
+                w, h, batch, connectivity == 8 ? 1 : 0, R); }
     { auto k = label_flatten_kernel;
       VA_LAUNCH(ctx, k, grid_a, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, parent, LOG, pf, rowcnt, w, h, batch, vec); }
     { auto k = label_scan_kernel;
@@ -563,10 +583,11 @@ static int label_write(va_ctx *ctx, va_stream stream, const char *name,
     VA_REQUIRE(ctx, va_scratch_acquire(ctx, stream, slot) == 0, "%s: cannot order the scratch set", name);
     auto k = label_write_kernel<T>;
     const int vec_out = va_aligned(labels, 4 * sizeof(T)) && labels_pitch_e % 4 == 0 && labels_fstride_e % 4 == 0;
-    const dim3 grid(va_div_up(h, LAB_WARPS), batch);
+    const int R = lab_rows_per_warp(w, false);
+    const dim3 grid(va_div_up(h, LAB_WARPS * R), batch);
     VA_LAUNCH(ctx, k, grid, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, (const int *)parent, LOG, pf,
               (const int *)rowcnt, (const int *)(rowcnt + (size_t)ctx->max_h * ctx->max_batch),
-              labels, labels_pitch_e, labels_fstride_e, w, h, batch, vec_out);
+              labels, labels_pitch_e, labels_fstride_e, w, h, batch, vec_out, R);
     VA_REQUIRE(ctx, va_scratch_release(ctx, stream, slot) == 0, "%s: cannot order the scratch set", name);
     return VA_OK;
 }
