@@ -20,6 +20,14 @@ __device__ __forceinline__ void va_cp_async4(void *smem_dst, const void *gmem_sr
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem_src) : "memory");
 #endif
 }
+__device__ __forceinline__ void va_cp_async8(void *smem_dst, const void *gmem_src) {
+#ifdef VA_EMU
+    std::memcpy(smem_dst, gmem_src, 8);
+#else
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem_src) : "memory");
+#endif
+}
 __device__ __forceinline__ void va_cp_async_commit() {
 #ifndef VA_EMU
     asm volatile("cp.async.commit_group;\n" ::: "memory");

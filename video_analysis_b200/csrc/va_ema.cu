@@ -21,6 +21,9 @@ __device__ __forceinline__ void ema_load(const uint8_t *rp, int x, int w, bool v
         if (PX == 16) {
             const uint4 q = va_ld_stream16(rp + x);
             v[0] = q.x; v[PX / 4 > 1 ? 1 : 0] = q.y; v[PX / 4 > 2 ? 2 : 0] = q.z; v[PX / 4 > 3 ? 3 : 0] = q.w;
+        } else if (PX == 8) {
+            const uint2 q = __ldg(reinterpret_cast<const uint2 *>(rp + x));
+            v[0] = q.x; v[PX / 4 > 1 ? 1 : 0] = q.y;
         } else {
             v[0] = __ldg(reinterpret_cast<const unsigned *>(rp + x));
         }
@@ -146,6 +149,7 @@ template <int PX>
 __device__ __forceinline__ void ema_issue(unsigned *slot, const uint8_t *rp, int x, int w, bool fast) {
     if (fast) {
         if (PX == 16) va_cp_async16(slot, rp + x);
+        else if (PX == 8) va_cp_async8(slot, rp + x);
         else va_cp_async4(slot, rp + x);
     } else if (x < w) {          // ragged row end / unaligned input: bytewise (lanes beyond the row do nothing)
         unsigned v[PX / 4];
@@ -172,7 +176,7 @@ ema_diff_thresh_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t i
                        int w, int h, int batch, float alpha, float thr, int first_init, int vec_in, int vec_bg, int flat,
                        float nz) {
     constexpr int NW = PX / 4;
-    constexpr int RING = PX == 16 ? 8 : 16;                            // frames in flight per thread
+    constexpr int RING = PX >= 8 ? 8 : 16;                             // frames in flight per thread
     __shared__ uint4 ring_raw[RING * NT * NW / 4];                     // uint4: 16-byte aligned slots
     unsigned(*ring)[NT * NW] = reinterpret_cast<unsigned(*)[NT * NW]>(ring_raw);
     const int lane = threadIdx.x & 31;
@@ -231,6 +235,7 @@ ema_diff_thresh_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t i
             auto frame = [&](int t, int uslot, bool may_init) {
                 if (t + RING - 1 < batch) {
                     if (PX == 16) va_cp_async16(myslot + ((uslot + RING - 1) % RING) * SLOT_STRIDE, rnext + x);
+                    else if (PX == 8) va_cp_async8(myslot + ((uslot + RING - 1) % RING) * SLOT_STRIDE, rnext + x);
                     else va_cp_async4(myslot + ((uslot + RING - 1) % RING) * SLOT_STRIDE, rnext + x);
                 }
                 va_cp_async_commit();
@@ -241,6 +246,9 @@ ema_diff_thresh_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t i
                 if (PX == 16) {
                     const uint4 q = *reinterpret_cast<const uint4 *>(slot);
                     v[0] = q.x; v[NW > 1 ? 1 : 0] = q.y; v[NW > 2 ? 2 : 0] = q.z; v[NW > 3 ? 3 : 0] = q.w;
+                } else if (PX == 8) {
+                    const uint2 q = *reinterpret_cast<const uint2 *>(slot);
+                    v[0] = q.x; v[NW > 1 ? 1 : 0] = q.y;
                 } else {
                     v[0] = slot[0];
                 }
@@ -277,6 +285,9 @@ ema_diff_thresh_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t i
             if (PX == 16) {
                 const uint4 q = *reinterpret_cast<const uint4 *>(slot);
                 v[0] = q.x; v[NW > 1 ? 1 : 0] = q.y; v[NW > 2 ? 2 : 0] = q.z; v[NW > 3 ? 3 : 0] = q.w;
+            } else if (PX == 8) {
+                const uint2 q = *reinterpret_cast<const uint2 *>(slot);
+                v[0] = q.x; v[NW > 1 ? 1 : 0] = q.y;
             } else {
                 v[0] = slot[0];
             }
@@ -319,18 +330,20 @@ extern "C" int va_ema_diff_thresh(va_ctx *ctx, va_stream stream,
     VA_REQUIRE(ctx, thr - thr == 0.0f, "va_ema_diff_thresh: threshold must be finite");
     thr += 0.0f;                                        // -0 -> +0 (the kernel tests the sign of thr - |d|)
     const int vec_bg = va_aligned(bg, 16) && bg_pitch_e % 4 == 0;
-    // 16 pixels per thread unless that leaves most SMs without a warp (measured: faster down to VGA), else 4
-    const long long threads16 = (long long)((w + 511) / 512) * 32 * h;
-    bool use16 = threads16 >= (long long)ctx->sm_count * 128;
-    if (getenv("VA_EMA_PX")) use16 = atoi(getenv("VA_EMA_PX")) == 16;     // tuning only
+    // pixels per thread: 16 while that gives every SM sub-partition two warps or more, 8 for smaller frames (VGA: 600 ->
+    // 1200 one-warp blocks), 4 for tiny ones
     const int packed = getenv("VA_EMA_PACKED") ? atoi(getenv("VA_EMA_PACKED")) : 1;      // 0: the scalar arithmetic of round 1
-    if (use16) {
-        const int vec_in = va_aligned(in, 16) && in_pitch % 16 == 0 && in_fstride % 16 == 0;
-        const int flat = w % 32 == 0 && w % 512 != 0 && !getenv("VA_EMA_NOFLAT");
-        const long long warps = flat ? ((long long)(w / 16) * h + 31) / 32 : (long long)((w + 511) / 512) * h;
+    const long long warps16 = (long long)((w + 511) / 512) * h;
+    int px = warps16 >= (long long)ctx->sm_count * 8 ? 16 : warps16 >= (long long)ctx->sm_count ? 8 : 4;
+    if (getenv("VA_EMA_PX")) px = atoi(getenv("VA_EMA_PX")) == 16 ? 16 : atoi(getenv("VA_EMA_PX")) == 8 ? 8 : 4;     // tuning only
+    if (px >= 8) {
+        const int span = 32 * px;
+        const int vec_in = va_aligned(in, px) && in_pitch % px == 0 && in_fstride % px == 0;
+        const int flat = w % 32 == 0 && w % span != 0 && !getenv("VA_EMA_NOFLAT");
+        const long long warps = flat ? ((long long)(w / px) * h + 31) / 32 : (long long)((w + span - 1) / span) * h;
         VA_REQUIRE(ctx, warps < (1ll << 31), "va_ema_diff_thresh: frame too large");
         const int nt = getenv("VA_EMA_NT") ? atoi(getenv("VA_EMA_NT")) : 32;                // tuning only
-        if (nt == 256) {
+        if (nt == 256 && px == 16) {
             const int grid = va_grid(ctx, (warps + 7) / 8, 8);
             auto kfn = ema_diff_thresh_kernel<16, 256, 0, false>;
             VA_LAUNCH(ctx, kfn, grid, 256, 0, stream, in, in_pitch, in_fstride, bg, bg_pitch_e, mask, mask_pitch_w,
@@ -338,9 +351,10 @@ extern "C" int va_ema_diff_thresh(va_ctx *ctx, va_stream stream,
             return VA_OK;
         }
         const int grid = (int)warps;                      // one warp per block, no grid-stride rounds
-        const bool allfast = vec_in && vec_bg && (flat ? ((long long)(w / 16) * h) % 32 == 0 : w % 512 == 0) && !getenv("VA_EMA_GENERAL");
-        auto kfn = !packed ? ema_diff_thresh_kernel<16, 32, 0, false>
-                 : allfast ? ema_diff_thresh_kernel<16, 32, 1, true> : ema_diff_thresh_kernel<16, 32, 1, false>;
+        const bool allfast = vec_in && vec_bg && (flat ? ((long long)(w / px) * h) % 32 == 0 : w % span == 0) && !getenv("VA_EMA_GENERAL");
+        auto kfn = px == 16 ? (!packed ? ema_diff_thresh_kernel<16, 32, 0, false>
+                               : allfast ? ema_diff_thresh_kernel<16, 32, 1, true> : ema_diff_thresh_kernel<16, 32, 1, false>)
+                            : (allfast ? ema_diff_thresh_kernel<8, 32, 1, true> : ema_diff_thresh_kernel<8, 32, 1, false>);
         VA_LAUNCH(ctx, kfn, grid, 32, 0, stream, in, in_pitch, in_fstride, bg, bg_pitch_e, mask, mask_pitch_w,
                   mask_fstride_w, w, h, batch, alpha, thr, first_frame_inits, vec_in, vec_bg, flat, -0.0f);
     } else {

@@ -429,9 +429,12 @@ label_write_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
                    const int *__restrict__ rowflag,
                    T *__restrict__ labels, size_t lpe, size_t lfe, int w, int h, int batch, int vec_out, int R) {
     // grid = (groups of 8 R rows, frames): R consecutive rows per warp (R > 1 for narrow frames)
-    __shared__ int slab_all[LAB_WARPS][1024 + 32];
+    // per-warp slab of min(w, 1024) pixels (+ skew): narrow frames leave room for more CTAs per SM, and the walk to the
+    // roots is a chain of dependent loads that only more rows in flight can hide
+    VA_DYN_SMEM(int, slab_all);
     const int lane = threadIdx.x & 31;
-    int *slab = slab_all[threadIdx.x >> 5];
+    const int slab_px = (w < 1024 ? ((w + 31) & ~31) : 1024);
+    int *slab = slab_all + (threadIdx.x >> 5) * (slab_px + (slab_px >> 5));
     const int wpw = (w + 31) >> 5;
     const unsigned lastmask = (w & 31) ? ((1u << (w & 31)) - 1u) : FULL;
     const int yw = (blockIdx.x * LAB_WARPS + (threadIdx.x >> 5)) * R;
@@ -465,36 +468,53 @@ label_write_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
             }
             int st_in, top;
             lab_scan_chunk(wd, lane, base, carry, st_in, top);
-            // ---- fill: one lookup per run
-            unsigned rem = wd;
-            while (rem) {
-                const int bit = __ffs((int)rem) - 1;
-                const unsigned t = ~(wd >> bit);
-                const int ones = t ? __ffs((int)t) - 1 : 32;
-                const int start_x = bit == 0 ? st_in : 32 * (base + lane) + bit;
+            // ---- fill: one lookup per run.  A word that holds a single run (the usual case inside a blob) keeps its label in
+            // a register and hands it to the store step by shuffle; only words with several runs go through the slab
+            // (writing a 32-pixel run to the slab pixel by pixel was 23 % of the kernel's instructions on blob masks)
+            auto run_label = [&](int start_x) {
                 // walk to the root: every root holds -k (kernel C), nothing else is negative; the
                 // forest is final, so ordinary cached loads are fine and chains are short (halving)
                 int idx = (y << LOG) + start_x;
                 int p = pr[start_x];
                 while (p >= 0) { idx = p; p = pf_[idx]; }
-                const int lab = ro[idx >> LOG] - p;                // p == -k
-                const int p0 = 32 * lane + bit;
-                for (int k = 0; k < ones; k++) slab[LAB_SKEW(p0 + k)] = lab;
-                rem &= ~((ones >= 32 ? FULL : ((1u << ones) - 1u)) << bit);
+                return ro[idx >> LOG] - p;                         // p == -k
+            };
+            int single = -1;                                       // labels are >= 1
+            const unsigned heads = wd & ~(wd << 1);                // first pixels of the runs of this word (bit 0: may continue)
+            if (wd != 0u && (heads & (heads - 1u)) == 0u) {
+                const int bit = __ffs((int)wd) - 1;
+                single = run_label(bit == 0 ? st_in : 32 * (base + lane) + bit);
+            } else {
+                unsigned rem = wd;
+                while (rem) {
+                    const int bit = __ffs((int)rem) - 1;
+                    const unsigned t = ~(wd >> bit);
+                    const int ones = t ? __ffs((int)t) - 1 : 32;
+                    const int lab = run_label(bit == 0 ? st_in : 32 * (base + lane) + bit);
+                    const int p0 = 32 * lane + bit;
+                    for (int k = 0; k < ones; k++) slab[LAB_SKEW(p0 + k)] = lab;
+                    rem &= ~((ones >= 32 ? FULL : ((1u << ones) - 1u)) << bit);
+                }
             }
             __syncwarp();
             // ---- store: 128 pixels per step
             for (int it = 0; 4 * it < nwords; it++) {
-                const unsigned wi = __shfl_sync(FULL, wd, 4 * it + (lane >> 3));
+                const int src = 4 * it + (lane >> 3);
+                const unsigned wi = __shfl_sync(FULL, wd, src);
+                const int sl = __shfl_sync(FULL, single, src);
                 const unsigned nib = (wi >> (4 * (lane & 7))) & 0xFu;
                 const int px = 128 * it + 4 * lane;
                 const int x = 32 * base + px;
                 int4 v = make_int4(0, 0, 0, 0);
                 if (nib) {
-                    if (nib & 1u) v.x = slab[LAB_SKEW(px)];
-                    if (nib & 2u) v.y = slab[LAB_SKEW(px + 1)];
-                    if (nib & 4u) v.z = slab[LAB_SKEW(px + 2)];
-                    if (nib & 8u) v.w = slab[LAB_SKEW(px + 3)];
+                    if (sl >= 0) {
+                        v = make_int4((nib & 1u) ? sl : 0, (nib & 2u) ? sl : 0, (nib & 4u) ? sl : 0, (nib & 8u) ? sl : 0);
+                    } else {
+                        if (nib & 1u) v.x = slab[LAB_SKEW(px)];
+                        if (nib & 2u) v.y = slab[LAB_SKEW(px + 1)];
+                        if (nib & 4u) v.z = slab[LAB_SKEW(px + 2)];
+                        if (nib & 8u) v.w = slab[LAB_SKEW(px + 3)];
+                    }
                 }
                 lab_store4(lr, x, w, v, vec_out != 0);
             }
@@ -585,7 +605,9 @@ static int label_write(va_ctx *ctx, va_stream stream, const char *name,
     const int vec_out = va_aligned(labels, 4 * sizeof(T)) && labels_pitch_e % 4 == 0 && labels_fstride_e % 4 == 0;
     const int R = lab_rows_per_warp(w, false);
     const dim3 grid(va_div_up(h, LAB_WARPS * R), batch);
-    VA_LAUNCH(ctx, k, grid, LAB_THREADS, 0, stream, mask, mask_pitch_w, mask_fstride_w, (const int *)parent, LOG, pf,
+    const int slab_px = (w < 1024 ? ((w + 31) & ~31) : 1024);
+    const size_t smem = (size_t)LAB_WARPS * (slab_px + (slab_px >> 5)) * sizeof(int);
+    VA_LAUNCH(ctx, k, grid, LAB_THREADS, smem, stream, mask, mask_pitch_w, mask_fstride_w, (const int *)parent, LOG, pf,
               (const int *)rowcnt, (const int *)(rowcnt + (size_t)ctx->max_h * ctx->max_batch),
               labels, labels_pitch_e, labels_fstride_e, w, h, batch, vec_out, R);
     VA_REQUIRE(ctx, va_scratch_release(ctx, stream, slot) == 0, "%s: cannot order the scratch set", name);
