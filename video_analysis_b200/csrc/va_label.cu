@@ -371,22 +371,32 @@ label_flatten_kernel(const uint32_t *__restrict__ mask, size_t mpw, size_t mfw,
 // ---- D: exclusive scan of row counts, one CTA per frame --------------------------------------
 __global__ void __launch_bounds__(LAB_THREADS)
 label_scan_kernel(int *__restrict__ rowcnt, int *__restrict__ counts, int h) {
-    __shared__ int part[LAB_THREADS];
     const int b = blockIdx.x, tid = threadIdx.x;
     int *rc = rowcnt + (size_t)b * h;
     const int per = (h + LAB_THREADS - 1) / LAB_THREADS;
     const int lo = min(tid * per, h), hi = min(lo + per, h);
     int sum = 0;
     for (int i = lo; i < hi; i++) sum += rc[i];
-    part[tid] = sum;
-    __syncthreads();
-    if (tid == 0) {
-        int run = 0;
-        for (int i = 0; i < LAB_THREADS; i++) { const int v = part[i]; part[i] = run; run += v; }
-        if (counts) counts[b] = run;
+    // exclusive prefix of the 256 partial sums: shuffle scan inside each warp, then over the 8 warp totals
+    const int lane = tid & 31, wid = tid >> 5;
+    int inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(FULL, inc, d);
+        if (lane >= d) inc += v;
     }
+    __shared__ int wtot[LAB_WARPS];
+    if (lane == 31) wtot[wid] = inc;
     __syncthreads();
-    int run = part[tid];
+    int wbase = 0, total = 0;
+#pragma unroll
+    for (int i = 0; i < LAB_WARPS; i++) {
+        const int v = wtot[i];
+        if (i < wid) wbase += v;
+        total += v;
+    }
+    if (tid == 0 && counts) counts[b] = total;
+    int run = wbase + inc - sum;
     for (int i = lo; i < hi; i++) { const int v = rc[i]; rc[i] = run; run += v; }
 }
 

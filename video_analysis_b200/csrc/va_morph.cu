@@ -380,11 +380,12 @@ extern "C" int va_morph_bits(va_ctx *ctx, va_stream stream,
         if (sq) {
             const int usable = 64 - 2 * passes;
             const int strips = va_div_up((long long)wpw, usable);
-            // rows per segment: the walk is a chain of load latencies, so many short segments (about 24
-            // warps per SM, at least 16 rows; each segment re-reads passes * (k - 1) rows), sized so that
+            // rows per segment: the walk is a chain of load latencies, so many short segments (about 32
+            // warps per SM -- measured 16 / 24 / 32 / 48 / 96: 26.6 / 24.6 / 22.5 / 24.1 / 23.8 us per 128 1080p frames --, at least 16 rows; each segment re-reads passes * (k - 1) rows), sized so that
             // the rows a warp reads fill whole prefetch batches
             const int halo_rows = passes * (kx - 1);
-            int segs = va_div_up((long long)ctx->sm_count * 24, (long long)strips * batch);
+            const int wps = getenv("VA_MORPH_WPS") ? atoi(getenv("VA_MORPH_WPS")) : 32;      // tuning only
+            int segs = va_div_up((long long)ctx->sm_count * wps, (long long)strips * batch);
             if (segs > h / 16) segs = h / 16;
             if (segs < 1) segs = 1;
             int SH = va_div_up(h, segs);
