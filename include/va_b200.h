@@ -374,19 +374,26 @@ int va_chain_run(va_ctx *ctx, va_stream stream, const va_chain_desc *desc, const
  * PAGE-LOCKED HOST memory (the kernels then store over PCIe and no copy has to be sized or issued), n_chunks_dev
  * (optional) is a device copy of the counts.  A frame with more than cap non-empty chunks reports its true count and
  * exports the first cap.  mask is the packed image the labels were made from (va_label_bits).  With ids = data = NULL
- * only the counts are produced (how sparse is this batch?). */
+ * only the counts are produced (how sparse is this batch?).
+ * runs [batch][cap][4] / n_runs [batch] (optional, both or neither; 16-byte aligned): chunks whose foreground pixels
+ * form a single horizontal run -- they carry one label -- are then exported as (id, label, low word, high word of the
+ * 64-bit pixel mask) records of 16 bytes instead of 260, and ids / data / n_chunks hold the remaining chunks only.
+ * The count-only call accepts n_runs alone and then counts the two kinds separately. */
 int va_label_export_chunks(va_ctx *ctx, va_stream stream,
                            const uint32_t *mask, size_t mask_pitch_w, size_t mask_fstride_w,
                            const int32_t *labels, size_t labels_pitch_e, size_t labels_fstride_e,
                            int w, int h, int batch,
-                           int32_t *ids, int32_t *data, int32_t *n_chunks, int32_t *n_chunks_dev, int cap);
+                           int32_t *ids, int32_t *data, int32_t *n_chunks, int32_t *n_chunks_dev,
+                           int32_t *runs, int32_t *n_runs, int cap);
 
-/* HOST function (no CUDA call, no ctx): rebuilds dense (batch, h, pitch_e) int32 label images from exported chunks.
- * dirty_ids [batch][cap] / n_dirty [batch] name the chunks of `dense` that are non-zero from its previous use: they
- * are cleared first and replaced by the chunk list written now, so a ring of result buffers never has to be zeroed
- * as a whole.  `threads` host threads share the frames. */
+/* HOST function (no CUDA call, no ctx): rebuilds dense (batch, h, pitch_e) int32 label images from exported chunks
+ * (and run chunks, when runs / n_runs are given).  dirty_ids [batch][cap] / n_dirty [batch] name the chunks of `dense`
+ * that are non-zero from its previous use: they are cleared first and replaced by the chunk list written now, so a
+ * ring of result buffers never has to be zeroed as a whole (n_chunks + n_runs <= cap).  `threads` host threads share
+ * the frames. */
 int va_host_densify_chunks(int32_t *dense, size_t pitch_e, size_t fstride_e, int w, int h, int batch,
-                           const int32_t *ids, const int32_t *data, const int32_t *n_chunks, int cap,
+                           const int32_t *ids, const int32_t *data, const int32_t *n_chunks,
+                           const int32_t *runs, const int32_t *n_runs, int cap,
                            int32_t *dirty_ids, int32_t *n_dirty, int threads);
 
 #ifdef __cplusplus

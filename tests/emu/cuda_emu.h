@@ -147,6 +147,7 @@ static inline int __all_sync(unsigned m, int pred) {
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
+static inline int __ffsll(long long x) { return __builtin_ffsll(x); }
 static inline unsigned __brev(unsigned x) {
     unsigned r = 0;
     for (int i = 0; i < 32; i++) r |= ((x >> i) & 1u) << (31 - i);

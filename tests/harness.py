@@ -396,10 +396,11 @@ def label(ctx, words, W, connectivity=4, lab_pad=0):
     return lab.get(), cnt.get()[0, 0]
 
 
-def label_export_dense(ctx, words, W, connectivity=4, lab_pad=0, cap=None, reuse=None, threads=3):
+def label_export_dense(ctx, words, W, connectivity=4, lab_pad=0, cap=None, reuse=None, threads=3, use_runs=True):
     """ va_label_bits, va_label_export_chunks into page-locked host memory (plain memory on the emulator) and
-    va_host_densify_chunks: returns (dense labels [B,H,W], n_chunks [B], state) -- `state` = (dense buffer, dirty ids,
-    dirty counts) to be passed back as `reuse` so that the next call rebuilds into the same buffer """
+    va_host_densify_chunks: returns (dense labels [B,H,W], n_chunks [B], state, dense copy, n_runs [B]) -- `state` =
+    (dense buffer, dirty ids, dirty counts) to be passed back as `reuse` so that the next call rebuilds into the same
+    buffer.  use_runs: single-run chunks travel as 16-byte records (n_chunks then counts the other chunks only) """
     be = ctx.be
     B, H, Wp = words.shape
     src = Img(be, B, H, Wp, np.uint32, data=words)
@@ -415,31 +416,35 @@ def label_export_dense(ctx, words, W, connectivity=4, lab_pad=0, cap=None, reuse
         ids_t = t.empty((B, cap), dtype=t.int32, pin_memory=True)
         data_t = t.empty((B, cap, 64), dtype=t.int32, pin_memory=True)
         n_t = t.empty((B,), dtype=t.int32, pin_memory=True)
-        ids, data, n = ids_t.numpy(), data_t.numpy(), n_t.numpy()
-        keep = (ids_t, data_t, n_t)
+        runs_t = t.empty((B, cap, 4), dtype=t.int32, pin_memory=True)
+        nr_t = t.zeros((B,), dtype=t.int32, pin_memory=True)
+        ids, data, n, runs, nr = ids_t.numpy(), data_t.numpy(), n_t.numpy(), runs_t.numpy(), nr_t.numpy()
+        keep = (ids_t, data_t, n_t, runs_t, nr_t)
     else:
         ids, data, n = np.empty((B, cap), np.int32), np.empty((B, cap, 64), np.int32), np.empty((B,), np.int32)
+        runs, nr = np.empty((B, cap, 4), np.int32), np.zeros((B,), np.int32)
         keep = None
+    rp, nrp = (runs.ctypes.data, nr.ctypes.data) if use_runs else (None, None)
     ndev = Img(be, 1, 1, B, np.int32)
     ctx.check(ctx.lib.va_label_export_chunks(ctx.h, be.stream, src.ptr, src.pitch, src.fstride, lab.ptr, lab.pitch, lab.fstride,
-                                             W, H, B, ids.ctypes.data, data.ctypes.data, n.ctypes.data, ndev.ptr, cap))
+                                             W, H, B, ids.ctypes.data, data.ctypes.data, n.ctypes.data, ndev.ptr, rp, nrp, cap))
     be.sync()
     assert np.array_equal(ndev.get()[0, 0], n)
-    if (n > cap).any():                   # more chunks than the export buffers hold: the caller copies densely instead
+    if (n > cap).any() or (nr > cap).any():   # more chunks than the export buffers hold: the caller copies densely instead
         rc = ctx.lib.va_host_densify_chunks(lab.get().ctypes.data, pitch, H * pitch, W, H, B, ids.ctypes.data, data.ctypes.data,
-                                            n.ctypes.data, cap, ids.ctypes.data, n.ctypes.data, 1)
+                                            n.ctypes.data, rp, nrp, cap, ids.ctypes.data, n.ctypes.data, 1)
         assert rc == valib.VA_ERR_CAPACITY
-        return None, n.copy(), None, lab.get()
+        return None, n.copy(), None, lab.get(), nr.copy()
     if reuse is None:
         dense = np.zeros((B, H, pitch), np.int32)
         dirty, n_dirty = np.zeros((B, cap), np.int32), np.zeros((B,), np.int32)
     else:
         dense, dirty, n_dirty = reuse
     rc = ctx.lib.va_host_densify_chunks(dense.ctypes.data, pitch, H * pitch, W, H, B, ids.ctypes.data, data.ctypes.data,
-                                        n.ctypes.data, cap, dirty.ctypes.data, n_dirty.ctypes.data, threads)
+                                        n.ctypes.data, rp, nrp, cap, dirty.ctypes.data, n_dirty.ctypes.data, threads)
     assert rc == 0, rc
     del keep
-    return dense[:, :, :W].copy(), n.copy(), (dense, dirty, n_dirty), lab.get()
+    return dense[:, :, :W].copy(), n.copy(), (dense, dirty, n_dirty), lab.get(), nr.copy()
 
 
 def label_two_batches_split(ctx, words_a, words_b, W, connectivity=4):

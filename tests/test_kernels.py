@@ -184,28 +184,47 @@ def test_luma_gauss_fused_equals_two_step(be, ctx):
 
 
 # ---- sparse egress of label images ----------------------------------------------------------------
+def _chunk_kinds(frame, W):
+    """ (non-empty 64-pixel chunks, those whose foreground is one horizontal run) of a boolean frame """
+    pad = (-W) % 64
+    f = np.concatenate([frame, np.zeros((frame.shape[0], pad), bool)], 1).reshape(frame.shape[0], -1, 64)
+    any_ = f.any(-1)
+    starts = (f & ~np.concatenate([np.zeros(f.shape[:2] + (1,), bool), f[..., :-1]], -1)).sum(-1)
+    return int(any_.sum()), int((starts == 1).sum())
+
+
 def test_label_export_chunks_and_host_densify(be, ctx):
     # the non-empty 64-label chunks written by the device (straight into page-locked host memory on the GPU) and the
-    # host-side rebuild give the dense label image bit for bit; the result buffer is reused without being zeroed
+    # host-side rebuild give the dense label image bit for bit; the result buffer is reused without being zeroed;
+    # chunks whose foreground is a single run travel as 16-byte records when the caller asks for them
     for (H, W) in sizes(be, [(20, 64), (23, 200), (9, 130)], [(1080, 1920), (480, 640), (271, 1003)]):
-        rng = np.random.default_rng(H * W)
-        state = None
-        for rep, density in enumerate((0.02, 0.5, 0.0, 0.001, 1.0)):
-            m = (rng.random((2, H, W)) < density)
-            if density == 0.02:
-                m[0, H // 3: H // 2, W // 4: W // 2] = True
-            words = ops.pack_bits(m)
-            dense, n, state, direct = hz.label_export_dense(ctx, words, W, reuse=state, lab_pad=(H + W) % 3)
-            assert np.array_equal(dense, direct), (H, W, density)
-            want = np.stack([ops.label(f)[0] for f in m])
-            assert np.array_equal(dense, want), (H, W, density)
-            cpr = (W + 63) // 64
-            nz = [(np.add.reduceat(f != 0, np.arange(0, W, 64), axis=1) > 0).sum() for f in m]
-            assert list(n) == nz and max(nz) <= cpr * H
+        for use_runs in (True, False):
+            rng = np.random.default_rng(H * W)
+            state = None
+            for rep, density in enumerate((0.02, 0.5, 0.0, 0.001, 1.0)):
+                m = (rng.random((2, H, W)) < density)
+                if density == 0.02:
+                    m[0, H // 3: H // 2, W // 4: W // 2] = True
+                words = ops.pack_bits(m)
+                dense, n, state, direct, nr = hz.label_export_dense(ctx, words, W, reuse=state, lab_pad=(H + W) % 3,
+                                                                    use_runs=use_runs)
+                assert np.array_equal(dense, direct), (H, W, density)
+                want = np.stack([ops.label(f)[0] for f in m])
+                assert np.array_equal(dense, want), (H, W, density)
+                kinds = [_chunk_kinds(f, W) for f in m]
+                if use_runs:
+                    assert list(nr) == [k[1] for k in kinds] and list(n) == [k[0] - k[1] for k in kinds]
+                else:
+                    assert list(n) == [k[0] for k in kinds] and not nr.any()
+                assert max(k[0] for k in kinds) <= ((W + 63) // 64) * H
     # capacity smaller than the number of chunks: the true count is reported (the caller falls back to a dense copy)
     m = np.ones((1, 8, 128), bool)
-    _, n, _, _ = hz.label_export_dense(ctx, ops.pack_bits(m), 128, cap=5)
+    m[:, :, ::7] = False
+    _, n, _, _, _ = hz.label_export_dense(ctx, ops.pack_bits(m), 128, cap=5)
     assert n[0] == 16
+    m = np.ones((1, 8, 128), bool)
+    _, n, _, _, nr = hz.label_export_dense(ctx, ops.pack_bits(m), 128, cap=5)
+    assert n[0] == 0 and nr[0] == 16
 
 
 # ---- K2b ----------------------------------------------------------------------------------------

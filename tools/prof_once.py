@@ -43,6 +43,6 @@ if os.environ.get('PROF_EXTRA', '1') != '0':
     data = _t.empty((B, 30 * H, 64), dtype=_t.int32, pin_memory=True)
     nn = _t.empty((B,), dtype=_t.int32, pin_memory=True)
     rt._check(rt.lib.va_label_export_chunks(rt._h, rt.stream, *mo.img(), *lab.img(), W, H, B, ids.data_ptr(), data.data_ptr(),
-                                            nn.data_ptr(), None, 30 * H))
+                                            nn.data_ptr(), None, None, None, 30 * H))
 torch.cuda.synchronize()
 print('ok', cnt[:4].tolist(), rt.launches)

@@ -91,9 +91,10 @@ SIGNATURES = {
     'va_time_diff_i16': (c_int, [c_void_p, c_void_p] + _IMG + _IMG + [c_int, c_int, c_int]),
     'va_rot90_u8': (c_int, [c_void_p, c_void_p] + _IMG + _IMG + [c_int, c_int, c_int, c_int, c_int]),
     'va_mean_update_f64': (c_int, [c_void_p, c_void_p] + _IMG + [c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_longlong]),
-    'va_label_export_chunks': (c_int, [c_void_p, c_void_p] + _IMG + _IMG + [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
-    'va_host_densify_chunks': (c_int, [c_void_p, c_size_t, c_size_t, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
+    'va_label_export_chunks': (c_int, [c_void_p, c_void_p] + _IMG + _IMG + [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_int]),
+    'va_host_densify_chunks': (c_int, [c_void_p, c_size_t, c_size_t, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int]),
     'va_chain_run': (c_int, [c_void_p, c_void_p, ctypes.POINTER(ChainDesc), ctypes.POINTER(ChainIO)]),
 }
 

@@ -26,7 +26,7 @@ class SparseLabelEgress(object):
     """ label images of one ring slot on their way to the host as non-empty 64-label chunks (csrc/va_export.cu): the
     device stores chunk data, chunk ids and per-frame chunk counts straight into page-locked host memory, `finish`
     rebuilds the dense int32 images in ordinary host memory -- clearing only the chunks the slot's previous batch left
-    behind -- and returns them.
+    behind -- and returns them.  Chunks whose foreground is a single run (one label) travel as 16-byte records.
 
     Masks that are mostly noise (a plain threshold on an unblurred frame) have foreground in most chunks; chunks then
     cost more than a dense copy.  `policy` (shared by the slots of one pipeline) watches the chunk fraction of the
@@ -50,6 +50,8 @@ class SparseLabelEgress(object):
         self.ids = t.empty((batch, self.cap), dtype=t.int32, pin_memory=True)
         self.data = t.empty((batch, self.cap, 64), dtype=t.int32, pin_memory=True)
         self.n = t.zeros((batch,), dtype=t.int32, pin_memory=True)
+        self.runs = t.empty((batch, self.cap, 4), dtype=t.int32, pin_memory=True)
+        self.n_runs = t.zeros((batch,), dtype=t.int32, pin_memory=True)
         self.dense = t.zeros((batch, h, pitch_e), dtype=t.int32)
         self.dirty_ids = t.zeros((batch, self.cap), dtype=t.int32)
         self.n_dirty = t.zeros((batch,), dtype=t.int32)
@@ -67,10 +69,11 @@ class SparseLabelEgress(object):
             if self._pinned_dense is None:
                 self._pinned_dense = torch().empty((self.batch, self.h, self.pitch_e), dtype=torch().int32, pin_memory=True)
             rt._check(rt.lib.va_label_export_chunks(rt._h, rt.stream, *seg.img(), *labels.img(), self.w, self.h, m,
-                                                    None, None, self.n.data_ptr(), None, self.cap))
+                                                    None, None, self.n.data_ptr(), None, None, self.n_runs.data_ptr(), self.cap))
         else:
             rt._check(rt.lib.va_label_export_chunks(rt._h, rt.stream, *seg.img(), *labels.img(), self.w, self.h, m,
-                                                    self.ids.data_ptr(), self.data.data_ptr(), self.n.data_ptr(), None, self.cap))
+                                                    self.ids.data_ptr(), self.data.data_ptr(), self.n.data_ptr(), None,
+                                                    self.runs.data_ptr(), self.n_runs.data_ptr(), self.cap))
 
     def enqueue_copy(self, labels, m):
         """ on the egress stream, after the kernels: the dense device -> host copy of a batch that travels densely """
@@ -80,17 +83,20 @@ class SparseLabelEgress(object):
     def finish(self, m):
         """ after the export has completed (event): dense (m, h, w) int32 view, valid until the slot is reused """
         n_chunks = int(self.n.numpy()[:m].sum())
-        self.policy.update(n_chunks / float(max(1, m * self.cap)))
+        n_runs = int(self.n_runs.numpy()[:m].sum())
+        # what the chunks cost on PCIe relative to the dense image: 260 bytes per raw chunk, 16 per run chunk
+        self.policy.update((n_chunks + n_runs / 16.0) / float(max(1, m * self.cap)))
         if self._mode_dense:
             self.bytes = m * self.h * self.pitch_e * 4 + 4 * m
             return self._pinned_dense.numpy()[:m, :, :self.w]
         d = self.dense
         rc = self.rt.lib.va_host_densify_chunks(d.data_ptr(), d.stride(1), d.stride(0), self.w, self.h, m,
-                                                self.ids.data_ptr(), self.data.data_ptr(), self.n.data_ptr(), self.cap,
+                                                self.ids.data_ptr(), self.data.data_ptr(), self.n.data_ptr(),
+                                                self.runs.data_ptr(), self.n_runs.data_ptr(), self.cap,
                                                 self.dirty_ids.data_ptr(), self.n_dirty.data_ptr(), self.host_threads)
         _lib.check(self.rt.lib, None, rc)
-        # bytes the device stored over PCIe for this block: chunk data + chunk ids + the count vector
-        self.bytes = n_chunks * (64 * 4 + 4) + 4 * m
+        # bytes the device stored over PCIe for this block: chunk data + chunk ids, run records, the two count vectors
+        self.bytes = n_chunks * (64 * 4 + 4) + n_runs * 16 + 8 * m
         return d.numpy()[:m, :, :self.w]
 
 
