@@ -235,22 +235,37 @@ extern "C" int va_resize_area_u8(va_ctx *ctx, va_stream stream,
     return VA_OK;
 }
 
+// thread = 4 consecutive output bytes of one row (one 4-byte store), grid = (groups of a row, rows, frames): no 64-bit
+// index arithmetic, the row's source pointer once per thread (one thread per output byte with a flat 64-bit index: 0.150 ms
+// per 32 frames 1080p -> 720p)
+template <int CS>
 __global__ void __launch_bounds__(256)
 resize_nearest_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstride,
                       uint8_t *__restrict__ out, size_t out_pitch, size_t out_fstride,
-                      int w, int h, int ow, int oh, int cs, int batch, double ifx, double ify) {
-    const unsigned rowb = (unsigned)(ow * cs);
-    const unsigned long long total = (unsigned long long)rowb * oh * batch;
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
-         i += (unsigned long long)gridDim.x * blockDim.x) {
-        const unsigned xb = (unsigned)(i % rowb);
-        const unsigned long long rest = i / rowb;
-        const unsigned y = (unsigned)(rest % oh), b = (unsigned)(rest / oh);
-        const unsigned x = xb / cs, c = xb - x * cs;
-        const int sx = min((int)floor(__dmul_rn((double)x, ifx)), w - 1);
-        const int sy = min((int)floor(__dmul_rn((double)y, ify)), h - 1);
-        out[(size_t)b * out_fstride + (size_t)y * out_pitch + xb] =
-            in[(size_t)b * in_fstride + (size_t)sy * in_pitch + (size_t)sx * cs + c];
+                      int w, int h, int ow, int oh, double ifx, double ify, int vec) {
+    const unsigned rowb = (unsigned)(ow * CS);
+    const unsigned xb0 = 4u * (blockIdx.x * blockDim.x + threadIdx.x);
+    const unsigned y = blockIdx.y, b = blockIdx.z;
+    if (xb0 >= rowb) return;
+    const int sy = min((int)floor(__dmul_rn((double)y, ify)), h - 1);
+    const uint8_t *srow = in + (size_t)b * in_fstride + (size_t)sy * in_pitch;
+    uint8_t *orow = out + (size_t)b * out_fstride + (size_t)y * out_pitch;
+    unsigned v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const unsigned xb = xb0 + k;
+        if (xb < rowb) {
+            const unsigned x = xb / CS, c = xb - x * CS;
+            const int sx = min((int)floor(__dmul_rn((double)x, ifx)), w - 1);
+            v |= (unsigned)srow[(size_t)sx * CS + c] << (8 * k);
+        }
+    }
+    if (vec && xb0 + 4 <= rowb) {
+        *reinterpret_cast<unsigned *>(orow + xb0) = v;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (xb0 + k < rowb) orow[xb0 + k] = (uint8_t)(v >> (8 * k));
     }
 }
 
@@ -262,13 +277,18 @@ extern "C" int va_resize_nearest_u8(va_ctx *ctx, va_stream stream,
     VA_REQUIRE(ctx, in && out && in != out, "va_resize_nearest_u8: null or aliased pointers");
     VA_REQUIRE(ctx, w > 0 && h > 0 && dw > 0 && dh > 0 && batch > 0 && (channels == 1 || channels == 3), "va_resize_nearest_u8: bad size");
     VA_REQUIRE(ctx, in_pitch >= (size_t)w * channels && out_pitch >= (size_t)dw * channels, "va_resize_nearest_u8: pitch smaller than a row");
+    VA_REQUIRE(ctx, dh <= 65535 && batch <= 65535, "va_resize_nearest_u8: more than 65535 rows or frames");
     // cv::resize: inv_scale = dsize / ssize, ifx = 1 / inv_scale (doubles), x_ofs[x] = min(cvFloor(x * ifx), ssize - 1)
     const double ifx = 1.0 / ((double)dw / (double)w), ify = 1.0 / ((double)dh / (double)h);
-    const long long items = (long long)dw * channels * dh * batch;
-    const int grid = va_grid(ctx, (items + 255) / 256, 16);
-    auto kfn = resize_nearest_kernel;
-    VA_LAUNCH(ctx, kfn, grid, 256, 0, stream, in, in_pitch, in_fstride, out, out_pitch, out_fstride, w, h, dw, dh, channels, batch,
-              ifx, ify);
+    const int vec = va_aligned(out, 4) && out_pitch % 4 == 0 && out_fstride % 4 == 0;
+    const dim3 grid(va_div_up(va_div_up(dw * channels, 4), 256), dh, batch);
+    if (channels == 1) {
+        auto kfn = resize_nearest_kernel<1>;
+        VA_LAUNCH(ctx, kfn, grid, 256, 0, stream, in, in_pitch, in_fstride, out, out_pitch, out_fstride, w, h, dw, dh, ifx, ify, vec);
+    } else {
+        auto kfn = resize_nearest_kernel<3>;
+        VA_LAUNCH(ctx, kfn, grid, 256, 0, stream, in, in_pitch, in_fstride, out, out_pitch, out_fstride, w, h, dw, dh, ifx, ify, vec);
+    }
     return VA_OK;
 }
 
@@ -746,14 +766,12 @@ __global__ void __launch_bounds__(256)
 resize_cubic_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t in_fstride,
                     uint8_t *__restrict__ out, size_t out_pitch, size_t out_fstride,
                     int w, int h, int ow, int oh, int cs, int batch, double scale_x, double scale_y) {
+    // grid = (bytes of a row, rows, frames): no 64-bit index arithmetic per output byte
     const unsigned rowb = (unsigned)(ow * cs);
     const unsigned vec_end = rowb & ~7u;
-    const unsigned long long total = (unsigned long long)rowb * oh * batch;
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
-         i += (unsigned long long)gridDim.x * blockDim.x) {
-        const unsigned xb = (unsigned)(i % rowb);
-        const unsigned long long rest = i / rowb;
-        const unsigned y = (unsigned)(rest % oh), b = (unsigned)(rest / oh);
+    const unsigned xb = blockIdx.x * blockDim.x + threadIdx.x;
+    if (xb < rowb) {
+        const unsigned y = blockIdx.y, b = blockIdx.z;
         const unsigned x = xb / cs, c = xb - x * cs;
         int sx, sy, a[4], bt[4];
         cubic_coef((int)x, scale_x, sx, a);
@@ -792,8 +810,8 @@ extern "C" int va_resize_cubic_u8(va_ctx *ctx, va_stream stream,
     VA_REQUIRE(ctx, w > 0 && h > 0 && dw > 0 && dh > 0 && batch > 0 && (channels == 1 || channels == 3), "va_resize_cubic_u8: bad size");
     VA_REQUIRE(ctx, in_pitch >= (size_t)w * channels && out_pitch >= (size_t)dw * channels, "va_resize_cubic_u8: pitch smaller than a row");
     const double sx = 1.0 / ((double)dw / (double)w), sy = 1.0 / ((double)dh / (double)h);
-    const long long items = (long long)dw * channels * dh * batch;
-    const int grid = va_grid(ctx, (items + 255) / 256, 16);
+    VA_REQUIRE(ctx, dh <= 65535 && batch <= 65535, "va_resize_cubic_u8: more than 65535 rows or frames");
+    const dim3 grid(va_div_up(dw * channels, 256), dh, batch);
     auto kfn = resize_cubic_kernel;
     VA_LAUNCH(ctx, kfn, grid, 256, 0, stream, in, in_pitch, in_fstride, out, out_pitch, out_fstride, w, h, dw, dh, channels, batch,
               sx, sy);
@@ -923,13 +941,11 @@ resize_lanczos4_kernel(const uint8_t *__restrict__ in, size_t in_pitch, size_t i
                        int w, int h, int ow, int oh, int cs, int batch,
                        const int *__restrict__ xofs, const short *__restrict__ alpha,
                        const int *__restrict__ yofs, const short *__restrict__ beta) {
+    // grid = (bytes of a row, rows, frames): no 64-bit index arithmetic per output byte
     const unsigned rowb = (unsigned)(ow * cs);
-    const unsigned long long total = (unsigned long long)rowb * oh * batch;
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
-         i += (unsigned long long)gridDim.x * blockDim.x) {
-        const unsigned xb = (unsigned)(i % rowb);
-        const unsigned long long rest = i / rowb;
-        const unsigned y = (unsigned)(rest % oh), b = (unsigned)(rest / oh);
+    const unsigned xb = blockIdx.x * blockDim.x + threadIdx.x;
+    if (xb < rowb) {
+        const unsigned y = blockIdx.y, b = blockIdx.z;
         const unsigned x = xb / cs, c = xb - x * cs;
         const int sx = xofs[x], sy = yofs[y];
         const short *a = alpha + 8 * (size_t)x, *bt = beta + 8 * (size_t)y;
@@ -971,8 +987,8 @@ extern "C" int va_resize_lanczos4_u8(va_ctx *ctx, va_stream stream,
     VA_CUDA(ctx, cudaMemcpyAsync(dev, host.data(), bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));   // pageable source: staged before the call returns
     const int *d_xofs = reinterpret_cast<const int *>(dev), *d_yofs = d_xofs + dw;
     const short *d_alpha = reinterpret_cast<const short *>(dev + n_ofs * sizeof(int)), *d_beta = d_alpha + 8 * (size_t)dw;
-    const long long items = (long long)dw * channels * dh * batch;
-    const int grid = va_grid(ctx, (items + 255) / 256, 16);
+    VA_REQUIRE(ctx, dh <= 65535 && batch <= 65535, "va_resize_lanczos4_u8: more than 65535 rows or frames");
+    const dim3 grid(va_div_up(dw * channels, 256), dh, batch);
     auto kfn = resize_lanczos4_kernel;
     VA_LAUNCH(ctx, kfn, grid, 256, 0, stream, in, in_pitch, in_fstride, out, out_pitch, out_fstride, w, h, dw, dh, channels, batch,
               d_xofs, d_alpha, d_yofs, d_beta);

@@ -254,7 +254,11 @@ __device__ __forceinline__ void morph_dilate_h2(unsigned &a, unsigned &b) {
     b = rb;
 }
 
-template <int K, int PASSES>
+// FAST: rows of an even number of words, 8-byte aligned, two passes -- every lane's word pair is then either inside the
+// row or outside it and either written or not, so all lanes load their pair unconditionally (lanes outside the row from a
+// clamped position: their bits are masked away) and a row costs one predicated load and one predicated store instead of
+// the nested branches of the ragged case (30 % of the instructions of the general kernel are branches and predicates)
+template <int K, int PASSES, bool FAST>
 __global__ void __launch_bounds__(MORPH_S_THREADS)
 morph_stream_kernel(const uint32_t *__restrict__ in, size_t in_pitch_w, size_t in_fstride_w,
                     uint32_t *__restrict__ out, size_t out_pitch_w, size_t out_fstride_w,
@@ -276,7 +280,7 @@ morph_stream_kernel(const uint32_t *__restrict__ in, size_t in_pitch_w, size_t i
     const unsigned keepb = !inb ? 0u : (ja + 1 == wpw - 1 ? lastmask : 0xffffffffu);
     const bool wra = ina && 2 * lane >= PASSES && 2 * lane < 64 - PASSES;
     const bool wrb = inb && 2 * lane + 1 >= PASSES && 2 * lane + 1 < 64 - PASSES;
-    const bool pair = vec && ina && inb;                                                // one 8-byte access
+    const bool pair = FAST || (vec && ina && inb);                                      // one 8-byte access
     const unsigned m1 = first == 0 ? 0xffffffffu : 0u;         // complement masks: erode = ~dilate(~x)
     const unsigned m2 = second == 0 ? 0xffffffffu : 0u;
     const unsigned m12 = m1 ^ m2;
@@ -284,7 +288,8 @@ morph_stream_kernel(const uint32_t *__restrict__ in, size_t in_pitch_w, size_t i
     const int y_first = ys - PASSES * H;                       // first input row needed
     const int n_in = (ye - ys) + 2 * PASSES * H;
     // row pointers run along with the walk (the ones outside the image are never dereferenced)
-    const uint32_t *src = in + (size_t)b * in_fstride_w + (ptrdiff_t)ja + (ptrdiff_t)y_first * (ptrdiff_t)in_pitch_w;
+    const int jl = FAST ? min(max(ja, 0), wpw - 2) : ja;       // FAST: lanes outside the row read inside it (and are masked)
+    const uint32_t *src = in + (size_t)b * in_fstride_w + (ptrdiff_t)jl + (ptrdiff_t)y_first * (ptrdiff_t)in_pitch_w;
     uint32_t *dst = out + (size_t)b * out_fstride_w + (ptrdiff_t)ja + (ptrdiff_t)(y_first - PASSES * H) * (ptrdiff_t)out_pitch_w;
 
     unsigned hwa[K], hwb[K], ewa[K], ewb[K];                   // windows of horizontally reduced rows
@@ -339,7 +344,9 @@ morph_stream_kernel(const uint32_t *__restrict__ in, size_t in_pitch_w, size_t i
                 oa = (oa ^ m2) & keepa; ob = (ob ^ m2) & keepb;
                 store = i >= 4 * H && yc - H < ye;
             }
-            if (store) {
+            if (FAST) {
+                if (store && wra) *reinterpret_cast<uint2 *>(dst) = make_uint2(oa, ob);
+            } else if (store) {
                 if (wra && wrb && pair) {
                     *reinterpret_cast<uint2 *>(dst) = make_uint2(oa, ob);
                 } else {
@@ -395,12 +402,13 @@ extern "C" int va_morph_bits(va_ctx *ctx, va_stream stream,
             // 8-byte accesses need even word offsets: rows start 8-byte aligned and strips start at even words
             const int vec = va_aligned(in, 8) && va_aligned(out, 8) && in_pitch_w % 2 == 0 && out_pitch_w % 2 == 0 &&
                             in_fstride_w % 2 == 0 && out_fstride_w % 2 == 0 && passes % 2 == 0;
+            const bool fast = vec && wpw % 2 == 0 && wpw >= 2 && !getenv("VA_MORPH_GENERAL");
             const long long n_warps = (long long)strips * segs * batch;
             VA_REQUIRE(ctx, n_warps < (1ll << 31), "va_morph_bits: too many strips");
             const int grid = va_div_up(n_warps, MORPH_S_THREADS / 32);
 #define MORPH_SGO(KK, PP)                                                                                  \
             do {                                                                                           \
-                auto kfn = morph_stream_kernel<KK, PP>;                                                    \
+                auto kfn = (PP == 2 && fast) ? morph_stream_kernel<KK, PP, PP == 2> : morph_stream_kernel<KK, PP, false>; \
                 VA_LAUNCH(ctx, kfn, grid, MORPH_S_THREADS, 0, stream, in, in_pitch_w, in_fstride_w, out,   \
                           out_pitch_w, out_fstride_w, w, h, strips, segs, SH, (int)n_warps, first, second, vec); \
             } while (0)
