@@ -416,7 +416,7 @@ def test_ema_flat_group_mapping(be, ctx, monkeypatch):
     # widths that are multiples of 32 but not of a whole warp step take the raster-order group mapping
     # (warps straddle rows, the last warp has idle lanes); both pixels-per-thread variants, and the
     # row-chunk mapping on the same input as the cross-check
-    for px in ('4', '16'):
+    for px in ('4', '8', '16'):
         monkeypatch.setenv('VA_EMA_PX', px)
         for (B, H, W) in sizes(be, [(5, 9, 96), (4, 7, 160), (3, 5, 1056), (6, 1, 32)], [(5, 1080, 1920), (4, 720, 1280)]):
             g = noisy_video(W, (B, H, W))
@@ -430,6 +430,25 @@ def test_ema_flat_group_mapping(be, ctx, monkeypatch):
                 assert np.array_equal(m, ops.pack_bits(m_ref)), (px, B, H, W, noflat)
                 assert np.array_equal(bg.view(np.uint32), bg_ref.view(np.uint32))
     monkeypatch.delenv('VA_EMA_NOFLAT', raising=False)
+
+
+def test_ema_unrolled_ring_rounds(be, ctx, monkeypatch):
+    # batches longer than the cp.async ring: whole turns of the unrolled frame loop plus a tail, on shapes where every
+    # lane is on the aligned path (the unrolled variant) and on one where it is not (the general loop), for every
+    # pixels-per-thread variant; continuation batches start from the state of the first
+    for px in ('16', '8', '4'):
+        monkeypatch.setenv('VA_EMA_PX', px)
+        for (B, H, W) in sizes(be, [(19, 4, 512), (9, 2, 1024), (17, 3, 96), (33, 2, 256)], [(19, 480, 640), (35, 64, 1024)]):
+            g = noisy_video(B + W, (B, H, W))
+            m_ref, bg_ref = ops.background_ema(list(g), 0.05, 25)
+            m, bg = hz.ema_diff_thresh(ctx, g, 0.05, 25)
+            assert np.array_equal(m, ops.pack_bits(m_ref)), (px, B, H, W)
+            assert np.array_equal(bg.view(np.uint32), bg_ref.view(np.uint32))
+            m2_ref, bg2_ref = ops.background_ema(list(g[::-1]), 0.05, 25, bg0=bg_ref)
+            m2, bg2 = hz.ema_diff_thresh(ctx, g[::-1].copy(), 0.05, 25, bg0=bg_ref)
+            assert np.array_equal(m2, ops.pack_bits(m2_ref)), (px, B, H, W)
+            assert np.array_equal(bg2.view(np.uint32), bg2_ref.view(np.uint32))
+    monkeypatch.delenv('VA_EMA_PX', raising=False)
 
 
 def test_ema_threshold_edge_cases(be, ctx):
