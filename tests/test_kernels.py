@@ -133,10 +133,16 @@ def test_gauss_tensor_core_kernel(be, ctx, monkeypatch):
         for s in sig:
             want = np.stack([ops.blur(f, s) for f in g])
             full = n == 0 and (be.name == 'cuda' or s in (2, 5, 15))
+            # the large radii (G > 2) run the CTA-per-strip kernel with two tiles per warp by default; VA_GM_CTA=0: the
+            # warp-per-strip kernel for them as well; VA_GMC_TPW: one / four tiles per warp
             variants = [dict(), dict(VA_GM_SEGS=1), dict(VA_GM_SEGS=3, VA_GM_TILES=8), dict(VA_GM_STAGES=2),
-                        dict(VA_GM_STAGES=3, VA_GM_MINB=3)] if full else [dict()]
+                        dict(VA_GM_STAGES=3, VA_GM_MINB=3), dict(VA_GM_CTA=0), dict(VA_GM_CTA=0, VA_GM_SEGS=2, VA_GM_TILES=8),
+                        dict(VA_GMC_TPW=1, VA_GM_MINB=2, VA_GM_SEGS=2, VA_GMC_STAGES=3), dict(VA_GMC_TPW=4),
+                        dict(VA_GMC_STAGES=9, VA_GM_SEGS=3)] if full else \
+                ([dict(), dict(VA_GM_CTA=0), dict(VA_GMC_TPW=1)] if be.name == 'cuda' else
+                 [dict(), dict(VA_GM_CTA=0)] if s in (3, 15) else [dict()])
             for var in variants:
-                for key in ('VA_GM_SEGS', 'VA_GM_TILES', 'VA_GM_STAGES', 'VA_GM_MINB'):
+                for key in ('VA_GM_SEGS', 'VA_GM_TILES', 'VA_GM_STAGES', 'VA_GM_MINB', 'VA_GM_CTA', 'VA_GMC_STAGES', 'VA_GMC_TPW'):
                     monkeypatch.delenv(key, raising=False)
                 for key, val in var.items():
                     monkeypatch.setenv(key, str(val))
@@ -145,7 +151,7 @@ def test_gauss_tensor_core_kernel(be, ctx, monkeypatch):
                 assert np.array_equal(hz.luma_gauss(ctx, fr, s, mode=2), want), (H, W, s, var)
                 if s in (1, 2, 15):
                     assert np.array_equal(hz.luma_gauss(ctx, fr, s), np.stack([ops.blur(ops.mono(f), s) for f in fr])), (H, W, s, var)
-    for key in ('VA_GM_SEGS', 'VA_GM_TILES', 'VA_GM_STAGES', 'VA_GM_MINB'):
+    for key in ('VA_GM_SEGS', 'VA_GM_TILES', 'VA_GM_STAGES', 'VA_GM_MINB', 'VA_GM_CTA', 'VA_GMC_STAGES', 'VA_GMC_TPW'):
         monkeypatch.delenv(key, raising=False)
     monkeypatch.setenv('VA_GAUSS_MMA', '0')
     assert np.array_equal(hz.gauss(ctx, g, 5), np.stack([ops.blur(f, 5) for f in g]))

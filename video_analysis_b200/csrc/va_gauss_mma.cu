@@ -31,6 +31,7 @@
 #define GM_OUT_PITCH(TILES) (16 * (TILES) + 16)   // bytes per row of the output tile: rows land in different banks
 #define GM_MAX_G 8
 #define GM_MAX_STAGES 4
+#define GMC_MAX_STAGES 16       // CTA-per-strip kernel: a stage is only 8 rows x (128 + 2 HL) bytes
 
 struct GaussMma {
     int r;                  // radius, taps K[0 .. 2r]
@@ -368,6 +369,216 @@ gauss_mma_kernel(const __grid_constant__ va_tmap map8, const __grid_constant__ v
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Large radii (G > 2 groups, sigma > 2.7): one CTA of 8 warps per 128-column strip.
+//
+// The warp-per-strip kernel above keeps a ring of 16 G rows x strip x 16 bit per WARP (14 KB at sigma = 15 with 64-column
+// strips) and stages strip + 160 halo columns per warp: 6 warps fit on an SM and each runs its phases one after the other.
+// Here the warps of a CTA share the staged source rows (one TMA box of 8 rows x (128 + 2 HL) bytes per half-step,
+// issued by thread 0) and every warp owns TPW of the eight 16-column tiles: its row pass reads the shared rows, its results
+// go to a lane-private ring of G x 512 bytes per tile that only the same warp reads again in the column pass -- no data
+// crosses warps except the source rows and the output tile.  Shared memory per tile drops threefold (sigma = 15: 5.4
+// instead of 17 KB), the staged halo is shared by 128 instead of 64 columns, 16 warps are resident instead of 6, and three
+// CTA barriers per 16 rows replace the per-warp TMA bookkeeping (sigma 15, 32 frames: 0.293 -> 0.197 ms):  [wait stage | mirror fix (edge strips) | row pass | barrier | refill stage] x 2,  column pass -> output
+// tile, barrier, 16 rows x 128 bytes to global memory.  Same arithmetic, same fragments, same bytes as above.
+// ---------------------------------------------------------------------------------------------------------
+#define GMC_WARPS 8            // 16-column tiles of a strip (the name is from the one-tile-per-warp layout)
+__host__ __device__ inline size_t gmc_smem(int G, int stages) {
+    const size_t LW = (size_t)(16 * GMC_WARPS + 2 * gm_hl(G, false));
+    const size_t SP = (LW + 127) & ~(size_t)127;
+    return 256 + (size_t)stages * 8 * SP + 16 * (size_t)GM_OUT_PITCH(GMC_WARPS) + (size_t)GMC_WARPS * G * 512 + 128;
+}
+
+// TPW = tiles per warp: 8 / TPW warps per CTA (a warp's fixed cost per 16 rows is spread over TPW tiles)
+template <int G, int MINB, int TPW>
+__global__ void __launch_bounds__(32 * GMC_WARPS / TPW, MINB)
+gauss_mma_cta_kernel(const __grid_constant__ va_tmap map8, const __grid_constant__ va_tmap map1,
+                     uint8_t *__restrict__ out, size_t out_pitch, size_t out_fstride,
+                     int w, int h, int batch, const __grid_constant__ GaussMma gp) {
+    typedef GmGeom<false, G, GMC_WARPS> Geo;
+    constexpr int KS = Geo::KS, HL = Geo::HL, off = Geo::OFF, LW = Geo::LW;
+    constexpr int STRIP = 16 * GMC_WARPS, OPITCH = GM_OUT_PITCH(GMC_WARPS);
+    constexpr int KF = G / 2;
+    constexpr int SP = (LW + 127) & ~127;
+    constexpr int NT = 32 * GMC_WARPS / TPW;
+    const int NS = gp.stages;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int r = gp.r, SH = gp.SH;
+
+    const long long task = blockIdx.x;
+    const int strip = (int)(task % gp.strips);
+    const int seg = (int)((task / gp.strips) % gp.segs);
+    const int frame = (int)(task / ((long long)gp.strips * gp.segs));
+    const int x0 = strip * STRIP, y0 = seg * SH;
+    const int rows = min(SH, h - y0);
+    const int nblocks = (rows + 15) >> 4;
+
+    VA_DYN_SMEM(unsigned char, smem_raw);
+#ifdef VA_EMU
+    unsigned char *sm0 = smem_raw;
+#else
+    unsigned char *sm0 = smem_raw + ((128u - ((unsigned)__cvta_generic_to_shared(smem_raw) & 127u)) & 127u);
+#endif
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm0);                               // [NS]
+    unsigned char *stage0 = sm0 + 256;
+    unsigned char *otile = stage0 + (size_t)NS * 8 * SP;
+    uint4 *ring = reinterpret_cast<uint4 *>(otile + 16 * OPITCH) + (size_t)warp * TPW * G * 32;   // [G][TPW][32] of this warp
+
+    // ---- constant Toeplitz fragments (as in gauss_mma_kernel) ----------------------------------------------
+    unsigned A1[KS][4];
+#pragma unroll
+    for (int ks = 0; ks < KS; ks++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int m = g + ((q & 1) ? 8 : 0);
+            const int xo = 4 * ((m & 7) >> 1) + (m & 1) + ((m & 8) ? 2 : 0);
+            unsigned wd = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int c = 32 * ks + 8 * t + ((q & 2) ? 4 : 0) + j;
+                wd |= gm_tap(gp, c - off - xo + r) << (8 * j);
+            }
+            A1[ks][q] = wd;
+        }
+    unsigned A2[KF > 0 ? KF : 1][4], A2t[2] = {0, 0};
+#pragma unroll
+    for (int grp = 0; grp < G; grp++)
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const int m = g + (q ? 8 : 0);
+            unsigned wd = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int rho = j < 2 ? 2 * t + j : 8 + 2 * t + (j - 2);
+                wd |= gm_tap(gp, 16 * grp + rho - m) << (8 * j);
+            }
+            if (grp < 2 * KF) A2[grp >> 1][q + ((grp & 1) ? 2 : 0)] = wd;
+            else A2t[q] = wd;
+        }
+
+    // ---- TMA producer (thread 0) ------------------------------------------------------------------------------
+    if (tid == 0) {
+        for (int i = 0; i < NS; i++) va_mbar_init(&bars[i], 1);
+        va_mbar_fence_init();
+    }
+    __syncthreads();
+    const int n_half = 2 * (nblocks + G - 1);
+    const int x32 = (x0 - HL) >> 2;                // x0 - HL is a multiple of 16 (may be negative)
+    auto issue = [&](int hs, int st) {             // rows 8 hs .. 8 hs + 7 of the segment's padded row space into stage st
+        if (tid != 0 || hs >= n_half) return;
+        uint64_t *bar = &bars[st];
+        unsigned char *dst = stage0 + (size_t)st * 8 * SP;
+        const int ya = y0 - r + 8 * hs;
+        va_mbar_expect_tx(bar, 8u * (unsigned)LW);
+        if (ya >= 0 && ya + 7 < h) va_tma_load_3d(dst, &map8, bar, x32, ya, frame);
+        else gm_issue_rows(dst, &map1, bar, x32, ya, h, frame, SP);
+    };
+    for (int i = 0; i < NS; i++) issue(i, i);
+    __syncthreads();
+
+    const bool fix_l = x0 - HL < 0, fix_r = x0 + STRIP + HL > w;
+    uint8_t *fout = out + (size_t)frame * out_fstride;
+    unsigned hold0[TPW], hold1[TPW];
+    int st = 0;
+    unsigned phases = 0;
+
+    for (int S = 0; S < nblocks + G - 1; S++) {
+        const int slot = S % G;
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            const int hs = 2 * S + half;
+            va_mbar_wait(&bars[st], (phases >> st) & 1u);
+            phases ^= 1u << st;
+            unsigned char *stg = stage0 + (size_t)st * 8 * SP;
+            const int ya = y0 - r + 8 * hs;
+            const int sp = (ya >= 0 && ya + 7 < h) ? LW : SP;      // row pitch of this stage (see issue())
+            if (fix_l || fix_r) {
+                // BORDER_REFLECT_101 in x, the whole CTA on the 8 staged rows (edge strips only)
+                for (int it = tid; it < 8 * r; it += NT) {
+                    const int row = it / r, k = it - row * r + 1;
+                    unsigned char *p = stg + (size_t)row * sp + HL;
+                    if (fix_l && x0 + k <= HL) p[-x0 - k] = p[-x0 + k];
+                    if (fix_r) {
+                        const int d = w - 1 - x0 + k;
+                        if (d < STRIP + HL) p[d] = p[w - 1 - x0 - k];
+                    }
+                }
+                __syncthreads();
+            }
+            // ---- row pass of this warp's tiles: 8 rows x 16 columns each
+#pragma unroll
+            for (int jj = 0; jj < TPW; jj++) {
+                int c[4] = {0, 0, 0, 0};
+                const unsigned char *bp = stg + (size_t)g * sp + (HL - off) + 16 * (warp * TPW + jj) + 8 * t;
+#pragma unroll
+                for (int ks = 0; ks < KS; ks++) {
+                    const uint2 bq = *reinterpret_cast<const uint2 *>(bp + 32 * ks);
+                    va_imma_16832(c, A1[ks], bq.x, bq.y);
+                }
+                const unsigned pg = __byte_perm((unsigned)c[0], (unsigned)c[1], 0x5140);
+                const unsigned pg8 = __byte_perm((unsigned)c[2], (unsigned)c[3], 0x5140);
+                if (half == 0) {
+                    hold0[jj] = pg;
+                    hold1[jj] = pg8;
+                } else {
+                    ring[(slot * TPW + jj) * 32 + lane] =
+                        make_uint4(__byte_perm(hold0[jj], pg, 0x5410), __byte_perm(hold0[jj], pg, 0x7632),
+                                   __byte_perm(hold1[jj], pg8, 0x5410), __byte_perm(hold1[jj], pg8, 0x7632));
+                }
+            }
+            __syncthreads();                                        // every warp is done with the stage
+            issue(hs + NS, st);
+            st = st + 1 == NS ? 0 : st + 1;
+        }
+        if (S >= G - 1) {
+            // ---- column pass of this warp's tiles: output rows y0 + 16 b .. + 15 from groups b .. b + G - 1
+            const int b = S - (G - 1);
+#pragma unroll
+            for (int jj = 0; jj < TPW; jj++) {
+                uint4 v[G];
+#pragma unroll
+                for (int i = 0; i < G; i++) {
+                    int sl = b + i;
+                    sl -= (sl / G) * G;
+                    v[i] = ring[(sl * TPW + jj) * 32 + lane];
+                }
+                unsigned res[2][2];
+#pragma unroll
+                for (int nh = 0; nh < 2; nh++) {
+                    // (splitting these into independent accumulator chains -- even / odd k steps, high / low plane -- was measured
+                    // slower, 0.279 vs 0.270 ms per 32 frames at sigma 15: the kernel waits at its barriers, not for the tensor pipe)
+                    int hi[4] = {0, 0, 0, 0};
+#pragma unroll
+                    for (int ks = 0; ks < KF; ks++)
+                        va_imma_16832(hi, A2[ks], nh ? v[2 * ks].w : v[2 * ks].y, nh ? v[2 * ks + 1].w : v[2 * ks + 1].y);
+                    if (G & 1) va_imma_16816(hi, A2t[0], A2t[1], nh ? v[G - 1].w : v[G - 1].y);
+                    int lo[4] = {hi[0] * 256 + 32768, hi[1] * 256 + 32768, hi[2] * 256 + 32768, hi[3] * 256 + 32768};
+#pragma unroll
+                    for (int ks = 0; ks < KF; ks++)
+                        va_imma_16832(lo, A2[ks], nh ? v[2 * ks].z : v[2 * ks].x, nh ? v[2 * ks + 1].z : v[2 * ks + 1].x);
+                    if (G & 1) va_imma_16816(lo, A2t[0], A2t[1], nh ? v[G - 1].z : v[G - 1].x);
+                    res[0][nh] = __byte_perm((unsigned)lo[0], (unsigned)lo[1], 0x0062);
+                    res[1][nh] = __byte_perm((unsigned)lo[2], (unsigned)lo[3], 0x0062);
+                }
+                unsigned char *op = otile + g * OPITCH + 16 * (warp * TPW + jj) + 4 * t;
+                *reinterpret_cast<unsigned *>(op) = __byte_perm(res[0][0], res[0][1], 0x5410);
+                *reinterpret_cast<unsigned *>(op + 8 * OPITCH) = __byte_perm(res[1][0], res[1][1], 0x5410);
+            }
+            __syncthreads();
+            // ---- 16 rows x 128 bytes -> global: 16-byte stores (the next write to the tile comes two barriers later)
+            for (int idx = tid; idx < 16 * GMC_WARPS; idx += NT) {
+                const int row = idx >> 3, c16 = idx & 7;
+                const int yl = 16 * b + row, x = x0 + 16 * c16;
+                if (yl < rows && x < w) {
+                    const uint4 val = *reinterpret_cast<const uint4 *>(otile + row * OPITCH + 16 * c16);
+                    va_st_stream16(fout + (size_t)(y0 + yl) * out_pitch + x, val);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // launch; returns VA_ERR_UNSUPPORTED when the shape is outside this kernel's range (the caller falls back)
 // ---------------------------------------------------------------------------------------------------------
 int va_gauss_mma_launch(va_ctx *ctx, va_stream stream, const char *name, bool fuse,
@@ -386,6 +597,63 @@ int va_gauss_mma_launch(va_ctx *ctx, va_stream stream, const char *name, bool fu
     // strip width: 128 columns; 64 where the ring of row-pass results (16 G rows x strip x 16 bit per warp) would leave too few
     // warps per SM.  The fused variant exists for G == 2 (the chain's sigma); larger radii convert first (gauss_launch).
     if (fuse && G > 2) return VA_ERR_UNSUPPORTED;
+    // large radii: one CTA per 128-column strip (gauss_mma_cta_kernel), two tiles per warp.  Measured per 32 frames of 1080p
+    // against the warp-per-strip kernel, sigma 5 / 9 / 15 (G = 3 / 5 / 7): 0.121 / 0.201 / 0.293 ms there; here 0.150 / 0.238 /
+    // 0.274 with one tile per warp (a warp's fixed cost per 16 rows on a single tile: twice the instructions, and the CTA
+    // waits at its barriers), 0.098 / 0.150 / 0.197 with two, 0.097 / 0.153 / 0.231 with four.  The number of TMA stages
+    // (4 ... 16) does not matter.  VA_GM_CTA = 0 forces the warp-per-strip kernel.
+    const bool use_cta = getenv("VA_GM_CTA") ? atoi(getenv("VA_GM_CTA")) != 0 : true;
+    if (!fuse && G > 2 && use_cta) {
+        GaussMma gp;
+        memset(&gp, 0, sizeof(gp));
+        gp.r = r;
+        gp.mode = mode;
+        gp.stages = 4;
+        if (getenv("VA_GMC_STAGES")) gp.stages = atoi(getenv("VA_GMC_STAGES"));
+        if (gp.stages < 2) gp.stages = 2;
+        if (gp.stages > GMC_MAX_STAGES) gp.stages = GMC_MAX_STAGES;
+        for (int i = 0; i < ksize; i++) gp.taps[i] = (unsigned char)taps[i];
+        const int LW = 16 * GMC_WARPS + 2 * gm_hl(G, false);
+        if ((unsigned)(LW / 4) > 256u) return VA_ERR_UNSUPPORTED;
+        gp.strips = va_div_up(w, 16 * GMC_WARPS);
+        const size_t smem = gmc_smem(G, gp.stages);
+        if (smem > 220 * 1024) return VA_ERR_UNSUPPORTED;
+        int ctas_per_sm = (int)((size_t)(224 * 1024) / (smem + 1024));
+        const int tpw = getenv("VA_GMC_TPW") ? atoi(getenv("VA_GMC_TPW")) : 2;            // tiles per warp: 1, 2 or 4
+        const int minb = getenv("VA_GM_MINB") ? atoi(getenv("VA_GM_MINB")) : 3;       // registers: 3 CTAs of 256 threads at <= 85
+        if (ctas_per_sm > (tpw > 1 ? 4 : minb)) ctas_per_sm = tpw > 1 ? 4 : minb;
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+        const long long slots = (long long)ctx->sm_count * ctas_per_sm;
+        int segs = (int)va_div_up(4 * slots, (long long)gp.strips * batch);
+        const int max_segs = h / (64 * (G - 1)) > 0 ? h / (64 * (G - 1)) : 1;             // re-staged rows <= 25 %
+        if (segs > max_segs) segs = max_segs;
+        if (getenv("VA_GM_SEGS")) segs = atoi(getenv("VA_GM_SEGS"));
+        if (segs < 1) segs = 1;
+        gp.SH = 16 * va_div_up(h, 16 * segs);
+        gp.segs = va_div_up(h, gp.SH);
+        va_tmap map8, map1;
+        if (va_tmap_encode(&map8, in, (size_t)w, h, batch, in_pitch, in_fstride, (unsigned)(LW / 4), 8) != 0 ||
+            va_tmap_encode(&map1, in, (size_t)w, h, batch, in_pitch, in_fstride, (unsigned)(LW / 4), 1) != 0)
+            return VA_ERR_UNSUPPORTED;
+        const long long grid = (long long)gp.strips * gp.segs * batch;
+        if (grid > 0x7fffffffll) return VA_ERR_UNSUPPORTED;
+#define GMC_GO(GG, MB, TP)                                                                                       \
+        do {                                                                                                     \
+            auto kfn = gauss_mma_cta_kernel<GG, MB, TP>;                                                         \
+            if (smem > 48 * 1024)                                                                                \
+                VA_CUDA(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            VA_LAUNCH(ctx, kfn, (unsigned)grid, 32 * GMC_WARPS / TP, smem, stream, map8, map1, out, out_pitch, out_fstride, w, h, batch, gp); \
+        } while (0)
+#define GMC_CASE(GG) case GG: if (tpw == 4) GMC_GO(GG, 4, 4); else if (tpw == 2) GMC_GO(GG, 4, 2); else if (minb >= 3) GMC_GO(GG, 3, 1); else GMC_GO(GG, 2, 1); break;
+        switch (G) {
+            GMC_CASE(3) GMC_CASE(4) GMC_CASE(5) GMC_CASE(6) GMC_CASE(7) GMC_CASE(8)
+            default: return VA_ERR_UNSUPPORTED;
+        }
+#undef GMC_CASE
+#undef GMC_GO
+        (void)name;
+        return VA_OK;
+    }
     int tiles = G <= 2 ? 8 : 4;
     if (getenv("VA_GM_TILES")) tiles = atoi(getenv("VA_GM_TILES")) == 8 ? 8 : 4;
     if (G == 2) tiles = 8;
