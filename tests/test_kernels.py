@@ -126,13 +126,16 @@ def test_gauss_tensor_core_kernel(be, ctx, monkeypatch):
     # both strip widths, 2 .. 4 TMA stages, one and several row segments, strips cut by the right image edge, images
     # barely larger than the radius, fused (mean and channel pick) and plain; identical to the dot-product kernels
     cases = sizes(be, [(40, 160), (70, 272), (21, 336), (130, 144)], [(480, 640), (1080, 1920), (271, 1008), (67, 2064)])
-    sig = [0.5, 1, 2, 2.6, 3, 3.5, 5, 6, 8, 9, 12, 15, 18]
+    # (the emulator takes one sigma per group count, and only three of them on the last two shapes)
+    sig = [0.5, 1, 2, 2.6, 3, 3.5, 5, 6, 8, 9, 12, 15, 18] if be.name == 'cuda' else [0.5, 2, 3, 6, 9, 12, 15, 18]
     for n, (H, W) in enumerate(cases):
         fr = rng_frames(H * W, (2, H, W, 3))
         g = fr[..., 2].copy()
         for s in sig:
+            if be.name != 'cuda' and n >= 2 and s not in (2, 15, 18):
+                continue
             want = np.stack([ops.blur(f, s) for f in g])
-            full = n == 0 and (be.name == 'cuda' or s in (2, 5, 15))
+            full = n == 0 and (be.name == 'cuda' or s in (2, 15))
             # the large radii (G > 2) run the CTA-per-strip kernel with two tiles per warp by default; VA_GM_CTA=0: the
             # warp-per-strip kernel for them as well; VA_GMC_TPW: one / four tiles per warp
             variants = [dict(), dict(VA_GM_SEGS=1), dict(VA_GM_SEGS=3, VA_GM_TILES=8), dict(VA_GM_STAGES=2),
