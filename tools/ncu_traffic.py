@@ -9,7 +9,7 @@ import subprocess
 import sys
 
 STAGES = {'luma_gauss': ['gauss_mma_kernel<1, 2', 'gauss_stream_kernel<6, 1'], 'gauss': ['gauss_mma_kernel<0, 2', 'gauss_stream_kernel<6, 0'],
-          'gauss_sigma15': ['gauss_mma_kernel<0, 7'], 'luma': ['luma_fast_kernel'],
+          'gauss_sigma15': ['gauss_mma_cta_kernel<7', 'gauss_mma_kernel<0, 7'], 'luma': ['luma_fast_kernel'],
           'ema_diff_thresh': ['ema_diff_thresh_kernel'], 'morph_open': ['morph_stream_kernel'],
           'label': ['label_init_kernel', 'label_merge_kernel', 'label_flatten_kernel', 'label_scan_kernel', 'label_write_kernel'],
           'label_forest': ['label_init_kernel', 'label_merge_kernel', 'label_flatten_kernel', 'label_scan_kernel'],

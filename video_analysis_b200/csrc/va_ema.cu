@@ -3,17 +3,16 @@
 //
 // The recurrence is sequential in t, parallel in pixels: a thread owns PX pixels,
 // keeps their float32 background in registers across the whole batch of T frames
-// and streams the T u8 frames through (4 frames of loads in flight per thread).
+// and streams the T u8 frames through (8 frames of loads in flight per thread, a cp.async ring in shared memory).
 // Algorithmic HBM bytes per frame: N (u8 in) + N/8 (bits out) + 8N/T (state in/out).
 //   d = float(x) - bg;  bit = |d| > thr;  bg = bg + alpha * d     (mul and add rounded
-// separately: __fmul_rn / __fadd_rn keep the compiler from contracting to an FMA, so the
-// result is bit-identical to the NumPy float32 oracle).
+// separately -- on packed float32 pairs, see ema_step_packed -- so the result is bit-identical to the NumPy
+// float32 oracle).
 #include <cstdlib>
 
 #include "va_device.cuh"
 
 #define EMA_THREADS 256
-#define EMA_DEPTH 4
 
 template <int PX>
 __device__ __forceinline__ void ema_load(const uint8_t *rp, int x, int w, bool vec, unsigned (&v)[PX / 4]) {
