@@ -42,7 +42,12 @@ if os.environ.get('PROF_EXTRA', '1') != '0':
     ids = _t.empty((B, 30 * H), dtype=_t.int32, pin_memory=True)
     data = _t.empty((B, 30 * H, 64), dtype=_t.int32, pin_memory=True)
     nn = _t.empty((B,), dtype=_t.int32, pin_memory=True)
+    runs = _t.empty((B, 30 * H, 4), dtype=_t.int32, pin_memory=True)
+    nr = _t.empty((B,), dtype=_t.int32, pin_memory=True)
+    # PROF_EXPORT_RAW=1: every chunk travels raw (260 bytes), as before the run chunks
+    raw = os.environ.get('PROF_EXPORT_RAW', '0') == '1'
     rt._check(rt.lib.va_label_export_chunks(rt._h, rt.stream, *mo.img(), *lab.img(), W, H, B, ids.data_ptr(), data.data_ptr(),
-                                            nn.data_ptr(), None, None, None, 30 * H))
+                                            nn.data_ptr(), None, None if raw else runs.data_ptr(), None if raw else nr.data_ptr(),
+                                            30 * H))
 torch.cuda.synchronize()
 print('ok', cnt[:4].tolist(), rt.launches)
