@@ -14,7 +14,7 @@
 //   order        raster order per frame (rows, then chunks), so the export is deterministic
 //   run chunk    a chunk whose foreground pixels are ONE horizontal run carries one label (a run lies in one component),
 //                so it travels as 16 bytes -- (id, label, 64-bit pixel mask) -- instead of 260: inside blobs that is
-//                nearly every chunk (1080p chain: 36.7 -> 3.6 MB per 64 frames).  Chunks with several runs travel raw.
+//                most chunks (1080p chain: 36.7 -> 6.7 MB per 64 frames).  Chunks with several runs travel raw.
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -228,11 +228,12 @@ extern "C" int va_host_densify_chunks(int32_t *dense, size_t pitch_e, size_t fst
         for (int i = 0; i < nr; i++) {
             const int id = fr[4 * i], lab = fr[4 * i + 1], y = id / cpr, c = id - y * cpr;
             const unsigned long long m = ((unsigned long long)(uint32_t)fr[4 * i + 3] << 32) | (uint32_t)fr[4 * i + 2];
+            dirty[n + i] = id;
+            if (m == 0ull) continue;                         // never written by the device; nothing to fill
             const int start = __builtin_ctzll(m), len = __builtin_popcountll(m);
             const int room = (c == cpr - 1 ? last_e : VA_CHUNK_E) - start;
             int32_t *p = img + (size_t)y * pitch_e + (size_t)c * VA_CHUNK_E + start;
             for (int k = 0; k < (len < room ? len : room); k++) p[k] = lab;
-            dirty[n + i] = id;
         }
         n_dirty[b] = n + nr;
     };
