@@ -195,3 +195,50 @@ def test_device_filter_pull_loop_sees_every_frame_of_a_stream(batch, ring):
     assert np.array_equal(np.concatenate(out), fr[start:])
     assert short > 1                                                # short blocks occurred and did not end the video
     v.close()
+
+
+def test_file_source_with_parallel_readers():
+    # the path of a regular file is read by several threads with os.preadv; frames come out in order, the ring is never
+    # overrun, a file shorter / longer than announced behaves like the single-reader stream
+    fr = frames_of(120)
+    path = os.path.join(os.path.dirname(__file__), '_raw_par_tmp.bin')
+    try:
+        fr.tofile(path)
+        for readers in (1, 2, 4, 7):
+            v = VideoRawStream(path, (W, H), 120, ring_frames=12, readers=readers, pinned=False)
+            assert (v._fd is not None) == (readers > 1)
+            pos, out = 0, []
+            while True:
+                b = v.frame_block(pos, pos + 2)
+                if len(b) == 0:
+                    break
+                out.append(b.copy())
+                assert v._produced - v._release <= 12
+                pos += len(b)
+            assert np.array_equal(np.concatenate(out), fr), readers
+            v.close()
+        # length over-estimated by a frame: the stream ends where the file ends; iteration yields every frame
+        v = VideoRawStream(path, (W, H), 121, ring_frames=12, pinned=False)
+        assert np.array_equal(np.stack(list(v)), fr)
+        v.close()
+        # length under-estimated: `frame_count` is an estimate, the stream delivers what the file holds (like one reader)
+        for readers in (1, 4):
+            v = VideoRawStream(path, (W, H), 100, ring_frames=12, pinned=False, readers=readers)
+            assert np.array_equal(np.stack(list(v)), fr)
+            v.close()
+        # a file that ends in the middle of a frame far from the announced end: the last good frame is repeated once
+        with open(path, 'r+b') as f:
+            f.truncate(60 * W * H * 3 + 17)
+        v = VideoRawStream(path, (W, H), 120, ring_frames=12, pinned=False)
+        got = np.stack(list(v))
+        assert len(got) == 61 and np.array_equal(got[:60], fr[:60]) and np.array_equal(got[60], fr[59])
+        v.close()
+        # an empty file raises like the stream that ends before its first frame
+        open(path, 'wb').close()
+        v = VideoRawStream(path, (W, H), 120, ring_frames=12, pinned=False)
+        with pytest.raises(RawStreamError):
+            v.get_next_frame()
+        v.close()
+    finally:
+        if os.path.exists(path):
+            os.remove(path)

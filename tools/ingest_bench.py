@@ -44,9 +44,12 @@ def main():
                 got += len(b)
                 pos += len(b)
 
-        for name, factory in (('file on tmpfs', lambda i: open(path, 'rb', buffering=0)),
-                              ('pipe from a child process (cat)', lambda i: ['cat', path])):
-            v = VideoRawStream(factory, (W, H), n, ring_frames=384, pinned=args.gpu)
+        for name, factory, readers in (('file on tmpfs, one reader (file object)', lambda i: open(path, 'rb', buffering=0), 1),
+                                       ('file on tmpfs by path, 2 readers (os.preadv)', lambda i: path, 2),
+                                       ('file on tmpfs by path, 4 readers (os.preadv)', lambda i: path, 4),
+                                       ('file on tmpfs by path, 8 readers (os.preadv)', lambda i: path, 8),
+                                       ('pipe from a child process (cat)', lambda i: ['cat', path], 1)):
+            v = VideoRawStream(factory, (W, H), n, ring_frames=384, pinned=args.gpu, readers=readers)
             drain(v)                                    # first pass touches the ring (page faults of a fresh allocation)
             t0 = time.perf_counter()
             v.set_frame_pos(0)                          # reopens the source
@@ -58,18 +61,19 @@ def main():
         if args.gpu:
             from video_analysis_b200.chain import SegmentChain
             ch = SegmentChain((W, H), batch=64)
-            for warm in (True, False):
-                v = VideoRawStream(['cat', path], (W, H), n, ring_frames=384)
-                _, blocks = ch._blocks_of(v)
-                t0 = time.perf_counter()
-                regions = 0
-                for stats, counts, largest in ch.process_blocks(blocks, max_regions=256):
-                    regions += int(counts.sum())
-                dt = time.perf_counter() - t0
-                v.close()
-                ch.reset()
-            print(json.dumps({'case': 'pipe -> ring -> SegmentChain.process_blocks(max_regions=256)', 'frames': n,
-                              'fps': round(n / dt, 1), 'regions': regions}), flush=True)
+            for name, src, readers in (('pipe', ['cat', path], 1), ('file by path, 8 readers', path, 8)):
+                for warm in (True, False):
+                    v = VideoRawStream(src, (W, H), n, ring_frames=384, readers=readers)
+                    _, blocks = ch._blocks_of(v)
+                    t0 = time.perf_counter()
+                    regions = 0
+                    for stats, counts, largest in ch.process_blocks(blocks, max_regions=256):
+                        regions += int(counts.sum())
+                    dt = time.perf_counter() - t0
+                    v.close()
+                    ch.reset()
+                print(json.dumps({'case': name + ' -> ring -> SegmentChain.process_blocks(max_regions=256)', 'frames': n,
+                                  'fps': round(n / dt, 1), 'regions': regions}), flush=True)
     finally:
         os.remove(path)
 
